@@ -1,0 +1,629 @@
+// tcgen05 / TMEM / TMA GEMM core for the SDXL UNet training step (sm_100a).
+//
+// One persistent, warp-specialised kernel serves every dense contraction of the hot path
+// (SURVEY.md 2.1 rows K3, K4, K5): the Linear layers (to_q/k/v, to_out, proj_in/out, GEGLU feed-forward,
+// time-embedding MLPs), their dgrad / wgrad, and the 3x3 / 1x1 convolutions as implicit GEMM over NHWC
+// activations (forward, dgrad, wgrad).  What the reference reaches through cuBLASLt / cuDNN calls inside
+// diffusers' UNet2DConditionModel (train.py:2760) is here:
+//
+//   warp 0      TMA producer : cp.async.bulk.tensor loads of A / B tiles into a 128B-swizzled smem ring
+//   warp 1      MMA issuer   : one elected thread issues tcgen05.mma (128 x BN x 16, bf16 -> fp32 in TMEM)
+//   warps 2..5  epilogue     : tcgen05.ld the accumulator (double-buffered in TMEM so the next tile's
+//                              main loop overlaps), fused bias / time-embedding / residual / GEGLU, bf16 store
+//
+// Operands are bf16.  Each operand is either K-major (rows = M or N index, 64 K-elements = 128 bytes per row)
+// or MN-major (rows = K index, 64 M/N-elements per row); both are expressed with the same 128B-swizzle
+// shared-memory layout and differ only in the UMMA descriptors, so x*W^T (forward), dy*W (dgrad) and
+// dy^T*x (wgrad) need no transposed copies.  Convolutions fetch the A operand (and B for wgrad) as shifted
+// 4-D TMA boxes of the NHWC tensor; out-of-bounds box elements are zero-filled by the TMA unit, which is
+// exactly the conv's zero padding.
+#include "common.cuh"
+#include <cstring>
+
+namespace aoz {
+
+constexpr int BM = 128;
+constexpr int BK = 64;
+constexpr int GEMM_THREADS = 192;   // 6 warps
+
+enum GemmMode : int { GM_LINEAR = 0, GM_CONV_FWD = 1, GM_CONV_WGRAD = 2 };
+enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
+
+struct GemmParams {
+    CUtensorMap tmA, tmB;
+    int mode, epi;
+    int a_mn, b_mn;                 // 1 = MN-major operand
+    int M, N, K;                    // logical extents (CONV_FWD: M = NB*H*W output pixels, K = taps*cin_chunks*64)
+    int m_tiles, n_tiles, k_iters;  // tile counts; k_iters = total K iterations (before split)
+    int splits;                     // split-K factor (EPI_PARTIAL when > 1)
+    // conv geometry (NHWC).  H, W = OUTPUT spatial size (CONV_FWD) / dy spatial size (CONV_WGRAD)
+    int NB, H, W, TH, TW, tiles_h, tiles_w;
+    int taps_s, pad, stride, cin_chunks, flip;   // taps_s = filter width (3 or 1); taps = taps_s*taps_s
+    int Cin, n_tiles_per_tap;       // CONV_WGRAD: column = tap*Cin + cin
+    int geglu_half;                 // EPI_GEGLU: N/2 (gate rows start here in W)
+    // epilogue
+    __nv_bfloat16* C; long long ldc;
+    const __nv_bfloat16* bias;      // [N] or null
+    const __nv_bfloat16* rowgroup_bias; int rows_per_group; long long ld_rgb;   // [groups, N] added per row group (temb)
+    const __nv_bfloat16* residual; long long ldr;
+    __nv_bfloat16* aux; long long ld_aux;          // GEGLU: pre-activation [M, 2*half]
+    float* partial;                 // EPI_PARTIAL: [splits][M][N] fp32
+    int accumulate;                 // EPI_STORE: C += result
+};
+
+template <int BN>
+struct SmemLayout {
+    static constexpr int A_BYTES = BM * BK * 2;             // 16 KB
+    static constexpr int B_BYTES = BN * BK * 2;             // 16 / 32 KB
+    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int BAR_BYTES = 1024;
+    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
+};
+
+// erf GELU (torch F.gelu default), fp32
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+template <int BN>
+__global__ void __launch_bounds__(GEMM_THREADS, 1)
+gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
+    using L = SmemLayout<BN>;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint8_t* bar_base = smem + L::STAGES * L::STAGE_BYTES;
+    uint64_t* full_bar = (uint64_t*)bar_base;                 // [STAGES]
+    uint64_t* empty_bar = full_bar + L::STAGES;               // [STAGES]
+    uint64_t* tfull_bar = empty_bar + L::STAGES;              // [2]
+    uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
+    uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+    if (warp == 0 && lane == 0) {
+        tma_prefetch_desc(&P.tmA);
+        tma_prefetch_desc(&P.tmB);
+        for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        fence_mbar_init();
+    }
+    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int total_work = P.m_tiles * P.n_tiles * P.splits;
+    const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
+
+    if (warp == 0) {
+        // ================================ TMA producer ================================
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+                const int tile = work / P.splits, split = work - tile * P.splits;
+                const int m_blk = tile % P.m_tiles, n_blk = tile / P.m_tiles;
+                const int k_begin = split * k_per_split;
+                const int k_end = min(P.k_iters, k_begin + k_per_split);
+                // conv tile origin
+                int img = 0, h0 = 0, w0 = 0;
+                if (P.mode == GM_CONV_FWD) {
+                    int t = m_blk;
+                    const int tw = t % P.tiles_w; t /= P.tiles_w;
+                    const int th = t % P.tiles_h; img = t / P.tiles_h;
+                    h0 = th * P.TH; w0 = tw * P.TW;
+                }
+                int wg_tap = 0, wg_c0 = 0;
+                if (P.mode == GM_CONV_WGRAD) {
+                    wg_tap = n_blk / P.n_tiles_per_tap;
+                    wg_c0 = (n_blk - wg_tap * P.n_tiles_per_tap) * BN;
+                }
+                for (int kit = k_begin; kit < k_end; ++kit) {
+                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
+                    uint8_t* sb = sa + L::A_BYTES;
+                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    if (P.mode == GM_LINEAR) {
+                        if (!P.a_mn) tma_load_2d(sa, &P.tmA, &full_bar[stage], kit * BK, m_blk * BM);
+                        else {
+#pragma unroll
+                            for (int j = 0; j < BM / 64; ++j)
+                                tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m_blk * BM + j * 64, kit * BK);
+                        }
+                        if (!P.b_mn) {
+                            if (P.epi == EPI_GEGLU) {
+                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * (BN / 2));
+                                tma_load_2d(sb + (BN / 2) * 128, &P.tmB, &full_bar[stage], kit * BK,
+                                            P.geglu_half + n_blk * (BN / 2));
+                            } else if (BN == 256) {
+                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
+                                tma_load_2d(sb + 128 * 128, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN + 128);
+                            } else {
+                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
+                            }
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < BN / 64; ++j)
+                                tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n_blk * BN + j * 64, kit * BK);
+                        }
+                    } else if (P.mode == GM_CONV_FWD) {
+                        const int tap = kit / P.cin_chunks, cc = kit - tap * P.cin_chunks;
+                        int r = tap / P.taps_s, s = tap - r * P.taps_s;
+                        if (P.flip) { r = P.taps_s - 1 - r; s = P.taps_s - 1 - s; }
+                        tma_load_4d(sa, &P.tmA, &full_bar[stage], cc * BK, w0 * P.stride + s - P.pad,
+                                    h0 * P.stride + r - P.pad, img);
+                        if (BN == 256) {
+                            tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
+                            tma_load_2d(sb + 128 * 128, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN + 128);
+                        } else {
+                            tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
+                        }
+                    } else {   // GM_CONV_WGRAD: K iteration = one 8x8 pixel tile of dy; both operands MN-major
+                        int t = kit;
+                        const int tw = t % P.tiles_w; t /= P.tiles_w;
+                        const int th = t % P.tiles_h; const int im = t / P.tiles_h;
+                        const int hh = th * P.TH, ww = tw * P.TW;
+                        const int r = wg_tap / P.taps_s, s = wg_tap - r * P.taps_s;
+#pragma unroll
+                        for (int j = 0; j < BM / 64; ++j)
+                            tma_load_4d(sa + j * 8192, &P.tmA, &full_bar[stage], m_blk * BM + j * 64, ww, hh, im);
+#pragma unroll
+                        for (int j = 0; j < BN / 64; ++j)
+                            tma_load_4d(sb + j * 8192, &P.tmB, &full_bar[stage], wg_c0 + j * 64,
+                                        ww * P.stride + s - P.pad, hh * P.stride + r - P.pad, im);
+                    }
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ================================ MMA issuer ================================
+        const uint32_t idesc = make_idesc_bf16(BM, BN, P.a_mn, P.b_mn);
+        uint32_t stage = 0, phase = 0;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+            const int tile = work / P.splits, split = work - tile * P.splits;
+            const int k_begin = split * k_per_split;
+            const int k_end = min(P.k_iters, k_begin + k_per_split);
+            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+            tc_fence_after();
+            const uint32_t tmem_d = tmem_base + acc * BN;
+            for (int kit = k_begin; kit < k_end; ++kit) {
+                mbar_wait(&full_bar[stage], phase);
+                tc_fence_after();
+                if (lane == 0) {
+                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                    const uint32_t sb = sa + L::A_BYTES;
+#pragma unroll
+                    for (int k = 0; k < BK / 16; ++k) {
+                        // K-major: advance 32 bytes inside the 128B row; MN-major: advance 16 K-rows = 2048 bytes
+                        const uint64_t da = P.a_mn ? make_sdesc_sw128(sa + k * 2048, 8192, 1024)
+                                                   : make_sdesc_sw128(sa + k * 32, 16, 1024);
+                        const uint64_t db = P.b_mn ? make_sdesc_sw128(sb + k * 2048, 8192, 1024)
+                                                   : make_sdesc_sw128(sb + k * 32, 16, 1024);
+                        umma_bf16(tmem_d, da, db, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+                    }
+                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
+                    if (kit == k_end - 1) umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
+                if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+            }
+            if (k_end <= k_begin && lane == 0) umma_commit(&tfull_bar[acc]);   // empty split: still signal
+            __syncwarp();
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    } else {
+        // ================================ epilogue (warps 2..5) ================================
+        const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int row_in_tile = q * 32 + lane;
+        uint32_t acc = 0, acc_phase = 0;
+        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+            const int tile = work / P.splits, split = work - tile * P.splits;
+            const int m_blk = tile % P.m_tiles, n_blk = tile / P.m_tiles;
+            const int k_begin = split * k_per_split;
+            const bool empty_split = min(P.k_iters, k_begin + k_per_split) <= k_begin;
+            // row mapping
+            long long row = 0; bool row_ok; int group = 0;
+            if (P.mode == GM_CONV_FWD) {
+                int t = m_blk;
+                const int tw = t % P.tiles_w; t /= P.tiles_w;
+                const int th = t % P.tiles_h; const int img = t / P.tiles_h;
+                const int h = th * P.TH + row_in_tile / P.TW, w = tw * P.TW + row_in_tile % P.TW;
+                row_ok = (h < P.H) && (w < P.W);
+                row = ((long long)img * P.H + h) * P.W + w;
+                group = img;
+            } else {
+                row = (long long)m_blk * BM + row_in_tile;
+                row_ok = row < P.M;
+                group = P.rows_per_group > 0 ? (int)(row / P.rows_per_group) : 0;
+            }
+            // column mapping
+            int col0, col_limit;                          // first output column of this tile / exclusive limit
+            long long col_shift = 0;                      // WGRAD: tap*Cin added to the column
+            constexpr int OUT_COLS = BN;
+            if (P.mode == GM_CONV_WGRAD) {
+                const int tap = n_blk / P.n_tiles_per_tap;
+                col0 = (n_blk - tap * P.n_tiles_per_tap) * BN;
+                col_limit = P.Cin;
+                col_shift = (long long)tap * P.Cin;
+            } else if (P.epi == EPI_GEGLU) {
+                col0 = n_blk * (BN / 2);
+                col_limit = P.geglu_half;
+            } else {
+                col0 = n_blk * BN;
+                col_limit = P.N;
+            }
+
+            mbar_wait(&tfull_bar[acc], acc_phase);
+            tc_fence_after();
+            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+
+            if (P.epi == EPI_GEGLU) {
+                // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
+#pragma unroll 1
+                for (int c = 0; c < BN / 2; c += 32) {
+                    uint32_t rv[32], rg[32];
+                    tmem_ld32(taddr + c, rv);
+                    tmem_ld32(taddr + BN / 2 + c, rg);
+                    tc_wait_ld();
+                    if (row_ok) {
+                        const int cbase = col0 + c;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            if (cbase + j < col_limit) {     // N/2 is a multiple of 8 for every SDXL layer
+                                uint32_t ov[4], oh[4], og[4];
+#pragma unroll
+                                for (int e = 0; e < 8; e += 2) {
+                                    float h0 = __uint_as_float(rv[j + e]), h1 = __uint_as_float(rv[j + e + 1]);
+                                    float g0 = __uint_as_float(rg[j + e]), g1 = __uint_as_float(rg[j + e + 1]);
+                                    if (P.bias) {
+                                        h0 += __bfloat162float(P.bias[cbase + j + e]);
+                                        h1 += __bfloat162float(P.bias[cbase + j + e + 1]);
+                                        g0 += __bfloat162float(P.bias[P.geglu_half + cbase + j + e]);
+                                        g1 += __bfloat162float(P.bias[P.geglu_half + cbase + j + e + 1]);
+                                    }
+                                    // autocast-faithful rounding points: linear out -> bf16, gelu -> bf16, product -> bf16
+                                    h0 = round_bf16(h0); h1 = round_bf16(h1); g0 = round_bf16(g0); g1 = round_bf16(g1);
+                                    oh[e >> 1] = pack_bf16(h0, h1);
+                                    og[e >> 1] = pack_bf16(g0, g1);
+                                    const float a0 = round_bf16(gelu_erf(g0)), a1 = round_bf16(gelu_erf(g1));
+                                    ov[e >> 1] = pack_bf16(h0 * a0, h1 * a1);
+                                }
+                                *reinterpret_cast<uint4*>(P.C + row * P.ldc + cbase + j) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                                if (P.aux) {
+                                    *reinterpret_cast<uint4*>(P.aux + row * P.ld_aux + cbase + j) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                                    *reinterpret_cast<uint4*>(P.aux + row * P.ld_aux + P.geglu_half + cbase + j) = make_uint4(og[0], og[1], og[2], og[3]);
+                                }
+                            }
+                        }
+                    }
+                }
+            } else {
+#pragma unroll 1
+                for (int c = 0; c < OUT_COLS; c += 32) {
+                    if (col0 + c >= col_limit) break;          // warp-uniform
+                    uint32_t r[32];
+                    if (!empty_split) {
+                        tmem_ld32(taddr + c, r);
+                        tc_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    if (!row_ok) continue;
+                    const int cbase = col0 + c;
+                    if (P.epi == EPI_PARTIAL) {
+                        float* dst = P.partial + ((long long)split * P.M + row) * P.N + col_shift + cbase;
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) {
+                            if (cbase + j + 3 < col_limit && ((((uintptr_t)(dst + j)) & 15) == 0)) {
+                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                            } else {
+                                for (int e = 0; e < 4; ++e)
+                                    if (cbase + j + e < col_limit) dst[j + e] = __uint_as_float(r[j + e]);
+                            }
+                        }
+                    } else {
+                        __nv_bfloat16* dst = P.C + row * P.ldc + col_shift + cbase;
+                        const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + cbase : nullptr;
+                        const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + cbase : nullptr;
+                        const bool vec_ok = ((((uintptr_t)dst) & 15) == 0) && (!res || ((((uintptr_t)res) & 15) == 0));
+#pragma unroll
+                        for (int j = 0; j < 32; j += 8) {
+                            float f[8];
+#pragma unroll
+                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j + e]);
+                            const bool full8 = (cbase + j + 7 < col_limit) && vec_ok;
+                            if (full8) {
+                                if (P.bias) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) f[e] += __bfloat162float(P.bias[cbase + j + e]);
+                                }
+                                if (rgb) {
+#pragma unroll
+                                    for (int e = 0; e < 8; ++e) f[e] = round_bf16(f[e]) + __bfloat162float(rgb[j + e]);
+                                }
+                                if (res) {
+                                    const uint4 rr = *reinterpret_cast<const uint4*>(res + j);
+                                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
+                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
+                                    }
+                                }
+                                if (P.accumulate) {
+                                    const uint4 oo = *reinterpret_cast<const uint4*>(dst + j);
+                                    const uint32_t ow[4] = {oo.x, oo.y, oo.z, oo.w};
+#pragma unroll
+                                    for (int e = 0; e < 4; ++e) {
+                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(ow[e]);
+                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(ow[e]);
+                                    }
+                                }
+                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
+                                                                               pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                            } else {
+                                for (int e = 0; e < 8; ++e) {
+                                    if (cbase + j + e < col_limit) {
+                                        float x = f[e];
+                                        if (P.bias) x += __bfloat162float(P.bias[cbase + j + e]);
+                                        if (rgb) x = round_bf16(x) + __bfloat162float(rgb[j + e]);
+                                        if (res) x = round_bf16(x) + __bfloat162float(res[j + e]);
+                                        if (P.accumulate) x = round_bf16(x) + __bfloat162float(dst[j + e]);
+                                        dst[j + e] = __float2bfloat16_rn(x);
+                                    }
+                                }
+                            }
+                        }
+                    }
+                }
+            }
+            // release the accumulator buffer
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+        }
+    }
+
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 2 * BN);
+    }
+}
+
+// ---- split-K reduction: sum fp32 partials, optional accumulate into existing bf16, optional OIHW permute ----
+// partial: [splits][rows][cols] fp32.  out (bf16):
+//   permute_taps == 0 : out[row*ld_out + col]
+//   permute_taps  > 0 : cols = taps*Cin, out is OIHW [rows=Cout][Cin][taps]: out[(row*Cin + cin)*taps + tap]
+__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
+                                     __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin,
+                                     int accumulate) {
+    const long long total = rows * cols;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float s = 0.f;
+        for (int k = 0; k < splits; ++k) s += partial[(long long)k * total + i];
+        const long long row = i / cols, col = i - row * cols;
+        long long o;
+        if (permute_taps > 0) {
+            const int tap = (int)(col / Cin), cin = (int)(col - (long long)tap * Cin);
+            o = (row * Cin + cin) * permute_taps + tap;
+        } else {
+            o = row * ld_out + col;
+        }
+        if (accumulate) s = round_bf16(s) + __bfloat162float(out[o]);
+        out[o] = __float2bfloat16_rn(s);
+    }
+}
+
+static int launch_gemm(GemmParams& P, int bn, cudaStream_t stream) {
+    const int total_work = P.m_tiles * P.n_tiles * P.splits;
+    if (total_work <= 0) return AOZ_OK;
+    int grid = total_work < sm_count() ? total_work : sm_count();
+    static bool attr_set[2] = {false, false};
+    if (bn == 256) {
+        if (!attr_set[1]) {
+            cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256>::TOTAL);
+            attr_set[1] = true;
+        }
+        gemm_bf16_kernel<256><<<grid, GEMM_THREADS, SmemLayout<256>::TOTAL, stream>>>(P);
+    } else {
+        if (!attr_set[0]) {
+            cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128>::TOTAL);
+            attr_set[0] = true;
+        }
+        gemm_bf16_kernel<128><<<grid, GEMM_THREADS, SmemLayout<128>::TOTAL, stream>>>(P);
+    }
+    AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
+    return AOZ_OK;
+}
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+static int pick_bn(int n_extent, long long m_tiles_est) {
+    // BN=256 halves B-operand smem traffic per MMA; use it when it does not starve the grid
+    if (n_extent >= 256 && (n_extent % 256 == 0 || n_extent >= 1024) &&
+        m_tiles_est * ceil_div(n_extent, 256) >= 120) return 256;
+    return 128;
+}
+
+}  // namespace aoz
+
+using namespace aoz;
+
+extern "C" {
+
+// C[M,N] (bf16) = op(A) * op(B)^T-ish with fused epilogue.
+//   a_mn == 0: A is [M, K] row-major (lda elements)       a_mn == 1: A is [K, M] row-major (lda)
+//   b_mn == 0: B is [N, K] row-major (ldb)                 b_mn == 1: B is [K, N] row-major (ldb)
+//   bias [N] / rowgroup_bias [M/rows_per_group, N] / residual [M, N] (ldr) optional (null = absent)
+//   epi == EPI_GEGLU: B is [2*half, K]; C is [M, half]; aux (optional) receives the bf16 pre-activation [M, 2*half]
+//   splits > 1: `workspace` must hold splits*M*N floats; the result is reduced into C afterwards
+int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
+                  int M, int N, int K, const void* bias, const void* rowgroup_bias, int rows_per_group, long long ld_rgb,
+                  const void* residual, long long ldr, int epi, void* aux, long long ld_aux, int accumulate, int splits,
+                  void* workspace, void* stream) {
+    AOZ_CHECK_ARG(A && B && C, "aoz_gemm_bf16: null operand");
+    AOZ_CHECK_ARG(M > 0 && N > 0 && K > 0, "aoz_gemm_bf16: bad extents M=%d N=%d K=%d", M, N, K);
+    AOZ_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "aoz_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
+    AOZ_CHECK_ARG((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "aoz_gemm_bf16: operands must be 16-byte aligned");
+    AOZ_CHECK_ARG(epi == EPI_STORE || epi == EPI_GEGLU, "aoz_gemm_bf16: bad epilogue %d", epi);
+    if (splits < 1) splits = 1;
+    GemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.mode = GM_LINEAR; P.epi = epi; P.a_mn = a_mn; P.b_mn = b_mn;
+    P.M = M; P.N = N; P.K = K;
+    P.k_iters = ceil_div(K, BK);
+    if (splits > P.k_iters) splits = P.k_iters;
+    int bn;
+    if (epi == EPI_GEGLU) {
+        AOZ_CHECK_ARG((N % 2) == 0 && !b_mn && splits == 1, "aoz_gemm_bf16: GEGLU needs even N, K-major B, no split");
+        P.geglu_half = N / 2;
+        bn = 256;
+        P.n_tiles = ceil_div(N / 2, bn / 2);
+    } else {
+        bn = pick_bn(N, ceil_div(M, BM));
+        P.n_tiles = ceil_div(N, bn);
+    }
+    P.m_tiles = ceil_div(M, BM);
+    P.splits = splits;
+    if (splits > 1) {
+        AOZ_CHECK_ARG(workspace != nullptr, "aoz_gemm_bf16: split-K needs a workspace");
+        AOZ_CHECK_ARG(!bias && !residual && !rowgroup_bias, "aoz_gemm_bf16: split-K does not fuse bias/residual");
+        P.epi = EPI_PARTIAL;
+        P.partial = (float*)workspace;
+    }
+    P.C = (__nv_bfloat16*)C; P.ldc = ldc;
+    P.bias = (const __nv_bfloat16*)bias;
+    P.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; P.rows_per_group = rows_per_group; P.ld_rgb = ld_rgb;
+    P.residual = (const __nv_bfloat16*)residual; P.ldr = ldr;
+    P.aux = (__nv_bfloat16*)aux; P.ld_aux = ld_aux;
+    P.accumulate = accumulate;
+    int rc;
+    {   // A map
+        uint64_t dims[2], strides[1]; uint32_t box[2];
+        if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = BM; }
+        else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+        strides[0] = (uint64_t)lda * 2;
+        if ((rc = make_tmap_bf16(&P.tmA, A, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+    }
+    {   // B map
+        uint64_t dims[2], strides[1]; uint32_t box[2];
+        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = 128; }
+        else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+        strides[0] = (uint64_t)ldb * 2;
+        if ((rc = make_tmap_bf16(&P.tmB, B, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+    }
+    if ((rc = launch_gemm(P, bn, (cudaStream_t)stream)) != AOZ_OK) return rc;
+    if (splits > 1) {
+        const long long total = (long long)M * N;
+        int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
+        splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, M, N, (__nv_bfloat16*)C,
+                                                                    ldc, 0, 0, accumulate);
+        AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
+    }
+    return AOZ_OK;
+}
+
+// Implicit-GEMM convolution forward over NHWC bf16 (also used for dgrad with a flipped, transposed weight pack).
+//   x      : [NB, Hin, Win, Cin]  (Cin multiple of 8; channel count seen by TMA)
+//   wpack  : [Cout, taps * cin_chunks*64] bf16, K index = tap*(cin_chunks*64) + cin  (zero padded)
+//   y      : [NB, H, W, Cout] with H = (Hin + 2*pad - ks)/stride + 1
+//   flip   : traverse the taps mirrored (dgrad)
+int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const void* wpack, int Cout, int ks, int stride,
+                      int pad, int flip, void* y, const void* bias, const void* rowgroup_bias, const void* residual,
+                      int accumulate, void* stream) {
+    AOZ_CHECK_ARG(x && wpack && y, "aoz_conv_fwd_bf16: null operand");
+    AOZ_CHECK_ARG(ks == 3 || ks == 1, "aoz_conv_fwd_bf16: kernel size %d", ks);
+    AOZ_CHECK_ARG(stride == 1 || stride == 2, "aoz_conv_fwd_bf16: stride %d", stride);
+    AOZ_CHECK_ARG((Cin % 8) == 0, "aoz_conv_fwd_bf16: Cin must be a multiple of 8 (got %d)", Cin);
+    const int H = (Hin + 2 * pad - ks) / stride + 1, W = (Win + 2 * pad - ks) / stride + 1;
+    GemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.mode = GM_CONV_FWD; P.epi = EPI_STORE;
+    P.NB = NB; P.H = H; P.W = W;
+    P.TW = W >= 16 ? 16 : 8; P.TH = BM / P.TW;
+    if (stride == 2) { P.TW = 8; P.TH = 16; }              // box extents are limited to 256 along each dim
+    P.tiles_h = ceil_div(H, P.TH); P.tiles_w = ceil_div(W, P.TW);
+    P.taps_s = ks; P.pad = pad; P.stride = stride; P.flip = flip;
+    P.cin_chunks = ceil_div(Cin, 64);
+    P.k_iters = ks * ks * P.cin_chunks;
+    P.M = NB * H * W; P.N = Cout; P.K = P.k_iters * 64;
+    P.m_tiles = NB * P.tiles_h * P.tiles_w;
+    const int bn = pick_bn(Cout, P.m_tiles);
+    P.n_tiles = ceil_div(Cout, bn);
+    P.splits = 1;
+    P.C = (__nv_bfloat16*)y; P.ldc = Cout;
+    P.bias = (const __nv_bfloat16*)bias;
+    P.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; P.ld_rgb = Cout;
+    P.residual = (const __nv_bfloat16*)residual; P.ldr = Cout;
+    P.accumulate = accumulate;
+    int rc;
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)(P.TW * stride), (uint32_t)(P.TH * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if ((rc = make_tmap_bf16(&P.tmA, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
+    }
+    {
+        uint64_t dims[2] = {(uint64_t)P.K, (uint64_t)Cout};
+        uint64_t strides[1] = {(uint64_t)P.K * 2};
+        uint32_t box[2] = {64, 128};
+        if ((rc = make_tmap_bf16(&P.tmB, wpack, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+    }
+    return launch_gemm(P, bn, (cudaStream_t)stream);
+}
+
+// Convolution weight gradient: dW[cout][tap][cin] = sum_pixels dy[pix][cout] * x[pix*stride + tap - pad][cin].
+//   dy : [NB, H, W, Cout], x : [NB, Hin, Win, Cin], grad_w : OIHW bf16 [Cout, Cin, ks, ks] (the parameter layout)
+//   workspace : splits * Cout * taps*Cin floats
+int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int Cout, int Hin, int Win, int Cin, int ks,
+                        int stride, int pad, void* grad_w, int accumulate, int splits, void* workspace, void* stream) {
+    AOZ_CHECK_ARG(dy && x && grad_w && workspace, "aoz_conv_wgrad_bf16: null operand");
+    AOZ_CHECK_ARG((Cin % 8) == 0 && (Cout % 8) == 0, "aoz_conv_wgrad_bf16: channel counts must be multiples of 8");
+    GemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.mode = GM_CONV_WGRAD; P.epi = EPI_PARTIAL; P.a_mn = 1; P.b_mn = 1;
+    P.NB = NB; P.H = H; P.W = W; P.TH = 8; P.TW = 8;
+    P.tiles_h = ceil_div(H, 8); P.tiles_w = ceil_div(W, 8);
+    P.taps_s = ks; P.pad = pad; P.stride = stride;
+    P.Cin = Cin;
+    const int taps = ks * ks;
+    P.M = Cout; P.N = taps * Cin; P.K = NB * H * W;
+    P.k_iters = NB * P.tiles_h * P.tiles_w;
+    P.m_tiles = ceil_div(Cout, BM);
+    const int bn = (Cin % 256 == 0 && P.m_tiles * taps * (Cin / 256) >= 100) ? 256 : 128;
+    P.n_tiles_per_tap = ceil_div(Cin, bn);
+    P.n_tiles = taps * P.n_tiles_per_tap;
+    if (splits < 1) splits = 1;
+    if (splits > P.k_iters) splits = P.k_iters;
+    P.splits = splits;
+    P.partial = (float*)workspace;
+    int rc;
+    {
+        uint64_t dims[4] = {(uint64_t)Cout, (uint64_t)W, (uint64_t)H, (uint64_t)NB};
+        uint64_t strides[3] = {(uint64_t)Cout * 2, (uint64_t)W * Cout * 2, (uint64_t)H * W * Cout * 2};
+        uint32_t box[4] = {64, 8, 8, 1};
+        if ((rc = make_tmap_bf16(&P.tmA, dy, 4, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+    }
+    {
+        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+        uint32_t box[4] = {64, (uint32_t)(8 * stride), (uint32_t)(8 * stride), 1};
+        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+        if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
+    }
+    if ((rc = launch_gemm(P, bn, (cudaStream_t)stream)) != AOZ_OK) return rc;
+    const long long total = (long long)Cout * taps * Cin;
+    int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
+    splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,
+                                                                (__nv_bfloat16*)grad_w, 0, taps, Cin, accumulate);
+    AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
+    return AOZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,492 @@
+// GroupNorm(32)(+SiLU) and LayerNorm, forward and backward, over channels-last bf16 activations (sm_100a).
+//
+// Replaces the ATen group_norm / silu / layer_norm calls inside diffusers' ResnetBlock2D, Transformer2DModel
+// and BasicTransformerBlock that the reference reaches through train.py:2760.
+// Numerics contract: statistics and the normalise(+SiLU) math in fp32, ONE rounding to bf16
+// on store -- what CUDA autocast does (fp32 norm output rounded when the next conv/linear casts its input).
+// All kernels are HBM-streaming: 16-byte vector accesses along the contiguous channel dimension, fp32
+// partial sums reduced with warp shuffles, deterministic two-level reductions (no atomics).
+//   GroupNorm fwd: 4 B/element (stats pass re-read is served from L2 for SDXL sizes, <= 84 MB per tensor)
+//   LayerNorm fwd: 4 B/element; bwd 6 B/element.
+#include "common.cuh"
+
+namespace aoz {
+
+constexpr int GN_GROUPS = 32;
+constexpr int GN_THREADS = 256;
+constexpr int GN_MAX_CHUNKS = 64;
+
+__device__ __forceinline__ void unpack8(const uint4& a, float* f) {
+    f[0] = bf16lo(a.x); f[1] = bf16hi(a.x); f[2] = bf16lo(a.y); f[3] = bf16hi(a.y);
+    f[4] = bf16lo(a.z); f[5] = bf16hi(a.z); f[6] = bf16lo(a.w); f[7] = bf16hi(a.w);
+}
+__device__ __forceinline__ uint4 pack8(const float* f) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+
+// ---------------------------------------------------------------------------------------------
+// GroupNorm statistics: x [NB, HW, C] -> partial [NB][chunks][GROUPS][2] (sum, sumsq)
+// grid (chunks, NB).  Each thread owns one 8-channel vector column and walks pixels.
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(GN_THREADS)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __restrict__ partial) {
+    extern __shared__ float sm[];          // [2][C] per-channel sums
+    const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int vec_per_row = C / 8;
+    const int rows_per_chunk = (HW + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    const __nv_bfloat16* xb = x + (size_t)n * HW * C;
+    // threads are laid out as (row lane, vector column): column = tid % vec_cols_per_pass
+    const int cols = min(vec_per_row, GN_THREADS);
+    const int row_lanes = GN_THREADS / cols;
+    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    if (tr < row_lanes) {
+        for (int v = tc; v < vec_per_row; v += cols) {
+            float s[8], q[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
+            for (int r = r0 + tr; r < r1; r += row_lanes) {
+                float f[8];
+                unpack8(ld_stream(xb + (size_t)r * C + v * 8), f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], s[e]); atomicAdd(&sm[C + v * 8 + e], q[e]); }
+        }
+    }
+    __syncthreads();
+    // channels -> groups (fixed order: deterministic given the smem atomics are over <= row_lanes addends)
+    const int cpg = C / GN_GROUPS;
+    if (threadIdx.x < 2 * GN_GROUPS) {
+        const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
+        float a = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
+        partial[(((size_t)n * chunks + chunk) * GN_GROUPS + g) * 2 + which] = a;
+    }
+}
+
+// GroupNorm apply: y = silu?((x - mean) * rstd * gamma + beta); also writes mean/rstd [NB][GROUPS] (chunk 0 block)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int HW, int C,
+                float eps, int silu, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
+                float* __restrict__ rstd_out) {
+    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    const int n = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    if (threadIdx.x < GN_GROUPS) {
+        float s = 0.f, q = 0.f;
+        for (int k = 0; k < stat_chunks; ++k) {
+            const float* p = partial + (((size_t)n * stat_chunks + k) * GN_GROUPS + threadIdx.x) * 2;
+            s += p[0]; q += p[1];
+        }
+        const float cnt = (float)HW * (float)cpg;
+        const float mean = s / cnt;
+        const float var = fmaxf(q / cnt - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + eps);
+        s_mean[threadIdx.x] = mean; s_rstd[threadIdx.x] = rstd;
+        if (blockIdx.x == 0) { mean_out[n * GN_GROUPS + threadIdx.x] = mean; rstd_out[n * GN_GROUPS + threadIdx.x] = rstd; }
+    }
+    __syncthreads();
+    const int vec_per_row = C / 8;
+    const size_t total_vec = (size_t)HW * vec_per_row;
+    const __nv_bfloat16* xb = x + (size_t)n * HW * C;
+    __nv_bfloat16* yb = y + (size_t)n * HW * C;
+    for (size_t i = (size_t)blockIdx.x * GN_THREADS + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * GN_THREADS) {
+        const int v = (int)(i % vec_per_row);
+        float f[8], gm[8], bt[8];
+        unpack8(ld_stream(xb + i * 8), f);
+        unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (v * 8 + e) / cpg;
+            float z = (f[e] - s_mean[g]) * s_rstd[g] * gm[e] + bt[e];
+            if (silu) z = z * sigmoidf_(z);
+            f[e] = z;
+        }
+        st_stream(yb + i * 8, pack8(f));
+    }
+}
+
+// GroupNorm backward pass 1: per-channel sums of dz and dz*xhat over a pixel chunk.
+// partial [NB][chunks][2][C]
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, int HW, int C, int silu,
+                    float* __restrict__ partial) {
+    extern __shared__ float sm[];          // [2][C]
+    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
+    const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int cpg = C / GN_GROUPS;
+    if (threadIdx.x < GN_GROUPS) { s_mean[threadIdx.x] = mean[n * GN_GROUPS + threadIdx.x]; s_rstd[threadIdx.x] = rstd[n * GN_GROUPS + threadIdx.x]; }
+    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+    __syncthreads();
+    const int vec_per_row = C / 8;
+    const int rows_per_chunk = (HW + chunks - 1) / chunks;
+    const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
+    const size_t base = (size_t)n * HW * C;
+    const int cols = min(vec_per_row, GN_THREADS);
+    const int row_lanes = GN_THREADS / cols;
+    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    if (tr < row_lanes) {
+        for (int v = tc; v < vec_per_row; v += cols) {
+            float gm[8], bt[8], a[8], b[8], mu[8], rs[8];
+            unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+            unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; const int g = (v * 8 + e) / cpg; mu[e] = s_mean[g]; rs[e] = s_rstd[g]; }
+            for (int r = r0 + tr; r < r1; r += row_lanes) {
+                float fx[8], fd[8];
+                unpack8(ld_stream(x + base + (size_t)r * C + v * 8), fx);
+                unpack8(ld_stream(dy + base + (size_t)r * C + v * 8), fd);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (fx[e] - mu[e]) * rs[e];
+                    float dz = fd[e];
+                    if (silu) {
+                        const float z = xh * gm[e] + bt[e];
+                        const float sg = sigmoidf_(z);
+                        dz *= sg * (1.0f + z * (1.0f - sg));
+                    }
+                    a[e] += dz; b[e] = fmaf(dz, xh, b[e]);
+                }
+            }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], a[e]); atomicAdd(&sm[C + v * 8 + e], b[e]); }
+        }
+    }
+    __syncthreads();
+    float* out = partial + ((size_t)n * chunks + chunk) * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) out[i] = sm[i];
+}
+
+// pass 2: reduce partials -> per (n, group) terms ds = sum_c gamma*B, db = sum_c gamma*A ; dgamma/dbeta over n.
+// grid = 1 block per 32 channels is plenty; here one block of 256 threads loops over channels.
+__global__ void __launch_bounds__(256)
+gn_bwd_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma, int NB, int chunks, int C,
+                       float* __restrict__ group_terms /* [NB][GROUPS][2] */, __nv_bfloat16* __restrict__ dgamma,
+                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    extern __shared__ float sm[];          // [NB][2][C] channel sums
+    for (int i = threadIdx.x; i < NB * 2 * C; i += blockDim.x) {
+        const int n = i / (2 * C), rem = i - n * 2 * C;
+        float s = 0.f;
+        for (int k = 0; k < chunks; ++k) s += partial[((size_t)n * chunks + k) * 2 * C + rem];
+        sm[i] = s;
+    }
+    __syncthreads();
+    const int cpg = C / GN_GROUPS;
+    for (int i = threadIdx.x; i < NB * GN_GROUPS; i += blockDim.x) {
+        const int n = i / GN_GROUPS, g = i - n * GN_GROUPS;
+        float db = 0.f, ds = 0.f;
+        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
+            const float gm = __bfloat162float(gamma[c]);
+            db = fmaf(gm, sm[(n * 2 + 0) * C + c], db);
+            ds = fmaf(gm, sm[(n * 2 + 1) * C + c], ds);
+        }
+        group_terms[i * 2 + 0] = db;
+        group_terms[i * 2 + 1] = ds;
+    }
+    if (dgamma) {
+        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+            float a = 0.f, b = 0.f;
+            for (int n = 0; n < NB; ++n) { a += sm[(n * 2 + 0) * C + c]; b += sm[(n * 2 + 1) * C + c]; }
+            if (accumulate) { a = round_bf16(a) + __bfloat162float(dbeta[c]); b = round_bf16(b) + __bfloat162float(dgamma[c]); }
+            dbeta[c] = __float2bfloat16_rn(a);
+            dgamma[c] = __float2bfloat16_rn(b);
+        }
+    }
+}
+
+// pass 3: dx = rstd * (dz*gamma - db/cnt - xhat * ds/cnt)
+__global__ void __launch_bounds__(GN_THREADS)
+gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+                    const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
+                    const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ group_terms,
+                    int HW, int C, int silu, __nv_bfloat16* __restrict__ dx) {
+    __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_db[GN_GROUPS], s_ds[GN_GROUPS];
+    const int n = blockIdx.y;
+    const int cpg = C / GN_GROUPS;
+    if (threadIdx.x < GN_GROUPS) {
+        const float inv = 1.0f / ((float)HW * (float)cpg);
+        s_mean[threadIdx.x] = mean[n * GN_GROUPS + threadIdx.x];
+        s_rstd[threadIdx.x] = rstd[n * GN_GROUPS + threadIdx.x];
+        s_db[threadIdx.x] = group_terms[(n * GN_GROUPS + threadIdx.x) * 2 + 0] * inv;
+        s_ds[threadIdx.x] = group_terms[(n * GN_GROUPS + threadIdx.x) * 2 + 1] * inv;
+    }
+    __syncthreads();
+    const int vec_per_row = C / 8;
+    const size_t total_vec = (size_t)HW * vec_per_row;
+    const size_t base = (size_t)n * HW * C;
+    for (size_t i = (size_t)blockIdx.x * GN_THREADS + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * GN_THREADS) {
+        const int v = (int)(i % vec_per_row);
+        float fx[8], fd[8], gm[8], bt[8];
+        unpack8(ld_stream(x + base + i * 8), fx);
+        unpack8(ld_stream(dy + base + i * 8), fd);
+        unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+        unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) {
+            const int g = (v * 8 + e) / cpg;
+            const float xh = (fx[e] - s_mean[g]) * s_rstd[g];
+            float dz = fd[e];
+            if (silu) {
+                const float z = xh * gm[e] + bt[e];
+                const float sg = sigmoidf_(z);
+                dz *= sg * (1.0f + z * (1.0f - sg));
+            }
+            fx[e] = s_rstd[g] * (dz * gm[e] - s_db[g] - xh * s_ds[g]);
+        }
+        st_stream(dx + base + i * 8, pack8(fx));
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// LayerNorm: one warp per row, C % 8 == 0, C <= 2048
+// ---------------------------------------------------------------------------------------------
+constexpr int LN_MAXV = 8;     // vectors of 8 per lane -> C <= 2048
+constexpr int LN_WARPS = 8;
+
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
+              const __nv_bfloat16* __restrict__ beta, long long rows, int C, float eps, __nv_bfloat16* __restrict__ y,
+              float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = C / 8;
+    for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+        float f[LN_MAXV][8];
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+                unpack8(ld_stream(x + row * C + v * 8), f[i]);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s += f[i][e];
+            }
+        }
+        const float mean = warp_sum(s) / (float)C;
+        float q = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q = fmaf(d, d, q); }
+            }
+        }
+        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+                float gm[8], bt[8];
+                unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
+                unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) f[i][e] = (f[i][e] - mean) * rstd * gm[e] + bt[e];
+                st_stream(y + row * C + v * 8, pack8(f[i]));
+            }
+        }
+        if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
+    }
+}
+
+// backward: dx per row; dgamma/dbeta partials per block -> partial [gridDim.x][2][C]
+__global__ void __launch_bounds__(LN_WARPS * 32)
+ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
+              const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
+              long long rows, int C, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+    extern __shared__ float sm[];      // [2][C]
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int nv = C / 8;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
+    __syncthreads();
+    float gm[LN_MAXV][8];
+    float ag[LN_MAXV][8], ab[LN_MAXV][8];
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int v = lane + 32 * i;
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; gm[i][e] = 0.f; }
+        if (v < nv) unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm[i]);
+    }
+    for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
+        const float mu = mean[row], rs = rstd[row];
+        float xh[LN_MAXV][8], dg[LN_MAXV][8];
+        float s1 = 0.f, s2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+                float fx[8], fd[8];
+                unpack8(ld_stream(x + row * C + v * 8), fx);
+                unpack8(ld_stream(dy + row * C + v * 8), fd);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    xh[i][e] = (fx[e] - mu) * rs;
+                    dg[i][e] = fd[e] * gm[i][e];
+                    s1 += dg[i][e];
+                    s2 = fmaf(dg[i][e], xh[i][e], s2);
+                    ag[i][e] = fmaf(fd[e], xh[i][e], ag[i][e]);
+                    ab[i][e] += fd[e];
+                }
+            }
+        }
+        s1 = warp_sum(s1) / (float)C;
+        s2 = warp_sum(s2) / (float)C;
+#pragma unroll
+        for (int i = 0; i < LN_MAXV; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+                float o[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) o[e] = rs * (dg[i][e] - s1 - xh[i][e] * s2);
+                st_stream(dx + row * C + v * 8, pack8(o));
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < LN_MAXV; ++i) {
+        const int v = lane + 32 * i;
+        if (v < nv) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], ag[i][e]); atomicAdd(&sm[C + v * 8 + e], ab[i][e]); }
+        }
+    }
+    __syncthreads();
+    float* out = partial + (size_t)blockIdx.x * 2 * C;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+}
+
+// reduce [blocks][2][C] -> dgamma (first C), dbeta (second C)
+__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
+                                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= 2 * C) return;
+    float s = 0.f;
+    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * 2 * C + i];
+    __nv_bfloat16* dst = i < C ? dgamma + i : dbeta + (i - C);
+    if (accumulate) s = round_bf16(s) + __bfloat162float(*dst);
+    *dst = __float2bfloat16_rn(s);
+}
+
+}  // namespace aoz
+
+using namespace aoz;
+
+extern "C" {
+
+static int gn_chunks(int NB, int HW) {
+    int chunks = (sm_count() * 2 + NB - 1) / NB;
+    if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
+    if (chunks > HW) chunks = HW;
+    if (chunks < 1) chunks = 1;
+    return chunks;
+}
+
+// workspace floats needed by the GroupNorm forward / backward (upper bound)
+long long aoz_groupnorm_workspace_floats(int NB, int HW, int C) {
+    const long long chunks = GN_MAX_CHUNKS;
+    return (long long)NB * chunks * 2 * C + (long long)NB * GN_GROUPS * 2 + 64;
+}
+
+// y = silu?(GroupNorm32(x)); x, y: [NB, HW, C] bf16 channels-last; mean/rstd out: [NB, 32] fp32
+int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB, int HW, int C, float eps, int silu,
+                      void* y, void* mean, void* rstd, void* workspace, void* stream) {
+    AOZ_CHECK_ARG(x && gamma && beta && y && mean && rstd && workspace, "aoz_groupnorm_fwd: null pointer");
+    AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_fwd: C=%d must be a multiple of 32", C);
+    AOZ_CHECK_ARG(NB > 0 && HW > 0, "aoz_groupnorm_fwd: empty input");
+    AOZ_CHECK_ARG(2 * C * (int)sizeof(float) <= 48 * 1024, "aoz_groupnorm_fwd: C=%d too large", C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int chunks = gn_chunks(NB, HW);
+    gn_stats_kernel<<<dim3(chunks, NB), GN_THREADS, 2 * C * sizeof(float), s>>>((const __nv_bfloat16*)x, HW, C, (float*)workspace);
+    AOZ_CHECK_LAUNCH("gn_stats_kernel");
+    long long vecs = (long long)HW * (C / 8);
+    int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
+    const int cap = (sm_count() * 8 + NB - 1) / NB;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    gn_apply_kernel<<<dim3(gx, NB), GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+                                                       (const float*)workspace, chunks, HW, C, eps, silu, (__nv_bfloat16*)y,
+                                                       (float*)mean, (float*)rstd);
+    AOZ_CHECK_LAUNCH("gn_apply_kernel");
+    return AOZ_OK;
+}
+
+int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const void* mean, const void* rstd,
+                      int NB, int HW, int C, int silu, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace,
+                      void* stream) {
+    AOZ_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && workspace, "aoz_groupnorm_bwd: null pointer");
+    AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_bwd: C=%d must be a multiple of 32", C);
+    AOZ_CHECK_ARG((long long)NB * 2 * C * (long long)sizeof(float) <= 200 * 1024, "aoz_groupnorm_bwd: NB*C too large (%d x %d)", NB, C);
+    cudaStream_t s = (cudaStream_t)stream;
+    const int chunks = gn_chunks(NB, HW);
+    float* partial = (float*)workspace;
+    float* group_terms = partial + (size_t)NB * GN_MAX_CHUNKS * 2 * C;
+    gn_bwd_stats_kernel<<<dim3(chunks, NB), GN_THREADS, 2 * C * sizeof(float), s>>>(
+        (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+        (const float*)mean, (const float*)rstd, HW, C, silu, partial);
+    AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
+    const size_t fin_smem = (size_t)NB * 2 * C * sizeof(float);
+    static size_t fin_attr = 0;
+    if (fin_smem > 48 * 1024 && fin_smem > fin_attr) {
+        cudaFuncSetAttribute(gn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
+        fin_attr = fin_smem;
+    }
+    gn_bwd_finalize_kernel<<<1, 256, fin_smem, s>>>(partial, (const __nv_bfloat16*)gamma, NB, chunks, C, group_terms,
+                                                    (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
+    AOZ_CHECK_LAUNCH("gn_bwd_finalize_kernel");
+    long long vecs = (long long)HW * (C / 8);
+    int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
+    const int cap = (sm_count() * 8 + NB - 1) / NB;
+    if (gx > cap) gx = cap;
+    if (gx < 1) gx = 1;
+    gn_bwd_apply_kernel<<<dim3(gx, NB), GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+                                                           (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd,
+                                                           group_terms, HW, C, silu, (__nv_bfloat16*)dx);
+    AOZ_CHECK_LAUNCH("gn_bwd_apply_kernel");
+    return AOZ_OK;
+}
+
+int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long long rows, int C, float eps, void* y, void* mean,
+                      void* rstd, void* stream) {
+    AOZ_CHECK_ARG(x && gamma && beta && y && mean && rstd, "aoz_layernorm_fwd: null pointer");
+    AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_fwd: C=%d unsupported (multiple of 8, <= 2048)", C);
+    if (rows <= 0) return AOZ_OK;
+    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
+    ln_fwd_kernel<<<(int)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+                                                                          (const __nv_bfloat16*)beta, rows, C, eps, (__nv_bfloat16*)y,
+                                                                          (float*)mean, (float*)rstd);
+    AOZ_CHECK_LAUNCH("ln_fwd_kernel");
+    return AOZ_OK;
+}
+
+long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 4 * 2 * C; }
+
+int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
+                      void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
+    AOZ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "aoz_layernorm_bwd: null pointer");
+    AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
+    if (rows <= 0) return AOZ_OK;
+    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
+    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+    cudaStream_t s = (cudaStream_t)stream;
+    ln_bwd_kernel<<<(int)blocks, LN_WARPS * 32, 2 * C * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+                                                                           (const __nv_bfloat16*)gamma, (const float*)mean,
+                                                                           (const float*)rstd, rows, C, (__nv_bfloat16*)dx,
+                                                                           (float*)workspace);
+    AOZ_CHECK_LAUNCH("ln_bwd_kernel");
+    ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
+                                                               (__nv_bfloat16*)dbeta, accumulate);
+    AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");
+    return AOZ_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,284 @@
+"""RavenAdamW for B200: same interface and math as the reference, moments resident in HBM, ONE kernel per step.
+
+Mirrors ``training_utils/optimizers/raven.py`` of the reference (ctor kwargs and validation raven.py:25-42, ``step``
+raven.py:89-149, ``state_dict`` / ``save_cpu_state`` / ``load_cpu_state`` / ``load_state_dict`` raven.py:151-222).
+What changes is *where* the state lives and how the update runs: the reference keeps ``exp_avg`` / ``exp_avg_sq`` in
+CPU RAM and streams them through a ``3 x max_numel`` fp32 GPU scratch, ~15 ATen launches and 5 copies per parameter
+tensor; here they are CUDA tensors in ``momentum_dtype`` and the whole parameter list is updated by one multi-tensor
+sm_100a kernel (``aoz_raven_step_mt``) at HBM bandwidth.  ``save_cpu_state()`` still returns the reference's
+CPU-tensor format so ``.pt`` training states stay interchangeable.
+
+There is no CPU fallback: parameters must be CUDA tensors.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+import torch
+from torch.optim import Optimizer
+
+from .. import _lib
+
+_DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
+VALID_MOMENTUM_DTYPES = [torch.float32, torch.float16, torch.bfloat16]
+
+
+def raven_host_scalars(lr, betas, eps, weight_decay, debias_strength, step):
+    """The float64 scalars of raven.py:101-137, packed as the 8 fp32 values the kernel consumes."""
+    beta1, beta2 = betas
+    wd_factor = 1.0 - lr * weight_decay if weight_decay != 0 else 1.0
+    bc1 = 1.0 - beta1 ** step
+    bc2 = 1.0 - beta2 ** step
+    if debias_strength < 1.0:
+        bc1 = 1.0 - (1.0 - bc1) * debias_strength
+        bc2 = 1.0 - (1.0 - bc2) * debias_strength
+    sqrt_bc2 = math.sqrt(bc2)
+    step_size = lr / bc1
+    # torch divides a CUDA tensor by a python scalar as a * (1/b) with 1/b formed in fp32
+    inv_sqrt_bc2 = float(np.float32(1.0) / np.float32(sqrt_bc2))
+    return (beta1, 1.0 - beta1, beta2, 1.0 - beta2, eps, step_size, inv_sqrt_bc2, wd_factor)
+
+
+class MultiTensorPlan:
+    """Device tables for the multi-tensor kernels (chunk map is rebuilt only when the tensor shapes change)."""
+
+    def __init__(self):
+        self.key = None
+        self.n_tensors = 0
+        self.n_chunks = 0
+        self.numel = self.chunk_start = self.chunk_tensor = None
+        self.partial = None
+
+    def ensure(self, numels, device):
+        key = (tuple(numels), str(device))
+        if key == self.key:
+            return
+        chunk = _lib.query("aoz_mt_chunk_elems")
+        counts = [(n + chunk - 1) // chunk for n in numels]
+        starts = np.zeros(len(numels) + 1, dtype=np.int32)
+        np.cumsum(counts, out=starts[1:])
+        chunk_tensor = np.repeat(np.arange(len(numels), dtype=np.int32), counts)
+        self.n_tensors = len(numels)
+        self.n_chunks = int(starts[-1])
+        self.numel = torch.from_numpy(np.asarray(numels, dtype=np.int64)).to(device)
+        self.chunk_start = torch.from_numpy(starts).to(device)
+        self.chunk_tensor = torch.from_numpy(chunk_tensor).to(device)
+        self.partial = torch.empty(max(self.n_chunks, 1), dtype=torch.float32, device=device)
+        self.key = key
+
+
+def _ptr_table(tensors, device):
+    arr = np.fromiter((t.data_ptr() for t in tensors), dtype=np.uint64, count=len(tensors))
+    return torch.from_numpy(arr.view(np.int64)).to(device, non_blocking=True)
+
+
+class RavenAdamW(Optimizer):
+    """AdamW with partial bias correction (``debias_strength``); FP32 update math, moments in ``momentum_dtype``."""
+
+    _name = "RavenAdamW"
+
+    def __init__(self, params, lr: float = 1e-4, betas: tuple[float, float] = (0.9, 0.98), weight_decay: float = 0.06,
+                 eps: float = 1e-8, debias_strength: float = 0.9, momentum_dtype: torch.dtype = torch.bfloat16):
+        if not 0.0 <= lr:
+            raise ValueError(f"Invalid learning rate: {lr}")
+        if momentum_dtype not in VALID_MOMENTUM_DTYPES:
+            raise ValueError(f"momentum_dtype must be one of {VALID_MOMENTUM_DTYPES}, got {momentum_dtype}")
+        defaults = dict(lr=lr, betas=betas, weight_decay=weight_decay, eps=eps, debias_strength=debias_strength,
+                        momentum_dtype=momentum_dtype)
+        super().__init__(params, defaults)
+        self.max_numel = 0
+        self.param_device = None
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.requires_grad:
+                    if self.param_device is None:
+                        self.param_device = p.device
+                    self.max_numel = max(self.max_numel, p.numel())
+        self._momentum_dtype = momentum_dtype
+        self._plan = MultiTensorPlan()
+        self._norm_out = None          # device [3]: total norm, clip coefficient, sum of squares
+        self.last_launches = 0
+
+    # -- state helpers ------------------------------------------------------------------------------------
+    def _new_state_tensor(self, p, dtype):
+        return torch.zeros_like(p, dtype=dtype, memory_format=torch.contiguous_format)
+
+    def _restore_state_tensor(self, tensor, p):
+        return tensor.to(device=p.device, dtype=self._momentum_dtype).contiguous()
+
+    def _grad_of(self, p):
+        return p.grad
+
+    def _collect(self):
+        """[(group, p, grad)] for every parameter that has a gradient, in param_groups order."""
+        out = []
+        for group in self.param_groups:
+            for p in group["params"]:
+                g = self._grad_of(p)
+                if g is None:
+                    continue
+                if not p.is_cuda:
+                    raise _lib.AozoraError(f"{self._name}: parameters must be CUDA tensors (no CPU fallback)")
+                if not p.is_contiguous():
+                    raise _lib.AozoraError(f"{self._name}: parameters must be contiguous")
+                if not g.is_contiguous():
+                    g = g.contiguous()
+                out.append((group, p, g))
+        return out
+
+    # -- gradient norm / clip (train.py:2772-2781) ---------------------------------------------------------
+    def _gradnorm(self, items, max_norm, emulate_bf16):
+        dev = items[0][1].device
+        grads = [g for _, _, g in items]
+        gdt = grads[0].dtype
+        if any(g.dtype != gdt for g in grads):
+            raise _lib.AozoraError(f"{self._name}: gradients must share one dtype")
+        self._plan.ensure([p.numel() for _, p, _ in items], dev)
+        if self._norm_out is None or self._norm_out.device != dev:
+            self._norm_out = torch.zeros(4, dtype=torch.float32, device=dev)
+        gp = _ptr_table(grads, dev)
+        pl = self._plan
+        _lib.call("aoz_gradnorm_mt", pl.n_tensors, pl.n_chunks, gp.data_ptr(), pl.numel.data_ptr(), pl.chunk_start.data_ptr(),
+                  pl.chunk_tensor.data_ptr(), pl.partial.data_ptr(), float(max_norm), int(emulate_bf16),
+                  self._norm_out.data_ptr(), _DT[gdt], torch.cuda.current_stream().cuda_stream)
+        self.last_launches += 2
+        return self._norm_out
+
+    @torch.no_grad()
+    def grad_norm(self, max_norm=float("inf"), emulate_torch_dtype=True):
+        """Global L2 norm of the gradients as a device tensor [3] = (norm, clip coefficient, sum of squares).
+        With ``emulate_torch_dtype`` and bf16 gradients the values carry torch's bf16 rounding."""
+        items = self._collect()
+        if not items:
+            return torch.zeros(3, device=self.param_device or "cuda")
+        emulate = emulate_torch_dtype and items[0][2].dtype == torch.bfloat16
+        mx = max_norm if math.isfinite(max_norm) else 3.0e38
+        return self._gradnorm(items, mx, emulate)[:3]
+
+    # -- the update -----------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, closure=None, clip_coef: torch.Tensor | None = None):
+        """One Raven update (raven.py:89-149).  ``clip_coef``: optional device scalar multiplied into every gradient
+        inside the kernel (fused ``clip_grad_norm_``); the reference calls ``step()`` without it."""
+        loss = None
+        if closure is not None:
+            with torch.enable_grad():
+                loss = closure()
+        self.last_launches = 0 if clip_coef is None else self.last_launches
+        items = self._collect()
+        if not items:
+            return loss
+        dev = items[0][1].device
+        pdt, gdt = items[0][1].dtype, items[0][2].dtype
+        hyper = np.empty((len(items), 8), dtype=np.float32)
+        ms, vs = [], []
+        mdt = None
+        for i, (group, p, g) in enumerate(items):
+            if p.dtype != pdt or g.dtype != gdt:
+                raise _lib.AozoraError(f"{self._name}: all parameters (and all gradients) must share one dtype")
+            momentum_dtype = group.get("momentum_dtype", self._momentum_dtype)
+            if mdt is None:
+                mdt = momentum_dtype
+            elif momentum_dtype != mdt:
+                raise _lib.AozoraError(f"{self._name}: one momentum_dtype per step() call")
+            state = self.state[p]
+            if "step" not in state:
+                state["step"] = 0
+                state["exp_avg"] = self._new_state_tensor(p, momentum_dtype)
+                state["exp_avg_sq"] = self._new_state_tensor(p, momentum_dtype)
+            state["step"] += 1
+            hyper[i] = raven_host_scalars(group["lr"], group["betas"], group["eps"], group["weight_decay"],
+                                          group["debias_strength"], state["step"])
+            m, v = state["exp_avg"], state["exp_avg_sq"]
+            if m.dtype != momentum_dtype or not m.is_cuda:
+                m = state["exp_avg"] = self._restore_state_tensor(m, p).to(momentum_dtype)
+                v = state["exp_avg_sq"] = self._restore_state_tensor(v, p).to(momentum_dtype)
+            ms.append(m)
+            vs.append(v)
+        pl = self._plan
+        pl.ensure([p.numel() for _, p, _ in items], dev)
+        pp = _ptr_table([p for _, p, _ in items], dev)
+        gp = _ptr_table([g for _, _, g in items], dev)
+        mp = _ptr_table(ms, dev)
+        vp = _ptr_table(vs, dev)
+        hy = torch.from_numpy(hyper).to(dev, non_blocking=True)
+        _lib.call("aoz_raven_step_mt", pl.n_tensors, pl.n_chunks, pp.data_ptr(), gp.data_ptr(), mp.data_ptr(), vp.data_ptr(),
+                  pl.numel.data_ptr(), pl.chunk_start.data_ptr(), pl.chunk_tensor.data_ptr(), hy.data_ptr(),
+                  0 if clip_coef is None else clip_coef.data_ptr(), _DT[pdt], _DT[gdt], _DT[mdt],
+                  torch.cuda.current_stream().cuda_stream)
+        self.last_launches += 1
+        return loss
+
+    @torch.no_grad()
+    def clip_and_step(self, max_norm: float, emulate_torch_dtype: bool = True):
+        """Fused replacement of ``clip_grad_norm_(params, max_norm)`` + ``step()`` (train.py:2772-2783) with no host
+        synchronisation: norm and coefficient stay on the device and the coefficient is applied inside the update
+        kernel.  ``max_norm <= 0`` means "norm only" as in train.py:2778.  Returns the device tensor
+        ``[norm, coef, sumsq]``."""
+        self.last_launches = 0
+        items = self._collect()
+        if not items:
+            return None
+        emulate = emulate_torch_dtype and items[0][2].dtype == torch.bfloat16
+        clip = max_norm is not None and max_norm > 0
+        out = self._gradnorm(items, max_norm if clip else 3.0e38, emulate)
+        self.step(clip_coef=out[1:2] if clip else None)
+        return out[:3]
+
+    # -- state I/O (raven.py:151-222) -----------------------------------------------------------------------
+    def state_dict(self):
+        state_dict = super().state_dict()
+        state_dict["_momentum_dtype"] = self._momentum_dtype
+        return state_dict
+
+    def save_cpu_state(self):
+        params_with_grad = [p for group in self.param_groups for p in group["params"] if p.requires_grad]
+        cpu_state = {"_momentum_dtype": self._momentum_dtype}
+        for i, p in enumerate(params_with_grad):
+            if p in self.state:
+                state = self.state[p]
+                m, v = state.get("exp_avg"), state.get("exp_avg_sq")
+                cpu_state[i] = {
+                    "step": state.get("step", 0),
+                    "exp_avg_cpu": None if m is None else m.detach().to("cpu"),
+                    "exp_avg_sq_cpu": None if v is None else v.detach().to("cpu"),
+                }
+        return cpu_state
+
+    def load_cpu_state(self, cpu_state):
+        saved_dtype = cpu_state.get("_momentum_dtype", self._momentum_dtype)
+        params_with_grad = [p for group in self.param_groups for p in group["params"] if p.requires_grad]
+        for i, p in enumerate(params_with_grad):
+            if i not in cpu_state:
+                continue
+            saved = cpu_state[i]
+            exp_avg = saved.get("exp_avg", saved.get("exp_avg_cpu"))
+            exp_avg_sq = saved.get("exp_avg_sq", saved.get("exp_avg_sq_cpu"))
+            step = saved.get("step", 0)
+            if torch.is_tensor(step):
+                step = int(step.item())
+            self.state[p] = {
+                "step": step,
+                "exp_avg": self._restore_state_tensor(exp_avg, p) if exp_avg is not None else None,
+                "exp_avg_sq": self._restore_state_tensor(exp_avg_sq, p) if exp_avg_sq is not None else None,
+            }
+        if saved_dtype != self._momentum_dtype:
+            print(f"[{self._name}] Loaded state saved in {saved_dtype}, converted to {self._momentum_dtype}.")
+
+    def load_state_dict(self, state_dict):
+        state_dict = dict(state_dict)
+        saved_dtype = state_dict.pop("_momentum_dtype", torch.float32)
+        if saved_dtype != self._momentum_dtype:
+            print(f"[{self._name}] Loading state saved in {saved_dtype}, but current optimizer uses "
+                  f"{self._momentum_dtype}. Converting...")
+        super().load_state_dict(state_dict)
+        for group in self.param_groups:
+            for p in group["params"]:
+                if p.requires_grad and p in self.state:
+                    state = self.state[p]
+                    if "exp_avg" in state:
+                        state["exp_avg"] = state["exp_avg"].to(self._momentum_dtype)
+                        state["exp_avg_sq"] = state["exp_avg_sq"].to(self._momentum_dtype)
+                    if torch.is_tensor(state.get("step")):
+                        state["step"] = int(state["step"].item())
