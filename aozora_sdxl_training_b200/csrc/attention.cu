@@ -1,11 +1,680 @@
-// placeholder -- replaced by the tcgen05 flash attention kernels
+// Flash-style attention forward and backward on tcgen05 / TMEM / TMA for head_dim 64 (sm_100a).
+//
+// Replaces F.scaled_dot_product_attention as called by diffusers' AttnProcessor2_0 for Attention.attn1
+// (self, Tk = Tq) and Attention.attn2 (cross, Tk = 77*n) inside the UNet (reference: train.py:213-229 selects the
+// processor, train.py:2760 runs it; no mask, no dropout, scale 1/sqrt(64)).  The reference's backward is autograd
+// through SDPA; here it is two kernels (dK/dV and dQ) that recompute P from the saved log-sum-exp.
+//
+// Common structure (per CTA, 192 threads):
+//   warps 0..3  one thread per tile row: softmax / dS math on the TMEM accumulators (tcgen05.ld), results written
+//               as bf16 MMA operands into 128B-swizzled shared memory
+//   warp 4      TMA producer (4-D tensor maps over [B, T, H, 64]; rows past T are zero-filled by the TMA unit)
+//   warp 5      MMA issuer (one thread, tcgen05.mma, completion through tcgen05.commit -> mbarrier)
+// S / dP / O / dK / dV / dQ accumulators live in TMEM.  Tiles: 128 query rows x 128 key rows.
+//
+// forward : S = Q K^T -> online softmax (log2 domain, lazy rescale of O) -> O += P V ; stores O (bf16), LSE (fp32)
+// dK/dV   : per KV tile, loop over Q tiles:  S^T = K Q^T, dP^T = V dO^T, P^T = exp(S^T - LSE), dS^T = P^T (dP^T - D),
+//           dV += P^T dO, dK += dS^T Q
+// dQ      : per Q tile, loop over KV tiles:  S = Q K^T, dP = dO V^T, dS = P (dP - D), dQ += dS K
+// A [rows, 64] tile loaded once by TMA serves both as a K-major operand (contraction over d) and as an
+// MN-major operand (contraction over its rows): only the UMMA descriptor changes.
 #include "common.cuh"
-using namespace aoz;
-extern "C" {
-int aoz_attn_fwd(const void*, long long, const void*, long long, const void*, long long, void*, long long, void*, int, int, int, int, float, void*) {
-    set_error("aoz_attn_fwd: not built yet"); return AOZ_ERR_UNSUPPORTED; }
-long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
-int aoz_attn_bwd(const void*, long long, const void*, long long, const void*, long long, const void*, long long, const void*, long long,
-                 const void*, void*, long long, void*, long long, void*, long long, int, int, int, int, float, void*, void*) {
-    set_error("aoz_attn_bwd: not built yet"); return AOZ_ERR_UNSUPPORTED; }
+#include <cstring>
+
+namespace aoz {
+
+constexpr int ATT_THREADS = 192;
+constexpr int TILE = 128;
+constexpr int HD = 64;
+constexpr int TILE_BYTES = TILE * HD * 2;     // 16 KB: one [128, 64] bf16 tile
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float LN2 = 0.6931471805599453f;
+
+struct AttnParams {
+    CUtensorMap tmQ, tmK, tmV, tmDO;
+    int B, H, Tq, Tk;
+    float scale;
+    __nv_bfloat16* O; long long ldo;
+    float* lse;                 // [B, H, Tq]
+    const float* Dvec;          // [B, H, Tq]  rowsum(dO * O)
+    __nv_bfloat16* dQ; long long lddq;
+    __nv_bfloat16* dK; long long lddk;
+    __nv_bfloat16* dV; long long lddv;
+};
+
+__device__ __forceinline__ float fast_exp2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
 }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+// descriptors for the three operand shapes used below
+__device__ __forceinline__ uint64_t desc_kmajor(uint32_t tile_addr, int k16) {            // [rows,64] tile, contraction over d
+    return make_sdesc_sw128(tile_addr + k16 * 32, 16, 1024);
+}
+__device__ __forceinline__ uint64_t desc_rows_as_k(uint32_t tile_addr, int k16) {         // [rows,64] tile, contraction over rows
+    return make_sdesc_sw128(tile_addr + k16 * 2048, 8192, 1024);
+}
+__device__ __forceinline__ uint64_t desc_ptile(uint32_t p_addr, int k16) {                 // [128, 128] as two [128,64] blocks
+    return make_sdesc_sw128(p_addr + (k16 >> 2) * TILE_BYTES + (k16 & 3) * 32, 16, 1024);
+}
+// write 32 consecutive bf16 values (packed in 16 words) of row `r`, columns [c0, c0+32) of a [128,128] P tile
+__device__ __forceinline__ void store_p_chunk(uint32_t p_addr, int r, int c0, const uint32_t* w) {
+    const uint32_t blk = p_addr + (c0 >> 6) * TILE_BYTES;
+    const int chunk0 = (c0 & 63) >> 3;                      // first 16-byte chunk inside the 128-byte row
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        st_shared_v4(blk + sw128_offset(r, chunk0 + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
+}
+
+// ================================================================================================
+// forward
+// ================================================================================================
+struct FwdSmem {
+    static constexpr int Q = 0;
+    static constexpr int K = Q + TILE_BYTES;            // 2 stages
+    static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
+    static constexpr int P = V + 2 * TILE_BYTES;        // 32 KB
+    static constexpr int BAR = P + 2 * TILE_BYTES;
+    static constexpr int TOTAL = BAR + 256 + 512;     // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 2)
+attn_fwd_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + FwdSmem::BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_ready = bars + 5;
+    uint64_t* p_ready = bars + 6;
+    uint64_t* o_ready = bars + 7;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (P.Tq + TILE - 1) / TILE;
+    const int qt = blockIdx.x % q_tiles;
+    const int bh = blockIdx.x / q_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int q0 = qt * TILE;
+    const int nkv = (P.Tk + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(o_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tO = tmem + 128;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV);
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_4d(smem + FwdSmem::Q, &P.tmQ, q_full, 0, h, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_4d(smem + FwdSmem::K + s * TILE_BYTES, &P.tmK, &kv_full[s], 0, h, j * TILE, b);
+                tma_load_4d(smem + FwdSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
+            }
+        }
+    } else if (warp == 5) {
+        const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+        const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sK = smem_u32(smem + FwdSmem::K);
+        const uint32_t sV = smem_u32(smem + FwdSmem::V), sP = smem_u32(smem + FwdSmem::P);
+        mbar_wait(q_full, 0);
+        mbar_wait(&kv_full[0], 0);
+        tc_fence_after();
+        if (lane == 0) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_qk, k > 0);
+            umma_commit(s_ready);
+        }
+        __syncwarp();
+        for (int j = 0; j < nkv; ++j) {
+            const int s = j & 1;
+            mbar_wait(p_ready, j & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tO, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+            }
+            __syncwarp();
+            if (j + 1 < nkv) {
+                const int s2 = (j + 1) & 1;
+                mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
+                tc_fence_after();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s2 * TILE_BYTES, k), idesc_qk, k > 0);
+                    umma_commit(s_ready);
+                }
+            } else if (lane == 0) {
+                umma_commit(o_ready);
+            }
+            __syncwarp();
+        }
+    } else {
+        // ---- softmax warps: thread <-> query row ----
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const uint32_t sP = smem_u32(smem + FwdSmem::P);
+        const float sl2 = P.scale * LOG2E;
+        float m_ref = -INFINITY, l = 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_ready, j & 1);
+            tc_fence_after();
+            const int kvalid = P.Tk - j * TILE;              // keys >= kvalid are padding
+            float mx = -INFINITY;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]) * sl2);
+            }
+            if (j == 0) {
+                m_ref = mx;
+            } else {
+                const float m_new = fmaxf(m_ref, mx);
+                const bool need = (m_new - m_ref) > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    const float alpha = fast_exp2(m_ref - m_new);
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tO + lane_off + c * 32, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                        tmem_st32(tO + lane_off + c * 32, v);
+                    }
+                    tc_wait_st();
+                    l *= alpha;
+                    m_ref = m_new;
+                }
+            }
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t v[32], w[16];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    float p0 = (c * 32 + e < kvalid) ? fast_exp2(__uint_as_float(v[e]) * sl2 - m_ref) : 0.f;
+                    float p1 = (c * 32 + e + 1 < kvalid) ? fast_exp2(__uint_as_float(v[e + 1]) * sl2 - m_ref) : 0.f;
+                    l += p0 + p1;
+                    w[e >> 1] = pack_bf16(p0, p1);
+                }
+                store_p_chunk(sP, r, c * 32, w);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        mbar_wait(o_ready, 0);
+        tc_fence_after();
+        const float inv_l = 1.0f / l;
+        const int q = q0 + r;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
+            tc_wait_ld();
+            if (q < P.Tq) {
+                __nv_bfloat16* dst = P.O + ((long long)b * P.Tq + q) * P.ldo + h * HD + c * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
+        }
+        if (q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// ================================================================================================
+// backward preprocess: D[b,h,q] = sum_d dO * O
+// ================================================================================================
+__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
+                                     long long lddo, int B, int H, int Tq, float* __restrict__ D) {
+    const long long total = (long long)B * Tq * H;
+    const int lane = threadIdx.x & 31;
+    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += ((long long)gridDim.x * blockDim.x) >> 5) {
+        const int h = (int)(w % H);
+        const long long bt = w / H;
+        const int t = (int)(bt % Tq), b = (int)(bt / Tq);
+        const uint32_t o2 = *reinterpret_cast<const uint32_t*>(O + bt * ldo + h * HD + lane * 2);
+        const uint32_t d2 = *reinterpret_cast<const uint32_t*>(dO + bt * lddo + h * HD + lane * 2);
+        float s = bf16lo(o2) * bf16lo(d2) + bf16hi(o2) * bf16hi(d2);
+        s = warp_sum(s);
+        if (lane == 0) D[((long long)b * H + h) * Tq + t] = s;
+    }
+}
+
+// ================================================================================================
+// backward: dK, dV  (CTA = one KV tile; loop over Q tiles)
+// ================================================================================================
+struct KvSmem {
+    static constexpr int K = 0;
+    static constexpr int V = K + TILE_BYTES;
+    static constexpr int Q = V + TILE_BYTES;             // 2 stages
+    static constexpr int DO = Q + 2 * TILE_BYTES;        // 2 stages
+    static constexpr int PT = DO + 2 * TILE_BYTES;       // 32 KB
+    static constexpr int DST = PT + 2 * TILE_BYTES;      // 32 KB
+    static constexpr int VEC = DST + 2 * TILE_BYTES;     // lse2[2][128], D[2][128] floats
+    static constexpr int BAR = VEC + 2048;
+    static constexpr int TOTAL = BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + KvSmem::BAR);
+    uint64_t* kv_once = bars;           // 1
+    uint64_t* q_full = bars + 1;        // 2
+    uint64_t* q_empty = bars + 3;       // 2
+    uint64_t* s_ready = bars + 5;
+    uint64_t* pds_ready = bars + 6;
+    uint64_t* acc_ready = bars + 7;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    float* vec = (float*)(smem + KvSmem::VEC);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kv_tiles = (P.Tk + TILE - 1) / TILE;
+    const int kt = blockIdx.x % kv_tiles;
+    const int bh = blockIdx.x / kv_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int k0 = kt * TILE;
+    const int nq = (P.Tq + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_once, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(pds_ready, 128); mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
+            mbar_arrive_expect_tx(kv_once, 2 * TILE_BYTES);
+            tma_load_4d(smem + KvSmem::K, &P.tmK, kv_once, 0, h, k0, b);
+            tma_load_4d(smem + KvSmem::V, &P.tmV, kv_once, 0, h, k0, b);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&q_full[s], 2 * TILE_BYTES);
+                tma_load_4d(smem + KvSmem::Q + s * TILE_BYTES, &P.tmQ, &q_full[s], 0, h, i * TILE, b);
+                tma_load_4d(smem + KvSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
+            }
+        }
+    } else if (warp == 5) {
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+        const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
+        const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
+        const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
+        mbar_wait(kv_once, 0);
+        for (int i = 0; i < nq; ++i) {
+            const int s = i & 1;
+            mbar_wait(&q_full[s], (i >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tSt, desc_kmajor(sK, k), desc_kmajor(sQ + s * TILE_BYTES, k), idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tdPt, desc_kmajor(sV, k), desc_kmajor(sDO + s * TILE_BYTES, k), idesc_s, k > 0);
+                umma_commit(s_ready);
+            }
+            __syncwarp();
+            mbar_wait(pds_ready, i & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tdV, desc_ptile(sPT, k), desc_rows_as_k(sDO + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tdK, desc_ptile(sDST, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&q_empty[s]);
+                if (i == nq - 1) umma_commit(acc_ready);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int r = warp * 32 + lane;                      // key row inside the tile
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
+        const float sl2 = P.scale * LOG2E;
+        const bool key_ok = (k0 + r) < P.Tk;
+        for (int i = 0; i < nq; ++i) {
+            float* lse2 = vec + (i & 1) * 256;
+            float* dv = lse2 + 128;
+            {
+                const int q = i * TILE + r;
+                const long long idx = ((long long)b * P.H + h) * P.Tq + q;
+                lse2[r] = q < P.Tq ? P.lse[idx] * LOG2E : INFINITY;      // +inf -> P = 0 for padded queries
+                dv[r] = q < P.Tq ? P.Dvec[idx] : 0.f;
+            }
+            named_bar_sync(1, 128);
+            mbar_wait(s_ready, i & 1);
+            tc_fence_after();
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t vs[32], vp[32], wp[16], wd[16];
+                tmem_ld32(tSt + lane_off + c * 32, vs);
+                tmem_ld32(tdPt + lane_off + c * 32, vp);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int qa = c * 32 + e;
+                    float p0 = key_ok ? fast_exp2(__uint_as_float(vs[e]) * sl2 - lse2[qa]) : 0.f;
+                    float p1 = key_ok ? fast_exp2(__uint_as_float(vs[e + 1]) * sl2 - lse2[qa + 1]) : 0.f;
+                    const float d0 = p0 * (__uint_as_float(vp[e]) - dv[qa]);
+                    const float d1 = p1 * (__uint_as_float(vp[e + 1]) - dv[qa + 1]);
+                    wp[e >> 1] = pack_bf16(p0, p1);
+                    wd[e >> 1] = pack_bf16(d0, d1);
+                }
+                store_p_chunk(sPT, r, c * 32, wp);
+                store_p_chunk(sDST, r, c * 32, wd);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(pds_ready);
+        }
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        const int key = k0 + r;
+#pragma unroll 1
+        for (int which = 0; which < 2; ++which) {
+            const uint32_t tacc = which == 0 ? tdV : tdK;
+            const float mul = which == 0 ? 1.0f : P.scale;
+            __nv_bfloat16* base = which == 0 ? P.dV : P.dK;
+            const long long ld = which == 0 ? P.lddv : P.lddk;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tacc + lane_off + c * 32, v);
+                tc_wait_ld();
+                if (key < P.Tk) {
+                    __nv_bfloat16* dst = base + ((long long)b * P.Tk + key) * ld + h * HD + c * 32;
+#pragma unroll
+                    for (int e = 0; e < 32; e += 8) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                        *reinterpret_cast<uint4*>(dst + e) = o;
+                    }
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// ================================================================================================
+// backward: dQ  (CTA = one Q tile; loop over KV tiles)
+// ================================================================================================
+struct DqSmem {
+    static constexpr int Q = 0;
+    static constexpr int DO = Q + TILE_BYTES;
+    static constexpr int K = DO + TILE_BYTES;            // 2 stages
+    static constexpr int V = K + 2 * TILE_BYTES;         // 2 stages
+    static constexpr int DS = V + 2 * TILE_BYTES;        // 32 KB
+    static constexpr int BAR = DS + 2 * TILE_BYTES;
+    static constexpr int TOTAL = BAR + 256 + 1024;
+};
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + DqSmem::BAR);
+    uint64_t* q_once = bars;
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_ready = bars + 5;
+    uint64_t* ds_ready = bars + 6;
+    uint64_t* acc_ready = bars + 7;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (P.Tq + TILE - 1) / TILE;
+    const int qt = blockIdx.x % q_tiles;
+    const int bh = blockIdx.x / q_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int q0 = qt * TILE;
+    const int nkv = (P.Tk + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_once, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(ds_ready, 128); mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
+            mbar_arrive_expect_tx(q_once, 2 * TILE_BYTES);
+            tma_load_4d(smem + DqSmem::Q, &P.tmQ, q_once, 0, h, q0, b);
+            tma_load_4d(smem + DqSmem::DO, &P.tmDO, q_once, 0, h, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_4d(smem + DqSmem::K + s * TILE_BYTES, &P.tmK, &kv_full[s], 0, h, j * TILE, b);
+                tma_load_4d(smem + DqSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
+            }
+        }
+    } else if (warp == 5) {
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+        const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
+        const uint32_t sK = smem_u32(smem + DqSmem::K), sV = smem_u32(smem + DqSmem::V);
+        const uint32_t sDS = smem_u32(smem + DqSmem::DS);
+        mbar_wait(q_once, 0);
+        for (int j = 0; j < nkv; ++j) {
+            const int s = j & 1;
+            mbar_wait(&kv_full[s], (j >> 1) & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s * TILE_BYTES, k), idesc_s, k > 0);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) umma_bf16(tdP, desc_kmajor(sDO, k), desc_kmajor(sV + s * TILE_BYTES, k), idesc_s, k > 0);
+                umma_commit(s_ready);
+            }
+            __syncwarp();
+            mbar_wait(ds_ready, j & 1);
+            tc_fence_after();
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tdQ, desc_ptile(sDS, k), desc_rows_as_k(sK + s * TILE_BYTES, k), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                if (j == nkv - 1) umma_commit(acc_ready);
+            }
+            __syncwarp();
+        }
+    } else {
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const uint32_t sDS = smem_u32(smem + DqSmem::DS);
+        const float sl2 = P.scale * LOG2E;
+        const int q = q0 + r;
+        const long long idx = ((long long)b * P.H + h) * P.Tq + q;
+        const float lse2 = q < P.Tq ? P.lse[idx] * LOG2E : INFINITY;
+        const float dvec = q < P.Tq ? P.Dvec[idx] : 0.f;
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_ready, j & 1);
+            tc_fence_after();
+            const int kvalid = P.Tk - j * TILE;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                uint32_t vs[32], vp[32], wd[16];
+                tmem_ld32(tS + lane_off + c * 32, vs);
+                tmem_ld32(tdP + lane_off + c * 32, vp);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int ka = c * 32 + e;
+                    float p0 = (ka < kvalid) ? fast_exp2(__uint_as_float(vs[e]) * sl2 - lse2) : 0.f;
+                    float p1 = (ka + 1 < kvalid) ? fast_exp2(__uint_as_float(vs[e + 1]) * sl2 - lse2) : 0.f;
+                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                }
+                store_p_chunk(sDS, r, c * 32, wd);
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(ds_ready);
+        }
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tdQ + lane_off + c * 32, v);
+            tc_wait_ld();
+            if (q < P.Tq) {
+                __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD + c * 32;
+                const float mul = P.scale;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int B, int H, int T) {
+    uint64_t dims[4] = {(uint64_t)HD, (uint64_t)H, (uint64_t)T, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)HD * 2, (uint64_t)ld * 2, (uint64_t)T * (uint64_t)ld * 2};
+    uint32_t box[4] = {HD, 1, TILE, 1};
+    return make_tmap_bf16(m, base, 4, dims, strides, box, nullptr);
+}
+
+}  // namespace aoz
+
+using namespace aoz;
+
+extern "C" {
+
+int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                 void* lse, int B, int H, int Tq, int Tk, float scale, void* stream) {
+    AOZ_CHECK_ARG(q && k && v && o && lse, "aoz_attn_fwd: null pointer");
+    AOZ_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk > 0, "aoz_attn_fwd: empty problem");
+    AOZ_CHECK_ARG((ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0, "aoz_attn_fwd: strides must be multiples of 8");
+    AttnParams P;
+    memset(&P, 0, sizeof(P));
+    int rc;
+    if ((rc = make_qkv_map(&P.tmQ, q, ldq, B, H, Tq)) != AOZ_OK) return rc;
+    if ((rc = make_qkv_map(&P.tmK, k, ldk, B, H, Tk)) != AOZ_OK) return rc;
+    if ((rc = make_qkv_map(&P.tmV, v, ldv, B, H, Tk)) != AOZ_OK) return rc;
+    P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
+    P.O = (__nv_bfloat16*)o; P.ldo = ldo; P.lse = (float*)lse;
+    static bool attr = false;
+    if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL); attr = true; }
+    const int grid = B * H * ((Tq + TILE - 1) / TILE);
+    attn_fwd_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, (cudaStream_t)stream>>>(P);
+    AOZ_CHECK_LAUNCH("attn_fwd_kernel");
+    return AOZ_OK;
+}
+
+long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
+
+int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
+                 long long ldo, const void* d_o, long long lddo, const void* lse, void* dq, long long lddq, void* dk,
+                 long long lddk, void* dv, long long lddv, int B, int H, int Tq, int Tk, float scale, void* workspace,
+                 void* stream) {
+    AOZ_CHECK_ARG(q && k && v && o && d_o && lse && dq && dk && dv && workspace, "aoz_attn_bwd: null pointer");
+    AOZ_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk > 0, "aoz_attn_bwd: empty problem");
+    AOZ_CHECK_ARG((ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0 && (lddo % 8) == 0 && (lddq % 8) == 0 &&
+                  (lddk % 8) == 0 && (lddv % 8) == 0, "aoz_attn_bwd: strides must be multiples of 8");
+    cudaStream_t s = (cudaStream_t)stream;
+    AttnParams P;
+    memset(&P, 0, sizeof(P));
+    int rc;
+    if ((rc = make_qkv_map(&P.tmQ, q, ldq, B, H, Tq)) != AOZ_OK) return rc;
+    if ((rc = make_qkv_map(&P.tmK, k, ldk, B, H, Tk)) != AOZ_OK) return rc;
+    if ((rc = make_qkv_map(&P.tmV, v, ldv, B, H, Tk)) != AOZ_OK) return rc;
+    if ((rc = make_qkv_map(&P.tmDO, d_o, lddo, B, H, Tq)) != AOZ_OK) return rc;
+    P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
+    P.lse = (float*)const_cast<void*>(lse); P.Dvec = (const float*)workspace;
+    P.dQ = (__nv_bfloat16*)dq; P.lddq = lddq; P.dK = (__nv_bfloat16*)dk; P.lddk = lddk; P.dV = (__nv_bfloat16*)dv; P.lddv = lddv;
+    {
+        const long long warps = (long long)B * Tq * H;
+        long long blocks = (warps * 32 + 255) / 256;
+        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+        attn_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace);
+        AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");
+    }
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(attn_bwd_dkv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, KvSmem::TOTAL);
+        cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL);
+        attr = true;
+    }
+    attn_bwd_dkv_kernel<<<B * H * ((Tk + TILE - 1) / TILE), ATT_THREADS, KvSmem::TOTAL, s>>>(P);
+    AOZ_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+    attn_bwd_dq_kernel<<<B * H * ((Tq + TILE - 1) / TILE), ATT_THREADS, DqSmem::TOTAL, s>>>(P);
+    AOZ_CHECK_LAUNCH("attn_bwd_dq_kernel");
+    return AOZ_OK;
+}
+
+}  // extern "C"

@@ -68,7 +68,7 @@ template <int BN>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     using L = SmemLayout<BN>;
-    extern __shared__ uint8_t smem_raw[];
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* bar_base = smem + L::STAGES * L::STAGE_BYTES;
     uint64_t* full_bar = (uint64_t*)bar_base;                 // [STAGES]

@@ -93,6 +93,29 @@ def case_conv(NB, H, W, Cin, Cout, ks, stride):
     return out
 
 
+def case_attn(B, H, Tq, Tk):
+    import torch
+    from aozora_sdxl_training_b200 import ops
+    g = torch.Generator(device="cuda").manual_seed(5)
+    q = torch.randn(B, Tq, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+    k = torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+    v = torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+    do = torch.randn(B, Tq, H, 64, device="cuda", generator=g).to(torch.bfloat16)
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    torch.cuda.synchronize()
+    qr, kr, vr = [t.float().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v)]
+    orf = torch.nn.functional.scaled_dot_product_attention(qr, kr, vr)
+    lse_ref = torch.logsumexp(torch.einsum("bhqd,bhkd->bhqk", qr, kr) * 0.125, dim=-1)
+    out = {"fwd": _stats(o, orf.permute(0, 2, 1, 3)), "lse": _stats(lse, lse_ref)}
+    orf.backward(do.float().permute(0, 2, 1, 3))
+    dq, dk, dv = ops.attn_bwd(q, k, v, o, do, lse, 0.125)
+    torch.cuda.synchronize()
+    out["dq"] = _stats(dq, qr.grad.permute(0, 2, 1, 3))
+    out["dk"] = _stats(dk, kr.grad.permute(0, 2, 1, 3))
+    out["dv"] = _stats(dv, vr.grad.permute(0, 2, 1, 3))
+    return out
+
+
 def case_norms():
     import torch
     from aozora_sdxl_training_b200 import ops
@@ -162,6 +185,11 @@ def case_raven():
 
 
 CASES = {
+    "attn_self_small": lambda: case_attn(1, 2, 128, 128),
+    "attn_self": lambda: case_attn(2, 5, 1024, 1024),
+    "attn_self_ragged": lambda: case_attn(1, 3, 1008, 1008),
+    "attn_cross": lambda: case_attn(2, 10, 1024, 77),
+    "attn_cross_ragged": lambda: case_attn(1, 5, 988, 154),
     "raven": lambda: case_raven(),
     "norms": lambda: case_norms(),
     "gemm_tn_small": lambda: case_gemm(False, False, 128, 128, 64),
