@@ -85,13 +85,15 @@ __global__ void noise_target_kernel(const __nv_bfloat16* __restrict__ latents, c
 }
 
 // ---- weighted MSE + gradient (train.py:2408-2416, 2765) ---------------------------------------------------
-// pred: NHWC bf16 [NB, HW, ldp>=C]; target fp32 NCHW.  per_sample[n] = mean_chw (pred-target)^2.
-// dpred = 2 (pred-target) * w_n * grad_scale / (C*HW)   with grad_scale = 1 / (global_batch * grad_accum)
+// pred / dpred: bf16 with explicit strides (sample, channel, pixel) so both NHWC [NB,HW,ld] and NCHW work;
+// target fp32 NCHW.  per_sample[n] = mean_chw (pred-target)^2.
+// dpred = 2 (pred-target) * w_n * grad_scale / (C*HW)   with grad_scale = upstream grad / global batch
 __global__ void __launch_bounds__(1024)
-mse_loss_kernel(const __nv_bfloat16* __restrict__ pred, int ldp, const float* __restrict__ target,
-                const long long* __restrict__ tickets, const float* __restrict__ table, int table_len, int C, int HW,
-                float grad_scale, float* __restrict__ per_sample, float* __restrict__ weight_out,
-                __nv_bfloat16* __restrict__ dpred) {
+mse_loss_kernel(const __nv_bfloat16* __restrict__ pred, long long p_sn, long long p_sc, long long p_shw,
+                const float* __restrict__ target, const long long* __restrict__ tickets, const float* __restrict__ table,
+                int table_len, int C, int HW, const float* __restrict__ grad_scale_ptr, float grad_scale,
+                float* __restrict__ per_sample, float* __restrict__ weight_out, __nv_bfloat16* __restrict__ dpred,
+                long long d_sn, long long d_sc, long long d_shw) {
     __shared__ float wsum[32];
     const int n = blockIdx.x;
     const int total = C * HW;
@@ -101,12 +103,13 @@ mse_loss_kernel(const __nv_bfloat16* __restrict__ pred, int ldp, const float* __
         t = t < 0 ? 0 : (t > table_len - 1 ? table_len - 1 : t);
         w = table[t];
     }
+    const float gs = grad_scale_ptr ? grad_scale * grad_scale_ptr[0] : grad_scale;
     float acc = 0.f;
     for (int i = threadIdx.x; i < total; i += blockDim.x) {
         const int c = i / HW, hw = i - c * HW;
-        const float d = __bfloat162float(pred[((long long)n * HW + hw) * ldp + c]) - target[(long long)n * total + i];
+        const float d = __bfloat162float(pred[n * p_sn + c * p_sc + hw * p_shw]) - target[(long long)n * total + i];
         acc = fmaf(d, d, acc);
-        if (dpred) dpred[((long long)n * HW + hw) * ldp + c] = __float2bfloat16_rn(2.0f * d * w * grad_scale / (float)total);
+        if (dpred) dpred[n * d_sn + c * d_sc + hw * d_shw] = __float2bfloat16_rn(2.0f * d * w * gs / (float)total);
     }
     acc = warp_sum(acc);
     if ((threadIdx.x & 31) == 0) wsum[threadIdx.x >> 5] = acc;
@@ -114,7 +117,7 @@ mse_loss_kernel(const __nv_bfloat16* __restrict__ pred, int ldp, const float* __
     if (threadIdx.x < 32) {
         float s = threadIdx.x < (blockDim.x >> 5) ? wsum[threadIdx.x] : 0.f;
         s = warp_sum(s);
-        if (threadIdx.x == 0) { per_sample[n] = s / (float)total; weight_out[n] = w; }
+        if (threadIdx.x == 0 && per_sample) { per_sample[n] = s / (float)total; weight_out[n] = w; }
     }
 }
 // loss = sum_n per_sample[n]*w[n] / denom   (denom = global batch size; reference: .mean() over the batch)
@@ -260,8 +263,11 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, long
 // ---- column sums: out[c] = sum_r x[r, c]  (bias gradients) ---------------------------------------------------
 // stage 1: grid (col blocks of 256 channels via 32 vectors, row chunks) -> partial [chunks][N]
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long M, int N, long long ld, float* __restrict__ partial) {
+colsum_partial_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
+                      float* __restrict__ partial0) {
     __shared__ float sm[8][256];
+    const __nv_bfloat16* x = x0 + (long long)blockIdx.z * group_stride;
+    float* partial = partial0 + (long long)blockIdx.z * gridDim.y * N;
     const int vcol = blockIdx.x * 32 + (threadIdx.x & 31);     // vector column (8 channels)
     const int rl = threadIdx.x >> 5;                           // 8 row lanes
     const int chunks = gridDim.y;
@@ -286,9 +292,11 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x, long long M, int N, l
     const int col = blockIdx.x * 256 + c;
     if (col < N) partial[(long long)blockIdx.y * N + col] = s;
 }
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial, int chunks, int N, __nv_bfloat16* __restrict__ out, int accumulate) {
+__global__ void colsum_finalize_kernel(const float* __restrict__ partial0, int chunks, int N, __nv_bfloat16* __restrict__ out0, int accumulate) {
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= N) return;
+    const float* partial = partial0 + (long long)blockIdx.y * chunks * N;
+    __nv_bfloat16* out = out0 + (long long)blockIdx.y * N;
     float s = 0.f;
     for (int k = 0; k < chunks; ++k) s += partial[(long long)k * N + c];
     if (accumulate) s = round_bf16(s) + __bfloat162float(out[c]);
@@ -380,20 +388,25 @@ int aoz_noise_target(const void* latents, const void* noise, const void* tickets
     return AOZ_OK;
 }
 
-// loss_out[0] = sum_n mse_n * w_n / denom; per_sample / weights: [NB] fp32 scratch (outputs); dpred may be null
-int aoz_mse_loss(const void* pred, int ldp, const void* target, const void* tickets, const void* table, int table_len, int NB,
-                 int C, int HW, float denom, float grad_scale, void* per_sample, void* weights, void* loss_out, void* dpred,
+// loss_out[0] = sum_n mse_n * w_n / denom; per_sample / weights: [NB] fp32 scratch (outputs).
+// Two uses: forward (dpred null) and forward+gradient (dpred set; grad_scale_ptr = optional device scalar multiplied
+// into grad_scale, e.g. autograd's upstream gradient).  Strides in elements: (sample, channel, pixel).
+int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_shw, const void* target, const void* tickets,
+                 const void* table, int table_len, int NB, int C, int HW, float denom, const void* grad_scale_ptr, float grad_scale,
+                 void* per_sample, void* weights, void* loss_out, void* dpred, long long d_sn, long long d_sc, long long d_shw,
                  void* stream) {
-    AOZ_CHECK_ARG(pred && target && per_sample && weights && loss_out, "aoz_mse_loss: null pointer");
+    AOZ_CHECK_ARG(pred && target && per_sample && weights, "aoz_mse_loss: null pointer");
     AOZ_CHECK_ARG(!table || tickets, "aoz_mse_loss: table without tickets");
     if (NB <= 0) return AOZ_OK;
     cudaStream_t s = (cudaStream_t)stream;
-    mse_loss_kernel<<<NB, 1024, 0, s>>>((const __nv_bfloat16*)pred, ldp, (const float*)target, (const long long*)tickets,
-                                       (const float*)table, table_len, C, HW, grad_scale, (float*)per_sample, (float*)weights,
-                                       (__nv_bfloat16*)dpred);
+    mse_loss_kernel<<<NB, 1024, 0, s>>>((const __nv_bfloat16*)pred, p_sn, p_sc, p_shw, (const float*)target, (const long long*)tickets,
+                                       (const float*)table, table_len, C, HW, (const float*)grad_scale_ptr, grad_scale,
+                                       (float*)per_sample, (float*)weights, (__nv_bfloat16*)dpred, d_sn, d_sc, d_shw);
     AOZ_CHECK_LAUNCH("mse_loss_kernel");
-    mse_finalize_kernel<<<1, 1, 0, s>>>((const float*)per_sample, (const float*)weights, NB, denom, (float*)loss_out);
-    AOZ_CHECK_LAUNCH("mse_finalize_kernel");
+    if (loss_out) {
+        mse_finalize_kernel<<<1, 1, 0, s>>>((const float*)per_sample, (const float*)weights, NB, denom, (float*)loss_out);
+        AOZ_CHECK_LAUNCH("mse_finalize_kernel");
+    }
     return AOZ_OK;
 }
 
@@ -469,21 +482,23 @@ int aoz_copy_channels(const void* src, long long src_ld, int src_off, void* dst,
     return AOZ_OK;
 }
 
-long long aoz_colsum_workspace_floats(int N) { return 64LL * N; }
+long long aoz_colsum_workspace_floats(int groups, int N) { return 64LL * N * (groups > 0 ? groups : 1); }
 
-// out[c] (+)= sum_r x[r, c]; x: [M, N] bf16 with leading dim ld (multiple of 8); workspace >= 64*N floats
-int aoz_colsum(const void* x, long long M, int N, long long ld, void* out, int accumulate, void* workspace, void* stream) {
-    AOZ_CHECK_ARG(x && out && workspace, "aoz_colsum: null pointer");
+// out[g, c] (+)= sum_r x[g, r, c]; x: [groups, M, N] bf16, row stride ld, group stride group_stride (elements);
+// out: [groups, N] bf16; workspace >= 64*N*groups floats
+int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long long group_stride, void* out, int accumulate,
+               void* workspace, void* stream) {
+    AOZ_CHECK_ARG(x && out && workspace && groups >= 1, "aoz_colsum: bad arguments");
     AOZ_CHECK_ARG(N % 8 == 0 && ld % 8 == 0, "aoz_colsum: N and ld must be multiples of 8");
     cudaStream_t s = (cudaStream_t)stream;
     const int colblocks = (N + 255) / 256;
-    int chunks = (sm_count() * 4 + colblocks - 1) / colblocks;
+    int chunks = (sm_count() * 4 + colblocks * groups - 1) / (colblocks * groups);
     if (chunks > 64) chunks = 64;
     if ((long long)chunks > (M + 7) / 8) chunks = (int)((M + 7) / 8);
     if (chunks < 1) chunks = 1;
-    colsum_partial_kernel<<<dim3(colblocks, chunks), 256, 0, s>>>((const __nv_bfloat16*)x, M, N, ld, (float*)workspace);
+    colsum_partial_kernel<<<dim3(colblocks, chunks, groups), 256, 0, s>>>((const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace);
     AOZ_CHECK_LAUNCH("colsum_partial_kernel");
-    colsum_finalize_kernel<<<(N + 255) / 256, 256, 0, s>>>((const float*)workspace, chunks, N, (__nv_bfloat16*)out, accumulate);
+    colsum_finalize_kernel<<<dim3((N + 255) / 256, groups), 256, 0, s>>>((const float*)workspace, chunks, N, (__nv_bfloat16*)out, accumulate);
     AOZ_CHECK_LAUNCH("colsum_finalize_kernel");
     return AOZ_OK;
 }

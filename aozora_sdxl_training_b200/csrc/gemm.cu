@@ -401,7 +401,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 //   permute_taps  > 0 : cols = taps*Cin, out is OIHW [rows=Cout][Cin][taps]: out[(row*Cin + cin)*taps + tap]
 __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
                                      __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin,
-                                     int accumulate) {
+                                     int cin_real, int accumulate) {
     const long long total = rows * cols;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
         float s = 0.f;
@@ -410,7 +410,8 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
         long long o;
         if (permute_taps > 0) {
             const int tap = (int)(col / Cin), cin = (int)(col - (long long)tap * Cin);
-            o = (row * Cin + cin) * permute_taps + tap;
+            if (cin >= cin_real) continue;
+            o = (row * cin_real + cin) * permute_taps + tap;
         } else {
             o = row * ld_out + col;
         }
@@ -522,7 +523,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         const long long total = (long long)M * N;
         int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
         splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, M, N, (__nv_bfloat16*)C,
-                                                                    ldc, 0, 0, accumulate);
+                                                                    ldc, 0, 0, 0, accumulate);
         AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
     }
     return AOZ_OK;
@@ -579,11 +580,13 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
 }
 
 // Convolution weight gradient: dW[cout][tap][cin] = sum_pixels dy[pix][cout] * x[pix*stride + tap - pad][cin].
-//   dy : [NB, H, W, Cout], x : [NB, Hin, Win, Cin], grad_w : OIHW bf16 [Cout, Cin, ks, ks] (the parameter layout)
+//   dy : [NB, H, W, Cout], x : [NB, Hin, Win, Cin], grad_w : OIHW bf16 [Cout, cin_real, ks, ks] (the parameter layout;
+//   cin_real <= Cin drops zero-padded input channels, e.g. conv_in's 4 real channels of 8)
 //   workspace : splits * Cout * taps*Cin floats
 int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int Cout, int Hin, int Win, int Cin, int ks,
-                        int stride, int pad, void* grad_w, int accumulate, int splits, void* workspace, void* stream) {
+                        int stride, int pad, int cin_real, void* grad_w, int accumulate, int splits, void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && x && grad_w && workspace, "aoz_conv_wgrad_bf16: null operand");
+    if (cin_real <= 0 || cin_real > Cin) cin_real = Cin;
     AOZ_CHECK_ARG((Cin % 8) == 0 && (Cout % 8) == 0, "aoz_conv_wgrad_bf16: channel counts must be multiples of 8");
     GemmParams P;
     memset(&P, 0, sizeof(P));
@@ -621,7 +624,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
     const long long total = (long long)Cout * taps * Cin;
     int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
     splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,
-                                                                (__nv_bfloat16*)grad_w, 0, taps, Cin, accumulate);
+                                                                (__nv_bfloat16*)grad_w, 0, taps, Cin, cin_real, accumulate);
     AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
     return AOZ_OK;
 }

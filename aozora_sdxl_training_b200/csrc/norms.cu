@@ -208,7 +208,7 @@ __global__ void __launch_bounds__(GN_THREADS)
 gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ group_terms,
-                    int HW, int C, int silu, __nv_bfloat16* __restrict__ dx) {
+                    int HW, int C, int silu, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx) {
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_db[GN_GROUPS], s_ds[GN_GROUPS];
     const int n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
@@ -241,6 +241,12 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                 dz *= sg * (1.0f + z * (1.0f - sg));
             }
             fx[e] = s_rstd[g] * (dz * gm[e] - s_db[g] - xh * s_ds[g]);
+        }
+        if (dres) {
+            float fr[8];
+            unpack8(ld_stream(dres + base + i * 8), fr);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) fx[e] = round_bf16(fx[e]) + fr[e];
         }
         st_stream(dx + base + i * 8, pack8(fx));
     }
@@ -301,7 +307,8 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
-              long long rows, int C, __nv_bfloat16* __restrict__ dx, float* __restrict__ partial) {
+              long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
+              float* __restrict__ partial) {
     extern __shared__ float sm[];      // [2][C]
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = C / 8;
@@ -347,6 +354,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
                 float o[8];
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = rs * (dg[i][e] - s1 - xh[i][e] * s2);
+                if (dres) {
+                    float fr[8];
+                    unpack8(ld_stream(dres + row * C + v * 8), fr);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
+                }
                 st_stream(dx + row * C + v * 8, pack8(o));
             }
         }
@@ -420,8 +433,8 @@ int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB
 }
 
 int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const void* mean, const void* rstd,
-                      int NB, int HW, int C, int silu, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace,
-                      void* stream) {
+                      int NB, int HW, int C, int silu, const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate,
+                      void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && workspace, "aoz_groupnorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_bwd: C=%d must be a multiple of 32", C);
     AOZ_CHECK_ARG((long long)NB * 2 * C * (long long)sizeof(float) <= 200 * 1024, "aoz_groupnorm_bwd: NB*C too large (%d x %d)", NB, C);
@@ -449,7 +462,7 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     if (gx < 1) gx = 1;
     gn_bwd_apply_kernel<<<dim3(gx, NB), GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                            (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd,
-                                                           group_terms, HW, C, silu, (__nv_bfloat16*)dx);
+                                                           group_terms, HW, C, silu, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx);
     AOZ_CHECK_LAUNCH("gn_bwd_apply_kernel");
     return AOZ_OK;
 }
@@ -471,7 +484,7 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
 long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 4 * 2 * C; }
 
 int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
-                      void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
+                      const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "aoz_layernorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
     if (rows <= 0) return AOZ_OK;
@@ -480,8 +493,8 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     cudaStream_t s = (cudaStream_t)stream;
     ln_bwd_kernel<<<(int)blocks, LN_WARPS * 32, 2 * C * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
                                                                            (const __nv_bfloat16*)gamma, (const float*)mean,
-                                                                           (const float*)rstd, rows, C, (__nv_bfloat16*)dx,
-                                                                           (float*)workspace);
+                                                                           (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
+                                                                           (__nv_bfloat16*)dx, (float*)workspace);
     AOZ_CHECK_LAUNCH("ln_bwd_kernel");
     ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
                                                                (__nv_bfloat16*)dbeta, accumulate);

@@ -129,20 +129,21 @@ def conv_fwd(x, wpack, cout, ks, *, stride=1, pad=1, flip=False, bias=None, rowg
     return out
 
 
-def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False):
+def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False, cin_real=None):
     """dW (OIHW bf16 [Cout, Cin, ks, ks]) from dy [NB,H,W,Cout] and x [NB,Hin,Win,Cin]."""
     _chk(dy, "conv_wgrad dy")
     _chk(x, "conv_wgrad x")
     NB, H, W, Cout = dy.shape
     _, Hin, Win, Cin = x.shape
     taps = ks * ks
+    cin_real = cin_real or Cin
     if grad_w is None:
-        grad_w = torch.empty((Cout, Cin, ks, ks), dtype=BF16, device=x.device)
+        grad_w = torch.empty((Cout, cin_real, ks, ks), dtype=BF16, device=x.device)
     k_iters = NB * ((H + 7) // 8) * ((W + 7) // 8)
     tiles = ((Cout + 127) // 128) * taps * ((Cin + 127) // 128)
     splits = _pick_splits(tiles, k_iters)
     ws = workspace(splits * Cout * taps * Cin, x.device)
-    _lib.call("aoz_conv_wgrad_bf16", dy.data_ptr(), x.data_ptr(), NB, H, W, Cout, Hin, Win, Cin, ks, stride, pad,
+    _lib.call("aoz_conv_wgrad_bf16", dy.data_ptr(), x.data_ptr(), NB, H, W, Cout, Hin, Win, Cin, ks, stride, pad, cin_real,
               grad_w.data_ptr(), int(accumulate), splits, ws.data_ptr(), _stream())
     _count(2)
     return grad_w
@@ -196,7 +197,7 @@ def groupnorm_fwd(x, gamma, beta, eps, silu):
     return y, mean, rstd
 
 
-def groupnorm_bwd(dy, x, gamma, beta, mean, rstd, silu, need_param_grads=True):
+def groupnorm_bwd(dy, x, gamma, beta, mean, rstd, silu, need_param_grads=True, dres=None):
     _chk(dy, "groupnorm dy")
     NB, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (NB * C)
@@ -205,7 +206,7 @@ def groupnorm_bwd(dy, x, gamma, beta, mean, rstd, silu, need_param_grads=True):
     dbeta = torch.empty_like(beta) if need_param_grads else None
     ws = workspace(_lib.query("aoz_groupnorm_workspace_floats", NB, HW, C), x.device)
     _lib.call("aoz_groupnorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
-              rstd.data_ptr(), NB, HW, C, int(silu), dx.data_ptr(), _p(dgamma), _p(dbeta), 0, ws.data_ptr(), _stream())
+              rstd.data_ptr(), NB, HW, C, int(silu), _p(dres), dx.data_ptr(), _p(dgamma), _p(dbeta), 0, ws.data_ptr(), _stream())
     _count(3)
     return dx, dgamma, dbeta
 
@@ -223,7 +224,7 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
     _chk(dy, "layernorm dy")
     C = x.shape[-1]
     rows = x.numel() // C
@@ -232,7 +233,7 @@ def layernorm_bwd(dy, x, gamma, mean, rstd):
     dbeta = torch.empty_like(gamma)
     ws = workspace(_lib.query("aoz_layernorm_bwd_workspace_floats", C), x.device)
     _lib.call("aoz_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
-              dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0, ws.data_ptr(), _stream())
+              _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0, ws.data_ptr(), _stream())
     _count(2)
     return dx, dgamma, dbeta
 
@@ -281,20 +282,42 @@ def noise_target(latents, noise, tickets, alphas_cumprod, jitter, prediction_typ
     return xt, target, cond
 
 
-def mse_loss(pred_nhwc, target_nchw, tickets, table, denom, grad_scale, need_grad=True):
-    """weighted_sdxl_mse_loss (train.py:2408-2416) + dL/dpred.  pred: [B,h,w,ldp] bf16; target fp32 NCHW.
-    Returns (loss[1] fp32, per_sample[B], dpred or None)."""
-    _chk(pred_nhwc, "mse_loss pred")
+def _strides3(t, nhwc, c):
+    """(sample, channel, pixel) element strides of a [B,h,w,ld] (nhwc) or [B,C,h,w] (nchw) contiguous tensor."""
+    if nhwc:
+        ld = t.shape[-1]
+        hw = t.numel() // (t.shape[0] * ld)
+        return hw * ld, 1, ld
+    hw = t.numel() // (t.shape[0] * c)
+    return c * hw, hw, 1
+
+
+def mse_loss(pred, target_nchw, tickets, table, denom, grad_scale=1.0, *, pred_nhwc=True, need_grad=True, dpred_ld=None,
+             grad_scale_tensor=None):
+    """weighted_sdxl_mse_loss (train.py:2408-2416) and dL/dpred in one pass.
+
+    pred: bf16 [B,h,w,ld] (pred_nhwc) or [B,C,h,w]; target fp32 NCHW.  Returns (loss[1] fp32, per_sample[B], dpred|None);
+    dpred has the layout of pred, with the last dim padded to ``dpred_ld`` channels (zeros) when given (NHWC only)."""
+    _chk(pred, "mse_loss pred")
+    _chk(target_nchw, "mse_loss target", dtype=torch.float32)
     B, C = target_nchw.shape[0], target_nchw.shape[1]
     HW = target_nchw.numel() // (B * C)
-    ldp = pred_nhwc.shape[-1]
-    per = torch.empty((B,), dtype=torch.float32, device=pred_nhwc.device)
-    w = torch.empty((B,), dtype=torch.float32, device=pred_nhwc.device)
-    loss = torch.empty((1,), dtype=torch.float32, device=pred_nhwc.device)
-    dpred = torch.zeros_like(pred_nhwc) if need_grad else None
-    _lib.call("aoz_mse_loss", pred_nhwc.data_ptr(), ldp, target_nchw.data_ptr(), _p(tickets), _p(table),
-              0 if table is None else table.numel(), B, C, HW, float(denom), float(grad_scale), per.data_ptr(), w.data_ptr(),
-              loss.data_ptr(), _p(dpred), _stream())
+    dev = pred.device
+    per = torch.empty((B,), dtype=torch.float32, device=dev)
+    w = torch.empty((B,), dtype=torch.float32, device=dev)
+    loss = torch.empty((1,), dtype=torch.float32, device=dev)
+    dpred = None
+    ds = (0, 0, 0)
+    if need_grad:
+        if pred_nhwc and dpred_ld and dpred_ld != pred.shape[-1]:
+            dpred = torch.zeros(tuple(pred.shape[:-1]) + (dpred_ld,), dtype=BF16, device=dev)
+        else:
+            dpred = torch.zeros_like(pred) if (pred_nhwc and pred.shape[-1] != C) else torch.empty_like(pred)
+        ds = _strides3(dpred, pred_nhwc, C)
+    ps = _strides3(pred, pred_nhwc, C)
+    _lib.call("aoz_mse_loss", pred.data_ptr(), ps[0], ps[1], ps[2], target_nchw.data_ptr(), _p(tickets), _p(table),
+              0 if table is None else table.numel(), B, C, HW, float(denom), _p(grad_scale_tensor), float(grad_scale),
+              per.data_ptr(), w.data_ptr(), loss.data_ptr(), _p(dpred), ds[0], ds[1], ds[2], _stream())
     _count(2)
     return loss, per, dpred
 
@@ -383,12 +406,25 @@ def concat_channels(a, b):
 
 
 def colsum(x2d, out=None, accumulate=False):
+    """out[c] = sum_r x[r, c]; x: [M, N] bf16 (row stride allowed)."""
     _chk(x2d, "colsum x", contiguous=False)
     M, N = x2d.shape
     if out is None:
         out = torch.empty((N,), dtype=BF16, device=x2d.device)
-    ws = workspace(_lib.query("aoz_colsum_workspace_floats", N), x2d.device)
-    _lib.call("aoz_colsum", x2d.data_ptr(), M, N, x2d.stride(0), out.data_ptr(), int(accumulate), ws.data_ptr(), _stream())
+    ws = workspace(_lib.query("aoz_colsum_workspace_floats", 1, N), x2d.device)
+    _lib.call("aoz_colsum", x2d.data_ptr(), 1, M, N, x2d.stride(0), 0, out.data_ptr(), int(accumulate), ws.data_ptr(), _stream())
+    _count(2)
+    return out
+
+
+def colsum_grouped(x3d):
+    """out[g, c] = sum_r x[g, r, c]; x: [G, M, N] contiguous bf16 -> [G, N] (per-image sums: time-embedding gradient)."""
+    _chk(x3d, "colsum_grouped x")
+    G, N = x3d.shape[0], x3d.shape[-1]
+    M = x3d.numel() // (G * N)
+    out = torch.empty((G, N), dtype=BF16, device=x3d.device)
+    ws = workspace(_lib.query("aoz_colsum_workspace_floats", G, N), x3d.device)
+    _lib.call("aoz_colsum", x3d.data_ptr(), G, M, N, N, M * N, out.data_ptr(), 0, ws.data_ptr(), _stream())
     _count(2)
     return out
 

@@ -1,0 +1,155 @@
+"""The SDXL micro-step of the reference (train.py:2719-2784) as one fused B200 pipeline.
+
+``SDXLTrainStep.step(batch)`` does, with hand-written sm_100a kernels only and no host synchronisation:
+
+  host->device copy of the cached batch (train.py:2719-2721) -> tickets (2733) -> seeded noise (2735-2742) ->
+  noising + target in one kernel (2743-2758) -> UNet forward (2760) -> weighted MSE + dL/dpred in one kernel
+  (2763, 2765) -> explicit reverse sweep (2765) -> [data-parallel: bucketed gradient reduce-scatter over NCCL,
+  overlapped with the sweep] -> gradient norm + clip coefficient on device (2772-2781) -> Raven update with the
+  coefficient applied in-kernel (2783) -> zero_grad (2784) -> LR curve (2769).
+
+The reference synchronises three times per micro-step (``loss.item()``, the clip norm ``.item()``, the sigma print);
+here the loss and the norm stay device tensors and are read back only when the caller asks (``result.loss_value()``).
+"""
+from __future__ import annotations
+
+from dataclasses import dataclass
+
+import torch
+
+from . import _lib, host, ops
+from .scheduler import DDPMScheduler
+
+BF16 = torch.bfloat16
+
+
+@dataclass
+class StepResult:
+    loss: torch.Tensor                 # device fp32 [1]
+    grad_norm: torch.Tensor | None     # device fp32 [3] (norm, clip coefficient, sum of squares) on optimizer steps
+    timesteps: torch.Tensor
+    did_optimizer_step: bool
+    lr: float
+
+    def loss_value(self) -> float:
+        return float(self.loss.item())
+
+    def grad_norm_value(self) -> float:
+        return float(self.grad_norm[0].item()) if self.grad_norm is not None else float("nan")
+
+
+class SDXLTrainStep:
+    """One object per training run.  ``config`` carries the reference's flat keys: SEED,
+    BATCH_SIZE (global batch), MAX_TRAIN_STEPS, GRADIENT_ACCUMULATION_STEPS, CLIP_GRAD_NORM, PREDICTION_TYPE,
+    TIMESTEP_ALLOCATION, TIMESTEP_STRATIFIED_SAMPLING, TIMESTEP_LOSS_WEIGHT_CURVE, LR_CUSTOM_CURVE."""
+
+    def __init__(self, unet, optimizer, config, *, device="cuda", dp=None):
+        self.unet = unet
+        self.optimizer = optimizer
+        self.config = config
+        self.device = torch.device(device)
+        self.dp = dp                                    # parallel.DataParallel or None
+        self.world = 1 if dp is None else dp.world
+        self.rank = 0 if dp is None else dp.rank
+        self.prediction_type = getattr(config, "PREDICTION_TYPE", "epsilon")
+        self.is_rf = self.prediction_type == "rectified_flow"
+        self.seed = config.SEED if config.SEED else 42
+        self.grad_accum = max(1, int(getattr(config, "GRADIENT_ACCUMULATION_STEPS", 1)))
+        self.clip = float(getattr(config, "CLIP_GRAD_NORM", 1.0))
+        self.global_batch = int(config.BATCH_SIZE)
+        if self.global_batch % self.world:
+            raise ValueError("BATCH_SIZE (global) must be divisible by the number of ranks")
+        self.local_batch = self.global_batch // self.world
+        if not hasattr(config, "is_rectified_flow"):
+            config.is_rectified_flow = self.is_rf
+        self.sampler = host.TimestepSampler(config, self.device)
+        self.loss_table = host.timestep_loss_curve_from_config(config, 1000, device=self.device)
+        self.scheduler = DDPMScheduler(prediction_type=self.prediction_type)
+        self.alphas_cumprod = self.scheduler.alphas_cumprod.to(self.device)
+        curve = getattr(config, "LR_CUSTOM_CURVE", None)
+        total_micro = int(config.MAX_TRAIN_STEPS)
+        self.lr_scheduler = host.CustomCurveLRScheduler(optimizer, [list(p) for p in curve], total_micro) if curve else None
+        self.noise_gen = torch.Generator(device=self.device)
+        self.micro_step = 0
+        self.optimizer_steps = 0
+        self._accum = None              # {param: grad} carried across micro-steps when GRADIENT_ACCUMULATION_STEPS > 1
+        self.trainable = [p for p in unet.parameters() if p.requires_grad]
+
+    # ---- pieces ------------------------------------------------------------------------------------------
+    def _to_device(self, t, dtype=None):
+        if t.device != self.device:
+            t = t.to(self.device, non_blocking=True)
+        if dtype is not None and t.dtype != dtype:
+            t = t.to(dtype)
+        return t.contiguous()
+
+    def _noise(self, shape_local):
+        """Global-batch equivalence: draw the whole global tensor with the reference's reseed and keep
+        this rank's rows, so N ranks x b samples see exactly the noise of one process with BATCH_SIZE = N*b."""
+        gshape = (self.global_batch,) + tuple(shape_local[1:])
+        noise = host.generate_noise(torch.empty(gshape, device="meta"), self.noise_gen, self.device, step=self.micro_step + 1,
+                                    seed=self.seed)
+        if self.world == 1:
+            return noise
+        return noise[self.rank * self.local_batch:(self.rank + 1) * self.local_batch].contiguous()
+
+    def _jitter(self):
+        gen = host.seeded_torch_generator(self.device, self.seed, self.micro_step + 1, 0x5D1)
+        j = torch.rand((self.global_batch,), device=self.device, dtype=torch.float32, generator=gen)
+        return j[self.rank * self.local_batch:(self.rank + 1) * self.local_batch].contiguous()
+
+    # ---- the step ------------------------------------------------------------------------------------------
+    @torch.no_grad()
+    def step(self, batch, *, noise=None, jitter=None, taps=None) -> StepResult:
+        """batch: dict with ``latents`` [b,4,h,w] (bf16, pinned host or device), ``embeds`` [b,L,2048], ``pooled`` [b,1280],
+        ``time_ids`` [b,6] (list or tensor; converted to bf16 as train.py:2726-2731 does)."""
+        latents = self._to_device(batch["latents"], BF16)
+        embeds = self._to_device(batch["embeds"], BF16)
+        pooled = self._to_device(batch["pooled"], BF16)
+        tid = batch["time_ids"]
+        if not torch.is_tensor(tid):
+            tid = torch.tensor(tid, dtype=BF16)
+        time_ids = self._to_device(tid, BF16)
+        b = latents.shape[0]
+        if self.world == 1:
+            tickets, _ = self.sampler.sample(b)
+        else:
+            tickets, _ = self.sampler.sample_rank(b, self.rank, self.world)
+        # ``noise`` / ``jitter`` overrides exist for parity tests (the CPU oracle cannot reproduce CUDA Philox draws)
+        noise = self._noise(latents.shape) if noise is None else self._to_device(noise, torch.float32)
+        if self.is_rf:
+            jitter = self._jitter() if jitter is None else self._to_device(jitter, torch.float32)
+        else:
+            jitter = None
+        xt8, target, cond = ops.noise_target(latents, noise, tickets, None if self.is_rf else self.alphas_cumprod, jitter,
+                                             self.prediction_type, cpad=8)
+        pred, bwd = self.unet.forward_nhwc(xt8, cond, embeds, pooled, time_ids, taps=taps)
+        denom = float(b * self.world)
+        loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
+                                       grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
+        hook = self.dp.grad_ready if self.dp is not None else None
+        grads = bwd(dpred8) if hook is None else bwd(dpred8, on_grad=hook)
+        self.micro_step += 1
+        if self.grad_accum > 1:
+            if self._accum is None:
+                self._accum = grads
+            else:
+                for p, g in grads.items():
+                    ops.add(self._accum[p], g, out=self._accum[p])
+            grads = self._accum
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step(self.micro_step)
+        did = self.micro_step % self.grad_accum == 0
+        norm = None
+        if did:
+            for p in self.trainable:
+                p.grad = grads.get(p)
+            if self.dp is not None:
+                norm = self.dp.reduce_clip_step(self.optimizer, self.clip)
+            else:
+                norm = self.optimizer.clip_and_step(self.clip)
+            self.optimizer.zero_grad(set_to_none=True)
+            self._accum = None
+            self.optimizer_steps += 1
+        return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=did,
+                          lr=self.optimizer.param_groups[0]["lr"])

@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- SDXL 1024x1024 UNet training-step throughput on N B200s (BASELINE.json metric), one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--batch B] [--mode v_prediction]
+
+Own arm: ``SDXLTrainStep.step`` (aozora_sdxl_training_b200/trainer.py) on synthetic SDXL-shaped batches and random-init
+weights of the exact SDXL UNet layout: noising -> UNet fwd -> weighted MSE -> reverse sweep -> clip -> Raven update,
+every step, nothing skipped.  ``value`` = imgs/s with inputs resident in HBM; ``e2e`` = the same call fed from pinned
+HOST buffers (H2D of latents / text embeddings inside the timed region) with the loss read back to the host each step.
+``roofline`` = the dominant kernel (the tcgen05 GEMM, at the GEGLU feed-forward shape) timed live with CUDA events.
+``cpu_baseline`` / ``--impl reference`` = the reference's step semantics on the box's host cores through the CPU oracle
+(oracle/train_step_ref.py; the UNet arithmetic is diffusers', restated -- kind "port").
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+TRAIN_TFLOP_PER_IMG = 20.28          # fwd + dgrad + wgrad at 1024x1024, SURVEY.md 8d (recompute not counted)
+
+
+def load_peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            p = json.load(f)
+        return dict(hbm=p["hbm_gbs"], tf_burst=p["bf16_tflops"], tf_sust=p["bf16_tflops_sustained"], src="measured")
+    except Exception:
+        return dict(hbm=6650.0, tf_burst=1590.0, tf_sust=1400.0, src="fallback")
+
+
+class Cfg:
+    SEED = 42
+    MAX_TRAIN_STEPS = 1000
+    GRADIENT_ACCUMULATION_STEPS = 1
+    CLIP_GRAD_NORM = 1.0
+    TIMESTEP_STRATIFIED_SAMPLING = False
+    TIMESTEP_LOSS_WEIGHT_CURVE = None
+    LR_CUSTOM_CURVE = [[0.0, 0.0], [0.05, 8.0e-7], [0.85, 8.0e-7], [1.0, 1.0e-7]]
+    RAVEN = dict(betas=(0.9, 0.999), eps=1e-8, weight_decay=0.01, debias_strength=0.3)
+
+
+def synth_batch(b, res, seed, device="cpu", pin=False):
+    import torch
+    g = torch.Generator().manual_seed(seed)
+    h = res // 8
+    out = dict(latents=(torch.randn(b, 4, h, h, generator=g) * 0.8).to(torch.bfloat16),
+               embeds=torch.randn(b, 77, 2048, generator=g).to(torch.bfloat16),
+               pooled=torch.randn(b, 1280, generator=g).to(torch.bfloat16),
+               time_ids=torch.tensor([[res, res, 0, 0, res, res]] * b, dtype=torch.bfloat16))
+    if device != "cpu":
+        out = {k: v.to(device) for k, v in out.items()}
+    elif pin:
+        out = {k: v.pin_memory() for k, v in out.items()}
+    return out
+
+
+class ClockSampler:
+    QUERY = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.proc = None
+        self.idx = gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.idx), f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits",
+                                          "-lms", "200"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return dict(sm_mhz=None, sm_max_mhz=None, reasons=["nvidia-smi unavailable"])
+        self.proc.terminate()
+        try:
+            out, _ = self.proc.communicate(timeout=5)
+        except Exception:
+            self.proc.kill()
+            out = ""
+        sm, mx, reasons = [], None, set()
+        for line in out.splitlines():
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1]))
+                mx = float(f[2])
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[4:8]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return dict(sm_mhz=(sm[len(sm) // 2] if sm else None), sm_max_mhz=mx, reasons=sorted(reasons), samples=len(sm))
+
+
+def gemm_roofline(torch, peaks, iters=20):
+    """Dominant kernel timed live: gemm_bf16_kernel at the GEGLU feed-forward shape (M = 4 x 32 x 32 tokens, C = 1280)."""
+    from aozora_sdxl_training_b200 import ops
+    M, K, N = 4096, 1280, 10240
+    x = torch.randn(M, K, device="cuda").to(torch.bfloat16)
+    w = (torch.randn(N, K, device="cuda") * 0.02).to(torch.bfloat16)
+    b = torch.zeros(N, device="cuda", dtype=torch.bfloat16)
+    aux = torch.empty(M, N, device="cuda", dtype=torch.bfloat16)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    for _ in range(3):
+        ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
+    times = []
+    for _ in range(iters):
+        flush.zero_()                                         # L2 flush between timed launches
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    ms = sum(times) / len(times)
+    flops = 2.0 * M * N * K
+    ach = flops / (ms * 1e-3) / 1e12
+    return dict(bound="tensor", kernel="gemm_bf16_kernel<256> (GEGLU epilogue) M=4096 K=1280 N=10240", achieved=round(ach, 1),
+                peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4), traffic=None,
+                peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
+                flops_per_launch=flops)
+
+
+def kernel_table(torch, peaks):
+    """Side metrics BASELINE.json names: attention TFLOPS (4096 tok x 10 heads x 64) and Raven step HBM GB/s."""
+    from aozora_sdxl_training_b200 import ops
+    from aozora_sdxl_training_b200.optimizers import RavenAdamW
+    out = {}
+
+    def timeit(fn, n=10):
+        for _ in range(2):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    B, H, T = 4, 10, 4096
+    q, k, v, do = [torch.randn(B, T, H, 64, device="cuda").to(torch.bfloat16) for _ in range(4)]
+    ms = timeit(lambda: ops.attn_fwd(q, k, v, 0.125))
+    f = 4.0 * B * H * T * T * 64
+    out["attn_fwd_tflops"] = round(f / ms / 1e9, 1)
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    ms = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, 0.125))
+    out["attn_bwd_tflops"] = round(2.5 * f / ms / 1e9, 1)
+    n = 512 * 1024 * 1024                                    # 0.5 G parameters in 16 tensors (bounded memory, > L2)
+    ps = [torch.nn.Parameter(torch.zeros(n // 16, device="cuda", dtype=torch.bfloat16)) for _ in range(16)]
+    for p in ps:
+        p.grad = torch.full_like(p, 1e-3)
+    opt = RavenAdamW(ps, lr=8e-7, **Cfg.RAVEN)
+    ms = timeit(lambda: opt.step(), n=5)
+    out["raven_step_gbs"] = round(14.0 * n / ms / 1e6, 1)
+    out["raven_frac_of_hbm"] = round(out["raven_step_gbs"] / peaks["hbm"], 4)
+    x = torch.randn(4, 32 * 32, 1280, device="cuda").to(torch.bfloat16)
+    ga, be = torch.ones(1280, device="cuda", dtype=torch.bfloat16), torch.zeros(1280, device="cuda", dtype=torch.bfloat16)
+    ms = timeit(lambda: ops.groupnorm_fwd(x, ga, be, 1e-5, True))
+    out["groupnorm_silu_gbs"] = round(4.0 * x.numel() / ms / 1e6, 1)
+    return out
+
+
+def cpu_reference_step(res, batch, steps, warmup, mode):
+    """The reference's step semantics on the host cores via the CPU oracle (bounded sample)."""
+    import torch
+    from oracle import host_ref
+    from oracle.scheduler_ref import RefDDPMScheduler
+    from oracle.train_step_ref import RefRaven, ref_train_step
+    from oracle.unet_ref import RefUNet2DConditionModel, sdxl_config
+    torch.manual_seed(0)
+    model = RefUNet2DConditionModel(sdxl_config())
+    with torch.no_grad():
+        for name, p in model.named_parameters():
+            if p.dim() == 1 and name.endswith("weight"):
+                p.fill_(1.0)
+            elif p.dim() == 1:
+                p.zero_()
+            else:
+                p.normal_(0.0, 0.02)
+    opt = RefRaven(list(model.parameters()), lr=8e-7, momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
+    sch = RefDDPMScheduler(prediction_type=mode)
+    sampler = host_ref.RefTimestepSampler(Cfg.MAX_TRAIN_STEPS, batch, Cfg.SEED, None, False)
+    b = synth_batch(batch, res, 1)
+    rb = dict(latents=b["latents"], embeds=b["embeds"].float(), pooled=b["pooled"].float(),
+              time_ids_data=[[res, res, 0, 0, res, res]] * batch)
+    times = []
+    for i in range(warmup + steps):
+        ts, _ = sampler.sample(batch)
+        t0 = time.perf_counter()
+        ref_train_step(model, sch, opt, rb, prediction_type=mode, timesteps=ts, micro_step=i + 1, seed=Cfg.SEED,
+                       compute_dtype=torch.float32, autocast=False, clip_grad_norm=Cfg.CLIP_GRAD_NORM)
+        dt = time.perf_counter() - t0
+        if i >= warmup:
+            times.append(dt)
+    return sum(times) / len(times), torch.get_num_threads()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="aozora")
+    ap.add_argument("--batch", type=int, default=4, help="images per GPU (BASELINE config 2: 4)")
+    ap.add_argument("--res", type=int, default=1024)
+    ap.add_argument("--mode", default="v_prediction")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kernel-table", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    metric = "SDXL 1024x1024 UNet train step throughput"
+    workload = (f"SDXL UNet bf16 {args.res}x{args.res} ({args.res // 8}x{args.res // 8}x4 latents) batch {args.batch}/GPU, {args.mode}, "
+                f"Raven (bf16 moments), cached 77x2048 text embeds + 1280 pooled, random-init weights")
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        # bounded sample of the same workload: one image at 256x256 per step (1/16 of a 1024x1024 image's pixels)
+        sres, sb = 256, 1
+        sec, threads = cpu_reference_step(sres, sb, max(1, args.steps), max(0, min(args.warmup, 1)), args.mode)
+        scale = (sres / args.res) ** 2
+        val = sb * scale / sec
+        line = dict(impl="reference", metric=metric, value=val, unit="imgs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
+                    ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
+                    config=dict(workload=workload), gpu_launches=0,
+                    cpu_baseline=dict(value=val, unit="imgs/s", cores=threads, kind="port",
+                                      sample=f"{sb} image at {sres}x{sres} per step on torch-CPU fp32 (full SDXL UNet, Raven step "
+                                             f"included), converted to 1024x1024-image equivalents by pixel count (x{scale:g})"),
+                    e2e=dict(value=val, unit="imgs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        print(json.dumps(line))
+        return
+
+    import torch
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: CUDA device required (aozora-b200 has no CPU path; use --impl reference for the CPU arm)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    dp = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+    from aozora_sdxl_training_b200 import ops
+    from aozora_sdxl_training_b200.optimizers import RavenAdamW
+    from aozora_sdxl_training_b200.trainer import SDXLTrainStep
+    from aozora_sdxl_training_b200.unet import UNet2DConditionModel, init_weights_fast_, sdxl_config
+    peaks = load_peaks()
+
+    with torch.device(dev):
+        unet = UNet2DConditionModel(sdxl_config()).to(torch.bfloat16)
+    init_weights_fast_(unet, seed=Cfg.SEED)
+    cfg = type("BenchCfg", (Cfg,), dict(BATCH_SIZE=args.batch * world, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=None))
+    if world > 1:
+        from aozora_sdxl_training_b200.parallel import DataParallel
+        dp = DataParallel(unet, momentum_dtype=torch.bfloat16)
+        opt = dp.make_optimizer(lr=8e-7, **Cfg.RAVEN)
+    else:
+        opt = RavenAdamW([{"params": [p for p in unet.parameters() if p.requires_grad], "lr_scale": 1.0}], lr=8e-7,
+                         momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
+    step = SDXLTrainStep(unet, opt, cfg, device=dev, dp=dp)
+
+    host_batch = synth_batch(args.batch, args.res, 100 + rank, pin=True)
+    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
+    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
+
+    def barrier():
+        if world > 1:
+            torch.distributed.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, n):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(n):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
+        return ms.item()
+
+    for _ in range(max(3, args.warmup)):
+        r = step.step(dev_batch)
+    loss0 = r.loss_value()
+    clocks = ClockSampler(local_rank)
+    clocks.start()
+    l0 = ops.launch_count
+    ms_dev = timed(lambda: step.step(dev_batch), args.steps)
+    launches = ops.launch_count - l0 + 3 * args.steps          # + gradnorm (2) and raven (1) launches per step
+    clk = clocks.stop()
+
+    def e2e_step():
+        res = step.step(host_batch)
+        return res.loss_value()                                 # device -> host read of the step's loss
+
+    e2e_step()
+    ms_e2e = timed(e2e_step, args.steps)
+
+    imgs = args.batch * world * args.steps
+    value = imgs / (ms_dev * 1e-3)
+    e2e_val = imgs / (ms_e2e * 1e-3)
+    line = dict(metric=metric, value=round(value, 3), unit="imgs/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
+                ms_per_step=round(ms_dev / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
+                data="synthetic",
+                config=dict(workload=workload, global_batch=args.batch * world, parallelism=f"dp{world}",
+                            l2="per-step working set (5.1 GB weights + activations) far exceeds the 126 MB L2; no explicit flush",
+                            recompute="none (all activations kept in HBM)"),
+                e2e=dict(value=round(e2e_val, 3), unit="imgs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
+                         ms_per_step=round(ms_e2e / args.steps, 3)),
+                gpu_launches=int(launches), clocks=clk, loss=loss0,
+                step_tflops=round(value * TRAIN_TFLOP_PER_IMG * (args.res / 1024) ** 2 / world, 1),
+                step_frac_of_sustained_bf16_peak=round(value * TRAIN_TFLOP_PER_IMG * (args.res / 1024) ** 2 / world / peaks["tf_sust"], 4))
+    if rank == 0:
+        del step, opt
+        torch.cuda.empty_cache()
+        line["roofline"] = gemm_roofline(torch, peaks)
+        if not args.no_kernel_table:
+            try:
+                line["kernels"] = kernel_table(torch, peaks)
+            except Exception as e:                              # side table must never take the headline down
+                line["kernels"] = dict(error=str(e)[:200])
+        if world == 1 and not args.no_cpu_baseline:
+            sres, sb = 256, 1
+            sec, threads = cpu_reference_step(sres, sb, 1, 0, args.mode)
+            scale = (sres / args.res) ** 2
+            line["cpu_baseline"] = dict(value=sb * scale / sec, unit="imgs/s", cores=threads, kind="port",
+                                        sample=f"1 step of {sb} image at {sres}x{sres} on torch-CPU fp32 (oracle UNet + Raven), "
+                                               f"scaled to 1024x1024-image equivalents by pixel count (x{scale:g}); {sec:.1f} s")
+        else:
+            line["cpu_baseline"] = None
+        print(json.dumps(line))
+    if world > 1:
+        torch.distributed.barrier()
+        torch.distributed.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

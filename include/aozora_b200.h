@@ -53,7 +53,7 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
                       int pad, int flip, void* y, const void* bias, const void* rowgroup_bias, const void* residual,
                       int accumulate, void* stream);
 int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int Cout, int Hin, int Win, int Cin, int ks,
-                        int stride, int pad, void* grad_w, int accumulate, int splits, void* workspace, void* stream);
+                        int stride, int pad, int cin_real, void* grad_w, int accumulate, int splits, void* workspace, void* stream);
 int aoz_pack_conv_weight(const void* w, int Cout, int Cin, int ks, int CinPad, int CoutPad, void* wf, void* wd, void* stream);
 
 /* ---- attention [3P]: Attention.attn1 / attn2 via AttnProcessor2_0 = F.scaled_dot_product_attention
@@ -74,13 +74,13 @@ long long aoz_groupnorm_workspace_floats(int NB, int HW, int C);
 int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB, int HW, int C, float eps, int silu,
                       void* y, void* mean, void* rstd, void* workspace, void* stream);
 int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const void* beta, const void* mean, const void* rstd,
-                      int NB, int HW, int C, int silu, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace,
-                      void* stream);
+                      int NB, int HW, int C, int silu, const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate,
+                      void* workspace, void* stream);
 int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long long rows, int C, float eps, void* y, void* mean,
                       void* rstd, void* stream);
 long long aoz_layernorm_bwd_workspace_floats(int C);
 int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
-                      void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream);
+                      const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream);
 
 /* ---- step glue: noising + target (train.py:2743-2758; DDPMScheduler.add_noise/get_velocity [3P]),
  *      weighted_sdxl_mse_loss + dL/dpred (train.py:2408-2416, 2765), layout and elementwise pieces [3P] ------- */
@@ -88,8 +88,9 @@ int aoz_nchw_to_nhwc(const void* src, int src_f32, int NB, int C, int HW, int Cp
 int aoz_nhwc_to_nchw(const void* src, int NB, int C, int HW, int ld, void* dst, int dst_f32, void* stream);
 int aoz_noise_target(const void* latents, const void* noise, const void* tickets, const void* alphas_cumprod, const void* jitter,
                      int mode, int NB, int C, int HW, int Cpad, void* xt, void* target, void* cond, void* stream);
-int aoz_mse_loss(const void* pred, int ldp, const void* target, const void* tickets, const void* table, int table_len, int NB,
-                 int C, int HW, float denom, float grad_scale, void* per_sample, void* weights, void* loss_out, void* dpred,
+int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_shw, const void* target, const void* tickets,
+                 const void* table, int table_len, int NB, int C, int HW, float denom, const void* grad_scale_ptr, float grad_scale,
+                 void* per_sample, void* weights, void* loss_out, void* dpred, long long d_sn, long long d_sc, long long d_shw,
                  void* stream);
 int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* stream);
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream);
@@ -100,8 +101,9 @@ int aoz_upsample2x_bwd(const void* dy, int NB, int H, int W, int C, void* dx, vo
 int aoz_zero_insert2x(const void* x, int NB, int H, int W, int C, int Hout, int Wout, void* y, void* stream);
 int aoz_copy_channels(const void* src, long long src_ld, int src_off, void* dst, long long dst_ld, int dst_off, long long rows, int ch,
                       int accumulate, void* stream);
-long long aoz_colsum_workspace_floats(int N);
-int aoz_colsum(const void* x, long long M, int N, long long ld, void* out, int accumulate, void* workspace, void* stream);
+long long aoz_colsum_workspace_floats(int groups, int N);
+int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long long group_stride, void* out, int accumulate,
+               void* workspace, void* stream);
 int aoz_timestep_embedding(const void* t, int n, int dim, void* out, void* stream);
 
 #ifdef __cplusplus
