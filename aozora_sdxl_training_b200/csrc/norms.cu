@@ -166,41 +166,60 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) out[i] = sm[i];
 }
 
-// pass 2: reduce partials -> per (n, group) terms ds = sum_c gamma*B, db = sum_c gamma*A ; dgamma/dbeta over n.
-// grid = 1 block per 32 channels is plenty; here one block of 256 threads loops over channels.
-__global__ void __launch_bounds__(256)
-gn_bwd_finalize_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma, int NB, int chunks, int C,
-                       float* __restrict__ group_terms /* [NB][GROUPS][2] */, __nv_bfloat16* __restrict__ dgamma,
-                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
-    extern __shared__ float sm[];          // [NB][2][C] channel sums
-    for (int i = threadIdx.x; i < NB * 2 * C; i += blockDim.x) {
-        const int n = i / (2 * C), rem = i - n * 2 * C;
-        float s = 0.f;
-        for (int k = 0; k < chunks; ++k) s += partial[((size_t)n * chunks + k) * 2 * C + rem];
-        sm[i] = s;
-    }
-    __syncthreads();
+// pass 2a: one block per (group, image): reduce the chunk partials of the group's channels, write the per-channel
+// sums chansum[n][2][C] and the group terms db = sum_c gamma*A, ds = sum_c gamma*B  -> group_terms[n][g][2]
+__global__ void __launch_bounds__(128)
+gn_bwd_group_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma, int chunks, int C,
+                    float* __restrict__ chansum, float* __restrict__ group_terms) {
+    __shared__ float s_db[128], s_ds[128];
+    const int g = blockIdx.x, n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
-    for (int i = threadIdx.x; i < NB * GN_GROUPS; i += blockDim.x) {
-        const int n = i / GN_GROUPS, g = i - n * GN_GROUPS;
-        float db = 0.f, ds = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) {
-            const float gm = __bfloat162float(gamma[c]);
-            db = fmaf(gm, sm[(n * 2 + 0) * C + c], db);
-            ds = fmaf(gm, sm[(n * 2 + 1) * C + c], ds);
-        }
-        group_terms[i * 2 + 0] = db;
-        group_terms[i * 2 + 1] = ds;
-    }
-    if (dgamma) {
-        for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float db = 0.f, ds = 0.f;
+    // thread t handles channel (t % cpg) of the group and chunk lanes (t / cpg) when cpg < 128
+    const int lanes = max(1, 128 / cpg);
+    const int cl = threadIdx.x % cpg, kl = threadIdx.x / cpg;
+    if (kl < lanes) {
+        for (int c0 = cl; c0 < cpg; c0 += (lanes > 1 ? cpg : 128)) {
+            const int c = g * cpg + c0;
             float a = 0.f, b = 0.f;
-            for (int n = 0; n < NB; ++n) { a += sm[(n * 2 + 0) * C + c]; b += sm[(n * 2 + 1) * C + c]; }
-            if (accumulate) { a = round_bf16(a) + __bfloat162float(dbeta[c]); b = round_bf16(b) + __bfloat162float(dgamma[c]); }
-            dbeta[c] = __float2bfloat16_rn(a);
-            dgamma[c] = __float2bfloat16_rn(b);
+            for (int k = kl; k < chunks; k += lanes) {
+                const float* p = partial + ((size_t)n * chunks + k) * 2 * C;
+                a += p[c]; b += p[C + c];
+            }
+            if (lanes == 1) {
+                chansum[((size_t)n * 2 + 0) * C + c] = a;
+                chansum[((size_t)n * 2 + 1) * C + c] = b;
+                const float gm = __bfloat162float(gamma[c]);
+                db = fmaf(gm, a, db); ds = fmaf(gm, b, ds);
+            } else {
+                atomicAdd(&chansum[((size_t)n * 2 + 0) * C + c], a);
+                atomicAdd(&chansum[((size_t)n * 2 + 1) * C + c], b);
+                const float gm = __bfloat162float(gamma[c]);
+                db = fmaf(gm, a, db); ds = fmaf(gm, b, ds);
+            }
         }
     }
+    s_db[threadIdx.x] = db; s_ds[threadIdx.x] = ds;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) { s_db[threadIdx.x] += s_db[threadIdx.x + o]; s_ds[threadIdx.x] += s_ds[threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        group_terms[((size_t)n * GN_GROUPS + g) * 2 + 0] = s_db[0];
+        group_terms[((size_t)n * GN_GROUPS + g) * 2 + 1] = s_ds[0];
+    }
+}
+// pass 2b: dgamma / dbeta = sum over images of the per-channel sums
+__global__ void gn_bwd_param_kernel(const float* __restrict__ chansum, int NB, int C, __nv_bfloat16* __restrict__ dgamma,
+                                    __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= C) return;
+    float a = 0.f, b = 0.f;
+    for (int n = 0; n < NB; ++n) { a += chansum[((size_t)n * 2 + 0) * C + c]; b += chansum[((size_t)n * 2 + 1) * C + c]; }
+    if (accumulate) { a = round_bf16(a) + __bfloat162float(dbeta[c]); b = round_bf16(b) + __bfloat162float(dgamma[c]); }
+    dbeta[c] = __float2bfloat16_rn(a);
+    dgamma[c] = __float2bfloat16_rn(b);
 }
 
 // pass 3: dx = rstd * (dz*gamma - db/cnt - xhat * ds/cnt)
@@ -303,44 +322,52 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
     }
 }
 
-// backward: dx per row; dgamma/dbeta partials per block -> partial [gridDim.x][2][C]
+// backward: dx per row (one warp per row); dgamma/dbeta partials per block -> partial [gridDim.x][2][C].
+// VPL = 16-byte vectors per lane (C <= 256*VPL).  x and dy stay packed (uint4) in registers between the two passes so
+// the per-thread footprint is ~ 20*VPL registers of data + 16*VPL of dgamma/dbeta accumulators: no spills at VPL = 5.
+template <int VPL>
 __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
               float* __restrict__ partial) {
-    extern __shared__ float sm[];      // [2][C]
+    extern __shared__ float sm[];      // [LN_WARPS][2][C] per-warp partials, reduced at the end
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = C / 8;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
-    __syncthreads();
-    float gm[LN_MAXV][8];
-    float ag[LN_MAXV][8], ab[LN_MAXV][8];
+    uint4 gpk[VPL];
+    float ag[VPL][8], ab[VPL][8];
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; gm[i][e] = 0.f; }
-        if (v < nv) unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm[i]);
+        for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; }
+        gpk[i] = v < nv ? *reinterpret_cast<const uint4*>(gamma + v * 8) : make_uint4(0, 0, 0, 0);
     }
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
         const float mu = mean[row], rs = rstd[row];
-        float xh[LN_MAXV][8], dg[LN_MAXV][8];
+        uint4 xpk[VPL], dpk[VPL];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < VPL; ++i) {
             const int v = lane + 32 * i;
             if (v < nv) {
-                float fx[8], fd[8];
-                unpack8(ld_stream(x + row * C + v * 8), fx);
-                unpack8(ld_stream(dy + row * C + v * 8), fd);
+                xpk[i] = ld_stream(x + row * C + v * 8);
+                dpk[i] = ld_stream(dy + row * C + v * 8);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
+            const int v = lane + 32 * i;
+            if (v < nv) {
+                float fx[8], fd[8], gm[8];
+                unpack8(xpk[i], fx); unpack8(dpk[i], fd); unpack8(gpk[i], gm);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    xh[i][e] = (fx[e] - mu) * rs;
-                    dg[i][e] = fd[e] * gm[i][e];
-                    s1 += dg[i][e];
-                    s2 = fmaf(dg[i][e], xh[i][e], s2);
-                    ag[i][e] = fmaf(fd[e], xh[i][e], ag[i][e]);
+                    const float xh = (fx[e] - mu) * rs;
+                    const float dg = fd[e] * gm[e];
+                    s1 += dg;
+                    s2 = fmaf(dg, xh, s2);
+                    ag[i][e] = fmaf(fd[e], xh, ag[i][e]);
                     ab[i][e] += fd[e];
                 }
             }
@@ -348,12 +375,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         s1 = warp_sum(s1) / (float)C;
         s2 = warp_sum(s2) / (float)C;
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+        for (int i = 0; i < VPL; ++i) {
             const int v = lane + 32 * i;
             if (v < nv) {
-                float o[8];
+                float fx[8], fd[8], gm[8], o[8];
+                unpack8(xpk[i], fx); unpack8(dpk[i], fd); unpack8(gpk[i], gm);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rs * (dg[i][e] - s1 - xh[i][e] * s2);
+                for (int e = 0; e < 8; ++e) o[e] = rs * (fd[e] * gm[e] - s1 - (fx[e] - mu) * rs * s2);
                 if (dres) {
                     float fr[8];
                     unpack8(ld_stream(dres + row * C + v * 8), fr);
@@ -364,17 +392,24 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             }
         }
     }
+    // per-warp partials -> smem (no atomics), then a column-parallel sum over the warps
+    float* mine = sm + (size_t)warp * 2 * C;
 #pragma unroll
-    for (int i = 0; i < LN_MAXV; ++i) {
+    for (int i = 0; i < VPL; ++i) {
         const int v = lane + 32 * i;
         if (v < nv) {
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], ag[i][e]); atomicAdd(&sm[C + v * 8 + e], ab[i][e]); }
+            for (int e = 0; e < 8; ++e) { mine[v * 8 + e] = ag[i][e]; mine[C + v * 8 + e] = ab[i][e]; }
         }
     }
     __syncthreads();
     float* out = partial + (size_t)blockIdx.x * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+        float a = 0.f;
+#pragma unroll
+        for (int w = 0; w < LN_WARPS; ++w) a += sm[(size_t)w * 2 * C + i];
+        out[i] = a;
+    }
 }
 
 // reduce [blocks][2][C] -> dgamma (first C), dbeta (second C)
@@ -393,6 +428,23 @@ __global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int bl
 
 using namespace aoz;
 
+template <int VPL>
+static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
+                         const void* dres, void* dx, void* workspace, int blocks, cudaStream_t s) {
+    const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
+    static size_t attr = 0;
+    if (smem > 48 * 1024 && smem > attr) {
+        cudaFuncSetAttribute(ln_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
+    ln_bwd_kernel<VPL><<<blocks, LN_WARPS * 32, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+                                                          (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
+                                                          (__nv_bfloat16*)dx, (float*)workspace);
+    AOZ_CHECK_LAUNCH("ln_bwd_kernel");
+    return AOZ_OK;
+}
+
+
 extern "C" {
 
 static int gn_chunks(int NB, int HW) {
@@ -406,7 +458,7 @@ static int gn_chunks(int NB, int HW) {
 // workspace floats needed by the GroupNorm forward / backward (upper bound)
 long long aoz_groupnorm_workspace_floats(int NB, int HW, int C) {
     const long long chunks = GN_MAX_CHUNKS;
-    return (long long)NB * chunks * 2 * C + (long long)NB * GN_GROUPS * 2 + 64;
+    return (long long)NB * chunks * 2 * C + (long long)NB * GN_GROUPS * 2 + 64 + (long long)NB * 2 * C + 64;
 }
 
 // y = silu?(GroupNorm32(x)); x, y: [NB, HW, C] bf16 channels-last; mean/rstd out: [NB, 32] fp32
@@ -437,7 +489,6 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
                       void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && workspace, "aoz_groupnorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_bwd: C=%d must be a multiple of 32", C);
-    AOZ_CHECK_ARG((long long)NB * 2 * C * (long long)sizeof(float) <= 200 * 1024, "aoz_groupnorm_bwd: NB*C too large (%d x %d)", NB, C);
     cudaStream_t s = (cudaStream_t)stream;
     const int chunks = gn_chunks(NB, HW);
     float* partial = (float*)workspace;
@@ -446,15 +497,14 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
         (const float*)mean, (const float*)rstd, HW, C, silu, partial);
     AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
-    const size_t fin_smem = (size_t)NB * 2 * C * sizeof(float);
-    static size_t fin_attr = 0;
-    if (fin_smem > 48 * 1024 && fin_smem > fin_attr) {
-        cudaFuncSetAttribute(gn_bwd_finalize_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)fin_smem);
-        fin_attr = fin_smem;
+    float* chansum = group_terms + (size_t)NB * GN_GROUPS * 2 + 64;
+    cudaMemsetAsync(chansum, 0, (size_t)NB * 2 * C * sizeof(float), s);
+    gn_bwd_group_kernel<<<dim3(GN_GROUPS, NB), 128, 0, s>>>(partial, (const __nv_bfloat16*)gamma, chunks, C, chansum, group_terms);
+    AOZ_CHECK_LAUNCH("gn_bwd_group_kernel");
+    if (dgamma) {
+        gn_bwd_param_kernel<<<(C + 255) / 256, 256, 0, s>>>(chansum, NB, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
+        AOZ_CHECK_LAUNCH("gn_bwd_param_kernel");
     }
-    gn_bwd_finalize_kernel<<<1, 256, fin_smem, s>>>(partial, (const __nv_bfloat16*)gamma, NB, chunks, C, group_terms,
-                                                    (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
-    AOZ_CHECK_LAUNCH("gn_bwd_finalize_kernel");
     long long vecs = (long long)HW * (C / 8);
     int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
     const int cap = (sm_count() * 8 + NB - 1) / NB;
@@ -481,7 +531,7 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
     return AOZ_OK;
 }
 
-long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 4 * 2 * C; }
+long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 2 * 2 * C; }
 
 int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
                       const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
@@ -489,13 +539,19 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
     if (rows <= 0) return AOZ_OK;
     long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-    if (blocks > sm_count() * 4) blocks = sm_count() * 4;
+    if (blocks > sm_count() * 2) blocks = sm_count() * 2;
     cudaStream_t s = (cudaStream_t)stream;
-    ln_bwd_kernel<<<(int)blocks, LN_WARPS * 32, 2 * C * sizeof(float), s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
-                                                                           (const __nv_bfloat16*)gamma, (const float*)mean,
-                                                                           (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
-                                                                           (__nv_bfloat16*)dx, (float*)workspace);
-    AOZ_CHECK_LAUNCH("ln_bwd_kernel");
+    const int vpl = (C / 8 + 31) / 32;
+    int rc;
+    switch (vpl) {
+        case 1: rc = launch_ln_bwd<1>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+        case 2: rc = launch_ln_bwd<2>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+        case 3: rc = launch_ln_bwd<3>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+        case 4: rc = launch_ln_bwd<4>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+        case 5: rc = launch_ln_bwd<5>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+        default: rc = launch_ln_bwd<8>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
+    }
+    if (rc != AOZ_OK) return rc;
     ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
                                                                (__nv_bfloat16*)dbeta, accumulate);
     AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");

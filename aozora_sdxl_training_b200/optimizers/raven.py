@@ -73,6 +73,49 @@ def _ptr_table(tensors, device):
     return torch.from_numpy(arr.view(np.int64)).to(device, non_blocking=True)
 
 
+class _Staging:
+    """Pinned-host -> device staging of the per-step tables (pointer tables, hyper-parameters).
+
+    Eager mode: a ring of pinned buffers per table, each guarded by a CUDA event, so the host can run ahead of the GPU
+    without overwriting a buffer whose copy has not executed yet.  Under CUDA-graph capture: the copy is captured from a
+    dedicated pinned buffer that is never touched again (replays re-read it), into the same device buffer."""
+
+    RING = 4
+
+    def __init__(self):
+        self.dev = {}
+        self.rings = {}
+        self.keep = []
+
+    def device_buffer(self, name):
+        return self.dev[name]
+
+    def put(self, name, array: np.ndarray, device):
+        flat = np.ascontiguousarray(array).reshape(-1)
+        tdtype = torch.from_numpy(flat[:0].copy()).dtype
+        dev = self.dev.get(name)
+        if dev is None or dev.numel() != flat.size or dev.dtype != tdtype or dev.device != device:
+            dev = self.dev[name] = torch.empty(flat.size, dtype=tdtype, device=device)
+            self.rings.pop(name, None)
+        if torch.cuda.is_current_stream_capturing():
+            host = torch.empty(flat.size, dtype=tdtype).pin_memory()
+            host.numpy()[:] = flat
+            self.keep.append(host)
+            dev.copy_(host, non_blocking=True)
+            return dev
+        ring = self.rings.get(name)
+        if ring is None:
+            ring = self.rings[name] = dict(i=0, slots=[(torch.empty(flat.size, dtype=tdtype).pin_memory(), torch.cuda.Event())
+                                                        for _ in range(self.RING)])
+        host, ev = ring["slots"][ring["i"]]
+        ring["i"] = (ring["i"] + 1) % self.RING
+        ev.synchronize()
+        host.numpy()[:] = flat
+        dev.copy_(host, non_blocking=True)
+        ev.record()
+        return dev
+
+
 class RavenAdamW(Optimizer):
     """AdamW with partial bias correction (``debias_strength``); FP32 update math, moments in ``momentum_dtype``."""
 
@@ -98,7 +141,10 @@ class RavenAdamW(Optimizer):
         self._momentum_dtype = momentum_dtype
         self._plan = MultiTensorPlan()
         self._norm_out = None          # device [3]: total norm, clip coefficient, sum of squares
+        self._stage = _Staging()
+        self._last_items = None
         self.last_launches = 0
+        self._grads_override = None
 
     # -- state helpers ------------------------------------------------------------------------------------
     def _new_state_tensor(self, p, dtype):
@@ -108,6 +154,8 @@ class RavenAdamW(Optimizer):
         return tensor.to(device=p.device, dtype=self._momentum_dtype).contiguous()
 
     def _grad_of(self, p):
+        if self._grads_override is not None:
+            return self._grads_override.get(p)
         return p.grad
 
     def _collect(self):
@@ -137,7 +185,7 @@ class RavenAdamW(Optimizer):
         self._plan.ensure([p.numel() for _, p, _ in items], dev)
         if self._norm_out is None or self._norm_out.device != dev:
             self._norm_out = torch.zeros(4, dtype=torch.float32, device=dev)
-        gp = _ptr_table(grads, dev)
+        gp = self._stage.put("norm_g", np.fromiter((g.data_ptr() for g in grads), dtype=np.uint64, count=len(grads)).view(np.int64), dev)
         pl = self._plan
         _lib.call("aoz_gradnorm_mt", pl.n_tensors, pl.n_chunks, gp.data_ptr(), pl.numel.data_ptr(), pl.chunk_start.data_ptr(),
                   pl.chunk_tensor.data_ptr(), pl.partial.data_ptr(), float(max_norm), int(emulate_bf16),
@@ -166,6 +214,7 @@ class RavenAdamW(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self.last_launches = 0 if clip_coef is None else self.last_launches
+        capturing = torch.cuda.is_current_stream_capturing()
         items = self._collect()
         if not items:
             return loss
@@ -184,10 +233,13 @@ class RavenAdamW(Optimizer):
                 raise _lib.AozoraError(f"{self._name}: one momentum_dtype per step() call")
             state = self.state[p]
             if "step" not in state:
+                if capturing:
+                    raise _lib.AozoraError(f"{self._name}: run at least one eager step before CUDA-graph capture")
                 state["step"] = 0
                 state["exp_avg"] = self._new_state_tensor(p, momentum_dtype)
                 state["exp_avg_sq"] = self._new_state_tensor(p, momentum_dtype)
-            state["step"] += 1
+            if not capturing:                      # a captured step is replayed later; advance_host_state() counts those
+                state["step"] += 1
             hyper[i] = raven_host_scalars(group["lr"], group["betas"], group["eps"], group["weight_decay"],
                                           group["debias_strength"], state["step"])
             m, v = state["exp_avg"], state["exp_avg_sq"]
@@ -198,33 +250,61 @@ class RavenAdamW(Optimizer):
             vs.append(v)
         pl = self._plan
         pl.ensure([p.numel() for _, p, _ in items], dev)
-        pp = _ptr_table([p for _, p, _ in items], dev)
-        gp = _ptr_table([g for _, _, g in items], dev)
-        mp = _ptr_table(ms, dev)
-        vp = _ptr_table(vs, dev)
-        hy = torch.from_numpy(hyper).to(dev, non_blocking=True)
+
+        def ptrs(ts):
+            return np.fromiter((t.data_ptr() for t in ts), dtype=np.uint64, count=len(ts)).view(np.int64)
+
+        pp = self._stage.put("p", ptrs([p for _, p, _ in items]), dev)
+        gp = self._stage.put("g", ptrs([g for _, _, g in items]), dev)
+        mp = self._stage.put("m", ptrs(ms), dev)
+        vp = self._stage.put("v", ptrs(vs), dev)
+        # hyper-parameters change every step: under capture they are NOT baked into the graph but uploaded eagerly
+        # before each replay by advance_host_state()
+        hy = self._stage.device_buffer("hyper") if capturing else self._stage.put("hyper", hyper, dev)
+        self._last_items = [(group, p) for group, p, _ in items]
         _lib.call("aoz_raven_step_mt", pl.n_tensors, pl.n_chunks, pp.data_ptr(), gp.data_ptr(), mp.data_ptr(), vp.data_ptr(),
                   pl.numel.data_ptr(), pl.chunk_start.data_ptr(), pl.chunk_tensor.data_ptr(), hy.data_ptr(),
                   0 if clip_coef is None else clip_coef.data_ptr(), _DT[pdt], _DT[gdt], _DT[mdt],
                   torch.cuda.current_stream().cuda_stream)
         self.last_launches += 1
+        if not capturing:
+            # the kernel wrote the parameters through raw pointers: tell torch (and the UNet's packed-weight cache)
+            torch.autograd.graph.increment_version([p for _, p, _ in items])
         return loss
 
     @torch.no_grad()
-    def clip_and_step(self, max_norm: float, emulate_torch_dtype: bool = True):
+    def clip_and_step(self, max_norm: float, emulate_torch_dtype: bool = True, grads=None):
         """Fused replacement of ``clip_grad_norm_(params, max_norm)`` + ``step()`` (train.py:2772-2783) with no host
         synchronisation: norm and coefficient stay on the device and the coefficient is applied inside the update
         kernel.  ``max_norm <= 0`` means "norm only" as in train.py:2778.  Returns the device tensor
         ``[norm, coef, sumsq]``."""
         self.last_launches = 0
-        items = self._collect()
-        if not items:
-            return None
-        emulate = emulate_torch_dtype and items[0][2].dtype == torch.bfloat16
-        clip = max_norm is not None and max_norm > 0
-        out = self._gradnorm(items, max_norm if clip else 3.0e38, emulate)
-        self.step(clip_coef=out[1:2] if clip else None)
+        self._grads_override = grads
+        try:
+            items = self._collect()
+            if not items:
+                return None
+            emulate = emulate_torch_dtype and items[0][2].dtype == torch.bfloat16
+            clip = max_norm is not None and max_norm > 0
+            out = self._gradnorm(items, max_norm if clip else 3.0e38, emulate)
+            self.step(clip_coef=out[1:2] if clip else None)
+        finally:
+            self._grads_override = None
         return out[:3]
+
+    def advance_host_state(self):
+        """CUDA-graph replay support: a captured ``clip_and_step`` replays only the device work (table copies + kernels).
+        This performs the HOST side of one more step -- bump the per-parameter step counters and upload the
+        hyper-parameter table (lr, bias corrections) that the replayed kernel reads."""
+        if not self._last_items:
+            raise _lib.AozoraError(f"{self._name}: advance_host_state() before any step()")
+        hyper = np.empty((len(self._last_items), 8), dtype=np.float32)
+        for i, (group, p) in enumerate(self._last_items):
+            state = self.state[p]
+            state["step"] += 1
+            hyper[i] = raven_host_scalars(group["lr"], group["betas"], group["eps"], group["weight_decay"],
+                                          group["debias_strength"], state["step"])
+        self._stage.put("hyper", hyper, self._last_items[0][1].device)      # eager, stream-ordered before the replay
 
     # -- state I/O (raven.py:151-222) -----------------------------------------------------------------------
     def state_dict(self):

@@ -176,7 +176,8 @@ class ShardedRavenAdamW(RavenAdamW):
 
 
 class DataParallel:
-    def __init__(self, unet, momentum_dtype=torch.bfloat16, bucket_mb=64, group=None, backend=None, flat_dtype=None):
+    def __init__(self, unet, momentum_dtype=torch.bfloat16, bucket_mb=64, group=None, backend=None, flat_dtype=None,
+                 bucket_elems=None):
         self.group = group
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
@@ -187,7 +188,7 @@ class DataParallel:
         self.device = self.params[0].device
         self.dtype = flat_dtype or self.params[0].dtype
         esize = torch.empty((), dtype=self.dtype).element_size()
-        self.layout = FlatLayout([p.numel() for p in self.params], self.world, bucket_mb * (1 << 20) // esize)
+        self.layout = FlatLayout([p.numel() for p in self.params], self.world, bucket_elems or bucket_mb * (1 << 20) // esize)
         L = self.layout
         self.flat_p = torch.zeros(L.total, dtype=self.dtype, device=self.device)
         self.flat_g = torch.zeros(L.total, dtype=self.dtype, device=self.device)

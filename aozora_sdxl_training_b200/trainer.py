@@ -43,7 +43,7 @@ class SDXLTrainStep:
     BATCH_SIZE (global batch), MAX_TRAIN_STEPS, GRADIENT_ACCUMULATION_STEPS, CLIP_GRAD_NORM, PREDICTION_TYPE,
     TIMESTEP_ALLOCATION, TIMESTEP_STRATIFIED_SAMPLING, TIMESTEP_LOSS_WEIGHT_CURVE, LR_CUSTOM_CURVE."""
 
-    def __init__(self, unet, optimizer, config, *, device="cuda", dp=None):
+    def __init__(self, unet, optimizer, config, *, device="cuda", dp=None, use_cuda_graph=False, graph_warmup=2):
         self.unet = unet
         self.optimizer = optimizer
         self.config = config
@@ -74,6 +74,9 @@ class SDXLTrainStep:
         self.optimizer_steps = 0
         self._accum = None              # {param: grad} carried across micro-steps when GRADIENT_ACCUMULATION_STEPS > 1
         self.trainable = [p for p in unet.parameters() if p.requires_grad]
+        self.use_cuda_graph = use_cuda_graph          # capture the device side of the step once, replay it afterwards
+        self.graph_warmup = graph_warmup
+        self._graphs = {}
 
     # ---- pieces ------------------------------------------------------------------------------------------
     def _to_device(self, t, dtype=None):
@@ -99,10 +102,19 @@ class SDXLTrainStep:
         return j[self.rank * self.local_batch:(self.rank + 1) * self.local_batch].contiguous()
 
     # ---- the step ------------------------------------------------------------------------------------------
-    @torch.no_grad()
-    def step(self, batch, *, noise=None, jitter=None, taps=None) -> StepResult:
-        """batch: dict with ``latents`` [b,4,h,w] (bf16, pinned host or device), ``embeds`` [b,L,2048], ``pooled`` [b,1280],
-        ``time_ids`` [b,6] (list or tensor; converted to bf16 as train.py:2726-2731 does)."""
+    def _device_step(self, latents, embeds, pooled, time_ids, tickets, noise, jitter, b, taps=None):
+        """Everything that runs on the GPU for one micro-step (graph-capturable: no host reads, static shapes)."""
+        xt8, target, cond = ops.noise_target(latents, noise, tickets, None if self.is_rf else self.alphas_cumprod, jitter,
+                                             self.prediction_type, cpad=8)
+        pred, bwd = self.unet.forward_nhwc(xt8, cond, embeds, pooled, time_ids, taps=taps)
+        denom = float(b * self.world)
+        loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
+                                       grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
+        hook = self.dp.grad_ready if self.dp is not None else None
+        grads = bwd(dpred8) if hook is None else bwd(dpred8, on_grad=hook)
+        return loss, grads
+
+    def _host_inputs(self, batch, noise, jitter):
         latents = self._to_device(batch["latents"], BF16)
         embeds = self._to_device(batch["embeds"], BF16)
         pooled = self._to_device(batch["pooled"], BF16)
@@ -121,14 +133,17 @@ class SDXLTrainStep:
             jitter = self._jitter() if jitter is None else self._to_device(jitter, torch.float32)
         else:
             jitter = None
-        xt8, target, cond = ops.noise_target(latents, noise, tickets, None if self.is_rf else self.alphas_cumprod, jitter,
-                                             self.prediction_type, cpad=8)
-        pred, bwd = self.unet.forward_nhwc(xt8, cond, embeds, pooled, time_ids, taps=taps)
-        denom = float(b * self.world)
-        loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
-                                       grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
-        hook = self.dp.grad_ready if self.dp is not None else None
-        grads = bwd(dpred8) if hook is None else bwd(dpred8, on_grad=hook)
+        return latents, embeds, pooled, time_ids, tickets, noise, jitter, b
+
+    @torch.no_grad()
+    def step(self, batch, *, noise=None, jitter=None, taps=None) -> StepResult:
+        """batch: dict with ``latents`` [b,4,h,w] (bf16, pinned host or device), ``embeds`` [b,L,2048], ``pooled`` [b,1280],
+        ``time_ids`` [b,6] (list or tensor; converted to bf16 as train.py:2726-2731 does)."""
+        inputs = self._host_inputs(batch, noise, jitter)
+        if self.use_cuda_graph and self.dp is None and self.grad_accum == 1 and taps is None:
+            return self._graph_step(inputs)
+        latents, embeds, pooled, time_ids, tickets, noise, jitter, b = inputs
+        loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b, taps=taps)
         self.micro_step += 1
         if self.grad_accum > 1:
             if self._accum is None:
@@ -142,14 +157,52 @@ class SDXLTrainStep:
         did = self.micro_step % self.grad_accum == 0
         norm = None
         if did:
-            for p in self.trainable:
-                p.grad = grads.get(p)
             if self.dp is not None:
                 norm = self.dp.reduce_clip_step(self.optimizer, self.clip)
             else:
-                norm = self.optimizer.clip_and_step(self.clip)
-            self.optimizer.zero_grad(set_to_none=True)
+                norm = self.optimizer.clip_and_step(self.clip, grads=grads)
             self._accum = None
             self.optimizer_steps += 1
         return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=did,
+                          lr=self.optimizer.param_groups[0]["lr"])
+
+    # ---- CUDA-graph path: the whole device side of the step is captured once and replayed ---------------------
+    def _graph_step(self, inputs):
+        latents, embeds, pooled, time_ids, tickets, noise, jitter, b = inputs
+        key = (tuple(latents.shape), tuple(embeds.shape))
+        self.micro_step += 1
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step(self.micro_step)
+        st = self._graphs.get(key)
+        if st is None:
+            st = self._graphs[key] = dict(calls=0, graph=None)
+        st["calls"] += 1
+        if st["graph"] is None and st["calls"] <= self.graph_warmup:
+            # eager warm-up: sizes the workspaces, allocates optimizer state, loads every kernel
+            loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b)
+            norm = self.optimizer.clip_and_step(self.clip, grads=grads)
+            self.optimizer_steps += 1
+            return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=True,
+                              lr=self.optimizer.param_groups[0]["lr"])
+        if st["graph"] is None:
+            st["static"] = [t.clone() if t is not None else None for t in (latents, embeds, pooled, time_ids, tickets, noise, jitter)]
+            self.unet._packs.d.clear()             # packed conv weights must be (re)built inside the graph on every replay
+            torch.cuda.synchronize()
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                sl, se, sp, sti, stk, sn, sj = st["static"]
+                loss, grads = self._device_step(sl, se, sp, sti, stk, sn, sj, b)
+                norm = self.optimizer.clip_and_step(self.clip, grads=grads)
+                st["out"] = (loss, norm)
+                del grads
+            st["graph"] = g
+            self.unet._packs.d.clear()
+        for dst, src in zip(st["static"], (latents, embeds, pooled, time_ids, tickets, noise, jitter)):
+            if dst is not None:
+                dst.copy_(src, non_blocking=True)
+        self.optimizer.advance_host_state()
+        st["graph"].replay()
+        self.optimizer_steps += 1
+        loss, norm = st["out"]
+        return StepResult(loss=loss.clone(), grad_norm=norm.clone(), timesteps=tickets, did_optimizer_step=True,
                           lr=self.optimizer.param_groups[0]["lr"])

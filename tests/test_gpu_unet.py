@@ -181,3 +181,29 @@ def test_gradient_accumulation_and_nonsquare_bucket():
     r2 = step.step(batch)
     assert not r1.did_optimizer_step and r2.did_optimizer_step
     assert torch.isfinite(r2.loss).all() and r2.grad_norm_value() > 0
+
+
+def test_cuda_graph_replay_matches_eager():
+    """The captured-and-replayed step must produce the same losses and weights as issuing every kernel eagerly."""
+    from aozora_sdxl_training_b200.optimizers import RavenAdamW
+    from aozora_sdxl_training_b200.trainer import SDXLTrainStep
+    results = []
+    for use_graph in (False, True):
+        prod, _ = build_pair()
+        opt = RavenAdamW([{"params": list(prod.parameters()), "lr_scale": 1.0}], lr=1e-3, betas=(0.9, 0.999), weight_decay=0.01,
+                         debias_strength=0.3)
+        cfg = type("C", (Cfg,), dict(LR_CUSTOM_CURVE=[[0.0, 1e-3], [1.0, 1e-4]], PREDICTION_TYPE="rectified_flow"))
+        step = SDXLTrainStep(prod, opt, cfg, use_cuda_graph=use_graph, graph_warmup=2)
+        losses = []
+        for i in range(6):
+            b = make_batch(seed=i)
+            res = step.step(dict(latents=b["latents"], embeds=b["embeds"], pooled=b["pooled"], time_ids=b["time_ids_data"]))
+            losses.append(res.loss_value())
+        results.append((losses, [p.detach().float().cpu().clone() for p in prod.parameters()],
+                        [opt.state[p]["step"] for p in prod.parameters()]))
+    (l0, p0, s0), (l1, p1, s1) = results
+    assert s0 == s1 and set(s0) == {6}
+    for a, b in zip(l0, l1):
+        assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
+    moved = sum(float((a - b).abs().sum()) for a, b in zip(p0, p1)) / sum(float(a.abs().sum()) for a in p0)
+    assert moved < 2e-3

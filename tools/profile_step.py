@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--steps", type=int, default=1)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--no-profiler", action="store_true")
+    ap.add_argument("--eager", action="store_true")
     args = ap.parse_args()
     from aozora_sdxl_training_b200.optimizers import RavenAdamW
     from aozora_sdxl_training_b200.trainer import SDXLTrainStep
@@ -34,7 +35,7 @@ def main():
     init_weights_fast_(unet)
     cfg = type("C", (Cfg,), dict(BATCH_SIZE=args.batch, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=None))
     opt = RavenAdamW([{"params": list(unet.parameters()), "lr_scale": 1.0}], lr=8e-7, momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
-    step = SDXLTrainStep(unet, opt, cfg, device=dev)
+    step = SDXLTrainStep(unet, opt, cfg, device=dev, use_cuda_graph=not args.eager)
     batch = synth_batch(args.batch, args.res, 1, device=dev)
     for _ in range(args.warmup):
         step.step(batch)
