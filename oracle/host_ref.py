@@ -294,7 +294,7 @@ def raven_update_(p, g, m, v, *, lr, betas, eps, weight_decay, debias_strength, 
 def clip_grad_norm_ref(grads, max_norm):
     """torch.nn.utils.clip_grad_norm_ semantics (train.py:2775-2778) incl. its dtype behaviour:
     with bf16 grads torch returns a bf16 norm and scales by a bf16 coefficient."""
-    params = [torch.nn.Parameter(torch.empty(0)) for _ in grads]
+    params = [torch.nn.Parameter(torch.empty_like(g)) for g in grads]
     for p, g in zip(params, grads):
         p.grad = g
     return torch.nn.utils.clip_grad_norm_(params, max_norm)
