@@ -51,12 +51,13 @@ struct GemmParams {
     int accumulate;                 // EPI_STORE: C += result
 };
 
-template <int BN>
+template <int BN, bool CTA2>
 struct SmemLayout {
-    static constexpr int A_BYTES = BM * BK * 2;             // 16 KB
-    static constexpr int B_BYTES = BN * BK * 2;             // 16 / 32 KB
+    static constexpr int A_BYTES = BM * BK * 2;                             // 16 KB: this CTA's 128 rows of A
+    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;                       // a CTA pair splits the B tile
+    static constexpr int B_BYTES = B_ROWS * BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (BN == 256) ? 4 : 6;
+    static constexpr int STAGES = (STAGE_BYTES > 32768) ? 4 : 6;
     static constexpr int BAR_BYTES = 1024;
     static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
@@ -64,10 +65,64 @@ struct SmemLayout {
 // erf GELU (torch F.gelu default), fp32
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-template <int BN>
+// ---- cluster helpers (CTA-pair mode) ----
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t mapa_rank(uint32_t local_smem_addr, uint32_t rank) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_smem_addr), "r"(rank));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" :: "r"(cluster_addr) : "memory");
+}
+// TMA loads issued by either CTA of a pair, completing on the LEADER's mbarrier (cluster address)
+__device__ __forceinline__ void tma2_load_2d(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma2_load_4d(void* smem_dst, const CUtensorMap* m, uint32_t bar_cluster_addr, int c0, int c1,
+                                             int c2, int c3) {
+    asm volatile(
+        "cp.async.bulk.tensor.4d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+        :: "r"(smem_u32(smem_dst)), "l"(m), "r"(bar_cluster_addr), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        :: "r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier at the same smem offset in BOTH CTAs of the pair once the issued MMAs have completed
+__device__ __forceinline__ void umma2_commit_both(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 :: "r"(smem_u32(bar)), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smem_result)), "r"(ncols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+
+// CTA2 = true: two CTAs of a cluster (one SM pair) compute a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
+// stages its own 128 rows of A and HALF of the B tile, so the L2 -> shared-memory traffic per FLOP drops by a third
+// (the 1-CTA 128 x 256 tile needs ~26 TB/s of L2 bandwidth at tensor peak -- more than the chip has).  Only the
+// leader CTA (cluster rank 0) issues MMAs; completion is multicast to both CTAs' barriers.
+template <int BN, bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
-    using L = SmemLayout<BN>;
+    using L = SmemLayout<BN, CTA2>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint8_t* bar_base = smem + L::STAGES * L::STAGE_BYTES;
@@ -78,32 +133,39 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
+    const bool leader = rank == 0;
+    const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent work unit (CTA or CTA pair)
+    const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&P.tmA);
         tma_prefetch_desc(&P.tmB);
         for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], 4); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 8 : 4); }
         fence_mbar_init();
     }
-    if (warp == 1) tmem_alloc(tmem_slot, 2 * BN);
+    if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_work = P.m_tiles * P.n_tiles * P.splits;
+    const int total_work = P.m_tiles * P.n_tiles * P.splits;      // m_tiles counts 256-row pair tiles when CTA2
     const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
+    const int m_sub = CTA2 ? 2 : 1;
 
     if (warp == 0) {
         // ================================ TMA producer ================================
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
-            for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+            for (int work = unit; work < total_work; work += n_units) {
                 const int tile = work / P.splits, split = work - tile * P.splits;
-                const int m_blk = tile % P.m_tiles, n_blk = tile / P.m_tiles;
+                const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank;          // 128-row tile index of THIS CTA
+                const int n_blk = tile / P.m_tiles;
                 const int k_begin = split * k_per_split;
                 const int k_end = min(P.k_iters, k_begin + k_per_split);
+                const int n_row0 = n_blk * BN + (CTA2 ? (int)rank * (BN / 2) : 0);  // first B row (N index) this CTA stages
                 // conv tile origin
                 int img = 0, h0 = 0, w0 = 0;
                 if (P.mode == GM_CONV_FWD) {
@@ -115,47 +177,58 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 int wg_tap = 0, wg_c0 = 0;
                 if (P.mode == GM_CONV_WGRAD) {
                     wg_tap = n_blk / P.n_tiles_per_tap;
-                    wg_c0 = (n_blk - wg_tap * P.n_tiles_per_tap) * BN;
+                    wg_c0 = (n_blk - wg_tap * P.n_tiles_per_tap) * BN + (CTA2 ? (int)rank * (BN / 2) : 0);
                 }
                 for (int kit = k_begin; kit < k_end; ++kit) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * L::STAGE_BYTES;
                     uint8_t* sb = sa + L::A_BYTES;
-                    mbar_arrive_expect_tx(&full_bar[stage], L::STAGE_BYTES);
+                    uint64_t* fb = &full_bar[stage];
+                    uint32_t fbc = 0;
+                    if (CTA2) {
+                        fbc = mapa_rank(smem_u32(fb), 0);                   // the leader's barrier collects both CTAs' bytes
+                        if (leader) mbar_arrive_expect_tx(fb, 2 * L::STAGE_BYTES);
+                    } else {
+                        mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
+                    }
+                    auto ld2 = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
+                        if (CTA2) tma2_load_2d(dst, m, fbc, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
+                    };
+                    auto ld4 = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
+                        if (CTA2) tma2_load_4d(dst, m, fbc, c0, c1, c2, c3); else tma_load_4d(dst, m, fb, c0, c1, c2, c3);
+                    };
+                    // ---- A operand ----
                     if (P.mode == GM_LINEAR) {
-                        if (!P.a_mn) tma_load_2d(sa, &P.tmA, &full_bar[stage], kit * BK, m_blk * BM);
+                        if (!P.a_mn) ld2(sa, &P.tmA, kit * BK, m_blk * BM);
                         else {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j)
-                                tma_load_2d(sa + j * 8192, &P.tmA, &full_bar[stage], m_blk * BM + j * 64, kit * BK);
-                        }
-                        if (!P.b_mn) {
-                            if (P.epi == EPI_GEGLU) {
-                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * (BN / 2));
-                                tma_load_2d(sb + (BN / 2) * 128, &P.tmB, &full_bar[stage], kit * BK,
-                                            P.geglu_half + n_blk * (BN / 2));
-                            } else if (BN == 256) {
-                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
-                                tma_load_2d(sb + 128 * 128, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN + 128);
-                            } else {
-                                tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
-                            }
-                        } else {
-#pragma unroll
-                            for (int j = 0; j < BN / 64; ++j)
-                                tma_load_2d(sb + j * 8192, &P.tmB, &full_bar[stage], n_blk * BN + j * 64, kit * BK);
+                            for (int j = 0; j < BM / 64; ++j) ld2(sa + j * 8192, &P.tmA, m_blk * BM + j * 64, kit * BK);
                         }
                     } else if (P.mode == GM_CONV_FWD) {
                         const int tap = kit / P.cin_chunks, cc = kit - tap * P.cin_chunks;
                         int r = tap / P.taps_s, s = tap - r * P.taps_s;
                         if (P.flip) { r = P.taps_s - 1 - r; s = P.taps_s - 1 - s; }
-                        tma_load_4d(sa, &P.tmA, &full_bar[stage], cc * BK, w0 * P.stride + s - P.pad,
-                                    h0 * P.stride + r - P.pad, img);
-                        if (BN == 256) {
-                            tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
-                            tma_load_2d(sb + 128 * 128, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN + 128);
+                        ld4(sa, &P.tmA, cc * BK, w0 * P.stride + s - P.pad, h0 * P.stride + r - P.pad, img);
+                    }
+                    // ---- B operand (K-major: [N rows, 64 k] boxes of <= 128 rows; MN-major: 64-wide N chunks) ----
+                    if (P.mode != GM_CONV_WGRAD) {
+                        if (!P.b_mn) {
+                            if (P.epi == EPI_GEGLU) {
+                                // accumulator columns [0, BN/2) = value rows, [BN/2, BN) = gate rows of the projection
+                                if (CTA2) {
+                                    ld2(sb, &P.tmB, kit * BK, (leader ? 0 : P.geglu_half) + n_blk * (BN / 2));
+                                } else {
+                                    ld2(sb, &P.tmB, kit * BK, n_blk * (BN / 2));
+                                    ld2(sb + (BN / 2) * 128, &P.tmB, kit * BK, P.geglu_half + n_blk * (BN / 2));
+                                }
+                            } else {
+#pragma unroll
+                                for (int j = 0; j < L::B_ROWS / 128 + (L::B_ROWS % 128 ? 1 : 0); ++j)
+                                    ld2(sb + j * 128 * 128, &P.tmB, kit * BK, n_row0 + j * 128);
+                            }
                         } else {
-                            tma_load_2d(sb, &P.tmB, &full_bar[stage], kit * BK, n_blk * BN);
+#pragma unroll
+                            for (int j = 0; j < L::B_ROWS / 64; ++j) ld2(sb + j * 8192, &P.tmB, n_row0 + j * 64, kit * BK);
                         }
                     } else {   // GM_CONV_WGRAD: K iteration = one 8x8 pixel tile of dy; both operands MN-major
                         int t = kit;
@@ -164,62 +237,66 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         const int hh = th * P.TH, ww = tw * P.TW;
                         const int r = wg_tap / P.taps_s, s = wg_tap - r * P.taps_s;
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j)
-                            tma_load_4d(sa + j * 8192, &P.tmA, &full_bar[stage], m_blk * BM + j * 64, ww, hh, im);
+                        for (int j = 0; j < BM / 64; ++j) ld4(sa + j * 8192, &P.tmA, m_blk * BM + j * 64, ww, hh, im);
 #pragma unroll
-                        for (int j = 0; j < BN / 64; ++j)
-                            tma_load_4d(sb + j * 8192, &P.tmB, &full_bar[stage], wg_c0 + j * 64,
-                                        ww * P.stride + s - P.pad, hh * P.stride + r - P.pad, im);
+                        for (int j = 0; j < L::B_ROWS / 64; ++j)
+                            ld4(sb + j * 8192, &P.tmB, wg_c0 + j * 64, ww * P.stride + s - P.pad, hh * P.stride + r - P.pad, im);
                     }
                     if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer ================================
-        const uint32_t idesc = make_idesc_bf16(BM, BN, P.a_mn, P.b_mn);
-        uint32_t stage = 0, phase = 0;
-        uint32_t acc = 0, acc_phase = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
-            const int tile = work / P.splits, split = work - tile * P.splits;
-            const int k_begin = split * k_per_split;
-            const int k_end = min(P.k_iters, k_begin + k_per_split);
-            mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-            tc_fence_after();
-            const uint32_t tmem_d = tmem_base + acc * BN;
-            for (int kit = k_begin; kit < k_end; ++kit) {
-                mbar_wait(&full_bar[stage], phase);
+        // ================================ MMA issuer (leader CTA only in pair mode) ================================
+        if (leader) {
+            const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : BM, BN, P.a_mn, P.b_mn);
+            uint32_t stage = 0, phase = 0;
+            uint32_t acc = 0, acc_phase = 0;
+            for (int work = unit; work < total_work; work += n_units) {
+                const int tile = work / P.splits, split = work - tile * P.splits;
+                const int k_begin = split * k_per_split;
+                const int k_end = min(P.k_iters, k_begin + k_per_split);
+                mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                if (lane == 0) {
-                    const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                    const uint32_t sb = sa + L::A_BYTES;
+                const uint32_t tmem_d = tmem_base + acc * BN;
+                for (int kit = k_begin; kit < k_end; ++kit) {
+                    mbar_wait(&full_bar[stage], phase);
+                    tc_fence_after();
+                    if (lane == 0) {
+                        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
+                        const uint32_t sb = sa + L::A_BYTES;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        // K-major: advance 32 bytes inside the 128B row; MN-major: advance 16 K-rows = 2048 bytes
-                        const uint64_t da = P.a_mn ? make_sdesc_sw128(sa + k * 2048, 8192, 1024)
-                                                   : make_sdesc_sw128(sa + k * 32, 16, 1024);
-                        const uint64_t db = P.b_mn ? make_sdesc_sw128(sb + k * 2048, 8192, 1024)
-                                                   : make_sdesc_sw128(sb + k * 32, 16, 1024);
-                        umma_bf16(tmem_d, da, db, idesc, (kit > k_begin || k > 0) ? 1u : 0u);
+                        for (int k = 0; k < BK / 16; ++k) {
+                            // K-major: advance 32 bytes inside the 128B row; MN-major: advance 16 K-rows = 2048 bytes
+                            const uint64_t da = P.a_mn ? make_sdesc_sw128(sa + k * 2048, 8192, 1024)
+                                                       : make_sdesc_sw128(sa + k * 32, 16, 1024);
+                            const uint64_t db = P.b_mn ? make_sdesc_sw128(sb + k * 2048, 8192, 1024)
+                                                       : make_sdesc_sw128(sb + k * 32, 16, 1024);
+                            const uint32_t accum = (kit > k_begin || k > 0) ? 1u : 0u;
+                            if (CTA2) umma2_bf16(tmem_d, da, db, idesc, accum); else umma_bf16(tmem_d, da, db, idesc, accum);
+                        }
+                        // frees the smem slot (in both CTAs) when the MMAs retire
+                        if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                        if (kit == k_end - 1) { if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]); }
                     }
-                    umma_commit(&empty_bar[stage]);                 // frees the smem slot when the MMAs retire
-                    if (kit == k_end - 1) umma_commit(&tfull_bar[acc]);
+                    __syncwarp();
+                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                }
+                if (k_end <= k_begin && lane == 0) {            // empty split: still signal the epilogue
+                    if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
-                if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
-            if (k_end <= k_begin && lane == 0) umma_commit(&tfull_bar[acc]);   // empty split: still signal
-            __syncwarp();
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     } else {
         // ================================ epilogue (warps 2..5) ================================
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int row_in_tile = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
-        for (int work = blockIdx.x; work < total_work; work += gridDim.x) {
+        for (int work = unit; work < total_work; work += n_units) {
             const int tile = work / P.splits, split = work - tile * P.splits;
-            const int m_blk = tile % P.m_tiles, n_blk = tile / P.m_tiles;
+            const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank, n_blk = tile / P.m_tiles;
             const int k_begin = split * k_per_split;
             const bool empty_split = min(P.k_iters, k_begin + k_per_split) <= k_begin;
             // row mapping
@@ -229,7 +306,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 const int tw = t % P.tiles_w; t /= P.tiles_w;
                 const int th = t % P.tiles_h; const int img = t / P.tiles_h;
                 const int h = th * P.TH + row_in_tile / P.TW, w = tw * P.TW + row_in_tile % P.TW;
-                row_ok = (h < P.H) && (w < P.W);
+                row_ok = (h < P.H) && (w < P.W) && (img < P.NB);
                 row = ((long long)img * P.H + h) * P.W + w;
                 group = img;
             } else {
@@ -382,16 +459,19 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             // release the accumulator buffer
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+            if (lane == 0) {
+                if (CTA2 && !leader) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
+                else mbar_arrive(&tempty_bar[acc]);
+            }
             if (++acc == 2) { acc = 0; acc_phase ^= 1; }
         }
     }
 
     tc_fence_before();
-    __syncthreads();
+    if (CTA2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        tmem_dealloc(tmem_base, 2 * BN);
+        if (CTA2) tmem_dealloc2(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
     }
 }
 
@@ -420,33 +500,57 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
     }
 }
 
-static int launch_gemm(GemmParams& P, int bn, cudaStream_t stream) {
+template <int BN, bool CTA2>
+static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
+    using L = SmemLayout<BN, CTA2>;
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaFuncSetAttribute(gemm_bf16_kernel<BN, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        attr_set = true;
+    }
     const int total_work = P.m_tiles * P.n_tiles * P.splits;
     if (total_work <= 0) return AOZ_OK;
-    int grid = total_work < sm_count() ? total_work : sm_count();
-    static bool attr_set[2] = {false, false};
-    if (bn == 256) {
-        if (!attr_set[1]) {
-            cudaFuncSetAttribute(gemm_bf16_kernel<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<256>::TOTAL);
-            attr_set[1] = true;
-        }
-        gemm_bf16_kernel<256><<<grid, GEMM_THREADS, SmemLayout<256>::TOTAL, stream>>>(P);
+    if (!CTA2) {
+        const int grid = total_work < sm_count() ? total_work : sm_count();
+        gemm_bf16_kernel<BN, false><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(P);
     } else {
-        if (!attr_set[0]) {
-            cudaFuncSetAttribute(gemm_bf16_kernel<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, SmemLayout<128>::TOTAL);
-            attr_set[0] = true;
-        }
-        gemm_bf16_kernel<128><<<grid, GEMM_THREADS, SmemLayout<128>::TOTAL, stream>>>(P);
+        const int pairs = sm_count() / 2;
+        const int grid = 2 * (total_work < pairs ? total_work : pairs);
+        cudaLaunchConfig_t cfg;
+        memset(&cfg, 0, sizeof(cfg));
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+        cfg.attrs = at; cfg.numAttrs = 1;
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, true>, P);
+        if (e != cudaSuccess) { set_error("gemm_bf16_kernel<pair> launch: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
     }
     AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
     return AOZ_OK;
+}
+
+static int g_force_single_cta = 0;       // debugging / A-B measurements (aoz_gemm_set_pair_mode)
+
+static bool decide_pair(int m_tiles128, int epi, int bn) {
+    return !g_force_single_cta && m_tiles128 >= 2 && !(epi == EPI_GEGLU && bn != 256);
+}
+
+// P.m_tiles must hold the number of 128-row tiles on entry; `pair` from decide_pair (the B tensor map's box height
+// depends on it: a pair CTA stages bn/2 rows of B)
+static int launch_gemm(GemmParams& P, int bn, bool pair, cudaStream_t stream) {
+    if (pair) {
+        P.m_tiles = (P.m_tiles + 1) / 2;
+        return bn == 256 ? launch_gemm_t<256, true>(P, stream) : launch_gemm_t<128, true>(P, stream);
+    }
+    return bn == 256 ? launch_gemm_t<256, false>(P, stream) : launch_gemm_t<128, false>(P, stream);
 }
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
 static int pick_bn(int n_extent, long long m_tiles_est) {
     // BN=256 halves B-operand smem traffic per MMA; use it when it does not starve the grid
-    if (n_extent >= 256 && (n_extent % 256 == 0 || n_extent >= 1024) &&
+    if (n_extent >= 256 && (n_extent % 256 == 0 || n_extent >= 512) &&
         m_tiles_est * ceil_div(n_extent, 256) >= 120) return 256;
     return 128;
 }
@@ -456,6 +560,9 @@ static int pick_bn(int n_extent, long long m_tiles_est) {
 using namespace aoz;
 
 extern "C" {
+
+// 1 = allow CTA-pair (cta_group::2) tiles (default), 0 = force the single-CTA kernel
+int aoz_gemm_set_pair_mode(int enable) { g_force_single_cta = enable ? 0 : 1; return AOZ_OK; }
 
 // C[M,N] (bf16) = op(A) * op(B)^T-ish with fused epilogue.
 //   a_mn == 0: A is [M, K] row-major (lda elements)       a_mn == 1: A is [K, M] row-major (lda)
@@ -490,6 +597,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         P.n_tiles = ceil_div(N, bn);
     }
     P.m_tiles = ceil_div(M, BM);
+    const bool pair = decide_pair(P.m_tiles, epi, bn);
     P.splits = splits;
     if (splits > 1) {
         AOZ_CHECK_ARG(workspace != nullptr, "aoz_gemm_bf16: split-K needs a workspace");
@@ -513,12 +621,12 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     }
     {   // B map
         uint64_t dims[2], strides[1]; uint32_t box[2];
-        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = 128; }
+        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = (pair && bn == 128) ? 64 : 128; }
         else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
         strides[0] = (uint64_t)ldb * 2;
         if ((rc = make_tmap_bf16(&P.tmB, B, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
     }
-    if ((rc = launch_gemm(P, bn, (cudaStream_t)stream)) != AOZ_OK) return rc;
+    if ((rc = launch_gemm(P, bn, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
     if (splits > 1) {
         const long long total = (long long)M * N;
         int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
@@ -555,6 +663,7 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     P.M = NB * H * W; P.N = Cout; P.K = P.k_iters * 64;
     P.m_tiles = NB * P.tiles_h * P.tiles_w;
     const int bn = pick_bn(Cout, P.m_tiles);
+    const bool pair = decide_pair(P.m_tiles, EPI_STORE, bn);
     P.n_tiles = ceil_div(Cout, bn);
     P.splits = 1;
     P.C = (__nv_bfloat16*)y; P.ldc = Cout;
@@ -573,10 +682,10 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     {
         uint64_t dims[2] = {(uint64_t)P.K, (uint64_t)Cout};
         uint64_t strides[1] = {(uint64_t)P.K * 2};
-        uint32_t box[2] = {64, 128};
+        uint32_t box[2] = {64, (uint32_t)((pair && bn == 128) ? 64 : 128)};
         if ((rc = make_tmap_bf16(&P.tmB, wpack, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
     }
-    return launch_gemm(P, bn, (cudaStream_t)stream);
+    return launch_gemm(P, bn, pair, (cudaStream_t)stream);
 }
 
 // Convolution weight gradient: dW[cout][tap][cin] = sum_pixels dy[pix][cout] * x[pix*stride + tap - pad][cin].
@@ -620,7 +729,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
-    if ((rc = launch_gemm(P, bn, (cudaStream_t)stream)) != AOZ_OK) return rc;
+    if ((rc = launch_gemm(P, bn, decide_pair(P.m_tiles, EPI_PARTIAL, bn), (cudaStream_t)stream)) != AOZ_OK) return rc;
     const long long total = (long long)Cout * taps * Cin;
     int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
     splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,

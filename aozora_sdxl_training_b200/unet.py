@@ -590,9 +590,8 @@ class _UNetFunction(torch.autograd.Function):
                                        time_ids.detach())
         ctx.bwd = bwd
         ctx.params = params
-        ctx.any_grad = any(p.requires_grad for p in params)
-        if not (torch.is_grad_enabled() and ctx.any_grad):
-            ctx.bwd = None
+        if not any(p.requires_grad for p in params):
+            ctx.bwd = None                      # inference call: drop the saved activations right away
         return ops.nhwc_to_nchw(pred, c=model.cfg.out_channels)
 
     @staticmethod
