@@ -183,16 +183,23 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(s_ready, j & 1);
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;              // keys >= kvalid are padding
+            const bool full = kvalid >= TILE;                // warp-uniform: full tiles skip every per-element predicate
             float mx = -INFINITY;
 #pragma unroll 1
             for (int c = 0; c < 4; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tS + lane_off + c * 32, v);
                 tc_wait_ld();
+                if (full) {
 #pragma unroll
-                for (int e = 0; e < 32; ++e)
-                    if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]) * sl2);
+                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+                }
             }
+            mx *= sl2;                                       // scale > 0: max commutes with the scaling
             if (j == 0) {
                 m_ref = mx;
             } else {
@@ -219,12 +226,22 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                 uint32_t v[32], w[16];
                 tmem_ld32(tS + lane_off + c * 32, v);
                 tc_wait_ld();
+                if (full) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    float p0 = (c * 32 + e < kvalid) ? fast_exp2(__uint_as_float(v[e]) * sl2 - m_ref) : 0.f;
-                    float p1 = (c * 32 + e + 1 < kvalid) ? fast_exp2(__uint_as_float(v[e + 1]) * sl2 - m_ref) : 0.f;
-                    l += p0 + p1;
-                    w[e >> 1] = pack_bf16(p0, p1);
+                    for (int e = 0; e < 32; e += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref));
+                        l += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        float p0 = (c * 32 + e < kvalid) ? fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref)) : 0.f;
+                        float p1 = (c * 32 + e + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref)) : 0.f;
+                        l += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
                 }
                 store_p_chunk(sP, r, c * 32, w);
             }
@@ -402,14 +419,19 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 tmem_ld32(tdPt + lane_off + c * 32, vp);
                 tc_wait_ld();
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
+                for (int e = 0; e < 32; e += 4) {
                     const int qa = c * 32 + e;
-                    float p0 = key_ok ? fast_exp2(__uint_as_float(vs[e]) * sl2 - lse2[qa]) : 0.f;
-                    float p1 = key_ok ? fast_exp2(__uint_as_float(vs[e + 1]) * sl2 - lse2[qa + 1]) : 0.f;
-                    const float d0 = p0 * (__uint_as_float(vp[e]) - dv[qa]);
-                    const float d1 = p1 * (__uint_as_float(vp[e + 1]) - dv[qa + 1]);
+                    const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
+                    const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
+                    float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -ls.x));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -ls.y));
+                    float p2 = fast_exp2(fmaf(__uint_as_float(vs[e + 2]), sl2, -ls.z));
+                    float p3 = fast_exp2(fmaf(__uint_as_float(vs[e + 3]), sl2, -ls.w));
+                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
                     wp[e >> 1] = pack_bf16(p0, p1);
-                    wd[e >> 1] = pack_bf16(d0, d1);
+                    wp[(e >> 1) + 1] = pack_bf16(p2, p3);
+                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dd.x), p1 * (__uint_as_float(vp[e + 1]) - dd.y));
+                    wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(vp[e + 2]) - dd.z), p3 * (__uint_as_float(vp[e + 3]) - dd.w));
                 }
                 store_p_chunk(sPT, r, c * 32, wp);
                 store_p_chunk(sDST, r, c * 32, wd);
@@ -562,12 +584,21 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
                 tmem_ld32(tS + lane_off + c * 32, vs);
                 tmem_ld32(tdP + lane_off + c * 32, vp);
                 tc_wait_ld();
+                if (kvalid >= TILE) {
 #pragma unroll
-                for (int e = 0; e < 32; e += 2) {
-                    const int ka = c * 32 + e;
-                    float p0 = (ka < kvalid) ? fast_exp2(__uint_as_float(vs[e]) * sl2 - lse2) : 0.f;
-                    float p1 = (ka + 1 < kvalid) ? fast_exp2(__uint_as_float(vs[e + 1]) * sl2 - lse2) : 0.f;
-                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                    for (int e = 0; e < 32; e += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2));
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const int ka = c * 32 + e;
+                        float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2)) : 0.f;
+                        float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2)) : 0.f;
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                    }
                 }
                 store_p_chunk(sDS, r, c * 32, wd);
             }

@@ -24,7 +24,10 @@ namespace aoz {
 
 constexpr int BM = 128;
 constexpr int BK = 64;
-constexpr int GEMM_THREADS = 192;   // 6 warps
+constexpr int GEMM_THREADS = 320;   // 10 warps: TMA, MMA, 8 epilogue
+constexpr int MAX_STAGES = 8;
+constexpr int SMEM_TILE_BYTES = 196608;                 // 192 KB ring of A/B stages
+constexpr int GEMM_SMEM_TOTAL = SMEM_TILE_BYTES + 1024 + 1024;   // + barriers + alignment slack
 
 enum GemmMode : int { GM_LINEAR = 0, GM_CONV_FWD = 1, GM_CONV_WGRAD = 2 };
 enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
@@ -32,6 +35,7 @@ enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
 struct GemmParams {
     CUtensorMap tmA, tmB;
     int mode, epi;
+    int bn, stages;                 // N extent of the accumulator tile (multiple of 32, <= 256); smem pipeline depth
     int a_mn, b_mn;                 // 1 = MN-major operand
     int M, N, K;                    // logical extents (CONV_FWD: M = NB*H*W output pixels, K = taps*cin_chunks*64)
     int m_tiles, n_tiles, k_iters;  // tile counts; k_iters = total K iterations (before split)
@@ -49,17 +53,6 @@ struct GemmParams {
     __nv_bfloat16* aux; long long ld_aux;          // GEGLU: pre-activation [M, 2*half]
     float* partial;                 // EPI_PARTIAL: [splits][M][N] fp32
     int accumulate;                 // EPI_STORE: C += result
-};
-
-template <int BN, bool CTA2>
-struct SmemLayout {
-    static constexpr int A_BYTES = BM * BK * 2;                             // 16 KB: this CTA's 128 rows of A
-    static constexpr int B_ROWS = CTA2 ? BN / 2 : BN;                       // a CTA pair splits the B tile
-    static constexpr int B_BYTES = B_ROWS * BK * 2;
-    static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int STAGES = (STAGE_BYTES > 32768) ? 4 : 6;
-    static constexpr int BAR_BYTES = 1024;
-    static constexpr int TOTAL = STAGES * STAGE_BYTES + BAR_BYTES + 1024;   // + alignment slack
 };
 
 // erf GELU (torch F.gelu default), fp32
@@ -119,18 +112,22 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
 // stages its own 128 rows of A and HALF of the B tile, so the L2 -> shared-memory traffic per FLOP drops by a third
 // (the 1-CTA 128 x 256 tile needs ~26 TB/s of L2 bandwidth at tensor peak -- more than the chip has).  Only the
 // leader CTA (cluster rank 0) issues MMAs; completion is multicast to both CTAs' barriers.
-template <int BN, bool CTA2>
+template <bool CTA2>
 __global__ void __launch_bounds__(GEMM_THREADS, 1)
 gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
-    using L = SmemLayout<BN, CTA2>;
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-    uint8_t* bar_base = smem + L::STAGES * L::STAGE_BYTES;
-    uint64_t* full_bar = (uint64_t*)bar_base;                 // [STAGES]
-    uint64_t* empty_bar = full_bar + L::STAGES;               // [STAGES]
-    uint64_t* tfull_bar = empty_bar + L::STAGES;              // [2]
+    uint8_t* bar_base = smem + SMEM_TILE_BYTES;
+    uint64_t* full_bar = (uint64_t*)bar_base;                 // [MAX_STAGES]
+    uint64_t* empty_bar = full_bar + MAX_STAGES;              // [MAX_STAGES]
+    uint64_t* tfull_bar = empty_bar + MAX_STAGES;             // [2]
     uint64_t* tempty_bar = tfull_bar + 2;                     // [2]
     uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+    const int BN = P.bn;                                      // accumulator tile width (runtime: picked by the host cost model)
+    const int B_ROWS = CTA2 ? BN / 2 : BN;                    // B rows this CTA stages (a pair splits the B tile)
+    const int A_BYTES = BM * BK * 2;
+    const int STAGE_BYTES = A_BYTES + B_ROWS * BK * 2;
+    const int STAGES = P.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
@@ -141,11 +138,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     if (warp == 0 && lane == 0) {
         tma_prefetch_desc(&P.tmA);
         tma_prefetch_desc(&P.tmB);
-        for (int i = 0; i < L::STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 8 : 4); }
+        for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 16 : 8); }
         fence_mbar_init();
     }
-    if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, 2 * BN); else tmem_alloc(tmem_slot, 2 * BN); }
+    if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
@@ -156,9 +153,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     const int m_sub = CTA2 ? 2 : 1;
 
     if (warp == 0) {
-        // ================================ TMA producer ================================
+        // ================================ TMA producer (one thread) ================================
+        // The inner loop is kept to: wait(empty) -> expect_tx -> TMA issues, with every coordinate advanced incrementally.
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            const uint32_t fb0_cluster = CTA2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0u;   // leader's full barriers
+            const bool a_mn = P.a_mn != 0, b_mn = P.b_mn != 0;
+            const int b_chunks = B_ROWS / 64;
             for (int work = unit; work < total_work; work += n_units) {
                 const int tile = work / P.splits, split = work - tile * P.splits;
                 const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank;          // 128-row tile index of THIS CTA
@@ -166,90 +167,101 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 const int k_begin = split * k_per_split;
                 const int k_end = min(P.k_iters, k_begin + k_per_split);
                 const int n_row0 = n_blk * BN + (CTA2 ? (int)rank * (BN / 2) : 0);  // first B row (N index) this CTA stages
-                // conv tile origin
-                int img = 0, h0 = 0, w0 = 0;
+                const int m_row0 = m_blk * BM;
+                // GEGLU: accumulator columns [0, BN/2) = value rows, [BN/2, BN) = gate rows of the projection weight
+                const int g_row0 = CTA2 ? (leader ? 0 : P.geglu_half) + n_blk * (BN / 2) : n_blk * (BN / 2);
+                // conv forward: tile origin and running (tap, channel chunk) position
+                int img = 0, h0 = 0, w0 = 0, cc = 0, tap_r = 0, tap_s = 0;
                 if (P.mode == GM_CONV_FWD) {
                     int t = m_blk;
                     const int tw = t % P.tiles_w; t /= P.tiles_w;
                     const int th = t % P.tiles_h; img = t / P.tiles_h;
-                    h0 = th * P.TH; w0 = tw * P.TW;
+                    h0 = th * P.TH * P.stride - P.pad; w0 = tw * P.TW * P.stride - P.pad;
+                    const int tap = k_begin / P.cin_chunks;
+                    cc = k_begin - tap * P.cin_chunks;
+                    tap_r = tap / P.taps_s; tap_s = tap - tap_r * P.taps_s;
                 }
-                int wg_tap = 0, wg_c0 = 0;
+                // conv wgrad: fixed tap / channel origin per tile, running pixel-tile position
+                int wg_c0 = 0, wg_dh = 0, wg_dw = 0, p_tw = 0, p_th = 0, p_im = 0;
                 if (P.mode == GM_CONV_WGRAD) {
-                    wg_tap = n_blk / P.n_tiles_per_tap;
+                    const int wg_tap = n_blk / P.n_tiles_per_tap;
                     wg_c0 = (n_blk - wg_tap * P.n_tiles_per_tap) * BN + (CTA2 ? (int)rank * (BN / 2) : 0);
+                    const int r = wg_tap / P.taps_s, sft = wg_tap - r * P.taps_s;
+                    wg_dh = r - P.pad; wg_dw = sft - P.pad;
+                    int t = k_begin;
+                    p_tw = t % P.tiles_w; t /= P.tiles_w;
+                    p_th = t % P.tiles_h; p_im = t / P.tiles_h;
                 }
                 for (int kit = k_begin; kit < k_end; ++kit) {
                     mbar_wait(&empty_bar[stage], phase ^ 1);
-                    uint8_t* sa = smem + stage * L::STAGE_BYTES;
-                    uint8_t* sb = sa + L::A_BYTES;
+                    uint8_t* sa = smem + stage * STAGE_BYTES;
+                    uint8_t* sb = sa + A_BYTES;
                     uint64_t* fb = &full_bar[stage];
-                    uint32_t fbc = 0;
-                    if (CTA2) {
-                        fbc = mapa_rank(smem_u32(fb), 0);                   // the leader's barrier collects both CTAs' bytes
-                        if (leader) mbar_arrive_expect_tx(fb, 2 * L::STAGE_BYTES);
-                    } else {
-                        mbar_arrive_expect_tx(fb, L::STAGE_BYTES);
-                    }
-                    auto ld2 = [&](void* dst, const CUtensorMap* m, int c0, int c1) {
-                        if (CTA2) tma2_load_2d(dst, m, fbc, c0, c1); else tma_load_2d(dst, m, fb, c0, c1);
-                    };
-                    auto ld4 = [&](void* dst, const CUtensorMap* m, int c0, int c1, int c2, int c3) {
-                        if (CTA2) tma2_load_4d(dst, m, fbc, c0, c1, c2, c3); else tma_load_4d(dst, m, fb, c0, c1, c2, c3);
-                    };
-                    // ---- A operand ----
+                    const uint32_t fbc = fb0_cluster + stage * 8;
+                    if (CTA2) { if (leader) mbar_arrive_expect_tx(fb, 2 * STAGE_BYTES); }
+                    else mbar_arrive_expect_tx(fb, STAGE_BYTES);
+                    const int k0 = kit * BK;
                     if (P.mode == GM_LINEAR) {
-                        if (!P.a_mn) ld2(sa, &P.tmA, kit * BK, m_blk * BM);
+                        if (!a_mn) { if (CTA2) tma2_load_2d(sa, &P.tmA, fbc, k0, m_row0); else tma_load_2d(sa, &P.tmA, fb, k0, m_row0); }
                         else {
 #pragma unroll
-                            for (int j = 0; j < BM / 64; ++j) ld2(sa + j * 8192, &P.tmA, m_blk * BM + j * 64, kit * BK);
+                            for (int jj = 0; jj < BM / 64; ++jj) {
+                                if (CTA2) tma2_load_2d(sa + jj * 8192, &P.tmA, fbc, m_row0 + jj * 64, k0);
+                                else tma_load_2d(sa + jj * 8192, &P.tmA, fb, m_row0 + jj * 64, k0);
+                            }
                         }
                     } else if (P.mode == GM_CONV_FWD) {
-                        const int tap = kit / P.cin_chunks, cc = kit - tap * P.cin_chunks;
-                        int r = tap / P.taps_s, s = tap - r * P.taps_s;
-                        if (P.flip) { r = P.taps_s - 1 - r; s = P.taps_s - 1 - s; }
-                        ld4(sa, &P.tmA, cc * BK, w0 * P.stride + s - P.pad, h0 * P.stride + r - P.pad, img);
+                        const int r = P.flip ? P.taps_s - 1 - tap_r : tap_r, sft = P.flip ? P.taps_s - 1 - tap_s : tap_s;
+                        if (CTA2) tma2_load_4d(sa, &P.tmA, fbc, cc * BK, w0 + sft, h0 + r, img);
+                        else tma_load_4d(sa, &P.tmA, fb, cc * BK, w0 + sft, h0 + r, img);
+                        if (++cc == P.cin_chunks) { cc = 0; if (++tap_s == P.taps_s) { tap_s = 0; ++tap_r; } }
                     }
-                    // ---- B operand (K-major: [N rows, 64 k] boxes of <= 128 rows; MN-major: 64-wide N chunks) ----
                     if (P.mode != GM_CONV_WGRAD) {
-                        if (!P.b_mn) {
+                        if (!b_mn) {
                             if (P.epi == EPI_GEGLU) {
-                                // accumulator columns [0, BN/2) = value rows, [BN/2, BN) = gate rows of the projection
-                                if (CTA2) {
-                                    ld2(sb, &P.tmB, kit * BK, (leader ? 0 : P.geglu_half) + n_blk * (BN / 2));
-                                } else {
-                                    ld2(sb, &P.tmB, kit * BK, n_blk * (BN / 2));
-                                    ld2(sb + (BN / 2) * 128, &P.tmB, kit * BK, P.geglu_half + n_blk * (BN / 2));
+                                if (CTA2) tma2_load_2d(sb, &P.tmB, fbc, k0, g_row0);
+                                else {
+                                    tma_load_2d(sb, &P.tmB, fb, k0, g_row0);
+                                    tma_load_2d(sb + (BN / 2) * 128, &P.tmB, fb, k0, P.geglu_half + g_row0);
                                 }
                             } else {
-#pragma unroll
-                                for (int j = 0; j < L::B_ROWS / 128 + (L::B_ROWS % 128 ? 1 : 0); ++j)
-                                    ld2(sb + j * 128 * 128, &P.tmB, kit * BK, n_row0 + j * 128);
+                                if (CTA2) tma2_load_2d(sb, &P.tmB, fbc, k0, n_row0); else tma_load_2d(sb, &P.tmB, fb, k0, n_row0);
                             }
                         } else {
-#pragma unroll
-                            for (int j = 0; j < L::B_ROWS / 64; ++j) ld2(sb + j * 8192, &P.tmB, n_row0 + j * 64, kit * BK);
+                            for (int jj = 0; jj < b_chunks; ++jj) {
+                                if (CTA2) tma2_load_2d(sb + jj * 8192, &P.tmB, fbc, n_row0 + jj * 64, k0);
+                                else tma_load_2d(sb + jj * 8192, &P.tmB, fb, n_row0 + jj * 64, k0);
+                            }
                         }
                     } else {   // GM_CONV_WGRAD: K iteration = one 8x8 pixel tile of dy; both operands MN-major
-                        int t = kit;
-                        const int tw = t % P.tiles_w; t /= P.tiles_w;
-                        const int th = t % P.tiles_h; const int im = t / P.tiles_h;
-                        const int hh = th * P.TH, ww = tw * P.TW;
-                        const int r = wg_tap / P.taps_s, s = wg_tap - r * P.taps_s;
+                        const int hh = p_th * P.TH, ww = p_tw * P.TW;
 #pragma unroll
-                        for (int j = 0; j < BM / 64; ++j) ld4(sa + j * 8192, &P.tmA, m_blk * BM + j * 64, ww, hh, im);
-#pragma unroll
-                        for (int j = 0; j < L::B_ROWS / 64; ++j)
-                            ld4(sb + j * 8192, &P.tmB, wg_c0 + j * 64, ww * P.stride + s - P.pad, hh * P.stride + r - P.pad, im);
+                        for (int jj = 0; jj < BM / 64; ++jj) {
+                            if (CTA2) tma2_load_4d(sa + jj * 8192, &P.tmA, fbc, m_row0 + jj * 64, ww, hh, p_im);
+                            else tma_load_4d(sa + jj * 8192, &P.tmA, fb, m_row0 + jj * 64, ww, hh, p_im);
+                        }
+                        for (int jj = 0; jj < b_chunks; ++jj) {
+                            if (CTA2) tma2_load_4d(sb + jj * 8192, &P.tmB, fbc, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
+                            else tma_load_4d(sb + jj * 8192, &P.tmB, fb, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
+                        }
+                        if (++p_tw == P.tiles_w) { p_tw = 0; if (++p_th == P.tiles_h) { p_th = 0; ++p_im; } }
                     }
-                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                    if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
                 }
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (leader CTA only in pair mode) ================================
-        if (leader) {
+        // ================================ MMA issuer (one thread; leader CTA only in pair mode) ================================
+        // Descriptors are advanced by integer adds on their low word: the issue loop must stay far below the
+        // 2*bn-cycle execution time of one K iteration or the tensor pipe starves.
+        if (leader && lane == 0) {
             const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : BM, BN, P.a_mn, P.b_mn);
+            const uint64_t hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);   // SBO, version, SW128
+            const uint32_t smem_lo = (smem_u32(smem) & 0x3ffffu) >> 4;
+            const uint32_t a_lo0 = smem_lo | ((P.a_mn ? (8192u >> 4) : 1u) << 16);
+            const uint32_t b_lo0 = (smem_lo + (uint32_t)(A_BYTES >> 4)) | ((P.b_mn ? (8192u >> 4) : 1u) << 16);
+            const uint32_t a_kstep = (P.a_mn ? 2048u : 32u) >> 4, b_kstep = (P.b_mn ? 2048u : 32u) >> 4;
+            const uint32_t stage_step = (uint32_t)STAGE_BYTES >> 4;
             uint32_t stage = 0, phase = 0;
             uint32_t acc = 0, acc_phase = 0;
             for (int work = unit; work < total_work; work += n_units) {
@@ -258,40 +270,34 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 const int k_end = min(P.k_iters, k_begin + k_per_split);
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * BN;
+                const uint32_t tmem_d = tmem_base + acc * 256;
+                uint32_t accum = 0;
                 for (int kit = k_begin; kit < k_end; ++kit) {
                     mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    if (lane == 0) {
-                        const uint32_t sa = smem_u32(smem + stage * L::STAGE_BYTES);
-                        const uint32_t sb = sa + L::A_BYTES;
+                    const uint32_t alo = a_lo0 + stage * stage_step, blo = b_lo0 + stage * stage_step;
 #pragma unroll
-                        for (int k = 0; k < BK / 16; ++k) {
-                            // K-major: advance 32 bytes inside the 128B row; MN-major: advance 16 K-rows = 2048 bytes
-                            const uint64_t da = P.a_mn ? make_sdesc_sw128(sa + k * 2048, 8192, 1024)
-                                                       : make_sdesc_sw128(sa + k * 32, 16, 1024);
-                            const uint64_t db = P.b_mn ? make_sdesc_sw128(sb + k * 2048, 8192, 1024)
-                                                       : make_sdesc_sw128(sb + k * 32, 16, 1024);
-                            const uint32_t accum = (kit > k_begin || k > 0) ? 1u : 0u;
-                            if (CTA2) umma2_bf16(tmem_d, da, db, idesc, accum); else umma_bf16(tmem_d, da, db, idesc, accum);
-                        }
-                        // frees the smem slot (in both CTAs) when the MMAs retire
-                        if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
-                        if (kit == k_end - 1) { if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]); }
+                    for (int k = 0; k < BK / 16; ++k) {
+                        const uint64_t da = hi | (uint64_t)(alo + k * a_kstep);
+                        const uint64_t db = hi | (uint64_t)(blo + k * b_kstep);
+                        if (CTA2) umma2_bf16(tmem_d, da, db, idesc, accum); else umma_bf16(tmem_d, da, db, idesc, accum);
+                        accum = 1;
                     }
-                    __syncwarp();
-                    if (++stage == L::STAGES) { stage = 0; phase ^= 1; }
+                    // frees the smem slot (in both CTAs) when the MMAs retire
+                    if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
                 }
-                if (k_end <= k_begin && lane == 0) {            // empty split: still signal the epilogue
-                    if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
-                }
-                __syncwarp();
+                // accumulator complete (an empty split still signals the epilogue)
+                if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
+        __syncwarp();
     } else {
-        // ================================ epilogue (warps 2..5) ================================
+        // ================================ epilogue (warps 2..9) ================================
+        // two warps per TMEM lane quarter; they split the tile's 32-column chunks (even / odd)
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
+        const int half = (warp - 2) >> 2;             // 0: even chunks, 1: odd chunks
         const int row_in_tile = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
         for (int work = unit; work < total_work; work += n_units) {
@@ -317,7 +323,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             // column mapping
             int col0, col_limit;                          // first output column of this tile / exclusive limit
             long long col_shift = 0;                      // WGRAD: tap*Cin added to the column
-            constexpr int OUT_COLS = BN;
+            const int OUT_COLS = BN;
             if (P.mode == GM_CONV_WGRAD) {
                 const int tap = n_blk / P.n_tiles_per_tap;
                 col0 = (n_blk - tap * P.n_tiles_per_tap) * BN;
@@ -333,12 +339,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + acc * BN + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
 
             if (P.epi == EPI_GEGLU) {
                 // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
 #pragma unroll 1
-                for (int c = 0; c < BN / 2; c += 32) {
+                for (int c = half * 32; c < BN / 2; c += 64) {
                     uint32_t rv[32], rg[32];
                     tmem_ld32(taddr + c, rv);
                     tmem_ld32(taddr + BN / 2 + c, rg);
@@ -349,16 +355,17 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         for (int j = 0; j < 32; j += 8) {
                             if (cbase + j < col_limit) {     // N/2 is a multiple of 8 for every SDXL layer
                                 uint32_t ov[4], oh[4], og[4];
+                                uint32_t bh[4] = {0u, 0u, 0u, 0u}, bg[4] = {0u, 0u, 0u, 0u};
+                                if (P.bias) {       // N/2 and the tile origin are multiples of 8: 16-byte aligned vectors
+                                    const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(P.bias + cbase + j));
+                                    const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(P.bias + P.geglu_half + cbase + j));
+                                    bh[0] = t0.x; bh[1] = t0.y; bh[2] = t0.z; bh[3] = t0.w;
+                                    bg[0] = t1.x; bg[1] = t1.y; bg[2] = t1.z; bg[3] = t1.w;
+                                }
 #pragma unroll
                                 for (int e = 0; e < 8; e += 2) {
-                                    float h0 = __uint_as_float(rv[j + e]), h1 = __uint_as_float(rv[j + e + 1]);
-                                    float g0 = __uint_as_float(rg[j + e]), g1 = __uint_as_float(rg[j + e + 1]);
-                                    if (P.bias) {
-                                        h0 += __bfloat162float(P.bias[cbase + j + e]);
-                                        h1 += __bfloat162float(P.bias[cbase + j + e + 1]);
-                                        g0 += __bfloat162float(P.bias[P.geglu_half + cbase + j + e]);
-                                        g1 += __bfloat162float(P.bias[P.geglu_half + cbase + j + e + 1]);
-                                    }
+                                    float h0 = __uint_as_float(rv[j + e]) + bf16lo(bh[e >> 1]), h1 = __uint_as_float(rv[j + e + 1]) + bf16hi(bh[e >> 1]);
+                                    float g0 = __uint_as_float(rg[j + e]) + bf16lo(bg[e >> 1]), g1 = __uint_as_float(rg[j + e + 1]) + bf16hi(bg[e >> 1]);
                                     // autocast-faithful rounding points: linear out -> bf16, gelu -> bf16, product -> bf16
                                     h0 = round_bf16(h0); h1 = round_bf16(h1); g0 = round_bf16(g0); g1 = round_bf16(g1);
                                     oh[e >> 1] = pack_bf16(h0, h1);
@@ -377,7 +384,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 }
             } else {
 #pragma unroll 1
-                for (int c = 0; c < OUT_COLS; c += 32) {
+                for (int c = half * 32; c < OUT_COLS; c += 64) {
                     if (col0 + c >= col_limit) break;          // warp-uniform
                     uint32_t r[32];
                     if (!empty_split) {
@@ -404,7 +411,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         __nv_bfloat16* dst = P.C + row * P.ldc + col_shift + cbase;
                         const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + cbase : nullptr;
                         const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + cbase : nullptr;
-                        const bool vec_ok = ((((uintptr_t)dst) & 15) == 0) && (!res || ((((uintptr_t)res) & 15) == 0));
+                        const bool vec_ok = ((((uintptr_t)dst) & 15) == 0) && (!res || ((((uintptr_t)res) & 15) == 0)) &&
+                                            (!P.bias || ((((uintptr_t)(P.bias + cbase)) & 15) == 0)) && (!rgb || ((((uintptr_t)rgb) & 15) == 0));
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             float f[8];
@@ -413,12 +421,19 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                             const bool full8 = (cbase + j + 7 < col_limit) && vec_ok;
                             if (full8) {
                                 if (P.bias) {
+                                    const uint4 bb = __ldg(reinterpret_cast<const uint4*>(P.bias + cbase + j));
+                                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] += __bfloat162float(P.bias[cbase + j + e]);
+                                    for (int e = 0; e < 4; ++e) { f[2 * e] += bf16lo(bw[e]); f[2 * e + 1] += bf16hi(bw[e]); }
                                 }
                                 if (rgb) {
+                                    const uint4 gg = __ldg(reinterpret_cast<const uint4*>(rgb + j));
+                                    const uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
 #pragma unroll
-                                    for (int e = 0; e < 8; ++e) f[e] = round_bf16(f[e]) + __bfloat162float(rgb[j + e]);
+                                    for (int e = 0; e < 4; ++e) {
+                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(gw[e]);
+                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(gw[e]);
+                                    }
                                 }
                                 if (res) {
                                     const uint4 rr = *reinterpret_cast<const uint4*>(res + j);
@@ -471,7 +486,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     if (CTA2) cluster_sync_all(); else __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        if (CTA2) tmem_dealloc2(tmem_base, 2 * BN); else tmem_dealloc(tmem_base, 2 * BN);
+        if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
 }
 
@@ -500,59 +515,97 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
     }
 }
 
-template <int BN, bool CTA2>
+static int g_force_bn = 0;        // > 0: experiments only (aoz_gemm_force_bn)
+static int g_pair_mode = 0;       // 0 = single-CTA tiles only (default), 1 = let the cost model use CTA pairs, 2 = force pairs
+
+static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+template <bool CTA2>
 static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
-    using L = SmemLayout<BN, CTA2>;
     static bool attr_set = false;
     if (!attr_set) {
-        cudaFuncSetAttribute(gemm_bf16_kernel<BN, CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, L::TOTAL);
+        cudaFuncSetAttribute(gemm_bf16_kernel<CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
         attr_set = true;
     }
     const int total_work = P.m_tiles * P.n_tiles * P.splits;
     if (total_work <= 0) return AOZ_OK;
+    const int b_rows = CTA2 ? P.bn / 2 : P.bn;
+    const int stage_bytes = BM * BK * 2 + b_rows * BK * 2;
+    P.stages = SMEM_TILE_BYTES / stage_bytes;
+    if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     if (!CTA2) {
         const int grid = total_work < sm_count() ? total_work : sm_count();
-        gemm_bf16_kernel<BN, false><<<grid, GEMM_THREADS, L::TOTAL, stream>>>(P);
+        gemm_bf16_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(P);
     } else {
         const int pairs = sm_count() / 2;
         const int grid = 2 * (total_work < pairs ? total_work : pairs);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
-        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = L::TOTAL; cfg.stream = stream;
+        cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL; cfg.stream = stream;
         cudaLaunchAttribute at[1];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
         cfg.attrs = at; cfg.numAttrs = 1;
-        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<BN, true>, P);
+        cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<true>, P);
         if (e != cudaSuccess) { set_error("gemm_bf16_kernel<pair> launch: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
     }
     AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
     return AOZ_OK;
 }
 
-static int g_force_single_cta = 0;       // debugging / A-B measurements (aoz_gemm_set_pair_mode)
+// ---- host-side tile / split selection ------------------------------------------------------------------------
+// Cycle model per CTA (or CTA pair) and K iteration of 64: the MMA needs 2*bn cycles (128 x bn x 64 at 8192 FLOP/cycle/SM),
+// shared memory must deliver the A (16 KB) and B (b_rows x 128 B) stage at 128 B/cycle.  A launch costs
+// rounds x max(main loop, epilogue) + one exposed epilogue + fixed fill/drain; the N extent is covered by ceil(N / n_out) tiles.
+struct TilePlan { int bn; bool pair; int n_tiles; double cycles; };
 
-static bool decide_pair(int m_tiles128, int epi, int bn) {
-    return !g_force_single_cta && m_tiles128 >= 2 && !(epi == EPI_GEGLU && bn != 256);
+static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, int splits, bool b_mn, bool geglu, int n_groups /*taps*/) {
+    TilePlan best{128, false, 0, 1e300};
+    const int sms = sm_count();
+    const int step = b_mn ? 64 : 32;
+    for (int pair = 0; pair <= 1; ++pair) {
+        if (pair && (g_pair_mode == 0 || m_tiles128 < 2)) continue;
+        if (!pair && g_pair_mode == 2 && m_tiles128 >= 2) continue;
+        for (int bn = 64; bn <= 256; bn += step) {
+            if (g_force_bn > 0 && bn != g_force_bn) continue;
+            if (geglu && bn != 256 && bn != 128) continue;
+            if (pair && (bn % (2 * step))) continue;
+            const int n_out = geglu ? bn / 2 : bn;
+            const int n_tiles = n_groups * ceil_div(n_extent, n_out);
+            const long long units = (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * n_tiles * splits;
+            const int slots = pair ? sms / 2 : sms;
+            const double rounds = (double)((units + slots - 1) / slots);
+            const double b_rows = pair ? bn / 2.0 : bn;
+            const double cyc = fmax(2.0 * bn, 128.0 + b_rows);
+            const double epi = (geglu ? 28.0 : 9.0) * bn + 400.0;
+            const double main_loop = k_iters_per_unit * cyc;
+            const double total = rounds * fmax(main_loop, epi) + epi + 2500.0;
+            if (total < best.cycles) best = TilePlan{bn, pair != 0, n_tiles, total};
+        }
+    }
+    return best;
 }
 
-// P.m_tiles must hold the number of 128-row tiles on entry; `pair` from decide_pair (the B tensor map's box height
-// depends on it: a pair CTA stages bn/2 rows of B)
-static int launch_gemm(GemmParams& P, int bn, bool pair, cudaStream_t stream) {
+// split-K factor for un-fused GEMMs (weight gradients): trades wave quantisation against fp32 partial traffic
+static int plan_splits(int m_tiles128, int n_extent, int k_iters, long long out_elems, bool b_mn, int n_groups) {
+    int best_s = 1;
+    double best_c = 1e300;
+    for (int s = 1; s <= 32 && s <= (k_iters + 1) / 2; ++s) {
+        const int kit = ceil_div(k_iters, s);
+        TilePlan tp = plan_tiles(m_tiles128, n_extent, kit, s, b_mn, false, n_groups);
+        double c = tp.cycles;
+        if (s > 1) c += (double)(2 * s + 1) * out_elems * 4.0 / 3400.0 / 2.0 + 3000.0;     // partial write + reduce read at ~HBM/L2 rate
+        if (c < best_c) { best_c = c; best_s = s; }
+    }
+    return best_s;
+}
+
+static int launch_gemm(GemmParams& P, bool pair, cudaStream_t stream) {
     if (pair) {
         P.m_tiles = (P.m_tiles + 1) / 2;
-        return bn == 256 ? launch_gemm_t<256, true>(P, stream) : launch_gemm_t<128, true>(P, stream);
+        return launch_gemm_t<true>(P, stream);
     }
-    return bn == 256 ? launch_gemm_t<256, false>(P, stream) : launch_gemm_t<128, false>(P, stream);
-}
-
-static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
-
-static int pick_bn(int n_extent, long long m_tiles_est) {
-    // BN=256 halves B-operand smem traffic per MMA; use it when it does not starve the grid
-    if (n_extent >= 256 && (n_extent % 256 == 0 || n_extent >= 512) &&
-        m_tiles_est * ceil_div(n_extent, 256) >= 120) return 256;
-    return 128;
+    return launch_gemm_t<false>(P, stream);
 }
 
 }  // namespace aoz
@@ -561,8 +614,19 @@ using namespace aoz;
 
 extern "C" {
 
-// 1 = allow CTA-pair (cta_group::2) tiles (default), 0 = force the single-CTA kernel
-int aoz_gemm_set_pair_mode(int enable) { g_force_single_cta = enable ? 0 : 1; return AOZ_OK; }
+// 0 = single-CTA tiles only (default), 1 = cost model may choose CTA-pair (cta_group::2) tiles, 2 = force pairs
+int aoz_gemm_set_pair_mode(int mode) { g_pair_mode = mode; return AOZ_OK; }
+
+int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }
+
+// split-K factor aoz_gemm_bf16 will use when called with splits <= 0 (so the caller can size the workspace)
+int aoz_gemm_auto_splits(int M, int N, int K, int b_mn) {
+    return plan_splits(ceil_div(M, BM), N, ceil_div(K, BK), (long long)M * N, b_mn != 0, 1);
+}
+int aoz_conv_wgrad_auto_splits(int NB, int H, int W, int Cout, int Cin, int ks) {
+    const int k_iters = NB * ceil_div(H, 8) * ceil_div(W, 8);
+    return plan_splits(ceil_div(Cout, BM), Cin, k_iters, (long long)Cout * ks * ks * Cin, true, ks * ks);
+}
 
 // C[M,N] (bf16) = op(A) * op(B)^T-ish with fused epilogue.
 //   a_mn == 0: A is [M, K] row-major (lda elements)       a_mn == 1: A is [K, M] row-major (lda)
@@ -579,25 +643,25 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     AOZ_CHECK_ARG((lda % 8) == 0 && (ldb % 8) == 0, "aoz_gemm_bf16: lda/ldb must be multiples of 8 elements (TMA 16-byte strides)");
     AOZ_CHECK_ARG((((uintptr_t)A | (uintptr_t)B) & 15) == 0, "aoz_gemm_bf16: operands must be 16-byte aligned");
     AOZ_CHECK_ARG(epi == EPI_STORE || epi == EPI_GEGLU, "aoz_gemm_bf16: bad epilogue %d", epi);
-    if (splits < 1) splits = 1;
+    const bool fused = bias || residual || rowgroup_bias || epi == EPI_GEGLU || accumulate;
     GemmParams P;
     memset(&P, 0, sizeof(P));
     P.mode = GM_LINEAR; P.epi = epi; P.a_mn = a_mn; P.b_mn = b_mn;
     P.M = M; P.N = N; P.K = K;
     P.k_iters = ceil_div(K, BK);
+    P.m_tiles = ceil_div(M, BM);
+    if (splits <= 0) splits = fused ? 1 : plan_splits(P.m_tiles, N, P.k_iters, (long long)M * N, b_mn != 0, 1);
     if (splits > P.k_iters) splits = P.k_iters;
-    int bn;
-    if (epi == EPI_GEGLU) {
+    const bool geglu = epi == EPI_GEGLU;
+    if (geglu) {
         AOZ_CHECK_ARG((N % 2) == 0 && !b_mn && splits == 1, "aoz_gemm_bf16: GEGLU needs even N, K-major B, no split");
         P.geglu_half = N / 2;
-        bn = 256;
-        P.n_tiles = ceil_div(N / 2, bn / 2);
-    } else {
-        bn = pick_bn(N, ceil_div(M, BM));
-        P.n_tiles = ceil_div(N, bn);
     }
-    P.m_tiles = ceil_div(M, BM);
-    const bool pair = decide_pair(P.m_tiles, epi, bn);
+    const TilePlan tp = plan_tiles(P.m_tiles, geglu ? N / 2 : N, ceil_div(P.k_iters, splits), splits, b_mn != 0, geglu, 1);
+    const int bn = tp.bn;
+    const bool pair = tp.pair;
+    P.bn = bn;
+    P.n_tiles = tp.n_tiles;
     P.splits = splits;
     if (splits > 1) {
         AOZ_CHECK_ARG(workspace != nullptr, "aoz_gemm_bf16: split-K needs a workspace");
@@ -621,12 +685,13 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     }
     {   // B map
         uint64_t dims[2], strides[1]; uint32_t box[2];
-        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = (pair && bn == 128) ? 64 : 128; }
+        const int b_rows = pair ? bn / 2 : bn;
+        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = (uint32_t)((geglu && !pair) ? bn / 2 : b_rows); }
         else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
         strides[0] = (uint64_t)ldb * 2;
         if ((rc = make_tmap_bf16(&P.tmB, B, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
     }
-    if ((rc = launch_gemm(P, bn, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
+    if ((rc = launch_gemm(P, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
     if (splits > 1) {
         const long long total = (long long)M * N;
         int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
@@ -662,9 +727,11 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     P.k_iters = ks * ks * P.cin_chunks;
     P.M = NB * H * W; P.N = Cout; P.K = P.k_iters * 64;
     P.m_tiles = NB * P.tiles_h * P.tiles_w;
-    const int bn = pick_bn(Cout, P.m_tiles);
-    const bool pair = decide_pair(P.m_tiles, EPI_STORE, bn);
-    P.n_tiles = ceil_div(Cout, bn);
+    const TilePlan tp = plan_tiles(P.m_tiles, Cout, P.k_iters, 1, false, false, 1);
+    const int bn = tp.bn;
+    const bool pair = tp.pair;
+    P.bn = bn;
+    P.n_tiles = tp.n_tiles;
     P.splits = 1;
     P.C = (__nv_bfloat16*)y; P.ldc = Cout;
     P.bias = (const __nv_bfloat16*)bias;
@@ -682,10 +749,10 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     {
         uint64_t dims[2] = {(uint64_t)P.K, (uint64_t)Cout};
         uint64_t strides[1] = {(uint64_t)P.K * 2};
-        uint32_t box[2] = {64, (uint32_t)((pair && bn == 128) ? 64 : 128)};
+        uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
         if ((rc = make_tmap_bf16(&P.tmB, wpack, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
     }
-    return launch_gemm(P, bn, pair, (cudaStream_t)stream);
+    return launch_gemm(P, pair, (cudaStream_t)stream);
 }
 
 // Convolution weight gradient: dW[cout][tap][cin] = sum_pixels dy[pix][cout] * x[pix*stride + tap - pad][cin].
@@ -708,11 +775,13 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
     P.M = Cout; P.N = taps * Cin; P.K = NB * H * W;
     P.k_iters = NB * P.tiles_h * P.tiles_w;
     P.m_tiles = ceil_div(Cout, BM);
-    const int bn = (Cin % 256 == 0 && P.m_tiles * taps * (Cin / 256) >= 100) ? 256 : 128;
+    if (splits <= 0) splits = plan_splits(P.m_tiles, Cin, P.k_iters, (long long)Cout * taps * Cin, true, taps);
+    if (splits > P.k_iters) splits = P.k_iters;
+    const TilePlan tp = plan_tiles(P.m_tiles, Cin, ceil_div(P.k_iters, splits), splits, true, false, taps);
+    const int bn = tp.bn;
+    P.bn = bn;
     P.n_tiles_per_tap = ceil_div(Cin, bn);
     P.n_tiles = taps * P.n_tiles_per_tap;
-    if (splits < 1) splits = 1;
-    if (splits > P.k_iters) splits = P.k_iters;
     P.splits = splits;
     P.partial = (float*)workspace;
     int rc;
@@ -729,7 +798,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
-    if ((rc = launch_gemm(P, bn, decide_pair(P.m_tiles, EPI_PARTIAL, bn), (cudaStream_t)stream)) != AOZ_OK) return rc;
+    if ((rc = launch_gemm(P, tp.pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
     const long long total = (long long)Cout * taps * Cin;
     int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
     splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,

@@ -58,14 +58,6 @@ def workspace(nfloats: int, device) -> torch.Tensor:
 EPI_STORE, EPI_GEGLU = 0, 1
 
 
-def _pick_splits(tiles: int, k_iters: int) -> int:
-    sms = _lib.query("aoz_sm_count")
-    if tiles >= sms or k_iters < 8:
-        return 1
-    s = max(1, min(k_iters // 4, (2 * sms) // max(tiles, 1)))
-    return max(1, min(s, 32))
-
-
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bias=None, rows_per_group=0,
          epi=EPI_STORE, aux=None, out=None, accumulate=False, splits=None):
     """C[M,N] = A·Bᵀ with fused epilogue.
@@ -85,10 +77,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bia
         out = torch.empty((M, n_out), dtype=BF16, device=a.device)
     _chk(out, "gemm out", contiguous=False)
     if splits is None:
-        splits = 1
-        if epi == EPI_STORE and bias is None and residual is None and rowgroup_bias is None:
-            tiles = ((M + 127) // 128) * ((N + 127) // 128)
-            splits = _pick_splits(tiles, (K + 63) // 64)
+        fused = bias is not None or residual is not None or rowgroup_bias is not None or epi != EPI_STORE or accumulate
+        splits = 1 if fused else _lib.query("aoz_gemm_auto_splits", M, N, K, int(b_mn))     # host cost model (gemm.cu)
     ws = None
     if splits > 1:
         ws = workspace(splits * M * N, a.device)
@@ -139,9 +129,7 @@ def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False, cin
     cin_real = cin_real or Cin
     if grad_w is None:
         grad_w = torch.empty((Cout, cin_real, ks, ks), dtype=BF16, device=x.device)
-    k_iters = NB * ((H + 7) // 8) * ((W + 7) // 8)
-    tiles = ((Cout + 127) // 128) * taps * ((Cin + 127) // 128)
-    splits = _pick_splits(tiles, k_iters)
+    splits = _lib.query("aoz_conv_wgrad_auto_splits", NB, H, W, Cout, Cin, ks)
     ws = workspace(splits * Cout * taps * Cin, x.device)
     _lib.call("aoz_conv_wgrad_bf16", dy.data_ptr(), x.data_ptr(), NB, H, W, Cout, Hin, Win, Cin, ks, stride, pad, cin_real,
               grad_w.data_ptr(), int(accumulate), splits, ws.data_ptr(), _stream())

@@ -145,7 +145,12 @@ def test_full_train_step_vs_oracle(mode):
     init_prod, _ = build_pair()
     flat_dp = torch.cat([(p.detach().float() - p0.detach().float()).cpu().flatten() for p, p0 in zip(prod.parameters(), init_prod.parameters())])
     flat_dr = torch.cat([(r.detach() - p0.detach().float().cpu()).flatten() for r, p0 in zip(ref.parameters(), init_prod.parameters())])
-    assert cos(flat_dp, flat_dr) >= 0.98
+    # bf16 weights round most of an lr=1e-4 update away, so the weight delta is a coarse check ...
+    assert cos(flat_dp, flat_dr) >= 0.9
+    # ... the first moments (linear in the clipped gradients of both steps) are the sharp one
+    flat_m = torch.cat([opt.state[p]["exp_avg"].float().cpu().flatten() for p in prod.parameters()])
+    flat_rm = torch.cat([ropt.state[r]["exp_avg"].float().flatten() for r in ref.parameters()])
+    assert cos(flat_m, flat_rm) >= 0.995
 
 
 def test_layer_exclusion_freezes_and_skips_wgrad():
