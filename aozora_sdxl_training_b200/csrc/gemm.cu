@@ -516,7 +516,7 @@ __global__ void splitk_reduce_kernel(const float* __restrict__ partial, int spli
 }
 
 static int g_force_bn = 0;        // > 0: experiments only (aoz_gemm_force_bn)
-static int g_pair_mode = 0;       // 0 = single-CTA tiles only (default), 1 = let the cost model use CTA pairs, 2 = force pairs
+static int g_pair_mode = 1;       // 0 = single-CTA tiles only, 1 = the cost model may use CTA pairs (default), 2 = force pairs
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -575,11 +575,13 @@ static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, i
             const long long units = (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * n_tiles * splits;
             const int slots = pair ? sms / 2 : sms;
             const double rounds = (double)((units + slots - 1) / slots);
-            const double b_rows = pair ? bn / 2.0 : bn;
-            const double cyc = fmax(2.0 * bn, 128.0 + b_rows);
+            // cycles per K iteration, calibrated on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep.json): a ~540-cycle
+            // floor per iteration, then growth with the tile width; a CTA pair shares B and grows more slowly
+            const double cyc = pair ? fmax(535.0, 535.0 + (bn - 64) * 0.30 + fmax(0.0, bn - 128.0) * 0.85)
+                                    : fmax(535.0, 535.0 + (bn - 64) * 0.60 + fmax(0.0, bn - 160.0) * 1.95);
             const double epi = (geglu ? 28.0 : 9.0) * bn + 400.0;
             const double main_loop = k_iters_per_unit * cyc;
-            const double total = rounds * fmax(main_loop, epi) + epi + 2500.0;
+            const double total = rounds * fmax(main_loop, epi) + epi + 3000.0;
             if (total < best.cycles) best = TilePlan{bn, pair != 0, n_tiles, total};
         }
     }
@@ -614,7 +616,7 @@ using namespace aoz;
 
 extern "C" {
 
-// 0 = single-CTA tiles only (default), 1 = cost model may choose CTA-pair (cta_group::2) tiles, 2 = force pairs
+// 0 = single-CTA tiles only, 1 = cost model may choose CTA-pair (cta_group::2) tiles (default), 2 = force pairs
 int aoz_gemm_set_pair_mode(int mode) { g_pair_mode = mode; return AOZ_OK; }
 
 int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }

@@ -28,14 +28,14 @@ ALIGN = 8                    # elements: keeps every parameter slot 16-byte alig
 
 
 class _KernelBackend:
-    """Device math through the C ABI (product path)."""
+    """Device math through the C ABI (product path).  ``tables``: device pointer tables of the owned segments, uploaded
+    once (the flat buffers never move), which also keeps the calls CUDA-graph capturable."""
 
     @staticmethod
-    def sumsq(seg_g, numels, plan, out3, gdt):
-        gp = _ptr_table(seg_g, out3.device)
-        _lib.call("aoz_gradnorm_mt", plan.n_tensors, plan.n_chunks, gp.data_ptr(), plan.numel.data_ptr(), plan.chunk_start.data_ptr(),
-                  plan.chunk_tensor.data_ptr(), plan.partial.data_ptr(), 3.0e38, 0, out3.data_ptr(), _DT[gdt],
-                  torch.cuda.current_stream().cuda_stream)
+    def sumsq(seg_g, numels, plan, out3, gdt, tables=None):
+        _lib.call("aoz_gradnorm_mt", plan.n_tensors, plan.n_chunks, tables["g"].data_ptr(), plan.numel.data_ptr(),
+                  plan.chunk_start.data_ptr(), plan.chunk_tensor.data_ptr(), plan.partial.data_ptr(), 3.0e38, 0, out3.data_ptr(),
+                  _DT[gdt], torch.cuda.current_stream().cuda_stream)
 
     @staticmethod
     def clip_coef(sumsq, max_norm, out2):
@@ -43,18 +43,16 @@ class _KernelBackend:
                   torch.cuda.current_stream().cuda_stream)
 
     @staticmethod
-    def raven(seg_p, seg_g, seg_m, seg_v, plan, hyper, clip_coef, pdt, gdt, mdt):
-        dev = hyper.device
-        pp, gp, mp, vp = (_ptr_table(t, dev) for t in (seg_p, seg_g, seg_m, seg_v))
-        _lib.call("aoz_raven_step_mt", plan.n_tensors, plan.n_chunks, pp.data_ptr(), gp.data_ptr(), mp.data_ptr(), vp.data_ptr(),
-                  plan.numel.data_ptr(), plan.chunk_start.data_ptr(), plan.chunk_tensor.data_ptr(), hyper.data_ptr(),
-                  0 if clip_coef is None else clip_coef.data_ptr(), _DT[pdt], _DT[gdt], _DT[mdt],
-                  torch.cuda.current_stream().cuda_stream)
+    def raven(seg_p, seg_g, seg_m, seg_v, plan, hyper, clip_coef, pdt, gdt, mdt, tables=None):
+        _lib.call("aoz_raven_step_mt", plan.n_tensors, plan.n_chunks, tables["p"].data_ptr(), tables["g"].data_ptr(),
+                  tables["m"].data_ptr(), tables["v"].data_ptr(), plan.numel.data_ptr(), plan.chunk_start.data_ptr(),
+                  plan.chunk_tensor.data_ptr(), hyper.data_ptr(), 0 if clip_coef is None else clip_coef.data_ptr(), _DT[pdt],
+                  _DT[gdt], _DT[mdt], torch.cuda.current_stream().cuda_stream)
 
 
 def _ptr_table(tensors, device):
     arr = np.fromiter((t.data_ptr() for t in tensors), dtype=np.uint64, count=len(tensors))
-    return torch.from_numpy(arr.view(np.int64)).to(device, non_blocking=True)
+    return torch.from_numpy(arr.view(np.int64)).to(device)
 
 
 class FlatLayout:
@@ -122,6 +120,11 @@ class ShardedRavenAdamW(RavenAdamW):
 
     def step(self, closure=None, clip_coef=None):
         raise _lib.AozoraError("ShardedRavenAdamW is stepped by DataParallel.reduce_clip_step()")
+
+    def advance_host_state(self):
+        """Host side of one replayed step (CUDA graphs): bump the step counter and upload the hyper-parameter table."""
+        self.step_count += 1
+        self.dp.upload_hyper(self)
 
     def hyper_table(self, seg_params):
         group_of = {}
@@ -215,6 +218,7 @@ class DataParallel:
             self._slice_base.append(base)
             base += hi - lo
         self._plan = None
+        self._seg_cache = None
         self._pending = None
         self._works = []
         self._norm = torch.zeros(4, dtype=torch.float32, device=self.device)
@@ -276,8 +280,36 @@ class DataParallel:
             if self._pending[k] == 0:
                 self._reduce_bucket(k)
 
+    def _segment_views(self, opt):
+        if self._seg_cache is None:
+            seg_p, seg_g, seg_m, seg_v, seg_params = [], [], [], [], []
+            for (i, _, flat_off, n, shard_off) in self._segs:
+                seg_p.append(self.flat_p[flat_off:flat_off + n])
+                seg_g.append(self.g_shard[shard_off:shard_off + n])
+                seg_m.append(opt.m_shard[shard_off:shard_off + n])
+                seg_v.append(opt.v_shard[shard_off:shard_off + n])
+                seg_params.append(self.params[i])
+            from .optimizers.raven import MultiTensorPlan
+            self._plan = MultiTensorPlan()
+            self._plan.ensure([s[3] for s in self._segs], self.device)
+            tables = None
+            if self.backend is _KernelBackend:
+                tables = dict(p=_ptr_table(seg_p, self.device), g=_ptr_table(seg_g, self.device),
+                              m=_ptr_table(seg_m, self.device), v=_ptr_table(seg_v, self.device))
+            self._seg_cache = (seg_p, seg_g, seg_m, seg_v, seg_params, tables)
+        return self._seg_cache
+
+    def upload_hyper(self, opt):
+        seg_params = self._segment_views(opt)[4]
+        hy = opt.hyper_table(seg_params)
+        if self.device.type == "cuda":
+            return opt._stage.put("dp_hyper", hy, self.device)
+        return torch.from_numpy(hy)
+
     def reduce_clip_step(self, optimizer, max_norm):
-        """Finish the reduce-scatter, clip by the GLOBAL norm, update this rank's slices, all-gather the parameters."""
+        """Finish the reduce-scatter, clip by the GLOBAL norm, update this rank's slices, all-gather the parameters.
+        CUDA-graph capturable: under capture the step counter / hyper table are left to ``advance_host_state``."""
+        capturing = self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()
         if any(c != 0 for c in self._pending):       # gradients that never arrived (unused parameters): reduce what is there
             for k, c in enumerate(self._pending):
                 if c != 0:
@@ -286,28 +318,21 @@ class DataParallel:
             w.wait()
         self._reset_pending()
         opt = optimizer
-        opt.step_count += 1
-        segs = self._segs
-        seg_p, seg_g, seg_m, seg_v, seg_params = [], [], [], [], []
-        for (i, _, flat_off, n, shard_off) in segs:
-            seg_p.append(self.flat_p[flat_off:flat_off + n])
-            seg_g.append(self.g_shard[shard_off:shard_off + n])
-            seg_m.append(opt.m_shard[shard_off:shard_off + n])
-            seg_v.append(opt.v_shard[shard_off:shard_off + n])
-            seg_params.append(self.params[i])
-        if self._plan is None:
-            from .optimizers.raven import MultiTensorPlan
-            self._plan = MultiTensorPlan()
-        self._plan.ensure([s[3] for s in segs], self.device)
+        seg_p, seg_g, seg_m, seg_v, seg_params, tables = self._segment_views(opt)
+        if capturing:
+            hyper = opt._stage.device_buffer("dp_hyper")
+        else:
+            opt.step_count += 1
+            hyper = self.upload_hyper(opt)
         be = self.backend
-        be.sumsq(seg_g, None, self._plan, self._norm, self.dtype)
+        kw = dict(tables=tables) if tables is not None else {}
+        be.sumsq(seg_g, None, self._plan, self._norm, self.dtype, **kw)
         sumsq = self._norm[2:3]
         dist.all_reduce(sumsq, op=dist.ReduceOp.SUM, group=self.group)
         clip = max_norm is not None and max_norm > 0
         be.clip_coef(sumsq, max_norm if clip else 3.0e38, self._coef)
-        hyper = torch.from_numpy(opt.hyper_table(seg_params)).to(self.device, non_blocking=True)
         be.raven(seg_p, seg_g, seg_m, seg_v, self._plan, hyper, self._coef[1:2] if clip else None, self.dtype, self.dtype,
-                 opt._momentum_dtype)
+                 opt._momentum_dtype, **kw)
         # all-gather the updated parameter slices (in place inside flat_p)
         for k, (s, e) in enumerate(self.layout.buckets):
             n = (e - s) // self.world

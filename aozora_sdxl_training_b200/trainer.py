@@ -140,7 +140,7 @@ class SDXLTrainStep:
         """batch: dict with ``latents`` [b,4,h,w] (bf16, pinned host or device), ``embeds`` [b,L,2048], ``pooled`` [b,1280],
         ``time_ids`` [b,6] (list or tensor; converted to bf16 as train.py:2726-2731 does)."""
         inputs = self._host_inputs(batch, noise, jitter)
-        if self.use_cuda_graph and self.dp is None and self.grad_accum == 1 and taps is None:
+        if self.use_cuda_graph and self.grad_accum == 1 and taps is None:
             return self._graph_step(inputs)
         latents, embeds, pooled, time_ids, tickets, noise, jitter, b = inputs
         loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b, taps=taps)
@@ -157,14 +157,16 @@ class SDXLTrainStep:
         did = self.micro_step % self.grad_accum == 0
         norm = None
         if did:
-            if self.dp is not None:
-                norm = self.dp.reduce_clip_step(self.optimizer, self.clip)
-            else:
-                norm = self.optimizer.clip_and_step(self.clip, grads=grads)
+            norm = self._optimizer_phase(grads)
             self._accum = None
             self.optimizer_steps += 1
         return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=did,
                           lr=self.optimizer.param_groups[0]["lr"])
+
+    def _optimizer_phase(self, grads):
+        if self.dp is not None:
+            return self.dp.reduce_clip_step(self.optimizer, self.clip)
+        return self.optimizer.clip_and_step(self.clip, grads=grads)
 
     # ---- CUDA-graph path: the whole device side of the step is captured once and replayed ---------------------
     def _graph_step(self, inputs):
@@ -180,7 +182,7 @@ class SDXLTrainStep:
         if st["graph"] is None and st["calls"] <= self.graph_warmup:
             # eager warm-up: sizes the workspaces, allocates optimizer state, loads every kernel
             loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b)
-            norm = self.optimizer.clip_and_step(self.clip, grads=grads)
+            norm = self._optimizer_phase(grads)
             self.optimizer_steps += 1
             return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=True,
                               lr=self.optimizer.param_groups[0]["lr"])
@@ -192,7 +194,7 @@ class SDXLTrainStep:
             with torch.cuda.graph(g):
                 sl, se, sp, sti, stk, sn, sj = st["static"]
                 loss, grads = self._device_step(sl, se, sp, sti, stk, sn, sj, b)
-                norm = self.optimizer.clip_and_step(self.clip, grads=grads)
+                norm = self._optimizer_phase(grads)
                 st["out"] = (loss, norm)
                 del grads
             st["graph"] = g

@@ -27,7 +27,7 @@ def main():
             res[f"{'pair' if pair else 'single'}_bn{bn}"] = dict(tflops=round(tf, 1), ms=round(ms, 4), ns_per_kiter=round(ns_per_kiter, 1))
             print(pair, bn, res[f"{'pair' if pair else 'single'}_bn{bn}"], flush=True)
     _lib.call("aoz_gemm_force_bn", 0)
-    _lib.call("aoz_gemm_set_pair_mode", 0)
+    _lib.call("aoz_gemm_set_pair_mode", 1)
     json.dump(res, open(os.path.join(ROOT, "gpurun_out", "gemm_sweep.json"), "w"), indent=1)
 
 main()

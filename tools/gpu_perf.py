@@ -36,7 +36,7 @@ def main():
     res = {}
     lin = [("attn_proj_1280", 4096, 1280, 1280), ("attn_proj_640", 16384, 640, 640), ("ff2_1280", 4096, 1280, 5120),
            ("ff2_640", 16384, 640, 2560), ("ff1_plain_1280", 4096, 10240, 1280), ("conv1x1_320", 65536, 320, 960)]
-    for pair in (1, 0):
+    for pair in (1,):
         _lib.call("aoz_gemm_set_pair_mode", pair)
         tag = "pair" if pair else "single"
         for name, M, N, K in lin:
