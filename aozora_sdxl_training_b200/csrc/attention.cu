@@ -23,7 +23,8 @@
 
 namespace aoz {
 
-constexpr int ATT_THREADS = 192;
+constexpr int ATT_THREADS = 192;          // forward: 4 softmax warps + producer + issuer
+constexpr int ATT_BWD_THREADS = 320;      // backward: 8 compute warps (two per TMEM lane quarter) + producer + issuer
 constexpr int TILE = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = TILE * HD * 2;     // 16 KB: one [128, 64] bf16 tile
@@ -81,14 +82,23 @@ struct FwdSmem {
     static constexpr int K = Q + TILE_BYTES;            // 2 stages
     static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
     static constexpr int P = V + 2 * TILE_BYTES;        // 32 KB
-    static constexpr int BAR = P + 2 * TILE_BYTES;
-    static constexpr int TOTAL = BAR + 256 + 512;     // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
+    static constexpr int BAR = P + 2 * TILE_BYTES;      // 256 B of mbarriers
+    static constexpr int XCH = BAR + 256;               // 512 B: row-max / row-sum exchange between the two column halves
+    static constexpr int TOTAL = XCH + 512;             // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 2)
+constexpr int ATT_FWD_THREADS = 320;                    // 8 softmax warps + producer + issuer
+
+// round a finite float UP to a bf16-representable value (exchanged row maxima only need to be consistent and >= true max)
+__device__ __forceinline__ float bf16_ceil(float x) {
+    const uint32_t t = __float_as_uint(x) & 0xffff0000u;        // truncate the magnitude
+    const float r = __uint_as_float(t);
+    return (r < x) ? __uint_as_float(t + 0x10000u) : r;         // only positive x can end up below: bump one bf16 ulp
+}
+
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
 attn_fwd_kernel(const __grid_constant__ AttnParams P) {
-    extern __shared__ __align__(1024) uint8_t smem_raw[];
-    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = (uint64_t*)(smem + FwdSmem::BAR);
     uint64_t* q_full = bars;            // 1
     uint64_t* kv_full = bars + 1;       // 2
@@ -109,17 +119,17 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(o_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(p_ready, 256); mbar_init(o_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 256);
+    if (warp == 9) tmem_alloc(tmem_slot, 256);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV);
             mbar_arrive_expect_tx(q_full, TILE_BYTES);
@@ -132,51 +142,48 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                 tma_load_4d(smem + FwdSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
             }
         }
-    } else if (warp == 5) {
-        const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
-        const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
-        const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sK = smem_u32(smem + FwdSmem::K);
-        const uint32_t sV = smem_u32(smem + FwdSmem::V), sP = smem_u32(smem + FwdSmem::P);
-        mbar_wait(q_full, 0);
-        mbar_wait(&kv_full[0], 0);
-        tc_fence_after();
+    } else if (warp == 9) {
         if (lane == 0) {
+            const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sK = smem_u32(smem + FwdSmem::K);
+            const uint32_t sV = smem_u32(smem + FwdSmem::V), sP = smem_u32(smem + FwdSmem::P);
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_qk, k > 0);
             umma_commit(s_ready);
-        }
-        __syncwarp();
-        for (int j = 0; j < nkv; ++j) {
-            const int s = j & 1;
-            mbar_wait(p_ready, j & 1);
-            tc_fence_after();
-            if (lane == 0) {
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tO, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[s]);
-            }
-            __syncwarp();
-            if (j + 1 < nkv) {
-                const int s2 = (j + 1) & 1;
-                mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
-                tc_fence_after();
-                if (lane == 0) {
+                if (j + 1 < nkv) {
+                    const int s2 = (j + 1) & 1;
+                    mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
+                    tc_fence_after();
 #pragma unroll
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s2 * TILE_BYTES, k), idesc_qk, k > 0);
                     umma_commit(s_ready);
+                } else {
+                    umma_commit(o_ready);
                 }
-            } else if (lane == 0) {
-                umma_commit(o_ready);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
-        // ---- softmax warps: thread <-> query row ----
-        const int r = warp * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        // ---- softmax warps 0..7: two threads per query row, each owns 64 of the 128 key columns of a tile ----
+        const int qtr = warp & 3, hf = warp >> 2;
+        const int r = qtr * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const uint32_t sP = smem_u32(smem + FwdSmem::P);
+        __nv_bfloat16* xmax = (__nv_bfloat16*)(smem + FwdSmem::XCH);      // [2][128] bf16 (256 B used per half)
+        float* xsum = (float*)(smem + FwdSmem::XCH);                     // [128] fp32, used once at the end
         const float sl2 = P.scale * LOG2E;
         float m_ref = -INFINITY, l = 0.f;
         for (int j = 0; j < nkv; ++j) {
@@ -184,9 +191,9 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;              // keys >= kvalid are padding
             const bool full = kvalid >= TILE;                // warp-uniform: full tiles skip every per-element predicate
-            float mx = -INFINITY;
+            float mx = -3.0e38f;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
                 uint32_t v[32];
                 tmem_ld32(tS + lane_off + c * 32, v);
                 tc_wait_ld();
@@ -199,30 +206,31 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                         if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
             }
-            mx *= sl2;                                       // scale > 0: max commutes with the scaling
+            // exchange the half-row maxima (rounded up to bf16: both threads of a row must use the SAME reference)
+            mx = bf16_ceil(mx * sl2);
+            xmax[hf * 128 + r] = __float2bfloat16_rn(mx);    // exact: mx is bf16-representable
+            named_bar_sync(1, 256);
+            mx = fmaxf(mx, __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
             if (j == 0) {
                 m_ref = mx;
             } else {
                 const float m_new = fmaxf(m_ref, mx);
                 const bool need = (m_new - m_ref) > 8.0f;
-                if (__any_sync(0xffffffffu, need)) {
+                if (__any_sync(0xffffffffu, need)) {         // identical decision in both warps that share these rows
                     const float alpha = fast_exp2(m_ref - m_new);
-#pragma unroll 1
-                    for (int c = 0; c < 2; ++c) {
-                        uint32_t v[32];
-                        tmem_ld32(tO + lane_off + c * 32, v);
-                        tc_wait_ld();
+                    uint32_t v[32];
+                    tmem_ld32(tO + lane_off + hf * 32, v);   // each half rescales its 32 of the 64 output columns
+                    tc_wait_ld();
 #pragma unroll
-                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-                        tmem_st32(tO + lane_off + c * 32, v);
-                    }
+                    for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                    tmem_st32(tO + lane_off + hf * 32, v);
                     tc_wait_st();
                     l *= alpha;
                     m_ref = m_new;
                 }
             }
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
                 uint32_t v[32], w[16];
                 tmem_ld32(tS + lane_off + c * 32, v);
                 tc_wait_ld();
@@ -251,10 +259,18 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
         }
         mbar_wait(o_ready, 0);
         tc_fence_after();
+        // total row sum = sum of the two halves
+        if (hf == 1) xsum[r] = l;
+        named_bar_sync(1, 256);
+        if (hf == 0) { l += xsum[r]; }
+        named_bar_sync(1, 256);
+        if (hf == 0) xsum[r] = l;
+        named_bar_sync(1, 256);
+        l = xsum[r];
         const float inv_l = 1.0f / l;
         const int q = q0 + r;
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = hf;
             uint32_t v[32];
             tmem_ld32(tO + lane_off + c * 32, v);
             tc_wait_ld();
@@ -271,11 +287,11 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                 }
             }
         }
-        if (q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
+        if (hf == 0 && q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // ================================================================================================
@@ -312,7 +328,7 @@ struct KvSmem {
     static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -337,17 +353,17 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(kv_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(pds_ready, 128); mbar_init(acc_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(pds_ready, 256); mbar_init(acc_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
             mbar_arrive_expect_tx(kv_once, 2 * TILE_BYTES);
@@ -361,7 +377,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 tma_load_4d(smem + KvSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
         const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
         const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
@@ -395,25 +411,27 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             __syncwarp();
         }
     } else {
-        const int r = warp * 32 + lane;                      // key row inside the tile
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        // warps 0..7: quarter = warp & 3 (TMEM lanes), hf = warp >> 2 selects which half of the 128 query columns
+        const int qtr = warp & 3, hf = warp >> 2;
+        const int r = qtr * 32 + lane;                       // key row inside the tile
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
         const float sl2 = P.scale * LOG2E;
         const bool key_ok = (k0 + r) < P.Tk;
         for (int i = 0; i < nq; ++i) {
             float* lse2 = vec + (i & 1) * 256;
             float* dv = lse2 + 128;
-            {
+            if (hf == 0) {
                 const int q = i * TILE + r;
                 const long long idx = ((long long)b * P.H + h) * P.Tq + q;
                 lse2[r] = q < P.Tq ? P.lse[idx] * LOG2E : INFINITY;      // +inf -> P = 0 for padded queries
                 dv[r] = q < P.Tq ? P.Dvec[idx] : 0.f;
             }
-            named_bar_sync(1, 128);
+            named_bar_sync(1, 256);
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
                 uint32_t vs[32], vp[32], wp[16], wd[16];
                 tmem_ld32(tSt + lane_off + c * 32, vs);
                 tmem_ld32(tdPt + lane_off + c * 32, vp);
@@ -449,8 +467,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             const float mul = which == 0 ? 1.0f : P.scale;
             __nv_bfloat16* base = which == 0 ? P.dV : P.dK;
             const long long ld = which == 0 ? P.lddv : P.lddk;
-#pragma unroll 1
-            for (int c = 0; c < 2; ++c) {
+            {
+                const int c = hf;                                  // each half-warp set stores one 32-column chunk
                 uint32_t v[32];
                 tmem_ld32(tacc + lane_off + c * 32, v);
                 tc_wait_ld();
@@ -471,7 +489,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ================================================================================================
@@ -487,7 +505,7 @@ struct DqSmem {
     static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
-__global__ void __launch_bounds__(ATT_THREADS, 1)
+__global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
@@ -511,17 +529,17 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(ds_ready, 128); mbar_init(acc_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(ds_ready, 256); mbar_init(acc_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 5) tmem_alloc(tmem_slot, 512);
+    if (warp == 9) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
 
-    if (warp == 4) {
+    if (warp == 8) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
             mbar_arrive_expect_tx(q_once, 2 * TILE_BYTES);
@@ -535,7 +553,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
                 tma_load_4d(smem + DqSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == 9) {
         const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
         const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
         const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
@@ -566,8 +584,9 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             __syncwarp();
         }
     } else {
-        const int r = warp * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
+        const int qtr = warp & 3, hf = warp >> 2;            // two warps per TMEM lane quarter, each owns 64 key columns
+        const int r = qtr * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const uint32_t sDS = smem_u32(smem + DqSmem::DS);
         const float sl2 = P.scale * LOG2E;
         const int q = q0 + r;
@@ -579,7 +598,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
                 uint32_t vs[32], vp[32], wd[16];
                 tmem_ld32(tS + lane_off + c * 32, vs);
                 tmem_ld32(tdP + lane_off + c * 32, vp);
@@ -608,8 +627,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
         }
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-#pragma unroll 1
-        for (int c = 0; c < 2; ++c) {
+        {
+            const int c = hf;
             uint32_t v[32];
             tmem_ld32(tdQ + lane_off + c * 32, v);
             tc_wait_ld();
@@ -630,7 +649,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int B, int H, int T) {
@@ -662,7 +681,7 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL); attr = true; }
     const int grid = B * H * ((Tq + TILE - 1) / TILE);
-    attn_fwd_kernel<<<grid, ATT_THREADS, FwdSmem::TOTAL, (cudaStream_t)stream>>>(P);
+    attn_fwd_kernel<<<grid, ATT_FWD_THREADS, FwdSmem::TOTAL, (cudaStream_t)stream>>>(P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
     return AOZ_OK;
 }
@@ -701,9 +720,9 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL);
         attr = true;
     }
-    attn_bwd_dkv_kernel<<<B * H * ((Tk + TILE - 1) / TILE), ATT_THREADS, KvSmem::TOTAL, s>>>(P);
+    attn_bwd_dkv_kernel<<<B * H * ((Tk + TILE - 1) / TILE), ATT_BWD_THREADS, KvSmem::TOTAL, s>>>(P);
     AOZ_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-    attn_bwd_dq_kernel<<<B * H * ((Tq + TILE - 1) / TILE), ATT_THREADS, DqSmem::TOTAL, s>>>(P);
+    attn_bwd_dq_kernel<<<B * H * ((Tq + TILE - 1) / TILE), ATT_BWD_THREADS, DqSmem::TOTAL, s>>>(P);
     AOZ_CHECK_LAUNCH("attn_bwd_dq_kernel");
     return AOZ_OK;
 }

@@ -492,26 +492,57 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 
 // ---- split-K reduction: sum fp32 partials, optional accumulate into existing bf16, optional OIHW permute ----
 // partial: [splits][rows][cols] fp32.  out (bf16):
-//   permute_taps == 0 : out[row*ld_out + col]
-//   permute_taps  > 0 : cols = taps*Cin, out is OIHW [rows=Cout][Cin][taps]: out[(row*Cin + cin)*taps + tap]
-__global__ void splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
-                                     __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin,
-                                     int cin_real, int accumulate) {
+//   permute_taps == 0 : out[row*ld_out + col]                       (4 columns per thread, 128-bit loads)
+//   permute_taps  > 0 : cols = taps*Cin, out is OIHW [rows=Cout][cin_real][taps]: one thread per (row, cin) gathers its
+//                       taps (reads coalesced along cin) and writes them contiguously
+__global__ void __launch_bounds__(256)
+splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
+                     __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin, int cin_real, int accumulate) {
     const long long total = rows * cols;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
-        float s = 0.f;
-        for (int k = 0; k < splits; ++k) s += partial[(long long)k * total + i];
-        const long long row = i / cols, col = i - row * cols;
-        long long o;
-        if (permute_taps > 0) {
-            const int tap = (int)(col / Cin), cin = (int)(col - (long long)tap * Cin);
+    if (permute_taps > 0) {
+        const long long items = rows * Cin;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
+            const long long row = i / Cin;
+            const int cin = (int)(i - row * Cin);
             if (cin >= cin_real) continue;
-            o = (row * cin_real + cin) * permute_taps + tap;
-        } else {
-            o = row * ld_out + col;
+            __nv_bfloat16* o = out + (row * cin_real + cin) * permute_taps;
+            for (int tap = 0; tap < permute_taps; ++tap) {
+                const long long idx = row * cols + (long long)tap * Cin + cin;
+                float sum = 0.f;
+                for (int k = 0; k < splits; ++k) sum += partial[(long long)k * total + idx];
+                if (accumulate) sum = round_bf16(sum) + __bfloat162float(o[tap]);
+                o[tap] = __float2bfloat16_rn(sum);
+            }
         }
-        if (accumulate) s = round_bf16(s) + __bfloat162float(out[o]);
-        out[o] = __float2bfloat16_rn(s);
+        return;
+    }
+    if ((cols & 3) == 0 && (ld_out & 3) == 0 && ((((uintptr_t)out) & 7) == 0)) {
+        const long long quads = total >> 2;
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (long long)gridDim.x * blockDim.x) {
+            const long long e = i << 2;
+            float4 acc = *reinterpret_cast<const float4*>(partial + e);
+            for (int k = 1; k < splits; ++k) {
+                const float4 v = *reinterpret_cast<const float4*>(partial + (long long)k * total + e);
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            const long long row = e / cols, col = e - row * cols;
+            __nv_bfloat16* o = out + row * ld_out + col;
+            if (accumulate) {
+                const uint2 old = *reinterpret_cast<const uint2*>(o);
+                acc.x = round_bf16(acc.x) + bf16lo(old.x); acc.y = round_bf16(acc.y) + bf16hi(old.x);
+                acc.z = round_bf16(acc.z) + bf16lo(old.y); acc.w = round_bf16(acc.w) + bf16hi(old.y);
+            }
+            *reinterpret_cast<uint2*>(o) = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+        }
+        return;
+    }
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        float sum = 0.f;
+        for (int k = 0; k < splits; ++k) sum += partial[(long long)k * total + i];
+        const long long row = i / cols, col = i - row * cols;
+        const long long o = row * ld_out + col;
+        if (accumulate) sum = round_bf16(sum) + __bfloat162float(out[o]);
+        out[o] = __float2bfloat16_rn(sum);
     }
 }
 
@@ -695,7 +726,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     }
     if ((rc = launch_gemm(P, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
     if (splits > 1) {
-        const long long total = (long long)M * N;
+        const long long total = ((long long)M * N + 3) / 4;
         int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
         splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, M, N, (__nv_bfloat16*)C,
                                                                     ldc, 0, 0, 0, accumulate);
@@ -801,7 +832,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
     if ((rc = launch_gemm(P, tp.pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
-    const long long total = (long long)Cout * taps * Cin;
+    const long long total = (long long)Cout * Cin;
     int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
     splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,
                                                                 (__nv_bfloat16*)grad_w, 0, taps, Cin, cin_real, accumulate);
