@@ -35,6 +35,7 @@ enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
 struct GemmParams {
     CUtensorMap tmA, tmB;
     int mode, epi;
+    int dbg;                        // experiment flags: 1 = epilogue does not load/store, 2 = MMA ignores full barriers, 4 = producer ignores empty barriers
     int bn, stages;                 // N extent of the accumulator tile (multiple of 32, <= 256); smem pipeline depth
     int a_mn, b_mn;                 // 1 = MN-major operand
     int M, N, K;                    // logical extents (CONV_FWD: M = NB*H*W output pixels, K = taps*cin_chunks*64)
@@ -157,6 +158,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         // The inner loop is kept to: wait(empty) -> expect_tx -> TMA issues, with every coordinate advanced incrementally.
         if (lane == 0) {
             uint32_t stage = 0, phase = 0;
+            long long issued = 0;
             const uint32_t fb0_cluster = CTA2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0u;   // leader's full barriers
             const bool a_mn = P.a_mn != 0, b_mn = P.b_mn != 0;
             const int b_chunks = B_ROWS / 64;
@@ -193,7 +195,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     p_th = t % P.tiles_h; p_im = t / P.tiles_h;
                 }
                 for (int kit = k_begin; kit < k_end; ++kit) {
-                    mbar_wait(&empty_bar[stage], phase ^ 1);
+                    if (!(P.dbg & 4)) mbar_wait(&empty_bar[stage], phase ^ 1);
                     uint8_t* sa = smem + stage * STAGE_BYTES;
                     uint8_t* sb = sa + A_BYTES;
                     uint64_t* fb = &full_bar[stage];
@@ -247,6 +249,17 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         if (++p_tw == P.tiles_w) { p_tw = 0; if (++p_th == P.tiles_h) { p_th = 0; ++p_im; } }
                     }
                     if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+                    ++issued;
+                }
+            }
+            if (P.dbg & 2) {      // experiment mode: nobody waited for the loads -- drain them before the CTA may exit
+                if (!CTA2 || leader) {
+                    for (int sidx = 0; sidx < STAGES; ++sidx) {
+                        const bool this_lap = (uint32_t)sidx < stage;
+                        if (!this_lap && issued < (long long)STAGES) continue;
+                        if (issued == 0) continue;
+                        mbar_wait(&full_bar[sidx], this_lap ? phase : (phase ^ 1));
+                    }
                 }
             }
         }
@@ -273,7 +286,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 const uint32_t tmem_d = tmem_base + acc * 256;
                 uint32_t accum = 0;
                 for (int kit = k_begin; kit < k_end; ++kit) {
-                    mbar_wait(&full_bar[stage], phase);
+                    if (!(P.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
                     const uint32_t alo = a_lo0 + stage * stage_step, blo = b_lo0 + stage * stage_step;
 #pragma unroll
@@ -339,6 +352,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (P.dbg & 1) goto epilogue_done;
+            {
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
 
             if (P.epi == EPI_GEGLU) {
@@ -471,6 +486,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     }
                 }
             }
+            }
+        epilogue_done:
             // release the accumulator buffer
             tc_fence_before();
             __syncwarp();
@@ -546,6 +563,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long ro
     }
 }
 
+static int g_dbg = 0;
 static int g_force_bn = 0;        // > 0: experiments only (aoz_gemm_force_bn)
 static int g_pair_mode = 1;       // 0 = single-CTA tiles only, 1 = the cost model may use CTA pairs (default), 2 = force pairs
 
@@ -560,6 +578,7 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     }
     const int total_work = P.m_tiles * P.n_tiles * P.splits;
     if (total_work <= 0) return AOZ_OK;
+    P.dbg = g_dbg;
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
     const int stage_bytes = BM * BK * 2 + b_rows * BK * 2;
     P.stages = SMEM_TILE_BYTES / stage_bytes;
@@ -651,6 +670,7 @@ extern "C" {
 int aoz_gemm_set_pair_mode(int mode) { g_pair_mode = mode; return AOZ_OK; }
 
 int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }
+int aoz_gemm_debug_flags(int flags) { g_dbg = flags; return AOZ_OK; }
 
 // split-K factor aoz_gemm_bf16 will use when called with splits <= 0 (so the caller can size the workspace)
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn) {

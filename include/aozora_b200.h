@@ -47,6 +47,7 @@ int aoz_clip_coef_from_sumsq(const void* sumsq, float max_norm, int emulate_bf16
  *      time/add embedding MLPs) forward, dgrad, wgrad; nn.Conv2d 3x3/1x1 as implicit GEMM -------------------- */
 int aoz_gemm_set_pair_mode(int mode);
 int aoz_gemm_force_bn(int bn);
+int aoz_gemm_debug_flags(int flags);
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn);
 int aoz_conv_wgrad_auto_splits(int NB, int H, int W, int Cout, int Cin, int ks);
 int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
