@@ -339,7 +339,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     uint64_t* s_ready = bars + 5;
     uint64_t* pds_ready = bars + 6;
     uint64_t* acc_ready = bars + 7;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    uint64_t* st_free = bars + 8;       // compute warps have moved S^T / dP^T into registers: next tile's MMAs may overwrite TMEM
+    uint64_t* pd_free = bars + 9;       // dV / dK MMAs that read the P^T / dS^T smem tiles have completed
+    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
     float* vec = (float*)(smem + KvSmem::VEC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -354,6 +356,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         mbar_init(kv_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         mbar_init(s_ready, 1); mbar_init(pds_ready, 256); mbar_init(acc_ready, 1);
+        mbar_init(st_free, 256); mbar_init(pd_free, 1);
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -378,27 +381,35 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             }
         }
     } else if (warp == 9) {
-        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
-        const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
-        const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
-        const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
-        mbar_wait(kv_once, 0);
-        for (int i = 0; i < nq; ++i) {
-            const int s = i & 1;
-            mbar_wait(&q_full[s], (i >> 1) & 1);
-            tc_fence_after();
-            if (lane == 0) {
+        // Software pipeline: S^T / dP^T of Q tile i+1 are issued as soon as the compute warps have pulled tile i's S^T / dP^T
+        // into registers, so the tensor pipe works on tile i+1 while they do the exp / dS math of tile i.
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
+            const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
+            const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
+            auto issue_scores = [&](int i) {
+                const int s = i & 1;
+                mbar_wait(&q_full[s], (i >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tSt, desc_kmajor(sK, k), desc_kmajor(sQ + s * TILE_BYTES, k), idesc_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tdPt, desc_kmajor(sV, k), desc_kmajor(sDO + s * TILE_BYTES, k), idesc_s, k > 0);
                 umma_commit(s_ready);
-            }
-            __syncwarp();
-            mbar_wait(pds_ready, i & 1);
-            tc_fence_after();
-            if (lane == 0) {
+            };
+            mbar_wait(kv_once, 0);
+            issue_scores(0);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i & 1;
+                if (i + 1 < nq) {
+                    mbar_wait(st_free, i & 1);
+                    tc_fence_after();
+                    issue_scores(i + 1);
+                }
+                mbar_wait(pds_ready, i & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tdV, desc_ptile(sPT, k), desc_rows_as_k(sDO + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
@@ -406,10 +417,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tdK, desc_ptile(sDST, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&q_empty[s]);
+                umma_commit(pd_free);
                 if (i == nq - 1) umma_commit(acc_ready);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         // warps 0..7: quarter = warp & 3 (TMEM lanes), hf = warp >> 2 selects which half of the 128 query columns
         const int qtr = warp & 3, hf = warp >> 2;
@@ -430,30 +442,36 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             named_bar_sync(1, 256);
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
-#pragma unroll 1
-            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
-                uint32_t vs[32], vp[32], wp[16], wd[16];
-                tmem_ld32(tSt + lane_off + c * 32, vs);
-                tmem_ld32(tdPt + lane_off + c * 32, vp);
-                tc_wait_ld();
+            // pull this thread's 64 columns of S^T and dP^T out of TMEM, then release TMEM for the next tile's MMAs
+            uint32_t vs[64], vp[64];
+            tmem_ld32(tSt + lane_off + hf * 64, vs);
+            tmem_ld32(tSt + lane_off + hf * 64 + 32, vs + 32);
+            tmem_ld32(tdPt + lane_off + hf * 64, vp);
+            tmem_ld32(tdPt + lane_off + hf * 64 + 32, vp + 32);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(st_free);
+            uint32_t wp[32], wd[32];
 #pragma unroll
-                for (int e = 0; e < 32; e += 4) {
-                    const int qa = c * 32 + e;
-                    const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
-                    const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
-                    float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -ls.x));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -ls.y));
-                    float p2 = fast_exp2(fmaf(__uint_as_float(vs[e + 2]), sl2, -ls.z));
-                    float p3 = fast_exp2(fmaf(__uint_as_float(vs[e + 3]), sl2, -ls.w));
-                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-                    wp[e >> 1] = pack_bf16(p0, p1);
-                    wp[(e >> 1) + 1] = pack_bf16(p2, p3);
-                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dd.x), p1 * (__uint_as_float(vp[e + 1]) - dd.y));
-                    wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(vp[e + 2]) - dd.z), p3 * (__uint_as_float(vp[e + 3]) - dd.w));
-                }
-                store_p_chunk(sPT, r, c * 32, wp);
-                store_p_chunk(sDST, r, c * 32, wd);
+            for (int e = 0; e < 64; e += 4) {
+                const int qa = hf * 64 + e;
+                const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
+                const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
+                float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -ls.x));
+                float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -ls.y));
+                float p2 = fast_exp2(fmaf(__uint_as_float(vs[e + 2]), sl2, -ls.z));
+                float p3 = fast_exp2(fmaf(__uint_as_float(vs[e + 3]), sl2, -ls.w));
+                if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+                wp[e >> 1] = pack_bf16(p0, p1);
+                wp[(e >> 1) + 1] = pack_bf16(p2, p3);
+                wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dd.x), p1 * (__uint_as_float(vp[e + 1]) - dd.y));
+                wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(vp[e + 2]) - dd.z), p3 * (__uint_as_float(vp[e + 3]) - dd.w));
             }
+            if (i > 0) mbar_wait(pd_free, (i - 1) & 1);          // the previous tile's dV / dK MMAs no longer read these smem tiles
+            store_p_chunk(sPT, r, hf * 64, wp);
+            store_p_chunk(sPT, r, hf * 64 + 32, wp + 16);
+            store_p_chunk(sDST, r, hf * 64, wd);
+            store_p_chunk(sDST, r, hf * 64 + 32, wd + 16);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(pds_ready);
@@ -516,7 +534,9 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     uint64_t* s_ready = bars + 5;
     uint64_t* ds_ready = bars + 6;
     uint64_t* acc_ready = bars + 7;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    uint64_t* st_free = bars + 8;
+    uint64_t* ds_free = bars + 9;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (P.Tq + TILE - 1) / TILE;
@@ -530,6 +550,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
         mbar_init(q_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         mbar_init(s_ready, 1); mbar_init(ds_ready, 256); mbar_init(acc_ready, 1);
+        mbar_init(st_free, 256); mbar_init(ds_free, 1);
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc(tmem_slot, 512);
@@ -554,35 +575,42 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             }
         }
     } else if (warp == 9) {
-        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
-        const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
-        const uint32_t sK = smem_u32(smem + DqSmem::K), sV = smem_u32(smem + DqSmem::V);
-        const uint32_t sDS = smem_u32(smem + DqSmem::DS);
-        mbar_wait(q_once, 0);
-        for (int j = 0; j < nkv; ++j) {
-            const int s = j & 1;
-            mbar_wait(&kv_full[s], (j >> 1) & 1);
-            tc_fence_after();
-            if (lane == 0) {
+        if (lane == 0) {
+            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
+            const uint32_t sK = smem_u32(smem + DqSmem::K), sV = smem_u32(smem + DqSmem::V);
+            const uint32_t sDS = smem_u32(smem + DqSmem::DS);
+            auto issue_scores = [&](int j) {
+                const int s = j & 1;
+                mbar_wait(&kv_full[s], (j >> 1) & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s * TILE_BYTES, k), idesc_s, k > 0);
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tdP, desc_kmajor(sDO, k), desc_kmajor(sV + s * TILE_BYTES, k), idesc_s, k > 0);
                 umma_commit(s_ready);
-            }
-            __syncwarp();
-            mbar_wait(ds_ready, j & 1);
-            tc_fence_after();
-            if (lane == 0) {
+            };
+            mbar_wait(q_once, 0);
+            issue_scores(0);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                if (j + 1 < nkv) {
+                    mbar_wait(st_free, j & 1);
+                    tc_fence_after();
+                    issue_scores(j + 1);
+                }
+                mbar_wait(ds_ready, j & 1);
+                tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tdQ, desc_ptile(sDS, k), desc_rows_as_k(sK + s * TILE_BYTES, k), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&kv_empty[s]);
+                umma_commit(ds_free);
                 if (j == nkv - 1) umma_commit(acc_ready);
             }
-            __syncwarp();
         }
+        __syncwarp();
     } else {
         const int qtr = warp & 3, hf = warp >> 2;            // two warps per TMEM lane quarter, each owns 64 key columns
         const int r = qtr * 32 + lane;
@@ -597,30 +625,33 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(s_ready, j & 1);
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;
-#pragma unroll 1
-            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
-                uint32_t vs[32], vp[32], wd[16];
-                tmem_ld32(tS + lane_off + c * 32, vs);
-                tmem_ld32(tdP + lane_off + c * 32, vp);
-                tc_wait_ld();
-                if (kvalid >= TILE) {
+            uint32_t vs[64], vp[64], wd[32];
+            tmem_ld32(tS + lane_off + hf * 64, vs);
+            tmem_ld32(tS + lane_off + hf * 64 + 32, vs + 32);
+            tmem_ld32(tdP + lane_off + hf * 64, vp);
+            tmem_ld32(tdP + lane_off + hf * 64 + 32, vp + 32);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(st_free);                            // TMEM S / dP may be overwritten by the next tile's MMAs
+            if (kvalid >= TILE) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2));
-                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const int ka = c * 32 + e;
-                        float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2)) : 0.f;
-                        float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2)) : 0.f;
-                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
-                    }
+                for (int e = 0; e < 64; e += 2) {
+                    const float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2));
+                    const float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2));
+                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
                 }
-                store_p_chunk(sDS, r, c * 32, wd);
+            } else {
+#pragma unroll
+                for (int e = 0; e < 64; e += 2) {
+                    const int ka = hf * 64 + e;
+                    float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2)) : 0.f;
+                    float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2)) : 0.f;
+                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                }
             }
+            if (j > 0) mbar_wait(ds_free, (j - 1) & 1);
+            store_p_chunk(sDS, r, hf * 64, wd);
+            store_p_chunk(sDS, r, hf * 64 + 32, wd + 16);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_ready);

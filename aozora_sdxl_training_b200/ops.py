@@ -153,12 +153,17 @@ def attn_fwd(q, k, v, scale):
     return o, lse
 
 
-def attn_bwd(q, k, v, o, do, lse, scale):
+def attn_bwd(q, k, v, o, do, lse, scale, out=None):
+    """-> (dq, dk, dv).  ``out``: optional (dq, dk, dv) destination views [B,T,H,64] with a row stride (e.g. the three
+    column blocks of one fused [B*T, 3C] buffer, so the projection dgrad / wgrad run as single GEMMs)."""
     B, Tq, H, D = q.shape
     Tk = k.shape[1]
-    dq = torch.empty((B, Tq, H, D), dtype=BF16, device=q.device)
-    dk = torch.empty((B, Tk, H, D), dtype=BF16, device=q.device)
-    dv = torch.empty((B, Tk, H, D), dtype=BF16, device=q.device)
+    if out is not None:
+        dq, dk, dv = out
+    else:
+        dq = torch.empty((B, Tq, H, D), dtype=BF16, device=q.device)
+        dk = torch.empty((B, Tk, H, D), dtype=BF16, device=q.device)
+        dv = torch.empty((B, Tk, H, D), dtype=BF16, device=q.device)
     ws = workspace(_lib.query("aoz_attn_bwd_workspace_floats", B, H, Tq), q.device)
     _lib.call("aoz_attn_bwd", q.data_ptr(), q.stride(1), k.data_ptr(), k.stride(1), v.data_ptr(), v.stride(1),
               o.data_ptr(), o.stride(1), do.data_ptr(), do.stride(1), lse.data_ptr(), dq.data_ptr(), dq.stride(1),

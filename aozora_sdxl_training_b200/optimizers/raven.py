@@ -214,10 +214,10 @@ class RavenAdamW(Optimizer):
             with torch.enable_grad():
                 loss = closure()
         self.last_launches = 0 if clip_coef is None else self.last_launches
-        capturing = torch.cuda.is_current_stream_capturing()
-        items = self._collect()
+        items = self._collect()                    # raises for CPU parameters before any CUDA call is made
         if not items:
             return loss
+        capturing = torch.cuda.is_current_stream_capturing()
         dev = items[0][1].device
         pdt, gdt = items[0][1].dtype, items[0][2].dtype
         hyper = np.empty((len(items), 8), dtype=np.float32)

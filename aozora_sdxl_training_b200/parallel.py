@@ -202,6 +202,7 @@ class DataParallel:
                 off, n = L.offsets[i], p.numel()
                 self.flat_p[off:off + n].copy_(p.detach().reshape(-1))
                 p.data = self.flat_p[off:off + n].view(p.shape)
+                p._aoz_flat = True             # UNet.fuse_projection_storage must not move it (q/k/v are adjacent here already)
                 self.index[p] = i
         self.param_buckets = [L.bucket_of_param(i) for i in range(len(self.params))]
         self.bucket_need = [0] * len(L.buckets)

@@ -281,37 +281,92 @@ def _layernorm(x, mod, G):
 
 
 def _attention(q2d, k2d, v2d, B, Tq, Tk):
+    """q2d / k2d / v2d: [B*T, C] (column blocks of a fused projection output are fine: only the row stride differs).
+    bwd(do2d, out=None): ``out`` = optional (dq2d, dk2d, dv2d) destinations of the same kind."""
     C = q2d.shape[1]
     H = C // 64
     q, k, v = q2d.view(B, Tq, H, 64), k2d.view(B, Tk, H, 64), v2d.view(B, Tk, H, 64)
     o, lse = ops.attn_fwd(q, k, v, 0.125)
 
-    def bwd(do2d):
-        dq, dk, dv = ops.attn_bwd(q, k, v, o, do2d.view(B, Tq, H, 64), lse, 0.125)
+    def bwd(do2d, out=None):
+        if out is not None:
+            out = (out[0].view(B, Tq, H, 64), out[1].view(B, Tk, H, 64), out[2].view(B, Tk, H, 64))
+        dq, dk, dv = ops.attn_bwd(q, k, v, o, do2d.view(B, Tq, H, 64), lse, 0.125, out=out)
         return dq.view(B * Tq, C), dk.view(B * Tk, C), dv.view(B * Tk, C)
 
     return o.view(B * Tq, C), bwd
+
+
+def _stacked(params):
+    """One [sum(rows), K] matrix over Linear weights that lie back to back in the same storage (see
+    ``fuse_projection_storage``), or None.  The fused matrix lets to_q/to_k/to_v (and cross-attention to_k/to_v) run as
+    ONE projection GEMM forward, one dgrad and one wgrad instead of three each."""
+    w0 = params[0]
+    if len({p.requires_grad for p in params}) != 1:
+        return None
+    K = w0.shape[1]
+    base = w0.untyped_storage().data_ptr()
+    rows = 0
+    for w in params:
+        if (w.dtype != w0.dtype or w.dim() != 2 or w.shape[1] != K or not w.is_contiguous()
+                or w.untyped_storage().data_ptr() != base or w.data_ptr() != w0.data_ptr() + rows * K * w.element_size()):
+            return None
+        rows += w.shape[0]
+    return torch.as_strided(w0.detach(), (rows, K), (K, 1))
+
+
+def _linear_stacked(x, wcat, params, G, *, need_dx=True):
+    """y = x [W_0; W_1; ...]ᵀ for bias-free projections sharing the input; returns (y [M, sum rows], bwd).
+    bwd(dy [M, sum rows]) -> dx; the weight gradient is produced by one GEMM and handed out as row blocks."""
+    y = ops.gemm(x, wcat)
+
+    def bwd(dy):
+        if params[0].requires_grad:
+            dw = ops.gemm(dy, x, a_mn=True, b_mn=True)
+            r = 0
+            for p in params:
+                G.add(p, dw[r:r + p.shape[0]])
+                r += p.shape[0]
+        if not need_dx:
+            return None
+        return ops.gemm(dy, wcat, b_mn=True)
+
+    return y, bwd
 
 
 def _basic_block(blk, x, ctx, B, T, Tc, G):
     """Pre-LN self-attention, cross-attention and GEGLU feed-forward, each with a residual fused into the
     producing GEMM's epilogue.  x: [B*T, C]; ctx: [B*Tc, ctx_dim]."""
     a1, a2, ff = blk.attn1, blk.attn2, blk.ff
+    C = x.shape[1]
     n1, b_n1 = _layernorm(x, blk.norm1, G)
-    q, b_q = _linear(n1, a1.to_q.weight, None, G)
-    k, b_k = _linear(n1, a1.to_k.weight, None, G)
-    v, b_v = _linear(n1, a1.to_v.weight, None, G)
+    p_qkv = (a1.to_q.weight, a1.to_k.weight, a1.to_v.weight)
+    w_qkv = _stacked(p_qkv)
+    if w_qkv is not None:
+        qkv, b_qkv = _linear_stacked(n1, w_qkv, p_qkv, G)
+        q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
+    else:
+        q, b_q = _linear(n1, a1.to_q.weight, None, G)
+        k, b_k = _linear(n1, a1.to_k.weight, None, G)
+        v, b_v = _linear(n1, a1.to_v.weight, None, G)
     o1, b_at1 = _attention(q, k, v, B, T, T)
     x1, b_o1 = _linear(o1, a1.to_out[0].weight, a1.to_out[0].bias, G, residual=x)
     n2, b_n2 = _layernorm(x1, blk.norm2, G)
     q2, b_q2 = _linear(n2, a2.to_q.weight, None, G)
-    k2, b_k2 = _linear(ctx, a2.to_k.weight, None, G, need_dx=False)
-    v2, b_v2 = _linear(ctx, a2.to_v.weight, None, G, need_dx=False)
+    p_kv = (a2.to_k.weight, a2.to_v.weight)
+    w_kv = _stacked(p_kv)
+    if w_kv is not None:
+        kv2, b_kv2 = _linear_stacked(ctx, w_kv, p_kv, G, need_dx=False)
+        k2, v2 = kv2[:, :C], kv2[:, C:]
+    else:
+        k2, b_k2 = _linear(ctx, a2.to_k.weight, None, G, need_dx=False)
+        v2, b_v2 = _linear(ctx, a2.to_v.weight, None, G, need_dx=False)
     o2, b_at2 = _attention(q2, k2, v2, B, T, Tc)
     x2, b_o2 = _linear(o2, a2.to_out[0].weight, a2.to_out[0].bias, G, residual=x1)
     n3, b_n3 = _layernorm(x2, blk.norm3, G)
     g, b_g = _geglu(n3, ff.net[0].proj.weight, ff.net[0].proj.bias, G)
     x3, b_f2 = _linear(g, ff.net[2].weight, ff.net[2].bias, G, residual=x2)
+    M, Mc = x.shape[0], ctx.shape[0]
     del n1, q, k, v, o1, n2, q2, k2, v2, o2, n3, g
 
     def bwd(dy):
@@ -319,16 +374,27 @@ def _basic_block(blk, x, ctx, B, T, Tc, G):
         dn3 = b_g(dg)
         dx2 = b_n3(dn3, dres=dy)
         do2 = b_o2(dx2)
-        dq2, dk2, dv2 = b_at2(do2)
-        b_k2(dk2)
-        b_v2(dv2)
+        if w_kv is not None:
+            dkv2 = torch.empty((Mc, 2 * C), dtype=BF16, device=dy.device)
+            dq2 = torch.empty((M, C), dtype=BF16, device=dy.device)
+            b_at2(do2, out=(dq2, dkv2[:, :C], dkv2[:, C:]))
+            b_kv2(dkv2)
+        else:
+            dq2, dk2, dv2 = b_at2(do2)
+            b_k2(dk2)
+            b_v2(dv2)
         dn2 = b_q2(dq2)
         dx1 = b_n2(dn2, dres=dx2)
         do1 = b_o1(dx1)
-        dq, dk, dv = b_at1(do1)
-        dn1 = b_q(dq)
-        b_k(dk, out=dn1, accumulate=True)
-        b_v(dv, out=dn1, accumulate=True)
+        if w_qkv is not None:
+            dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dy.device)
+            b_at1(do1, out=(dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]))
+            dn1 = b_qkv(dqkv)
+        else:
+            dq, dk, dv = b_at1(do1)
+            dn1 = b_q(dq)
+            b_k(dk, out=dn1, accumulate=True)
+            b_v(dv, out=dn1, accumulate=True)
         return b_n1(dn1, dres=dx1)
 
     return x3, bwd
@@ -423,6 +489,34 @@ class UNet2DConditionModel(nn.Module):
         self.conv_out = nn.Conv2d(boc[0], cfg.out_channels, 3, padding=1)
         self._packs = _PackCache()
         self.gradient_checkpointing = False
+        self._fused_storage_ok = False
+
+    # ---- fused projection storage ------------------------------------------------------------------------------
+    def _apply(self, fn, *a, **k):
+        # .to() / .cuda() / .bfloat16() give every parameter fresh storage: the stacked layout must be rebuilt
+        self._fused_storage_ok = False
+        return super()._apply(fn, *a, **k)
+
+    def fuse_projection_storage(self):
+        """Place attn1.{to_q,to_k,to_v}.weight and attn2.{to_k,to_v}.weight of every transformer block back to back in one
+        buffer (the parameters become row-block views; names, shapes, values and order are untouched) so each group runs
+        as ONE projection GEMM.  Groups with mixed ``requires_grad`` or parameters owned by a
+        data-parallel flat buffer (already adjacent there) are left as they are.  Idempotent; called lazily by forward."""
+        for m in self.modules():
+            if not isinstance(m, BasicTransformerBlock):
+                continue
+            for group in ((m.attn1.to_q.weight, m.attn1.to_k.weight, m.attn1.to_v.weight), (m.attn2.to_k.weight, m.attn2.to_v.weight)):
+                if _stacked(group) is not None or len({p.requires_grad for p in group}) != 1:
+                    continue
+                if any(getattr(p, "_aoz_flat", False) for p in group) or len({(p.dtype, p.shape[1]) for p in group}) != 1:
+                    continue
+                with torch.no_grad():
+                    buf = torch.cat([p.detach() for p in group], dim=0)
+                    r = 0
+                    for p in group:
+                        p.data = buf[r:r + p.shape[0]]
+                        r += p.shape[0]
+        self._fused_storage_ok = True
 
     # ---- reference boundary no-ops (train.py:199-229, 2660) ----------------------------------------------
     def enable_gradient_checkpointing(self):
@@ -440,6 +534,8 @@ class UNet2DConditionModel(nn.Module):
         text_embeds [B,pooled] bf16; time_ids [B,6] (bf16 values).  Returns (pred [B,H,W,out_channels] bf16, bwd) where
         ``bwd(dpred8)`` takes dL/dpred padded to 8 channels and returns {param: grad}."""
         cfg = self.cfg
+        if not self._fused_storage_ok:
+            self.fuse_projection_storage()
         G = GradSink()
         packs = self._packs
         B = x8.shape[0]

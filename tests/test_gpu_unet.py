@@ -212,3 +212,37 @@ def test_cuda_graph_replay_matches_eager():
         assert abs(a - b) <= 2e-3 * abs(a), (l0, l1)
     moved = sum(float((a - b).abs().sum()) for a, b in zip(p0, p1)) / sum(float(a.abs().sum()) for a in p0)
     assert moved < 2e-3
+
+
+def test_stacked_projections_match_separate_projections():
+    """attn1 q/k/v and attn2 k/v run as single stacked GEMMs when their weights share storage; a group with mixed
+    requires_grad falls back to one GEMM per projection.  Both paths must agree (prediction and every gradient)."""
+    from aozora_sdxl_training_b200 import ops
+    from aozora_sdxl_training_b200 import unet as U
+    b = make_batch()
+    x8 = ops.nchw_to_nhwc(b["latents"].cuda(), cpad=8)
+    cond = torch.tensor([37.0, 801.0], device="cuda")
+    tid = torch.tensor(b["time_ids_data"], dtype=BF16).cuda()
+    d8 = (torch.randn(2, 16, 16, 8, generator=torch.Generator().manual_seed(5)) * 0.1).to(BF16).cuda()
+    outs = []
+    for stacked in (True, False):
+        prod, _ = build_pair()
+        if not stacked:
+            prod._fused_storage_ok = True            # keep every weight in its own storage -> per-projection GEMMs
+        pred, bwd = prod.forward_nhwc(x8, cond, b["embeds"].cuda(), b["pooled"].cuda(), tid)
+        blk = prod.mid_block.attentions[0].transformer_blocks[0]
+        group = (blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight)
+        assert (U._stacked(group) is not None) == stacked
+        grads = bwd(d8)
+        outs.append((pred.float().cpu(), {n: grads[p].float().cpu() for n, p in prod.named_parameters()}))
+    (p0, g0), (p1, g1) = outs
+    assert cos(p0, p1) >= 0.9999
+    for n in g0:
+        if g1[n].norm() > 1e-6:
+            assert cos(g0[n], g1[n]) >= 0.999, n
+    # names / values / order are untouched by the storage change, and .to() invalidates it
+    prod, ref = build_pair()
+    prod.fuse_projection_storage()
+    assert [k for k, _ in prod.named_parameters()] == [k for k, _ in ref.named_parameters()]
+    for (k, v), (_, r) in zip(prod.state_dict().items(), ref.state_dict().items()):
+        assert torch.equal(v.float().cpu(), r), k

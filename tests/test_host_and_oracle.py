@@ -190,3 +190,27 @@ def test_live_reference_matches_product_host():
     class LC:
         TIMESTEP_LOSS_WEIGHT_CURVE = [[0.1, 0.3], [0.6, 2.5], [0.9, 0.2]]
     assert torch.equal(host.timestep_loss_curve_from_config(LC, 1000), tr.timestep_loss_curve_from_config(LC, 1000))
+
+
+def test_stacked_projection_storage_keeps_the_state_dict_contract():
+    """fuse_projection_storage() only changes WHERE q/k/v (and cross k/v) weights live: names, order, shapes and values of
+    named_parameters() / state_dict() -- the reference's checkpoint contract (train.py:2478-2479, raven.py:157-168) -- stay."""
+    import torch
+    from aozora_sdxl_training_b200.unet import UNet2DConditionModel, _stacked, init_weights_, tiny_config
+    m = init_weights_(UNet2DConditionModel(tiny_config())).to(torch.bfloat16)
+    names = [n for n, _ in m.named_parameters()]
+    before = {k: v.clone() for k, v in m.state_dict().items()}
+    m.fuse_projection_storage()
+    assert names == [n for n, _ in m.named_parameters()]
+    for k, v in m.state_dict().items():
+        assert torch.equal(v, before[k]) and v.is_contiguous(), k
+    blk = m.mid_block.attentions[0].transformer_blocks[1]
+    qkv = (blk.attn1.to_q.weight, blk.attn1.to_k.weight, blk.attn1.to_v.weight)
+    w = _stacked(qkv)
+    assert w is not None and w.shape == (3 * 256, 256) and torch.equal(w[256:512], blk.attn1.to_k.weight)
+    assert _stacked((blk.attn2.to_k.weight, blk.attn2.to_v.weight)).shape == (512, 128)
+    assert _stacked((blk.attn1.to_q.weight, blk.attn2.to_q.weight)) is None          # different storages
+    blk.attn1.to_k.weight.requires_grad_(False)
+    assert _stacked(qkv) is None                                                     # mixed requires_grad: separate GEMMs
+    m2 = m.float()                                                                   # fresh storages: layout must be rebuilt
+    assert not m2._fused_storage_ok

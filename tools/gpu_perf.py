@@ -14,10 +14,12 @@ BF = torch.bfloat16
 
 
 def timeit(fn, n=10, flush=None):
+    """Median device time (ms).  Launches are queued back to back (events around each launch, one synchronize at the
+    end) so the GPU never idles waiting for the host inside a timed region; ``flush`` (a buffer > L2) is zeroed first."""
     for _ in range(3):
         fn()
     torch.cuda.synchronize()
-    ts = []
+    evs = []
     for _ in range(n):
         if flush is not None:
             flush.zero_()
@@ -25,14 +27,14 @@ def timeit(fn, n=10, flush=None):
         e0.record()
         fn()
         e1.record()
-        torch.cuda.synchronize()
-        ts.append(e0.elapsed_time(e1))
-    ts.sort()
+        evs.append((e0, e1))
+    torch.cuda.synchronize()
+    ts = sorted(a.elapsed_time(b) for a, b in evs)
     return ts[len(ts) // 2]
 
 
 def main():
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    flush = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
     res = {}
     lin = [("attn_proj_1280", 4096, 1280, 1280), ("attn_proj_640", 16384, 640, 640), ("ff2_1280", 4096, 1280, 5120),
            ("ff2_640", 16384, 640, 2560), ("ff1_plain_1280", 4096, 10240, 1280), ("conv1x1_320", 65536, 320, 960)]

@@ -41,9 +41,12 @@ def main():
         step.step(batch)
     torch.cuda.synchronize()
     if args.no_profiler:
+        # cudaProfilerStart/Stop bracket exactly the measured step(s): `ncu --profile-from-start off` lists only those launches
+        torch.cuda.profiler.start()
         for _ in range(args.steps):
             step.step(batch)
         torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
         return
     import time
     t0 = time.perf_counter()
