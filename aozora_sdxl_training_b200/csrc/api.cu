@@ -10,6 +10,7 @@
 namespace aoz {
 
 static thread_local char g_err[512] = "";
+long long g_launch_count = 0;
 
 void set_error(const char* fmt, ...) {
     va_list ap;
@@ -87,5 +88,7 @@ const char* aoz_last_error(void) { return aoz::g_err; }
 int aoz_abi_version(void) { return 1; }
 
 int aoz_sm_count(void) { return aoz::sm_count(); }
+
+long long aoz_launch_count(void) { return aoz::g_launch_count; }
 
 }  // extern "C"

@@ -29,8 +29,11 @@ void set_error(const char* fmt, ...);
         }                                        \
     } while (0)
 
+extern long long g_launch_count;      // kernels launched by this library (api.cu; read through aoz_launch_count())
+
 #define AOZ_CHECK_LAUNCH(what)                                                         \
     do {                                                                               \
+        ++::aoz::g_launch_count;                                                       \
         cudaError_t e__ = cudaGetLastError();                                          \
         if (e__ != cudaSuccess) {                                                      \
             ::aoz::set_error("%s: %s", what, cudaGetErrorString(e__));                 \
@@ -54,6 +57,25 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+
+// Standard normal CDF Phi(x) = 0.5 * erfc(-x / sqrt(2)) for the erf GELU (torch F.gelu default), and exp(-x^2 / 2).
+// Abramowitz-Stegun 7.1.26 evaluated in erfc form (no 1 - erf cancellation for x < 0): 1 rcp + 1 ex2 + 7 FMA-class ops
+// instead of erff's ~30.  x * Phi(x) rounded to bf16 is identical to the erff result for x >= -2.5, within one bf16
+// ulp on [-4, -2.5) and within 5e-6 absolute below (tests/test_gpu_kernels.py pins this against torch's erf GELU).
+__device__ __forceinline__ float gelu_cdf(float x, float& exp_mhalf_x2) {
+    const float z = fabsf(x) * 0.70710678118654752440f;
+    float t;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, z, 1.0f)));
+    float poly = fmaf(1.061405429f, t, -1.453152027f);
+    poly = fmaf(poly, t, 1.421413741f);
+    poly = fmaf(poly, t, -0.284496736f);
+    poly = fmaf(poly, t, 0.254829592f);
+    float e;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(z * z * -1.4426950408889634f));
+    exp_mhalf_x2 = e;
+    const float h = 0.5f * poly * t * e;                 // 0.5 * erfc(|x| / sqrt 2)
+    return x < 0.f ? h : 1.0f - h;
+}
 
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

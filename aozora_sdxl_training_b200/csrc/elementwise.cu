@@ -142,8 +142,9 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __n
         unpack8e(ld_stream(aux + row * 2 * half + half + v * 8), g);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            const float cdf = 0.5f * (1.0f + erff(g[e] * 0.70710678118654752440f));
-            const float pdf = 0.39894228040143267794f * __expf(-0.5f * g[e] * g[e]);
+            float ex;                                           // exp(-g^2 / 2), shared by the CDF and the density
+            const float cdf = gelu_cdf(g[e], ex);
+            const float pdf = 0.39894228040143267794f * ex;
             const float gelu = round_bf16(g[e] * cdf);          // forward rounded gelu(g) to bf16
             dh[e] = d[e] * gelu;
             dg[e] = round_bf16(d[e] * h[e]) * (cdf + g[e] * pdf);

@@ -41,6 +41,12 @@ struct GemmParams {
     int M, N, K;                    // logical extents (CONV_FWD: M = NB*H*W output pixels, K = taps*cin_chunks*64)
     int m_tiles, n_tiles, k_iters;  // tile counts; k_iters = total K iterations (before split)
     int splits;                     // split-K factor (EPI_PARTIAL when > 1)
+    // tail split: work items [0, full_work) are whole tiles (x splits); the last `tail_tiles` tiles -- the ones that would
+    // run as a mostly empty final wave -- are cut along K into `tail_splits` slices each, written as fp32 partials to
+    // `tail_ws` ([slice][128 rows][bn]) and finished (sum + fused epilogue) by tail_fixup_kernel.
+    int full_work, tail_tiles, tail_splits;
+    float* tail_ws;
+    int vec_ok;                     // EPI_STORE: every output / bias / residual row segment is 16-byte aligned
     // conv geometry (NHWC).  H, W = OUTPUT spatial size (CONV_FWD) / dy spatial size (CONV_WGRAD)
     int NB, H, W, TH, TW, tiles_h, tiles_w;
     int taps_s, pad, stride, cin_chunks, flip;   // taps_s = filter width (3 or 1); taps = taps_s*taps_s
@@ -56,8 +62,8 @@ struct GemmParams {
     int accumulate;                 // EPI_STORE: C += result
 };
 
-// erf GELU (torch F.gelu default), fp32
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+// erf GELU (torch F.gelu default), fp32: x * Phi(x)
+__device__ __forceinline__ float gelu_erf(float x) { float e; return x * gelu_cdf(x, e); }
 
 // ---- cluster helpers (CTA-pair mode) ----
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -109,6 +115,105 @@ __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
 }
 
+struct WorkItem { int tile, split, k_begin, k_end, tail_slot; };      // tail_slot < 0: not a tail slice
+
+__device__ __forceinline__ WorkItem decode_work(const GemmParams& P, int work, int k_per_split) {
+    WorkItem w;
+    if (work < P.full_work) {
+        w.tile = work / P.splits;
+        w.split = work - w.tile * P.splits;
+        w.k_begin = w.split * k_per_split;
+        w.k_end = min(P.k_iters, w.k_begin + k_per_split);
+        w.tail_slot = -1;
+    } else {
+        const int j = work - P.full_work;
+        const int t = j / P.tail_splits;
+        const int kps = (P.k_iters + P.tail_splits - 1) / P.tail_splits;
+        w.tile = P.full_work / P.splits + t;
+        w.split = j - t * P.tail_splits;
+        w.k_begin = w.split * kps;
+        w.k_end = min(P.k_iters, w.k_begin + kps);
+        w.tail_slot = j;
+    }
+    return w;
+}
+
+struct RowMap { long long row; bool ok; int group; };
+
+// output row (and time-embedding row group) of row `row_in_tile` of the 128-row tile `m_blk`
+__device__ __forceinline__ RowMap map_row(const GemmParams& P, int m_blk, int row_in_tile) {
+    RowMap r;
+    if (P.mode == GM_CONV_FWD) {
+        int t = m_blk;
+        const int tw = t % P.tiles_w; t /= P.tiles_w;
+        const int th = t % P.tiles_h; const int img = t / P.tiles_h;
+        const int h = th * P.TH + row_in_tile / P.TW, w = tw * P.TW + row_in_tile % P.TW;
+        r.ok = (h < P.H) && (w < P.W) && (img < P.NB);
+        r.row = ((long long)img * P.H + h) * P.W + w;
+        r.group = img;
+    } else {
+        r.row = (long long)m_blk * BM + row_in_tile;
+        r.ok = r.row < P.M;
+        r.group = P.rows_per_group > 0 ? (int)(r.row / P.rows_per_group) : 0;
+    }
+    return r;
+}
+
+// EPI_STORE for 8 consecutive output columns [col, col+8) of output row `row`: bias -> per-image time embedding -> residual
+// -> accumulate, each with the bf16 rounding point the op-by-op autocast path has, then one 16-byte store.
+__device__ __forceinline__ void epi_store8(const GemmParams& P, long long row, int group, int col, int col_limit, float* f) {
+    __nv_bfloat16* dst = P.C + row * P.ldc + col;
+    const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + col : nullptr;
+    const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + col : nullptr;
+    if (P.vec_ok && col + 7 < col_limit) {
+        if (P.bias) {
+            const uint4 bb = __ldg(reinterpret_cast<const uint4*>(P.bias + col));
+            const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) { f[2 * e] += bf16lo(bw[e]); f[2 * e + 1] += bf16hi(bw[e]); }
+        }
+        if (rgb) {
+            const uint4 gg = __ldg(reinterpret_cast<const uint4*>(rgb));
+            const uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(gw[e]);
+                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(gw[e]);
+            }
+        }
+        if (res) {
+            const uint4 rr = *reinterpret_cast<const uint4*>(res);
+            const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
+                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
+            }
+        }
+        if (P.accumulate) {
+            const uint4 oo = *reinterpret_cast<const uint4*>(dst);
+            const uint32_t ow[4] = {oo.x, oo.y, oo.z, oo.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(ow[e]);
+                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(ow[e]);
+            }
+        }
+        *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+    } else {
+        for (int e = 0; e < 8; ++e) {
+            if (col + e < col_limit) {
+                float x = f[e];
+                if (P.bias) x += __bfloat162float(P.bias[col + e]);
+                if (rgb) x = round_bf16(x) + __bfloat162float(rgb[e]);
+                if (res) x = round_bf16(x) + __bfloat162float(res[e]);
+                if (P.accumulate) x = round_bf16(x) + __bfloat162float(dst[e]);
+                dst[e] = __float2bfloat16_rn(x);
+            }
+        }
+    }
+}
+
 // CTA2 = true: two CTAs of a cluster (one SM pair) compute a 256 x BN tile with tcgen05.mma.cta_group::2.  Each CTA
 // stages its own 128 rows of A and HALF of the B tile, so the L2 -> shared-memory traffic per FLOP drops by a third
 // (the 1-CTA 128 x 256 tile needs ~26 TB/s of L2 bandwidth at tensor peak -- more than the chip has).  Only the
@@ -149,7 +254,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int total_work = P.m_tiles * P.n_tiles * P.splits;      // m_tiles counts 256-row pair tiles when CTA2
+    const int total_work = P.full_work + P.tail_tiles * P.tail_splits;      // (m_tiles counts 256-row pair tiles when CTA2)
     const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
     const int m_sub = CTA2 ? 2 : 1;
 
@@ -163,11 +268,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             const bool a_mn = P.a_mn != 0, b_mn = P.b_mn != 0;
             const int b_chunks = B_ROWS / 64;
             for (int work = unit; work < total_work; work += n_units) {
-                const int tile = work / P.splits, split = work - tile * P.splits;
+                const WorkItem wi = decode_work(P, work, k_per_split);
+                const int tile = wi.tile;
                 const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank;          // 128-row tile index of THIS CTA
                 const int n_blk = tile / P.m_tiles;
-                const int k_begin = split * k_per_split;
-                const int k_end = min(P.k_iters, k_begin + k_per_split);
+                const int k_begin = wi.k_begin, k_end = wi.k_end;
                 const int n_row0 = n_blk * BN + (CTA2 ? (int)rank * (BN / 2) : 0);  // first B row (N index) this CTA stages
                 const int m_row0 = m_blk * BM;
                 // GEGLU: accumulator columns [0, BN/2) = value rows, [BN/2, BN) = gate rows of the projection weight
@@ -278,9 +383,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             uint32_t stage = 0, phase = 0;
             uint32_t acc = 0, acc_phase = 0;
             for (int work = unit; work < total_work; work += n_units) {
-                const int tile = work / P.splits, split = work - tile * P.splits;
-                const int k_begin = split * k_per_split;
-                const int k_end = min(P.k_iters, k_begin + k_per_split);
+                const WorkItem wi = decode_work(P, work, k_per_split);
+                const int k_begin = wi.k_begin, k_end = wi.k_end;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * 256;
@@ -314,25 +418,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         const int row_in_tile = q * 32 + lane;
         uint32_t acc = 0, acc_phase = 0;
         for (int work = unit; work < total_work; work += n_units) {
-            const int tile = work / P.splits, split = work - tile * P.splits;
+            const WorkItem wi = decode_work(P, work, k_per_split);
+            const int tile = wi.tile, split = wi.split;
             const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank, n_blk = tile / P.m_tiles;
-            const int k_begin = split * k_per_split;
-            const bool empty_split = min(P.k_iters, k_begin + k_per_split) <= k_begin;
-            // row mapping
-            long long row = 0; bool row_ok; int group = 0;
-            if (P.mode == GM_CONV_FWD) {
-                int t = m_blk;
-                const int tw = t % P.tiles_w; t /= P.tiles_w;
-                const int th = t % P.tiles_h; const int img = t / P.tiles_h;
-                const int h = th * P.TH + row_in_tile / P.TW, w = tw * P.TW + row_in_tile % P.TW;
-                row_ok = (h < P.H) && (w < P.W) && (img < P.NB);
-                row = ((long long)img * P.H + h) * P.W + w;
-                group = img;
-            } else {
-                row = (long long)m_blk * BM + row_in_tile;
-                row_ok = row < P.M;
-                group = P.rows_per_group > 0 ? (int)(row / P.rows_per_group) : 0;
-            }
+            const bool empty_split = wi.k_end <= wi.k_begin;
+            const RowMap rm = map_row(P, m_blk, row_in_tile);
+            const long long row = rm.row;
+            const bool row_ok = rm.ok;
+            const int group = rm.group;
             // column mapping
             int col0, col_limit;                          // first output column of this tile / exclusive limit
             long long col_shift = 0;                      // WGRAD: tap*Cin added to the column
@@ -397,6 +490,22 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         }
                     }
                 }
+            } else if (wi.tail_slot >= 0) {
+                // K slice of a tail tile: raw fp32 accumulator rows to the scratch buffer, [slice][128][BN]
+                float* dstp = P.tail_ws + ((long long)(wi.tail_slot * m_sub + (int)rank) * BM + row_in_tile) * BN;
+#pragma unroll 1
+                for (int c = half * 32; c < BN; c += 64) {
+                    uint32_t r[32];
+                    if (!empty_split) {
+                        tmem_ld32(taddr + c, r);
+                        tc_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dstp + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                }
             } else {
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
@@ -423,65 +532,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                             }
                         }
                     } else {
-                        __nv_bfloat16* dst = P.C + row * P.ldc + col_shift + cbase;
-                        const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + cbase : nullptr;
-                        const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + cbase : nullptr;
-                        const bool vec_ok = ((((uintptr_t)dst) & 15) == 0) && (!res || ((((uintptr_t)res) & 15) == 0)) &&
-                                            (!P.bias || ((((uintptr_t)(P.bias + cbase)) & 15) == 0)) && (!rgb || ((((uintptr_t)rgb) & 15) == 0));
 #pragma unroll
                         for (int j = 0; j < 32; j += 8) {
                             float f[8];
 #pragma unroll
                             for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j + e]);
-                            const bool full8 = (cbase + j + 7 < col_limit) && vec_ok;
-                            if (full8) {
-                                if (P.bias) {
-                                    const uint4 bb = __ldg(reinterpret_cast<const uint4*>(P.bias + cbase + j));
-                                    const uint32_t bw[4] = {bb.x, bb.y, bb.z, bb.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) { f[2 * e] += bf16lo(bw[e]); f[2 * e + 1] += bf16hi(bw[e]); }
-                                }
-                                if (rgb) {
-                                    const uint4 gg = __ldg(reinterpret_cast<const uint4*>(rgb + j));
-                                    const uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(gw[e]);
-                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(gw[e]);
-                                    }
-                                }
-                                if (res) {
-                                    const uint4 rr = *reinterpret_cast<const uint4*>(res + j);
-                                    const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
-                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
-                                    }
-                                }
-                                if (P.accumulate) {
-                                    const uint4 oo = *reinterpret_cast<const uint4*>(dst + j);
-                                    const uint32_t ow[4] = {oo.x, oo.y, oo.z, oo.w};
-#pragma unroll
-                                    for (int e = 0; e < 4; ++e) {
-                                        f[2 * e] = round_bf16(f[2 * e]) + bf16lo(ow[e]);
-                                        f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(ow[e]);
-                                    }
-                                }
-                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]),
-                                                                               pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-                            } else {
-                                for (int e = 0; e < 8; ++e) {
-                                    if (cbase + j + e < col_limit) {
-                                        float x = f[e];
-                                        if (P.bias) x += __bfloat162float(P.bias[cbase + j + e]);
-                                        if (rgb) x = round_bf16(x) + __bfloat162float(rgb[j + e]);
-                                        if (res) x = round_bf16(x) + __bfloat162float(res[j + e]);
-                                        if (P.accumulate) x = round_bf16(x) + __bfloat162float(dst[j + e]);
-                                        dst[j + e] = __float2bfloat16_rn(x);
-                                    }
-                                }
-                            }
+                            epi_store8(P, row, group, cbase + j, col_limit, f);
                         }
                     }
                 }
@@ -505,6 +561,36 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         tc_fence_after();
         if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
     }
+}
+
+// ---- tail fix-up: sum the K slices of the tail tiles and apply the fused EPI_STORE epilogue -----------------------
+// grid = tail_tiles x m_sub x (bn / 32); 128 threads = the 128 rows of one (sub-)tile; a block owns 32 columns.
+__global__ void __launch_bounds__(128)
+tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
+    const int chunks = P.bn / 32;
+    int b = blockIdx.x;
+    const int chunk = b % chunks; b /= chunks;
+    const int sub = b % m_sub;
+    const int t = b / m_sub;
+    const int tile = P.full_work + t;                       // tail split implies splits == 1
+    const int m_blk = (tile % P.m_tiles) * m_sub + sub, n_blk = tile / P.m_tiles;
+    const int row_in_tile = threadIdx.x;
+    const RowMap rm = map_row(P, m_blk, row_in_tile);
+    const int col0 = n_blk * P.bn + chunk * 32;
+    if (!rm.ok || col0 >= P.N) return;
+    float acc[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int sp = 0; sp < P.tail_splits; ++sp) {
+        const float* src = P.tail_ws + ((long long)((t * P.tail_splits + sp) * m_sub + sub) * BM + row_in_tile) * P.bn + chunk * 32;
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            const float4 v = *reinterpret_cast<const float4*>(src + j);
+            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < 32; j += 8) epi_store8(P, rm.row, rm.group, col0 + j, P.N, acc + j);
 }
 
 // ---- split-K reduction: sum fp32 partials, optional accumulate into existing bf16, optional OIHW permute ----
@@ -566,6 +652,9 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long ro
 static int g_dbg = 0;
 static int g_force_bn = 0;        // > 0: experiments only (aoz_gemm_force_bn)
 static int g_pair_mode = 1;       // 0 = single-CTA tiles only, 1 = the cost model may use CTA pairs (default), 2 = force pairs
+static int g_tail_mode = 1;       // 0 = never cut the last wave along K, 1 = the cost model may (default), 2 = whenever possible
+static float* g_tail_ws = nullptr;        // caller-owned scratch for the tail slices (aoz_gemm_set_scratch)
+static long long g_tail_bytes = 0;
 
 static inline int ceil_div(long long a, long long b) { return (int)((a + b - 1) / b); }
 
@@ -576,7 +665,16 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
         cudaFuncSetAttribute(gemm_bf16_kernel<CTA2>, cudaFuncAttributeMaxDynamicSharedMemorySize, GEMM_SMEM_TOTAL);
         attr_set = true;
     }
-    const int total_work = P.m_tiles * P.n_tiles * P.splits;
+    // P.m_tiles counts work-unit rows here (256-row pair tiles when CTA2); the planner's tail decision is in P.tail_*
+    const int tiles = P.m_tiles * P.n_tiles;
+    if (P.tail_tiles > 0) {
+        P.full_work = tiles - P.tail_tiles;
+        P.tail_ws = g_tail_ws;
+    } else {
+        P.full_work = tiles * P.splits;
+        P.tail_tiles = 0; P.tail_splits = 1;
+    }
+    const int total_work = P.full_work + P.tail_tiles * P.tail_splits;
     if (total_work <= 0) return AOZ_OK;
     P.dbg = g_dbg;
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
@@ -600,6 +698,11 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
         if (e != cudaSuccess) { set_error("gemm_bf16_kernel<pair> launch: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
     }
     AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
+    if (P.tail_tiles > 0) {
+        const int m_sub = CTA2 ? 2 : 1;
+        tail_fixup_kernel<<<P.tail_tiles * m_sub * (P.bn / 32), 128, 0, stream>>>(P, m_sub);
+        AOZ_CHECK_LAUNCH("tail_fixup_kernel");
+    }
     return AOZ_OK;
 }
 
@@ -607,10 +710,13 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
 // Cycle model per CTA (or CTA pair) and K iteration of 64: the MMA needs 2*bn cycles (128 x bn x 64 at 8192 FLOP/cycle/SM),
 // shared memory must deliver the A (16 KB) and B (b_rows x 128 B) stage at 128 B/cycle.  A launch costs
 // rounds x max(main loop, epilogue) + one exposed epilogue + fixed fill/drain; the N extent is covered by ceil(N / n_out) tiles.
-struct TilePlan { int bn; bool pair; int n_tiles; double cycles; };
+struct TilePlan { int bn; bool pair; int n_tiles; double cycles; int tail_tiles, tail_splits; };
 
-static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, int splits, bool b_mn, bool geglu, int n_groups /*taps*/) {
-    TilePlan best{128, false, 0, 1e300};
+// `allow_tail`: the caller's epilogue is EPI_STORE with splits == 1, so the last (partial) wave may be cut along K instead
+// (decode_work / tail_fixup_kernel): 80 tiles on 74 CTA pairs then cost ~1.1 tile times instead of 2.
+static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, int splits, bool b_mn, bool geglu, int n_groups /*taps*/,
+                           bool allow_tail = false) {
+    TilePlan best{128, false, 0, 1e300, 0, 1}, best_tail{128, false, 0, 1e300, 0, 1};
     const int sms = sm_count();
     const int step = b_mn ? 64 : 32;
     for (int pair = 0; pair <= 1; ++pair) {
@@ -629,12 +735,28 @@ static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, i
             // floor per iteration, then growth with the tile width; a CTA pair shares B and grows more slowly
             const double cyc = pair ? fmax(535.0, 535.0 + (bn - 64) * 0.30 + fmax(0.0, bn - 128.0) * 0.85)
                                     : fmax(535.0, 535.0 + (bn - 64) * 0.60 + fmax(0.0, bn - 160.0) * 1.95);
-            const double epi = (geglu ? 28.0 : 9.0) * bn + 400.0;
+            const double epi = (geglu ? 20.0 : 9.0) * bn + 400.0;
             const double main_loop = k_iters_per_unit * cyc;
             const double total = rounds * fmax(main_loop, epi) + epi + 3000.0;
-            if (total < best.cycles) best = TilePlan{bn, pair != 0, n_tiles, total};
+            if (total < best.cycles) best = TilePlan{bn, pair != 0, n_tiles, total, 0, 1};
+            // the same tiles with the last wave cut along K
+            const int r = (int)(units % slots);
+            if (allow_tail && g_tail_mode > 0 && splits == 1 && !geglu && r > 0 && g_tail_ws) {
+                int ts = slots / r;
+                if (ts > k_iters_per_unit / 2) ts = k_iters_per_unit / 2;
+                if (ts > 16) ts = 16;
+                const long long ws_bytes = (long long)r * ts * (pair ? 2 : 1) * BM * bn * 4;
+                if (ts >= 2 && ws_bytes <= g_tail_bytes) {
+                    const double full_rounds = (double)(units / slots);
+                    const double slice = ceil_div(k_iters_per_unit, ts) * cyc;
+                    const double fix = 6000.0 + (double)ws_bytes * 2.0 / 3000.0;         // extra launch + partial write / read
+                    const double t2 = full_rounds * fmax(main_loop, epi) + slice + 4.0 * bn + 400.0 + epi + 3000.0 + fix;
+                    if (t2 < best_tail.cycles) best_tail = TilePlan{bn, pair != 0, n_tiles, t2, r, ts};
+                }
+            }
         }
     }
+    if (best_tail.tail_tiles > 0 && (g_tail_mode == 2 || best_tail.cycles < best.cycles)) return best_tail;
     return best;
 }
 
@@ -668,6 +790,17 @@ extern "C" {
 
 // 0 = single-CTA tiles only, 1 = cost model may choose CTA-pair (cta_group::2) tiles (default), 2 = force pairs
 int aoz_gemm_set_pair_mode(int mode) { g_pair_mode = mode; return AOZ_OK; }
+
+// 0 = never split the last wave along K, 1 = cost model decides (default), 2 = split whenever the shape allows it
+int aoz_gemm_set_tail_mode(int mode) { g_tail_mode = mode; return AOZ_OK; }
+
+// Caller-owned fp32 scratch for the K slices of tail tiles (stream-ordered: every GEMM that uses it must run on the
+// same stream).  Without it the tail split is off.  20 MB covers every shape (148 slices x 128 x 256 floats).
+int aoz_gemm_set_scratch(void* ptr, long long bytes) {
+    g_tail_ws = (float*)ptr;
+    g_tail_bytes = ptr ? bytes : 0;
+    return AOZ_OK;
+}
 
 int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }
 int aoz_gemm_debug_flags(int flags) { g_dbg = flags; return AOZ_OK; }
@@ -710,12 +843,16 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         AOZ_CHECK_ARG((N % 2) == 0 && !b_mn && splits == 1, "aoz_gemm_bf16: GEGLU needs even N, K-major B, no split");
         P.geglu_half = N / 2;
     }
-    const TilePlan tp = plan_tiles(P.m_tiles, geglu ? N / 2 : N, ceil_div(P.k_iters, splits), splits, b_mn != 0, geglu, 1);
+    const TilePlan tp = plan_tiles(P.m_tiles, geglu ? N / 2 : N, ceil_div(P.k_iters, splits), splits, b_mn != 0, geglu, 1,
+                                   /*allow_tail=*/splits == 1 && !geglu);
     const int bn = tp.bn;
     const bool pair = tp.pair;
     P.bn = bn;
     P.n_tiles = tp.n_tiles;
     P.splits = splits;
+    P.tail_tiles = tp.tail_tiles; P.tail_splits = tp.tail_splits;
+    P.vec_ok = ((((uintptr_t)C | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (ldc % 8) == 0 &&
+               (ld_rgb % 8) == 0 && (ldr % 8) == 0;
     if (splits > 1) {
         AOZ_CHECK_ARG(workspace != nullptr, "aoz_gemm_bf16: split-K needs a workspace");
         AOZ_CHECK_ARG(!bias && !residual && !rowgroup_bias, "aoz_gemm_bf16: split-K does not fuse bias/residual");
@@ -780,12 +917,14 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     P.k_iters = ks * ks * P.cin_chunks;
     P.M = NB * H * W; P.N = Cout; P.K = P.k_iters * 64;
     P.m_tiles = NB * P.tiles_h * P.tiles_w;
-    const TilePlan tp = plan_tiles(P.m_tiles, Cout, P.k_iters, 1, false, false, 1);
+    const TilePlan tp = plan_tiles(P.m_tiles, Cout, P.k_iters, 1, false, false, 1, /*allow_tail=*/true);
     const int bn = tp.bn;
     const bool pair = tp.pair;
     P.bn = bn;
     P.n_tiles = tp.n_tiles;
     P.splits = 1;
+    P.tail_tiles = tp.tail_tiles; P.tail_splits = tp.tail_splits;
+    P.vec_ok = ((((uintptr_t)y | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (Cout % 8) == 0;
     P.C = (__nv_bfloat16*)y; P.ldc = Cout;
     P.bias = (const __nv_bfloat16*)bias;
     P.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; P.ld_rgb = Cout;

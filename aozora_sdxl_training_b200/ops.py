@@ -57,6 +57,20 @@ def workspace(nfloats: int, device) -> torch.Tensor:
 # ------------------------------------------------------------------------------------------------------------
 EPI_STORE, EPI_GEGLU = 0, 1
 
+_gemm_scratch = {}
+GEMM_SCRATCH_BYTES = 24 << 20          # fp32 K slices of tail tiles (csrc/gemm.cu: tail split); 148 x 128 x 256 x 4 B fits
+
+
+def _ensure_gemm_scratch(device):
+    """Hand the library its caller-owned scratch once per device (one device per process: the pointer is process-global)."""
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    if key not in _gemm_scratch:
+        if _gemm_scratch:
+            raise _lib.AozoraError("aozora-b200 drives one GPU per process (launch one process per GPU)")
+        buf = torch.empty(GEMM_SCRATCH_BYTES, dtype=torch.uint8, device=device)
+        _lib.call("aoz_gemm_set_scratch", buf.data_ptr(), buf.numel())
+        _gemm_scratch[key] = buf
+
 
 def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bias=None, rows_per_group=0,
          epi=EPI_STORE, aux=None, out=None, accumulate=False, splits=None):
@@ -73,6 +87,7 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bia
     if K != Kb:
         raise _lib.AozoraError(f"gemm: K mismatch {K} vs {Kb}")
     n_out = N // 2 if epi == EPI_GEGLU else N
+    _ensure_gemm_scratch(a.device)
     if out is None:
         out = torch.empty((M, n_out), dtype=BF16, device=a.device)
     _chk(out, "gemm out", contiguous=False)
@@ -111,6 +126,7 @@ def conv_fwd(x, wpack, cout, ks, *, stride=1, pad=1, flip=False, bias=None, rowg
     NB, Hin, Win, Cin = x.shape
     H = (Hin + 2 * pad - ks) // stride + 1
     W = (Win + 2 * pad - ks) // stride + 1
+    _ensure_gemm_scratch(x.device)
     if out is None:
         out = torch.empty((NB, H, W, cout), dtype=BF16, device=x.device)
     _lib.call("aoz_conv_fwd_bf16", x.data_ptr(), NB, Hin, Win, Cin, wpack.data_ptr(), cout, ks, stride, pad, int(flip),

@@ -26,6 +26,7 @@ extern "C" {
 const char* aoz_last_error(void);
 int aoz_abi_version(void);
 int aoz_sm_count(void);
+long long aoz_launch_count(void);      /* kernels launched by this library so far (every launch site counts itself) */
 
 /* ---- optimizer: RavenAdamW.step / TitanAdamW.step (training_utils/optimizers/raven.py:89-149,
  *      titan.py:237-296) and torch.nn.utils.clip_grad_norm_ (train.py:2772-2781) ----------------------------
@@ -47,6 +48,11 @@ int aoz_clip_coef_from_sumsq(const void* sumsq, float max_norm, int emulate_bf16
  *      time/add embedding MLPs) forward, dgrad, wgrad; nn.Conv2d 3x3/1x1 as implicit GEMM -------------------- */
 int aoz_gemm_set_pair_mode(int mode);
 int aoz_gemm_force_bn(int bn);
+/* tail split: tiles of the last, partly filled wave are cut along K across the idle SMs (fp32 slices in the caller-owned
+ * scratch, finished by a fix-up kernel).  mode 0 = off, 1 = cost model decides (default), 2 = whenever possible.
+ * The scratch (>= 20 MB covers every shape) is used stream-ordered: all GEMM / conv calls must share one stream. */
+int aoz_gemm_set_tail_mode(int mode);
+int aoz_gemm_set_scratch(void* ptr, long long bytes);
 int aoz_gemm_debug_flags(int flags);
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn);
 int aoz_conv_wgrad_auto_splits(int NB, int H, int W, int Cout, int Cin, int ks);

@@ -48,6 +48,9 @@ def sweep(fn, b_mn, geglu=False):
     _lib.call("aoz_gemm_set_pair_mode", 1)
     _lib.call("aoz_gemm_force_bn", 0)
     out["auto"] = timeit_queued(fn)
+    _lib.call("aoz_gemm_set_tail_mode", 0)
+    out["auto_notail"] = timeit_queued(fn)
+    _lib.call("aoz_gemm_set_tail_mode", 1)
     step = 64 if b_mn else 32
     for pair in (0, 2):
         _lib.call("aoz_gemm_set_pair_mode", pair)
