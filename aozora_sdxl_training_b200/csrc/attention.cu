@@ -74,6 +74,14 @@ __device__ __forceinline__ void store_p_chunk(uint32_t p_addr, int r, int c0, co
         st_shared_v4(blk + sw128_offset(r, chunk0 + q), w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
 }
 
+// write 16 consecutive bf16 values (8 words) of row `r`, columns [c0, c0+16) of a [128,128] P tile
+__device__ __forceinline__ void store_p_16(uint32_t p_addr, int r, int c0, const uint32_t* w) {
+    const uint32_t blk = p_addr + (c0 >> 6) * TILE_BYTES;
+    const int chunk0 = (c0 & 63) >> 3;
+    st_shared_v4(blk + sw128_offset(r, chunk0), w[0], w[1], w[2], w[3]);
+    st_shared_v4(blk + sw128_offset(r, chunk0 + 1), w[4], w[5], w[6], w[7]);
+}
+
 // ================================================================================================
 // forward
 // ================================================================================================
@@ -186,34 +194,74 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
         float* xsum = (float*)(smem + FwdSmem::XCH);                     // [128] fp32, used once at the end
         const float sl2 = P.scale * LOG2E;
         float m_ref = -INFINITY, l = 0.f;
+        // exp2(s * sl2 - m_ref) of this thread's 64 columns -> bf16 P tile in shared memory; returns the partial row sum and
+        // (through mx) the raw maximum.  ONE pass over TMEM: reading S is the scarce resource (64 B/clk/SM), not the math.
+        auto softmax_pass = [&](int kvalid, bool full, float& mx) -> float {
+            float lsum = 0.f;
+#pragma unroll 1
+            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
+                uint32_t v[32], w[16];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tc_wait_ld();
+                if (full) {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+                        mx = fmaxf(mx, fmaxf(s0, s1));
+                        const float p0 = fast_exp2(fmaf(s0, sl2, -m_ref));
+                        const float p1 = fast_exp2(fmaf(s1, sl2, -m_ref));
+                        lsum += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 32; e += 2) {
+                        const bool ok0 = c * 32 + e < kvalid, ok1 = c * 32 + e + 1 < kvalid;
+                        const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+                        if (ok0) mx = fmaxf(mx, s0);
+                        if (ok1) mx = fmaxf(mx, s1);
+                        const float p0 = ok0 ? fast_exp2(fmaf(s0, sl2, -m_ref)) : 0.f;
+                        const float p1 = ok1 ? fast_exp2(fmaf(s1, sl2, -m_ref)) : 0.f;
+                        lsum += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
+                }
+                store_p_chunk(sP, r, c * 32, w);
+            }
+            return lsum;
+        };
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_ready, j & 1);
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;              // keys >= kvalid are padding
             const bool full = kvalid >= TILE;                // warp-uniform: full tiles skip every per-element predicate
-            float mx = -3.0e38f;
+            if (j == 0) {
+                // first tile: a max-only pass seeds the reference (rounded up to bf16: both threads of a row must use the SAME one)
+                float mx = -3.0e38f;
 #pragma unroll 1
-            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
-                uint32_t v[32];
-                tmem_ld32(tS + lane_off + c * 32, v);
-                tc_wait_ld();
-                if (full) {
-#pragma unroll
-                    for (int e = 0; e < 32; ++e) mx = fmaxf(mx, __uint_as_float(v[e]));
-                } else {
+                for (int c = hf * 2; c < hf * 2 + 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tc_wait_ld();
 #pragma unroll
                     for (int e = 0; e < 32; ++e)
-                        if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+                        if (full || c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
                 }
-            }
-            // exchange the half-row maxima (rounded up to bf16: both threads of a row must use the SAME reference)
-            mx = bf16_ceil(mx * sl2);
-            xmax[hf * 128 + r] = __float2bfloat16_rn(mx);    // exact: mx is bf16-representable
-            named_bar_sync(1, 256);
-            mx = fmaxf(mx, __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
-            if (j == 0) {
-                m_ref = mx;
+                mx = bf16_ceil(mx * sl2);
+                xmax[hf * 128 + r] = __float2bfloat16_rn(mx);    // exact: mx is bf16-representable
+                named_bar_sync(1, 256);
+                m_ref = fmaxf(mx, __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
+                named_bar_sync(1, 256);                          // xmax is reused by the next tile
+                float dummy = -3.0e38f;
+                l = softmax_pass(kvalid, full, dummy);
             } else {
+                // optimistic single pass against the running reference; redo only if the row maximum jumped by > 2^8
+                float mx = -3.0e38f;
+                float lsum = softmax_pass(kvalid, full, mx);
+                mx = bf16_ceil(mx * sl2);
+                xmax[hf * 128 + r] = __float2bfloat16_rn(mx);
+                named_bar_sync(1, 256);
+                mx = fmaxf(mx, __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
                 const float m_new = fmaxf(m_ref, mx);
                 const bool need = (m_new - m_ref) > 8.0f;
                 if (__any_sync(0xffffffffu, need)) {         // identical decision in both warps that share these rows
@@ -227,31 +275,11 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                     tc_wait_st();
                     l *= alpha;
                     m_ref = m_new;
+                    float dummy = -3.0e38f;
+                    lsum = softmax_pass(kvalid, full, dummy);    // P of this tile again, against the new reference
                 }
-            }
-#pragma unroll 1
-            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
-                uint32_t v[32], w[16];
-                tmem_ld32(tS + lane_off + c * 32, v);
-                tc_wait_ld();
-                if (full) {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const float p0 = fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref));
-                        const float p1 = fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref));
-                        l += p0 + p1;
-                        w[e >> 1] = pack_bf16(p0, p1);
-                    }
-                } else {
-#pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        float p0 = (c * 32 + e < kvalid) ? fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref)) : 0.f;
-                        float p1 = (c * 32 + e + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref)) : 0.f;
-                        l += p0 + p1;
-                        w[e >> 1] = pack_bf16(p0, p1);
-                    }
-                }
-                store_p_chunk(sP, r, c * 32, w);
+                l += lsum;
+                named_bar_sync(1, 256);                          // xmax is reused by the next tile
             }
             fence_proxy_async_smem();
             tc_fence_before();
@@ -430,48 +458,75 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
         const float sl2 = P.scale * LOG2E;
         const bool key_ok = (k0 + r) < P.Tk;
+        // per-query LSE / D of the NEXT Q tile are fetched one tile ahead (their global-load latency hides behind this tile's math)
+        float nx_lse = INFINITY, nx_d = 0.f;
+        auto fetch_vec = [&](int i) {
+            const int q = i * TILE + r;
+            const long long idx = ((long long)b * P.H + h) * P.Tq + q;
+            nx_lse = q < P.Tq ? P.lse[idx] : INFINITY;                   // +inf -> P = 0 for padded queries (scaled by
+            nx_d = q < P.Tq ? P.Dvec[idx] : 0.f;                         // log2 e when consumed: no use of the loads here)
+        };
+        if (hf == 0) fetch_vec(0);
         for (int i = 0; i < nq; ++i) {
             float* lse2 = vec + (i & 1) * 256;
             float* dv = lse2 + 128;
             if (hf == 0) {
-                const int q = i * TILE + r;
-                const long long idx = ((long long)b * P.H + h) * P.Tq + q;
-                lse2[r] = q < P.Tq ? P.lse[idx] * LOG2E : INFINITY;      // +inf -> P = 0 for padded queries
-                dv[r] = q < P.Tq ? P.Dvec[idx] : 0.f;
+                lse2[r] = nx_lse * LOG2E;
+                dv[r] = nx_d;
             }
             named_bar_sync(1, 256);
+            if (hf == 0 && i + 1 < nq) fetch_vec(i + 1);
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
-            // pull this thread's 64 columns of S^T and dP^T out of TMEM, then release TMEM for the next tile's MMAs
-            uint32_t vs[64], vp[64];
-            tmem_ld32(tSt + lane_off + hf * 64, vs);
-            tmem_ld32(tSt + lane_off + hf * 64 + 32, vs + 32);
-            tmem_ld32(tdPt + lane_off + hf * 64, vp);
-            tmem_ld32(tdPt + lane_off + hf * 64 + 32, vp + 32);
-            tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(st_free);
-            uint32_t wp[32], wd[32];
+            // This thread's 64 columns of S^T and dP^T in four 16-column chunks, software-pipelined: the tcgen05.ld of chunk
+            // c+1 is in flight while chunk c goes through the exp / dS math, so the TMEM read port (the scarce resource at
+            // 64 B/clk/SM) and the MUFU / FMA pipes work at the same time.  TMEM is released for the next tile's score MMAs
+            // as soon as the last chunk has landed in registers.
+            uint32_t vs[2][16], vp[2][16], hp[2][8], hd[2][8];
+            tmem_ld16(tSt + lane_off + hf * 64, vs[0]);
+            tmem_ld16(tdPt + lane_off + hf * 64, vp[0]);
 #pragma unroll
-            for (int e = 0; e < 64; e += 4) {
-                const int qa = hf * 64 + e;
-                const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
-                const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
-                float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -ls.x));
-                float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -ls.y));
-                float p2 = fast_exp2(fmaf(__uint_as_float(vs[e + 2]), sl2, -ls.z));
-                float p3 = fast_exp2(fmaf(__uint_as_float(vs[e + 3]), sl2, -ls.w));
-                if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-                wp[e >> 1] = pack_bf16(p0, p1);
-                wp[(e >> 1) + 1] = pack_bf16(p2, p3);
-                wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dd.x), p1 * (__uint_as_float(vp[e + 1]) - dd.y));
-                wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(vp[e + 2]) - dd.z), p3 * (__uint_as_float(vp[e + 3]) - dd.w));
+            for (int c = 0; c < 4; ++c) {
+                tc_wait_ld();
+                if (c + 1 < 4) {
+                    tmem_ld16(tSt + lane_off + hf * 64 + (c + 1) * 16, vs[(c + 1) & 1]);
+                    tmem_ld16(tdPt + lane_off + hf * 64 + (c + 1) * 16, vp[(c + 1) & 1]);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive(st_free);
+                }
+                uint32_t* wp = hp[c & 1];
+                uint32_t* wd = hd[c & 1];
+                const uint32_t* cs = vs[c & 1];
+                const uint32_t* cp = vp[c & 1];
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    const int qa = hf * 64 + c * 16 + e;
+                    const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
+                    const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
+                    float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -ls.x));
+                    float p1 = fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -ls.y));
+                    float p2 = fast_exp2(fmaf(__uint_as_float(cs[e + 2]), sl2, -ls.z));
+                    float p3 = fast_exp2(fmaf(__uint_as_float(cs[e + 3]), sl2, -ls.w));
+                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
+                    wp[e >> 1] = pack_bf16(p0, p1);
+                    wp[(e >> 1) + 1] = pack_bf16(p2, p3);
+                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dd.x), p1 * (__uint_as_float(cp[e + 1]) - dd.y));
+                    wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(cp[e + 2]) - dd.z), p3 * (__uint_as_float(cp[e + 3]) - dd.w));
+                }
+                // chunks 0 and 1 wait in registers: the previous tile's dV / dK MMAs (issued when that tile's P^T / dS^T were
+                // complete) still read these smem tiles for the first few hundred cycles of this tile
+                if (c == 1) {
+                    if (i > 0) mbar_wait(pd_free, (i - 1) & 1);
+                    store_p_16(sPT, r, hf * 64, hp[0]);
+                    store_p_16(sDST, r, hf * 64, hd[0]);
+                    store_p_16(sPT, r, hf * 64 + 16, hp[1]);
+                    store_p_16(sDST, r, hf * 64 + 16, hd[1]);
+                } else if (c >= 2) {
+                    store_p_16(sPT, r, hf * 64 + c * 16, wp);
+                    store_p_16(sDST, r, hf * 64 + c * 16, wd);
+                }
             }
-            if (i > 0) mbar_wait(pd_free, (i - 1) & 1);          // the previous tile's dV / dK MMAs no longer read these smem tiles
-            store_p_chunk(sPT, r, hf * 64, wp);
-            store_p_chunk(sPT, r, hf * 64 + 32, wp + 16);
-            store_p_chunk(sDST, r, hf * 64, wd);
-            store_p_chunk(sDST, r, hf * 64 + 32, wd + 16);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(pds_ready);
@@ -625,33 +680,47 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(s_ready, j & 1);
             tc_fence_after();
             const int kvalid = P.Tk - j * TILE;
-            uint32_t vs[64], vp[64], wd[32];
-            tmem_ld32(tS + lane_off + hf * 64, vs);
-            tmem_ld32(tS + lane_off + hf * 64 + 32, vs + 32);
-            tmem_ld32(tdP + lane_off + hf * 64, vp);
-            tmem_ld32(tdP + lane_off + hf * 64 + 32, vp + 32);
-            tc_wait_ld();
-            tc_fence_before();
-            mbar_arrive(st_free);                            // TMEM S / dP may be overwritten by the next tile's MMAs
-            if (kvalid >= TILE) {
+            // four 16-column chunks, software-pipelined like the dK/dV kernel
+            uint32_t vs[2][16], vp[2][16], hd[2][8];
+            tmem_ld16(tS + lane_off + hf * 64, vs[0]);
+            tmem_ld16(tdP + lane_off + hf * 64, vp[0]);
 #pragma unroll
-                for (int e = 0; e < 64; e += 2) {
-                    const float p0 = fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2));
-                    const float p1 = fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2));
-                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+            for (int c = 0; c < 4; ++c) {
+                tc_wait_ld();
+                if (c + 1 < 4) {
+                    tmem_ld16(tS + lane_off + hf * 64 + (c + 1) * 16, vs[(c + 1) & 1]);
+                    tmem_ld16(tdP + lane_off + hf * 64 + (c + 1) * 16, vp[(c + 1) & 1]);
+                } else {
+                    tc_fence_before();
+                    mbar_arrive(st_free);                    // TMEM S / dP may be overwritten by the next tile's MMAs
                 }
-            } else {
+                uint32_t* wd = hd[c & 1];
+                const uint32_t* cs = vs[c & 1];
+                const uint32_t* cp = vp[c & 1];
+                if (kvalid >= TILE) {
 #pragma unroll
-                for (int e = 0; e < 64; e += 2) {
-                    const int ka = hf * 64 + e;
-                    float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e]), sl2, -lse2)) : 0.f;
-                    float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(vs[e + 1]), sl2, -lse2)) : 0.f;
-                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(vp[e]) - dvec), p1 * (__uint_as_float(vp[e + 1]) - dvec));
+                    for (int e = 0; e < 16; e += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -lse2));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -lse2));
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dvec), p1 * (__uint_as_float(cp[e + 1]) - dvec));
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const int ka = hf * 64 + c * 16 + e;
+                        float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -lse2)) : 0.f;
+                        float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -lse2)) : 0.f;
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dvec), p1 * (__uint_as_float(cp[e + 1]) - dvec));
+                    }
+                }
+                if (c == 1) {                                // see the dK/dV kernel: the previous tile's dQ MMAs still read sDS
+                    if (j > 0) mbar_wait(ds_free, (j - 1) & 1);
+                    store_p_16(sDS, r, hf * 64, hd[0]);
+                    store_p_16(sDS, r, hf * 64 + 16, hd[1]);
+                } else if (c >= 2) {
+                    store_p_16(sDS, r, hf * 64 + c * 16, wd);
                 }
             }
-            if (j > 0) mbar_wait(ds_free, (j - 1) & 1);
-            store_p_chunk(sDS, r, hf * 64, wd);
-            store_p_chunk(sDS, r, hf * 64 + 32, wd + 16);
             fence_proxy_async_smem();
             tc_fence_before();
             mbar_arrive(ds_ready);

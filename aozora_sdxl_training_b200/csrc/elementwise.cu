@@ -262,11 +262,16 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, long
 }
 
 // ---- column sums: out[c] = sum_r x[r, c]  (bias gradients) ---------------------------------------------------
-// stage 1: grid (col blocks of 256 channels via 32 vectors, row chunks) -> partial [chunks][N]
+// One launch: grid (col blocks of 256 channels via 32 vectors, row chunks, groups).  Every block writes its partial
+// [chunk][N] row; the LAST block to finish a (group, column block) -- found with a self-resetting atomicInc ticket --
+// sums the chunk partials in fixed order (deterministic) and writes the bf16 result.  No second launch.
+__device__ unsigned int g_colsum_tickets[4096];     // zero at module load; atomicInc wraps back to zero after every use
+
 __global__ void __launch_bounds__(256)
-colsum_partial_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
-                      float* __restrict__ partial0) {
+colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
+              float* __restrict__ partial0, __nv_bfloat16* __restrict__ out0, int accumulate) {
     __shared__ float sm[8][256];
+    __shared__ unsigned int s_last;
     const __nv_bfloat16* x = x0 + (long long)blockIdx.z * group_stride;
     float* partial = partial0 + (long long)blockIdx.z * gridDim.y * N;
     const int vcol = blockIdx.x * 32 + (threadIdx.x & 31);     // vector column (8 channels)
@@ -276,7 +281,16 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, 
     const long long r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (vcol * 8 < N) {
-        for (long long r = r0 + rl; r < r1; r += 8) {
+        long long r = r0 + rl;
+        for (; r + 8 < r1; r += 16) {                          // two rows in flight per thread
+            float f[8], g[8];
+            const uint4 a = ld_stream(x + r * ld + vcol * 8);
+            const uint4 b = ld_stream(x + (r + 8) * ld + vcol * 8);
+            unpack8e(a, f); unpack8e(b, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) acc[e] += f[e] + g[e];
+        }
+        if (r < r1) {
             float f[8];
             unpack8e(ld_stream(x + r * ld + vcol * 8), f);
 #pragma unroll
@@ -292,16 +306,23 @@ colsum_partial_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, 
     for (int k = 0; k < 8; ++k) s += sm[k][c];
     const int col = blockIdx.x * 256 + c;
     if (col < N) partial[(long long)blockIdx.y * N + col] = s;
-}
-__global__ void colsum_finalize_kernel(const float* __restrict__ partial0, int chunks, int N, __nv_bfloat16* __restrict__ out0, int accumulate) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= N) return;
-    const float* partial = partial0 + (long long)blockIdx.y * chunks * N;
-    __nv_bfloat16* out = out0 + (long long)blockIdx.y * N;
-    float s = 0.f;
-    for (int k = 0; k < chunks; ++k) s += partial[(long long)k * N + c];
-    if (accumulate) s = round_bf16(s) + __bfloat162float(out[c]);
-    out[c] = __float2bfloat16_rn(s);
+    // ticket: the last of the `chunks` blocks of this (group, column block) finishes the sum
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicInc(&g_colsum_tickets[(blockIdx.z * gridDim.x + blockIdx.x) & 4095], (unsigned int)chunks - 1);
+        s_last = (t == (unsigned int)chunks - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (col < N) {
+        float t = 0.f;
+        for (int k = 0; k < chunks; ++k) t += __ldcg(partial + (long long)k * N + col);
+        __nv_bfloat16* out = out0 + (long long)blockIdx.z * N;
+        if (accumulate) t = round_bf16(t) + __bfloat162float(out[col]);
+        out[col] = __float2bfloat16_rn(t);
+    }
 }
 
 // ---- conv weight packing: OIHW -> [Cout][taps][CinPad] (forward) and [Cin][taps][CoutPad] (dgrad) -------------
@@ -497,10 +518,10 @@ int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long
     if (chunks > 64) chunks = 64;
     if ((long long)chunks > (M + 7) / 8) chunks = (int)((M + 7) / 8);
     if (chunks < 1) chunks = 1;
-    colsum_partial_kernel<<<dim3(colblocks, chunks, groups), 256, 0, s>>>((const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace);
-    AOZ_CHECK_LAUNCH("colsum_partial_kernel");
-    colsum_finalize_kernel<<<dim3((N + 255) / 256, groups), 256, 0, s>>>((const float*)workspace, chunks, N, (__nv_bfloat16*)out, accumulate);
-    AOZ_CHECK_LAUNCH("colsum_finalize_kernel");
+    AOZ_CHECK_ARG((long long)colblocks * groups <= 4096, "aoz_colsum: too many column blocks (%d x %d)", colblocks, groups);
+    colsum_kernel<<<dim3(colblocks, chunks, groups), 256, 0, s>>>((const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace,
+                                                                 (__nv_bfloat16*)out, accumulate);
+    AOZ_CHECK_LAUNCH("colsum_kernel");
     return AOZ_OK;
 }
 

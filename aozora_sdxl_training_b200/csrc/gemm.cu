@@ -27,7 +27,8 @@ constexpr int BK = 64;
 constexpr int GEMM_THREADS = 320;   // 10 warps: TMA, MMA, 8 epilogue
 constexpr int MAX_STAGES = 8;
 constexpr int SMEM_TILE_BYTES = 196608;                 // 192 KB ring of A/B stages
-constexpr int GEMM_SMEM_TOTAL = SMEM_TILE_BYTES + 1024 + 1024;   // + barriers + alignment slack
+constexpr int EPI_STAGE_BYTES = 8 * 4096;               // 8 epilogue warps x (32 rows x 32 fp32): register-layout -> row-segment transpose
+constexpr int GEMM_SMEM_TOTAL = SMEM_TILE_BYTES + 1024 + EPI_STAGE_BYTES + 1024;   // + barriers + staging + alignment slack (226 KB)
 
 enum GemmMode : int { GM_LINEAR = 0, GM_CONV_FWD = 1, GM_CONV_WGRAD = 2 };
 enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
@@ -113,6 +114,30 @@ __device__ __forceinline__ void tmem_alloc2(uint32_t* smem_result, uint32_t ncol
 }
 __device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(ncols) : "memory");
+}
+
+__device__ __forceinline__ void st_shared_v4u(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+    asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ void ld_shared_v4f(uint32_t addr, float* f) {
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(f[0]), "=f"(f[1]), "=f"(f[2]), "=f"(f[3]) : "r"(addr) : "memory");
+}
+// Epilogue transpose.  tcgen05.ld hands every thread ONE accumulator row (32 consecutive fp32 columns); storing from that
+// layout makes each warp store touch 32 different rows with 16 bytes each -- half-used sectors, ~5 cycles per transaction,
+// ~21k cycles per 128x256 tile, which made every K <= 1280 GEMM epilogue-bound.  Each warp therefore bounces its 32x32
+// chunk through 4 KB of shared memory (XOR-swizzled 16-byte chunks, conflict-free both ways) and continues with 4 lanes
+// per row: lane l owns row (l >> 2) + 8*step, columns (l & 3)*8..+8, so loads of the residual and stores of the result
+// are 64-byte row segments (full sectors), 8 rows per instruction.
+__device__ __forceinline__ void stage_chunk(uint32_t stg, int lane, const uint32_t* r) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+        st_shared_v4u(stg + lane * 128 + ((j ^ (lane & 7)) << 4), r[4 * j], r[4 * j + 1], r[4 * j + 2], r[4 * j + 3]);
+}
+__device__ __forceinline__ void unstage8(uint32_t stg, int lane, int step, float* f) {
+    const int rr = step * 8 + (lane >> 2);
+    const int j0 = (lane & 3) * 2;
+    ld_shared_v4f(stg + rr * 128 + ((j0 ^ (rr & 7)) << 4), f);
+    ld_shared_v4f(stg + rr * 128 + (((j0 + 1) ^ (rr & 7)) << 4), f + 4);
 }
 
 struct WorkItem { int tile, split, k_begin, k_end, tail_slot; };      // tail_slot < 0: not a tail slice
@@ -416,6 +441,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         const int q = warp & 3;                       // TMEM lane quarter this warp may access
         const int half = (warp - 2) >> 2;             // 0: even chunks, 1: odd chunks
         const int row_in_tile = q * 32 + lane;
+        const uint32_t stg = smem_u32(bar_base + 1024) + (uint32_t)(warp - 2) * 4096;     // this warp's 4 KB transpose buffer
         uint32_t acc = 0, acc_phase = 0;
         for (int work = unit; work < total_work; work += n_units) {
             const WorkItem wi = decode_work(P, work, k_per_split);
@@ -448,47 +474,62 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             if (P.dbg & 1) goto epilogue_done;
             {
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            const int lcol = (lane & 3) * 8;               // this lane's 8 columns inside a 32-column chunk (transposed layout)
 
             if (P.epi == EPI_GEGLU) {
                 // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
+                RowMap rmap[4];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, m_blk, q * 32 + st * 8 + (lane >> 2));
 #pragma unroll 1
                 for (int c = half * 32; c < BN / 2; c += 64) {
                     uint32_t rv[32], rg[32];
                     tmem_ld32(taddr + c, rv);
                     tmem_ld32(taddr + BN / 2 + c, rg);
                     tc_wait_ld();
-                    if (row_ok) {
-                        const int cbase = col0 + c;
+                    float hv[4][8];
+                    stage_chunk(stg, lane, rv);
+                    __syncwarp();
 #pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            if (cbase + j < col_limit) {     // N/2 is a multiple of 8 for every SDXL layer
-                                uint32_t ov[4], oh[4], og[4];
-                                uint32_t bh[4] = {0u, 0u, 0u, 0u}, bg[4] = {0u, 0u, 0u, 0u};
-                                if (P.bias) {       // N/2 and the tile origin are multiples of 8: 16-byte aligned vectors
-                                    const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(P.bias + cbase + j));
-                                    const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(P.bias + P.geglu_half + cbase + j));
-                                    bh[0] = t0.x; bh[1] = t0.y; bh[2] = t0.z; bh[3] = t0.w;
-                                    bg[0] = t1.x; bg[1] = t1.y; bg[2] = t1.z; bg[3] = t1.w;
-                                }
+                    for (int st = 0; st < 4; ++st) unstage8(stg, lane, st, hv[st]);
+                    __syncwarp();
+                    stage_chunk(stg, lane, rg);
+                    __syncwarp();
+                    const int col = col0 + c + lcol;
+                    if (col < col_limit) {                   // N/2 is a multiple of 8 for every SDXL layer
+                        uint32_t bh[4] = {0u, 0u, 0u, 0u}, bg[4] = {0u, 0u, 0u, 0u};
+                        if (P.bias) {       // N/2 and the tile origin are multiples of 8: 16-byte aligned vectors
+                            const uint4 t0 = __ldg(reinterpret_cast<const uint4*>(P.bias + col));
+                            const uint4 t1 = __ldg(reinterpret_cast<const uint4*>(P.bias + P.geglu_half + col));
+                            bh[0] = t0.x; bh[1] = t0.y; bh[2] = t0.z; bh[3] = t0.w;
+                            bg[0] = t1.x; bg[1] = t1.y; bg[2] = t1.z; bg[3] = t1.w;
+                        }
 #pragma unroll
-                                for (int e = 0; e < 8; e += 2) {
-                                    float h0 = __uint_as_float(rv[j + e]) + bf16lo(bh[e >> 1]), h1 = __uint_as_float(rv[j + e + 1]) + bf16hi(bh[e >> 1]);
-                                    float g0 = __uint_as_float(rg[j + e]) + bf16lo(bg[e >> 1]), g1 = __uint_as_float(rg[j + e + 1]) + bf16hi(bg[e >> 1]);
-                                    // autocast-faithful rounding points: linear out -> bf16, gelu -> bf16, product -> bf16
-                                    h0 = round_bf16(h0); h1 = round_bf16(h1); g0 = round_bf16(g0); g1 = round_bf16(g1);
-                                    oh[e >> 1] = pack_bf16(h0, h1);
-                                    og[e >> 1] = pack_bf16(g0, g1);
-                                    const float a0 = round_bf16(gelu_erf(g0)), a1 = round_bf16(gelu_erf(g1));
-                                    ov[e >> 1] = pack_bf16(h0 * a0, h1 * a1);
-                                }
-                                *reinterpret_cast<uint4*>(P.C + row * P.ldc + cbase + j) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
-                                if (P.aux) {
-                                    *reinterpret_cast<uint4*>(P.aux + row * P.ld_aux + cbase + j) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
-                                    *reinterpret_cast<uint4*>(P.aux + row * P.ld_aux + P.geglu_half + cbase + j) = make_uint4(og[0], og[1], og[2], og[3]);
-                                }
+                        for (int st = 0; st < 4; ++st) {
+                            float gv[8];
+                            unstage8(stg, lane, st, gv);
+                            if (!rmap[st].ok) continue;
+                            const long long orow = rmap[st].row;
+                            uint32_t ov[4], oh[4], og[4];
+#pragma unroll
+                            for (int e = 0; e < 8; e += 2) {
+                                float h0 = hv[st][e] + bf16lo(bh[e >> 1]), h1 = hv[st][e + 1] + bf16hi(bh[e >> 1]);
+                                float g0 = gv[e] + bf16lo(bg[e >> 1]), g1 = gv[e + 1] + bf16hi(bg[e >> 1]);
+                                // autocast-faithful rounding points: linear out -> bf16, gelu -> bf16, product -> bf16
+                                h0 = round_bf16(h0); h1 = round_bf16(h1); g0 = round_bf16(g0); g1 = round_bf16(g1);
+                                oh[e >> 1] = pack_bf16(h0, h1);
+                                og[e >> 1] = pack_bf16(g0, g1);
+                                const float a0 = round_bf16(gelu_erf(g0)), a1 = round_bf16(gelu_erf(g1));
+                                ov[e >> 1] = pack_bf16(h0 * a0, h1 * a1);
+                            }
+                            *reinterpret_cast<uint4*>(P.C + orow * P.ldc + col) = make_uint4(ov[0], ov[1], ov[2], ov[3]);
+                            if (P.aux) {
+                                *reinterpret_cast<uint4*>(P.aux + orow * P.ld_aux + col) = make_uint4(oh[0], oh[1], oh[2], oh[3]);
+                                *reinterpret_cast<uint4*>(P.aux + orow * P.ld_aux + P.geglu_half + col) = make_uint4(og[0], og[1], og[2], og[3]);
                             }
                         }
                     }
+                    __syncwarp();
                 }
             } else if (wi.tail_slot >= 0) {
                 // K slice of a tail tile: raw fp32 accumulator rows to the scratch buffer, [slice][128][BN]
@@ -506,7 +547,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dstp + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
                 }
-            } else {
+            } else if (P.epi == EPI_PARTIAL) {
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
                     if (col0 + c >= col_limit) break;          // warp-uniform
@@ -520,26 +561,42 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     }
                     if (!row_ok) continue;
                     const int cbase = col0 + c;
-                    if (P.epi == EPI_PARTIAL) {
-                        float* dst = P.partial + ((long long)split * P.M + row) * P.N + col_shift + cbase;
+                    float* dst = P.partial + ((long long)split * P.M + row) * P.N + col_shift + cbase;
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) {
-                            if (cbase + j + 3 < col_limit && ((((uintptr_t)(dst + j)) & 15) == 0)) {
-                                *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
-                            } else {
-                                for (int e = 0; e < 4; ++e)
-                                    if (cbase + j + e < col_limit) dst[j + e] = __uint_as_float(r[j + e]);
-                            }
-                        }
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j += 8) {
-                            float f[8];
-#pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = __uint_as_float(r[j + e]);
-                            epi_store8(P, row, group, cbase + j, col_limit, f);
+                    for (int j = 0; j < 32; j += 4) {
+                        if (cbase + j + 3 < col_limit && ((((uintptr_t)(dst + j)) & 15) == 0)) {
+                            *reinterpret_cast<uint4*>(dst + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
+                        } else {
+                            for (int e = 0; e < 4; ++e)
+                                if (cbase + j + e < col_limit) dst[j + e] = __uint_as_float(r[j + e]);
                         }
                     }
+                }
+            } else {
+                RowMap rmap[4];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, m_blk, q * 32 + st * 8 + (lane >> 2));
+#pragma unroll 1
+                for (int c = half * 32; c < OUT_COLS; c += 64) {
+                    if (col0 + c >= col_limit) break;          // warp-uniform
+                    uint32_t r[32];
+                    if (!empty_split) {
+                        tmem_ld32(taddr + c, r);
+                        tc_wait_ld();
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) r[j] = 0u;
+                    }
+                    stage_chunk(stg, lane, r);
+                    __syncwarp();
+                    const int col = col0 + c + lcol;
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        float f[8];
+                        unstage8(stg, lane, st, f);
+                        if (rmap[st].ok && col < col_limit) epi_store8(P, rmap[st].row, rmap[st].group, col, col_limit, f);
+                    }
+                    __syncwarp();
                 }
             }
             }
@@ -564,33 +621,37 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 }
 
 // ---- tail fix-up: sum the K slices of the tail tiles and apply the fused EPI_STORE epilogue -----------------------
-// grid = tail_tiles x m_sub x (bn / 32); 128 threads = the 128 rows of one (sub-)tile; a block owns 32 columns.
+// grid = tail_tiles x m_sub x 4 row blocks x (bn / 32) column blocks; a 128-thread block owns 32 rows x 32 columns:
+// 4 lanes cover the 32 columns (128 B) of one row, so a warp reads 8 whole rows of a slice per step (coalesced) and
+// writes 8 x 64-byte output segments.
 __global__ void __launch_bounds__(128)
 tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
     const int chunks = P.bn / 32;
     int b = blockIdx.x;
     const int chunk = b % chunks; b /= chunks;
+    const int rblk = b & 3; b >>= 2;
     const int sub = b % m_sub;
     const int t = b / m_sub;
     const int tile = P.full_work + t;                       // tail split implies splits == 1
     const int m_blk = (tile % P.m_tiles) * m_sub + sub, n_blk = tile / P.m_tiles;
-    const int row_in_tile = threadIdx.x;
+    const int row_in_tile = rblk * 32 + (threadIdx.x >> 2);
+    const int cq = (threadIdx.x & 3) * 8;                   // this lane's 8 columns inside the 32-column block
     const RowMap rm = map_row(P, m_blk, row_in_tile);
-    const int col0 = n_blk * P.bn + chunk * 32;
-    if (!rm.ok || col0 >= P.N) return;
-    float acc[32];
+    const int col = n_blk * P.bn + chunk * 32 + cq;
+    if (!rm.ok || col >= P.N) return;
+    float acc[8];
 #pragma unroll
-    for (int j = 0; j < 32; ++j) acc[j] = 0.f;
+    for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+    const long long slice_stride = (long long)m_sub * BM * P.bn;
+    const float* src = P.tail_ws + ((long long)(t * P.tail_splits * m_sub + sub) * BM + row_in_tile) * P.bn + chunk * 32 + cq;
+#pragma unroll 4
     for (int sp = 0; sp < P.tail_splits; ++sp) {
-        const float* src = P.tail_ws + ((long long)((t * P.tail_splits + sp) * m_sub + sub) * BM + row_in_tile) * P.bn + chunk * 32;
-#pragma unroll
-        for (int j = 0; j < 32; j += 4) {
-            const float4 v = *reinterpret_cast<const float4*>(src + j);
-            acc[j] += v.x; acc[j + 1] += v.y; acc[j + 2] += v.z; acc[j + 3] += v.w;
-        }
+        const float4 v0 = *reinterpret_cast<const float4*>(src + sp * slice_stride);
+        const float4 v1 = *reinterpret_cast<const float4*>(src + sp * slice_stride + 4);
+        acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
+        acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
     }
-#pragma unroll
-    for (int j = 0; j < 32; j += 8) epi_store8(P, rm.row, rm.group, col0 + j, P.N, acc + j);
+    epi_store8(P, rm.row, rm.group, col, P.N, acc);
 }
 
 // ---- split-K reduction: sum fp32 partials, optional accumulate into existing bf16, optional OIHW permute ----
@@ -602,23 +663,6 @@ __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
                      __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin, int cin_real, int accumulate) {
     const long long total = rows * cols;
-    if (permute_taps > 0) {
-        const long long items = rows * Cin;
-        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < items; i += (long long)gridDim.x * blockDim.x) {
-            const long long row = i / Cin;
-            const int cin = (int)(i - row * Cin);
-            if (cin >= cin_real) continue;
-            __nv_bfloat16* o = out + (row * cin_real + cin) * permute_taps;
-            for (int tap = 0; tap < permute_taps; ++tap) {
-                const long long idx = row * cols + (long long)tap * Cin + cin;
-                float sum = 0.f;
-                for (int k = 0; k < splits; ++k) sum += partial[(long long)k * total + idx];
-                if (accumulate) sum = round_bf16(sum) + __bfloat162float(o[tap]);
-                o[tap] = __float2bfloat16_rn(sum);
-            }
-        }
-        return;
-    }
     if ((cols & 3) == 0 && (ld_out & 3) == 0 && ((((uintptr_t)out) & 7) == 0)) {
         const long long quads = total >> 2;
         for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < quads; i += (long long)gridDim.x * blockDim.x) {
@@ -646,6 +690,35 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long ro
         const long long o = row * ld_out + col;
         if (accumulate) sum = round_bf16(sum) + __bfloat162float(out[o]);
         out[o] = __float2bfloat16_rn(sum);
+    }
+}
+
+// conv weight-gradient finish: partial [splits][rows][taps*Cin] fp32 -> OIHW bf16 [rows][cin_real][taps].
+// One block = one output row x 128 input channels: per tap the 128 threads read 512 contiguous bytes of every split,
+// the [cin][tap] block is transposed through shared memory (stride 9: conflict-free) and leaves as one contiguous run.
+__global__ void __launch_bounds__(128)
+wgrad_permute_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, int Cin, int cin_real, int taps,
+                            __nv_bfloat16* __restrict__ out, int accumulate) {
+    __shared__ float sm[128 * 9];
+    const long long row = blockIdx.y;
+    const int c0 = blockIdx.x * 128, c = c0 + threadIdx.x;
+    const long long cols = (long long)taps * Cin, total = rows * cols;
+    if (c < Cin) {
+        for (int tap = 0; tap < taps; ++tap) {
+            const float* src = partial + row * cols + (long long)tap * Cin + c;
+            float sum = 0.f;
+            for (int k = 0; k < splits; ++k) sum += src[(long long)k * total];
+            sm[threadIdx.x * taps + tap] = sum;
+        }
+    }
+    __syncthreads();
+    const int nch = min(128, cin_real - c0);
+    if (nch <= 0) return;
+    __nv_bfloat16* o = out + (row * cin_real + c0) * taps;
+    for (int i = threadIdx.x; i < nch * taps; i += 128) {
+        float v = sm[i];
+        if (accumulate) v = round_bf16(v) + __bfloat162float(o[i]);
+        o[i] = __float2bfloat16_rn(v);
     }
 }
 
@@ -700,7 +773,7 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
     if (P.tail_tiles > 0) {
         const int m_sub = CTA2 ? 2 : 1;
-        tail_fixup_kernel<<<P.tail_tiles * m_sub * (P.bn / 32), 128, 0, stream>>>(P, m_sub);
+        tail_fixup_kernel<<<P.tail_tiles * m_sub * 4 * (P.bn / 32), 128, 0, stream>>>(P, m_sub);
         AOZ_CHECK_LAUNCH("tail_fixup_kernel");
     }
     return AOZ_OK;
@@ -760,15 +833,18 @@ static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, i
     return best;
 }
 
-// split-K factor for un-fused GEMMs (weight gradients): trades wave quantisation against fp32 partial traffic
-static int plan_splits(int m_tiles128, int n_extent, int k_iters, long long out_elems, bool b_mn, int n_groups) {
+// split-K factor for un-fused GEMMs: trades wave quantisation against fp32 partial traffic.  `store_direct`: with one split
+// the result is stored straight from the epilogue (Linear layers), so the tail split is available as an alternative to
+// split-K; conv weight gradients always go through fp32 partials + the permuting reduce.
+static int plan_splits(int m_tiles128, int n_extent, int k_iters, long long out_elems, bool b_mn, int n_groups, bool store_direct) {
     int best_s = 1;
     double best_c = 1e300;
     for (int s = 1; s <= 32 && s <= (k_iters + 1) / 2; ++s) {
         const int kit = ceil_div(k_iters, s);
-        TilePlan tp = plan_tiles(m_tiles128, n_extent, kit, s, b_mn, false, n_groups);
+        TilePlan tp = plan_tiles(m_tiles128, n_extent, kit, s, b_mn, false, n_groups, /*allow_tail=*/store_direct && s == 1);
         double c = tp.cycles;
-        if (s > 1) c += (double)(2 * s + 1) * out_elems * 4.0 / 3400.0 / 2.0 + 3000.0;     // partial write + reduce read at ~HBM/L2 rate
+        // partial write + reduce read, measured ~1.6 B/cycle/SM-equivalent on B200 (tools/kernel_times.py), + a launch
+        if (s > 1 || !store_direct) c += (double)(2 * s + 1) * out_elems * 4.0 / 2400.0 / 2.0 + 4000.0;
         if (c < best_c) { best_c = c; best_s = s; }
     }
     return best_s;
@@ -805,13 +881,22 @@ int aoz_gemm_set_scratch(void* ptr, long long bytes) {
 int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }
 int aoz_gemm_debug_flags(int flags) { g_dbg = flags; return AOZ_OK; }
 
+// what the planner picks for C[M,N] = A[M,K] B with `splits` (<= 0: automatic): bn + 1000*pair + 10000*tail_splits +
+// 1000000*tail_tiles + 100000000*splits  (tools / tests only)
+long long aoz_gemm_describe_plan(int M, int N, int K, int b_mn, int splits) {
+    const int mt = ceil_div(M, BM), kit = ceil_div(K, BK);
+    if (splits <= 0) splits = plan_splits(mt, N, kit, (long long)M * N, b_mn != 0, 1, true);
+    const TilePlan tp = plan_tiles(mt, N, ceil_div(kit, splits), splits, b_mn != 0, false, 1, splits == 1);
+    return tp.bn + 1000LL * tp.pair + 10000LL * (tp.tail_tiles ? tp.tail_splits : 0) + 1000000LL * tp.tail_tiles + 100000000LL * splits;
+}
+
 // split-K factor aoz_gemm_bf16 will use when called with splits <= 0 (so the caller can size the workspace)
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn) {
-    return plan_splits(ceil_div(M, BM), N, ceil_div(K, BK), (long long)M * N, b_mn != 0, 1);
+    return plan_splits(ceil_div(M, BM), N, ceil_div(K, BK), (long long)M * N, b_mn != 0, 1, true);
 }
 int aoz_conv_wgrad_auto_splits(int NB, int H, int W, int Cout, int Cin, int ks) {
     const int k_iters = NB * ceil_div(H, 8) * ceil_div(W, 8);
-    return plan_splits(ceil_div(Cout, BM), Cin, k_iters, (long long)Cout * ks * ks * Cin, true, ks * ks);
+    return plan_splits(ceil_div(Cout, BM), Cin, k_iters, (long long)Cout * ks * ks * Cin, true, ks * ks, false);
 }
 
 // C[M,N] (bf16) = op(A) * op(B)^T-ish with fused epilogue.
@@ -836,7 +921,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     P.M = M; P.N = N; P.K = K;
     P.k_iters = ceil_div(K, BK);
     P.m_tiles = ceil_div(M, BM);
-    if (splits <= 0) splits = fused ? 1 : plan_splits(P.m_tiles, N, P.k_iters, (long long)M * N, b_mn != 0, 1);
+    if (splits <= 0) splits = fused ? 1 : plan_splits(P.m_tiles, N, P.k_iters, (long long)M * N, b_mn != 0, 1, true);
     if (splits > P.k_iters) splits = P.k_iters;
     const bool geglu = epi == EPI_GEGLU;
     if (geglu) {
@@ -967,7 +1052,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
     P.M = Cout; P.N = taps * Cin; P.K = NB * H * W;
     P.k_iters = NB * P.tiles_h * P.tiles_w;
     P.m_tiles = ceil_div(Cout, BM);
-    if (splits <= 0) splits = plan_splits(P.m_tiles, Cin, P.k_iters, (long long)Cout * taps * Cin, true, taps);
+    if (splits <= 0) splits = plan_splits(P.m_tiles, Cin, P.k_iters, (long long)Cout * taps * Cin, true, taps, false);
     if (splits > P.k_iters) splits = P.k_iters;
     const TilePlan tp = plan_tiles(P.m_tiles, Cin, ceil_div(P.k_iters, splits), splits, true, false, taps);
     const int bn = tp.bn;
@@ -991,11 +1076,9 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
     if ((rc = launch_gemm(P, tp.pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
-    const long long total = (long long)Cout * Cin;
-    int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
-    splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, Cout, (long long)taps * Cin,
-                                                                (__nv_bfloat16*)grad_w, 0, taps, Cin, cin_real, accumulate);
-    AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
+    wgrad_permute_reduce_kernel<<<dim3(ceil_div(Cin, 128), Cout), 128, 0, (cudaStream_t)stream>>>(
+        (const float*)workspace, splits, Cout, Cin, cin_real, taps, (__nv_bfloat16*)grad_w, accumulate);
+    AOZ_CHECK_LAUNCH("wgrad_permute_reduce_kernel");
     return AOZ_OK;
 }
 

@@ -413,15 +413,27 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 }
 
 // reduce [blocks][2][C] -> dgamma (first C), dbeta (second C)
-__global__ void ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
-                                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
-    if (i >= 2 * C) return;
+// block = 32 columns x 8 row lanes: lane (cx, ry) sums partial rows ry, ry+8, ... of its column (a warp reads 128
+// contiguous bytes per row), then the 8 row lanes are combined through shared memory
+__global__ void __launch_bounds__(256)
+ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
+                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    __shared__ float sm[8][33];
+    const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
+    const int i = blockIdx.x * 32 + cx;
     float s = 0.f;
-    for (int b = 0; b < blocks; ++b) s += partial[(size_t)b * 2 * C + i];
-    __nv_bfloat16* dst = i < C ? dgamma + i : dbeta + (i - C);
-    if (accumulate) s = round_bf16(s) + __bfloat162float(*dst);
-    *dst = __float2bfloat16_rn(s);
+    if (i < 2 * C)
+        for (int b = ry; b < blocks; b += 8) s += partial[(size_t)b * 2 * C + i];
+    sm[ry][cx] = s;
+    __syncthreads();
+    if (ry == 0 && i < 2 * C) {
+        float t = 0.f;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        __nv_bfloat16* dst = i < C ? dgamma + i : dbeta + (i - C);
+        if (accumulate) t = round_bf16(t) + __bfloat162float(*dst);
+        *dst = __float2bfloat16_rn(t);
+    }
 }
 
 }  // namespace aoz
@@ -552,7 +564,7 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         default: rc = launch_ln_bwd<8>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
     }
     if (rc != AOZ_OK) return rc;
-    ln_bwd_finalize_kernel<<<(2 * C + 255) / 256, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
+    ln_bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
                                                                (__nv_bfloat16*)dbeta, accumulate);
     AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");
     return AOZ_OK;

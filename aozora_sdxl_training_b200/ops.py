@@ -14,6 +14,7 @@ BF16 = torch.bfloat16
 _DT = {torch.float32: 0, torch.bfloat16: 1, torch.float16: 2}
 
 launch_count = 0          # number of aoz_* compute calls issued (each is >= 1 kernel launch)
+trace = None              # tools/gemm_in_step.py: when a list, every GEMM / conv call appends (kind, shape...) in launch order
 
 
 def _count(n=1):
@@ -97,6 +98,8 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bia
     ws = None
     if splits > 1:
         ws = workspace(splits * M * N, a.device)
+    if trace is not None:
+        trace.append(("gemm", M, N, K, int(a_mn), int(b_mn), int(epi), int(splits), 2.0 * M * N * K))
     _lib.call("aoz_gemm_bf16", a.data_ptr(), a.stride(0), int(a_mn), b.data_ptr(), b.stride(0), int(b_mn),
               out.data_ptr(), out.stride(0), M, N, K, _p(bias), _p(rowgroup_bias), int(rows_per_group),
               0 if rowgroup_bias is None else rowgroup_bias.stride(0), _p(residual),
@@ -129,13 +132,15 @@ def conv_fwd(x, wpack, cout, ks, *, stride=1, pad=1, flip=False, bias=None, rowg
     _ensure_gemm_scratch(x.device)
     if out is None:
         out = torch.empty((NB, H, W, cout), dtype=BF16, device=x.device)
+    if trace is not None:
+        trace.append(("conv_dgrad" if flip else "conv_fwd", NB * H * W, cout, ks * ks * Cin, 0, 0, 0, 1, 2.0 * NB * H * W * cout * ks * ks * Cin))
     _lib.call("aoz_conv_fwd_bf16", x.data_ptr(), NB, Hin, Win, Cin, wpack.data_ptr(), cout, ks, stride, pad, int(flip),
               out.data_ptr(), _p(bias), _p(rowgroup_bias), _p(residual), 0, _stream())
     _count()
     return out
 
 
-def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False, cin_real=None):
+def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False, cin_real=None, splits=None):
     """dW (OIHW bf16 [Cout, Cin, ks, ks]) from dy [NB,H,W,Cout] and x [NB,Hin,Win,Cin]."""
     _chk(dy, "conv_wgrad dy")
     _chk(x, "conv_wgrad x")
@@ -145,8 +150,11 @@ def conv_wgrad(dy, x, ks, *, stride=1, pad=1, grad_w=None, accumulate=False, cin
     cin_real = cin_real or Cin
     if grad_w is None:
         grad_w = torch.empty((Cout, cin_real, ks, ks), dtype=BF16, device=x.device)
-    splits = _lib.query("aoz_conv_wgrad_auto_splits", NB, H, W, Cout, Cin, ks)
+    if splits is None:
+        splits = _lib.query("aoz_conv_wgrad_auto_splits", NB, H, W, Cout, Cin, ks)      # host cost model (gemm.cu)
     ws = workspace(splits * Cout * taps * Cin, x.device)
+    if trace is not None:
+        trace.append(("conv_wgrad", Cout, taps * Cin, NB * H * W, 1, 1, 0, int(splits), 2.0 * NB * H * W * Cout * taps * Cin))
     _lib.call("aoz_conv_wgrad_bf16", dy.data_ptr(), x.data_ptr(), NB, H, W, Cout, Hin, Win, Cin, ks, stride, pad, cin_real,
               grad_w.data_ptr(), int(accumulate), splits, ws.data_ptr(), _stream())
     _count(2)

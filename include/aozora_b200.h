@@ -55,6 +55,7 @@ int aoz_gemm_set_tail_mode(int mode);
 int aoz_gemm_set_scratch(void* ptr, long long bytes);
 int aoz_gemm_debug_flags(int flags);
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn);
+long long aoz_gemm_describe_plan(int M, int N, int K, int b_mn, int splits);   /* planner introspection for tools / tests */
 int aoz_conv_wgrad_auto_splits(int NB, int H, int W, int Cout, int Cin, int ks);
 int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long long ldb, int b_mn, void* C, long long ldc,
                   int M, int N, int K, const void* bias, const void* rowgroup_bias, int rows_per_group, long long ld_rgb,

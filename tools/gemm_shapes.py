@@ -4,8 +4,8 @@ For every (shape, op) the kernel is timed with the host cost model's own choice 
 (pair mode, tile width) combination; weight-gradient GEMMs are also swept over the split-K factor.  The output
 (gpurun_out/gemm_shapes.json) is what the cost model in csrc/gemm.cu is calibrated against.
 
-Timing: all launches are queued back to back with a 1 GiB L2-flushing memset in front of each timed launch and CUDA
-events around the launch only, so the GPU never waits for the host (no launch-latency bubble inside the timed region).
+Timing: 8 back-to-back launches between one CUDA-event pair (warm L2: inside a training step the operands of these
+mid-size GEMMs were just written by the previous kernel).
 
     python tools/gemm_shapes.py [--quick]
 """
@@ -23,23 +23,18 @@ BF = torch.bfloat16
 _flush = None
 
 
-def timeit_queued(fn, n=5):
-    """Median device time (ms) of fn() over n launches, cold L2, no host bubbles."""
-    global _flush
-    if _flush is None:
-        _flush = torch.empty(1 << 30, dtype=torch.uint8, device="cuda")
+def timeit_queued(fn, n=8):
+    """Mean device time (ms) of n back-to-back launches (warm L2, as inside a training step where the operands were just
+    produced; one event pair around the whole batch: the 2 us event granularity is amortised)."""
     fn()
-    evs = []
+    fn()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
     for _ in range(n):
-        _flush.zero_()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
         fn()
-        e1.record()
-        evs.append((e0, e1))
+    e1.record()
     torch.cuda.synchronize()
-    ts = sorted(a.elapsed_time(b) for a, b in evs)
-    return ts[len(ts) // 2]
+    return e0.elapsed_time(e1) / n
 
 
 def sweep(fn, b_mn, geglu=False):

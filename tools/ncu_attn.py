@@ -1,0 +1,15 @@
+"""A few launches of the attention kernels at the SDXL self-attention shape (B=4, H=20, T=1024, d=64) for `ncu --set full`."""
+import os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+from aozora_sdxl_training_b200 import ops
+B, H, T = 4, 20, 1024
+if len(sys.argv) > 1 and sys.argv[1] == "4096":
+    H, T = 10, 4096
+q, k, v, do = [torch.randn(B, T, H, 64, device="cuda").to(torch.bfloat16) for _ in range(4)]
+for _ in range(2):
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    ops.attn_bwd(q, k, v, o, do, lse, 0.125)
+torch.cuda.synchronize()
+print("ok")
