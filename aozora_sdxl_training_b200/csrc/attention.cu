@@ -24,7 +24,9 @@
 namespace aoz {
 
 constexpr int ATT_THREADS = 192;          // forward: 4 softmax warps + producer + issuer
-constexpr int ATT_BWD_THREADS = 320;      // backward: 8 compute warps (two per TMEM lane quarter) + producer + issuer
+constexpr int BWD_CW = 16;                 // backward: 16 compute warps = four per TMEM lane quarter, 32 of a tile's 128 columns each
+constexpr int BWD_CT = BWD_CW * 32;        // (the math is latency-bound: 8 warps left the issue slots 73 % idle, ncu r01)
+constexpr int ATT_BWD_THREADS = BWD_CT + 64;   // + TMA producer warp + MMA issuer warp
 constexpr int TILE = 128;
 constexpr int HD = 64;
 constexpr int TILE_BYTES = TILE * HD * 2;     // 16 KB: one [128, 64] bf16 tile
@@ -325,19 +327,32 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
 // ================================================================================================
 // backward preprocess: D[b,h,q] = sum_d dO * O
 // ================================================================================================
-__global__ void attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
-                                     long long lddo, int B, int H, int Tq, float* __restrict__ D) {
-    const long long total = (long long)B * Tq * H;
-    const int lane = threadIdx.x & 31;
-    for (long long w = ((long long)blockIdx.x * blockDim.x + threadIdx.x) >> 5; w < total; w += ((long long)gridDim.x * blockDim.x) >> 5) {
-        const int h = (int)(w % H);
-        const long long bt = w / H;
-        const int t = (int)(bt % Tq), b = (int)(bt / Tq);
-        const uint32_t o2 = *reinterpret_cast<const uint32_t*>(O + bt * ldo + h * HD + lane * 2);
-        const uint32_t d2 = *reinterpret_cast<const uint32_t*>(dO + bt * lddo + h * HD + lane * 2);
-        float s = bf16lo(o2) * bf16lo(d2) + bf16hi(o2) * bf16hi(d2);
-        s = warp_sum(s);
-        if (lane == 0) D[((long long)b * H + h) * Tq + t] = s;
+// 8 lanes per (token, head) row: each lane multiplies 8 elements (one 16-byte load of O and of dO), three shuffles sum
+// the row; a warp covers 4 rows = 512 contiguous bytes per tensor when the heads are adjacent
+__global__ void __launch_bounds__(256)
+attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
+                     long long lddo, int B, int H, int Tq, float* __restrict__ D) {
+    const long long total = (long long)B * Tq * H * 8;                    // one work item = 8 elements of one row
+    const long long bound = (total + 31) & ~31LL;                         // whole warps stay in the loop (full-mask shuffles)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += (long long)gridDim.x * blockDim.x) {
+        const long long w = i >> 3;                                       // (token, head) row; whole 8-lane groups stay together
+        const int part = (int)(i & 7);
+        float s = 0.f;
+        int h = 0, t = 0, b = 0;
+        if (w < (long long)B * Tq * H) {
+            h = (int)(w % H);
+            const long long bt = w / H;
+            t = (int)(bt % Tq); b = (int)(bt / Tq);
+            const uint4 o4 = ld_stream(O + bt * ldo + h * HD + part * 8);
+            const uint4 d4 = ld_stream(dO + bt * lddo + h * HD + part * 8);
+            const uint32_t ow[4] = {o4.x, o4.y, o4.z, o4.w}, dw[4] = {d4.x, d4.y, d4.z, d4.w};
+#pragma unroll
+            for (int e = 0; e < 4; ++e) s += bf16lo(ow[e]) * bf16lo(dw[e]) + bf16hi(ow[e]) * bf16hi(dw[e]);
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        if (part == 0 && w < (long long)B * Tq * H) D[((long long)b * H + h) * Tq + t] = s;
     }
 }
 
@@ -383,18 +398,18 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(kv_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(pds_ready, 256); mbar_init(acc_ready, 1);
-        mbar_init(st_free, 256); mbar_init(pd_free, 1);
+        mbar_init(s_ready, 1); mbar_init(pds_ready, BWD_CT); mbar_init(acc_ready, 1);
+        mbar_init(st_free, BWD_CT); mbar_init(pd_free, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (warp == BWD_CW + 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
 
-    if (warp == 8) {
+    if (warp == BWD_CW) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
             mbar_arrive_expect_tx(kv_once, 2 * TILE_BYTES);
@@ -408,7 +423,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 tma_load_4d(smem + KvSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == BWD_CW + 1) {
         // Software pipeline: S^T / dP^T of Q tile i+1 are issued as soon as the compute warps have pulled tile i's S^T / dP^T
         // into registers, so the tensor pipe works on tile i+1 while they do the exp / dS math of tile i.
         if (lane == 0) {
@@ -451,7 +466,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         }
         __syncwarp();
     } else {
-        // warps 0..7: quarter = warp & 3 (TMEM lanes), hf = warp >> 2 selects which half of the 128 query columns
+        // compute warps: quarter = warp & 3 (TMEM lanes), hf = warp >> 2 selects which 32 of the 128 query columns
         const int qtr = warp & 3, hf = warp >> 2;
         const int r = qtr * 32 + lane;                       // key row inside the tile
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
@@ -474,7 +489,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 lse2[r] = nx_lse * LOG2E;
                 dv[r] = nx_d;
             }
-            named_bar_sync(1, 256);
+            named_bar_sync(1, BWD_CT);
             if (hf == 0 && i + 1 < nq) fetch_vec(i + 1);
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
@@ -483,14 +498,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             // 64 B/clk/SM) and the MUFU / FMA pipes work at the same time.  TMEM is released for the next tile's score MMAs
             // as soon as the last chunk has landed in registers.
             uint32_t vs[2][16], vp[2][16], hp[2][8], hd[2][8];
-            tmem_ld16(tSt + lane_off + hf * 64, vs[0]);
-            tmem_ld16(tdPt + lane_off + hf * 64, vp[0]);
+            tmem_ld16(tSt + lane_off + hf * 32, vs[0]);
+            tmem_ld16(tdPt + lane_off + hf * 32, vp[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 tc_wait_ld();
-                if (c + 1 < 4) {
-                    tmem_ld16(tSt + lane_off + hf * 64 + (c + 1) * 16, vs[(c + 1) & 1]);
-                    tmem_ld16(tdPt + lane_off + hf * 64 + (c + 1) * 16, vp[(c + 1) & 1]);
+                if (c + 1 < 2) {
+                    tmem_ld16(tSt + lane_off + hf * 32 + (c + 1) * 16, vs[(c + 1) & 1]);
+                    tmem_ld16(tdPt + lane_off + hf * 32 + (c + 1) * 16, vp[(c + 1) & 1]);
                 } else {
                     tc_fence_before();
                     mbar_arrive(st_free);
@@ -501,7 +516,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 const uint32_t* cp = vp[c & 1];
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) {
-                    const int qa = hf * 64 + c * 16 + e;
+                    const int qa = hf * 32 + c * 16 + e;
                     const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
                     const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
                     float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -ls.x));
@@ -518,13 +533,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 // complete) still read these smem tiles for the first few hundred cycles of this tile
                 if (c == 1) {
                     if (i > 0) mbar_wait(pd_free, (i - 1) & 1);
-                    store_p_16(sPT, r, hf * 64, hp[0]);
-                    store_p_16(sDST, r, hf * 64, hd[0]);
-                    store_p_16(sPT, r, hf * 64 + 16, hp[1]);
-                    store_p_16(sDST, r, hf * 64 + 16, hd[1]);
-                } else if (c >= 2) {
-                    store_p_16(sPT, r, hf * 64 + c * 16, wp);
-                    store_p_16(sDST, r, hf * 64 + c * 16, wd);
+                    store_p_16(sPT, r, hf * 32, hp[0]);
+                    store_p_16(sDST, r, hf * 32, hd[0]);
+                    store_p_16(sPT, r, hf * 32 + 16, hp[1]);
+                    store_p_16(sDST, r, hf * 32 + 16, hd[1]);
                 }
             }
             fence_proxy_async_smem();
@@ -534,35 +546,32 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         mbar_wait(acc_ready, 0);
         tc_fence_after();
         const int key = k0 + r;
-#pragma unroll 1
-        for (int which = 0; which < 2; ++which) {
+        {
+            const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
             const uint32_t tacc = which == 0 ? tdV : tdK;
             const float mul = which == 0 ? 1.0f : P.scale;
             __nv_bfloat16* base = which == 0 ? P.dV : P.dK;
             const long long ld = which == 0 ? P.lddv : P.lddk;
-            {
-                const int c = hf;                                  // each half-warp set stores one 32-column chunk
-                uint32_t v[32];
-                tmem_ld32(tacc + lane_off + c * 32, v);
-                tc_wait_ld();
-                if (key < P.Tk) {
-                    __nv_bfloat16* dst = base + ((long long)b * P.Tk + key) * ld + h * HD + c * 32;
+            uint32_t v[32];
+            tmem_ld32(tacc + lane_off + c * 32, v);
+            tc_wait_ld();
+            if (key < P.Tk) {
+                __nv_bfloat16* dst = base + ((long long)b * P.Tk + key) * ld + h * HD + c * 32;
 #pragma unroll
-                    for (int e = 0; e < 32; e += 8) {
-                        uint4 o;
-                        o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
-                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
-                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
-                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
-                        *reinterpret_cast<uint4*>(dst + e) = o;
-                    }
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
                 }
             }
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == BWD_CW + 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 // ================================================================================================
@@ -604,18 +613,18 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_once, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(ds_ready, 256); mbar_init(acc_ready, 1);
-        mbar_init(st_free, 256); mbar_init(ds_free, 1);
+        mbar_init(s_ready, 1); mbar_init(ds_ready, BWD_CT); mbar_init(acc_ready, 1);
+        mbar_init(st_free, BWD_CT); mbar_init(ds_free, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 512);
+    if (warp == BWD_CW + 1) tmem_alloc(tmem_slot, 512);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
 
-    if (warp == 8) {
+    if (warp == BWD_CW) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
             mbar_arrive_expect_tx(q_once, 2 * TILE_BYTES);
@@ -629,7 +638,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
                 tma_load_4d(smem + DqSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == BWD_CW + 1) {
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
@@ -667,7 +676,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
         }
         __syncwarp();
     } else {
-        const int qtr = warp & 3, hf = warp >> 2;            // two warps per TMEM lane quarter, each owns 64 key columns
+        const int qtr = warp & 3, hf = warp >> 2;            // four warps per TMEM lane quarter, each owns 32 key columns
         const int r = qtr * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const uint32_t sDS = smem_u32(smem + DqSmem::DS);
@@ -682,14 +691,14 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             const int kvalid = P.Tk - j * TILE;
             // four 16-column chunks, software-pipelined like the dK/dV kernel
             uint32_t vs[2][16], vp[2][16], hd[2][8];
-            tmem_ld16(tS + lane_off + hf * 64, vs[0]);
-            tmem_ld16(tdP + lane_off + hf * 64, vp[0]);
+            tmem_ld16(tS + lane_off + hf * 32, vs[0]);
+            tmem_ld16(tdP + lane_off + hf * 32, vp[0]);
 #pragma unroll
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 0; c < 2; ++c) {
                 tc_wait_ld();
-                if (c + 1 < 4) {
-                    tmem_ld16(tS + lane_off + hf * 64 + (c + 1) * 16, vs[(c + 1) & 1]);
-                    tmem_ld16(tdP + lane_off + hf * 64 + (c + 1) * 16, vp[(c + 1) & 1]);
+                if (c + 1 < 2) {
+                    tmem_ld16(tS + lane_off + hf * 32 + (c + 1) * 16, vs[(c + 1) & 1]);
+                    tmem_ld16(tdP + lane_off + hf * 32 + (c + 1) * 16, vp[(c + 1) & 1]);
                 } else {
                     tc_fence_before();
                     mbar_arrive(st_free);                    // TMEM S / dP may be overwritten by the next tile's MMAs
@@ -707,7 +716,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
                 } else {
 #pragma unroll
                     for (int e = 0; e < 16; e += 2) {
-                        const int ka = hf * 64 + c * 16 + e;
+                        const int ka = hf * 32 + c * 16 + e;
                         float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -lse2)) : 0.f;
                         float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -lse2)) : 0.f;
                         wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dvec), p1 * (__uint_as_float(cp[e + 1]) - dvec));
@@ -715,10 +724,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
                 }
                 if (c == 1) {                                // see the dK/dV kernel: the previous tile's dQ MMAs still read sDS
                     if (j > 0) mbar_wait(ds_free, (j - 1) & 1);
-                    store_p_16(sDS, r, hf * 64, hd[0]);
-                    store_p_16(sDS, r, hf * 64 + 16, hd[1]);
-                } else if (c >= 2) {
-                    store_p_16(sDS, r, hf * 64 + c * 16, wd);
+                    store_p_16(sDS, r, hf * 32, hd[0]);
+                    store_p_16(sDS, r, hf * 32 + 16, hd[1]);
                 }
             }
             fence_proxy_async_smem();
@@ -728,15 +735,14 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
         mbar_wait(acc_ready, 0);
         tc_fence_after();
         {
-            const int c = hf;
-            uint32_t v[32];
-            tmem_ld32(tdQ + lane_off + c * 32, v);
+            uint32_t v[16];                                      // each of the four warps of a lane quarter stores 16 of the 64 columns
+            tmem_ld16(tdQ + lane_off + hf * 16, v);
             tc_wait_ld();
             if (q < P.Tq) {
-                __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD + c * 32;
+                __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD + hf * 16;
                 const float mul = P.scale;
 #pragma unroll
-                for (int e = 0; e < 32; e += 8) {
+                for (int e = 0; e < 16; e += 8) {
                     uint4 o;
                     o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
                     o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
@@ -749,7 +755,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+    if (warp == BWD_CW + 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
 static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int B, int H, int T) {
@@ -808,8 +814,8 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
     P.lse = (float*)const_cast<void*>(lse); P.Dvec = (const float*)workspace;
     P.dQ = (__nv_bfloat16*)dq; P.lddq = lddq; P.dK = (__nv_bfloat16*)dk; P.lddk = lddk; P.dV = (__nv_bfloat16*)dv; P.lddv = lddv;
     {
-        const long long warps = (long long)B * Tq * H;
-        long long blocks = (warps * 32 + 255) / 256;
+        const long long items = (long long)B * Tq * H * 8;
+        long long blocks = (items + 255) / 256;
         if (blocks > sm_count() * 16) blocks = sm_count() * 16;
         attn_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace);
         AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");

@@ -326,22 +326,49 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
 }
 
 // ---- conv weight packing: OIHW -> [Cout][taps][CinPad] (forward) and [Cin][taps][CoutPad] (dgrad) -------------
-__global__ void pack_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, int Cout, int Cin, int taps, int CinPad,
-                                        int CoutPad, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
-    const long long nf = (long long)Cout * taps * CinPad;
-    const long long nd = wd ? (long long)Cin * taps * CoutPad : 0;
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < nf + nd; i += (long long)gridDim.x * blockDim.x) {
-        if (i < nf) {
-            const int ci = (int)(i % CinPad);
-            const long long p = i / CinPad;
-            const int t = (int)(p % taps), co = (int)(p / taps);
-            wf[i] = ci < Cin ? w[((long long)co * Cin + ci) * taps + t] : __float2bfloat16_rn(0.f);
-        } else {
-            const long long j = i - nf;
-            const int co = (int)(j % CoutPad);
-            const long long p = j / CoutPad;
-            const int t = (int)(p % taps), ci = (int)(p / taps);
-            wd[j] = co < Cout ? w[((long long)co * Cin + ci) * taps + t] : __float2bfloat16_rn(0.f);
+// block = 32 output channels x 32 input channels x all taps.  The OIHW source is read as 32 runs of 32*taps contiguous
+// elements, staged in shared memory, and leaves as 64-byte runs of both packs: wf[co][tap][ci..ci+32) and
+// wd[ci][tap][co..co+32) (the dgrad pack is the co <-> ci transpose).  Pad rows / columns are written as zeros.
+__global__ void __launch_bounds__(256)
+pack_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, int Cout, int Cin, int taps, int CinPad,
+                        int CoutPad, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+    __shared__ __nv_bfloat16 sm[32][32 * 9 + 2];          // [co][ci * taps + tap], +2: odd word stride (conflict-free column reads)
+    const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
+    const int run = 32 * taps;
+    const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
+    for (int i = threadIdx.x; i < 32 * run; i += 256) {
+        const int co = i / run, k = i - co * run;         // k = ci_local * taps + tap
+        const int ci = ci0 + k / taps;
+        sm[co][k] = (co0 + co < Cout && ci < Cin) ? w[((long long)(co0 + co) * Cin + ci0) * taps + k] : zero;
+    }
+    __syncthreads();
+    // wf: rows co (< Cout only), for every tap a 32-element run along ci, written as four 16-byte vectors
+    for (int i = threadIdx.x; i < 32 * taps * 4; i += 256) {
+        const int c8 = (i & 3) * 8, t = (i >> 2) % taps, co = (i >> 2) / taps;
+        if (co0 + co < Cout && ci0 + c8 < CinPad) {
+            uint32_t v[4];
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const uint32_t lo = __bfloat16_as_ushort(sm[co][(c8 + 2 * e) * taps + t]);
+                const uint32_t hi = __bfloat16_as_ushort(sm[co][(c8 + 2 * e + 1) * taps + t]);
+                v[e] = lo | (hi << 16);
+            }
+            *reinterpret_cast<uint4*>(wf + ((long long)(co0 + co) * taps + t) * CinPad + ci0 + c8) = make_uint4(v[0], v[1], v[2], v[3]);
+        }
+    }
+    if (wd) {
+        for (int i = threadIdx.x; i < 32 * taps * 4; i += 256) {
+            const int c8 = (i & 3) * 8, t = (i >> 2) % taps, ci = (i >> 2) / taps;
+            if (ci0 + ci < Cin && co0 + c8 < CoutPad) {
+                uint32_t v[4];
+#pragma unroll
+                for (int e = 0; e < 4; ++e) {
+                    const uint32_t lo = __bfloat16_as_ushort(sm[c8 + 2 * e][ci * taps + t]);
+                    const uint32_t hi = __bfloat16_as_ushort(sm[c8 + 2 * e + 1][ci * taps + t]);
+                    v[e] = lo | (hi << 16);
+                }
+                *reinterpret_cast<uint4*>(wd + ((long long)(ci0 + ci) * taps + t) * CoutPad + co0 + c8) = make_uint4(v[0], v[1], v[2], v[3]);
+            }
         }
     }
 }
@@ -529,9 +556,10 @@ int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long
 int aoz_pack_conv_weight(const void* w, int Cout, int Cin, int ks, int CinPad, int CoutPad, void* wf, void* wd, void* stream) {
     AOZ_CHECK_ARG(w && wf && CinPad >= Cin && CoutPad >= Cout, "aoz_pack_conv_weight: bad arguments");
     const int taps = ks * ks;
-    const long long total = (long long)Cout * taps * CinPad + (wd ? (long long)Cin * taps * CoutPad : 0);
-    pack_conv_weight_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)w, Cout, Cin, taps, CinPad, CoutPad,
-                                                                                    (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
+    AOZ_CHECK_ARG(taps <= 9, "aoz_pack_conv_weight: kernel size %d unsupported", ks);
+    const int cmax = CoutPad > Cout ? CoutPad : Cout;
+    pack_conv_weight_kernel<<<dim3((CinPad + 31) / 32, (cmax + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)w, Cout, Cin, taps, CinPad, CoutPad, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
     AOZ_CHECK_LAUNCH("pack_conv_weight_kernel");
     return AOZ_OK;
 }

@@ -31,6 +31,16 @@ constexpr int EPI_STAGE_BYTES = 8 * 4096;               // 8 epilogue warps x (3
 constexpr int GEMM_SMEM_TOTAL = SMEM_TILE_BYTES + 1024 + EPI_STAGE_BYTES + 1024;   // + barriers + staging + alignment slack (226 KB)
 
 enum GemmMode : int { GM_LINEAR = 0, GM_CONV_FWD = 1, GM_CONV_WGRAD = 2 };
+constexpr int MAX_GROUPS = 8;
+
+// one problem of a grouped launch (GM_LINEAR, EPI_STORE, same K / operand majors / tile shape for all problems): the
+// weight gradients of one transformer block run as ONE persistent launch, so ~900 tiles fill the 148 SMs in ~6 full
+// waves instead of six launches with one or two ragged waves each
+struct alignas(64) GroupDesc {
+    CUtensorMap tmA, tmB;
+    __nv_bfloat16* C; long long ldc;
+    int M, N, m_tiles, tile_start;      // m_tiles counts work-unit rows (256-row pair tiles when CTA2)
+};
 enum GemmEpi : int { EPI_STORE = 0, EPI_GEGLU = 1, EPI_PARTIAL = 2 };
 
 struct GemmParams {
@@ -61,6 +71,8 @@ struct GemmParams {
     __nv_bfloat16* aux; long long ld_aux;          // GEGLU: pre-activation [M, 2*half]
     float* partial;                 // EPI_PARTIAL: [splits][M][N] fp32
     int accumulate;                 // EPI_STORE: C += result
+    int n_groups;                   // > 0: grouped launch, tile indices run over grp[0..n_groups) back to back
+    GroupDesc grp[MAX_GROUPS];
 };
 
 // erf GELU (torch F.gelu default), fp32: x * Phi(x)
@@ -163,10 +175,28 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& P, int work, i
     return w;
 }
 
+// the problem a tile belongs to (the launch's own operands unless this is a grouped launch)
+struct Prob { const CUtensorMap* tmA; const CUtensorMap* tmB; __nv_bfloat16* C; long long ldc; int M, N, m_tiles, ltile; };
+
+__device__ __forceinline__ Prob select_prob(const GemmParams& P, int tile) {
+    Prob pr;
+    if (P.n_groups == 0) {
+        pr.tmA = &P.tmA; pr.tmB = &P.tmB; pr.C = P.C; pr.ldc = P.ldc; pr.M = P.M; pr.N = P.N; pr.m_tiles = P.m_tiles; pr.ltile = tile;
+    } else {
+        int g = 0;
+#pragma unroll 1
+        while (g + 1 < P.n_groups && tile >= P.grp[g + 1].tile_start) ++g;
+        const GroupDesc& d = P.grp[g];
+        pr.tmA = &d.tmA; pr.tmB = &d.tmB; pr.C = d.C; pr.ldc = d.ldc; pr.M = d.M; pr.N = d.N; pr.m_tiles = d.m_tiles;
+        pr.ltile = tile - d.tile_start;
+    }
+    return pr;
+}
+
 struct RowMap { long long row; bool ok; int group; };
 
 // output row (and time-embedding row group) of row `row_in_tile` of the 128-row tile `m_blk`
-__device__ __forceinline__ RowMap map_row(const GemmParams& P, int m_blk, int row_in_tile) {
+__device__ __forceinline__ RowMap map_row(const GemmParams& P, int M, int m_blk, int row_in_tile) {
     RowMap r;
     if (P.mode == GM_CONV_FWD) {
         int t = m_blk;
@@ -178,7 +208,7 @@ __device__ __forceinline__ RowMap map_row(const GemmParams& P, int m_blk, int ro
         r.group = img;
     } else {
         r.row = (long long)m_blk * BM + row_in_tile;
-        r.ok = r.row < P.M;
+        r.ok = r.row < M;
         r.group = P.rows_per_group > 0 ? (int)(r.row / P.rows_per_group) : 0;
     }
     return r;
@@ -186,8 +216,9 @@ __device__ __forceinline__ RowMap map_row(const GemmParams& P, int m_blk, int ro
 
 // EPI_STORE for 8 consecutive output columns [col, col+8) of output row `row`: bias -> per-image time embedding -> residual
 // -> accumulate, each with the bf16 rounding point the op-by-op autocast path has, then one 16-byte store.
-__device__ __forceinline__ void epi_store8(const GemmParams& P, long long row, int group, int col, int col_limit, float* f) {
-    __nv_bfloat16* dst = P.C + row * P.ldc + col;
+__device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C, long long ldc, long long row, int group, int col,
+                                           int col_limit, float* f) {
+    __nv_bfloat16* dst = C + row * ldc + col;
     const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + col : nullptr;
     const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + col : nullptr;
     if (P.vec_ok && col + 7 < col_limit) {
@@ -267,8 +298,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     const int n_units = CTA2 ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
     if (warp == 0 && lane == 0) {
-        tma_prefetch_desc(&P.tmA);
-        tma_prefetch_desc(&P.tmB);
+        if (P.n_groups == 0) { tma_prefetch_desc(&P.tmA); tma_prefetch_desc(&P.tmB); }
         for (int i = 0; i < STAGES; ++i) { mbar_init(&full_bar[i], 1); mbar_init(&empty_bar[i], 1); }
         for (int i = 0; i < 2; ++i) { mbar_init(&tfull_bar[i], 1); mbar_init(&tempty_bar[i], CTA2 ? 16 : 8); }
         fence_mbar_init();
@@ -294,9 +324,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             const int b_chunks = B_ROWS / 64;
             for (int work = unit; work < total_work; work += n_units) {
                 const WorkItem wi = decode_work(P, work, k_per_split);
-                const int tile = wi.tile;
-                const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank;          // 128-row tile index of THIS CTA
-                const int n_blk = tile / P.m_tiles;
+                const Prob pr = select_prob(P, wi.tile);
+                const CUtensorMap* tmA = pr.tmA;
+                const CUtensorMap* tmB = pr.tmB;
+                const int m_blk = (pr.ltile % pr.m_tiles) * m_sub + (int)rank;     // 128-row tile index of THIS CTA
+                const int n_blk = pr.ltile / pr.m_tiles;
                 const int k_begin = wi.k_begin, k_end = wi.k_end;
                 const int n_row0 = n_blk * BN + (CTA2 ? (int)rank * (BN / 2) : 0);  // first B row (N index) this CTA stages
                 const int m_row0 = m_blk * BM;
@@ -334,47 +366,47 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     else mbar_arrive_expect_tx(fb, STAGE_BYTES);
                     const int k0 = kit * BK;
                     if (P.mode == GM_LINEAR) {
-                        if (!a_mn) { if (CTA2) tma2_load_2d(sa, &P.tmA, fbc, k0, m_row0); else tma_load_2d(sa, &P.tmA, fb, k0, m_row0); }
+                        if (!a_mn) { if (CTA2) tma2_load_2d(sa, tmA, fbc, k0, m_row0); else tma_load_2d(sa, tmA, fb, k0, m_row0); }
                         else {
 #pragma unroll
                             for (int jj = 0; jj < BM / 64; ++jj) {
-                                if (CTA2) tma2_load_2d(sa + jj * 8192, &P.tmA, fbc, m_row0 + jj * 64, k0);
-                                else tma_load_2d(sa + jj * 8192, &P.tmA, fb, m_row0 + jj * 64, k0);
+                                if (CTA2) tma2_load_2d(sa + jj * 8192, tmA, fbc, m_row0 + jj * 64, k0);
+                                else tma_load_2d(sa + jj * 8192, tmA, fb, m_row0 + jj * 64, k0);
                             }
                         }
                     } else if (P.mode == GM_CONV_FWD) {
                         const int r = P.flip ? P.taps_s - 1 - tap_r : tap_r, sft = P.flip ? P.taps_s - 1 - tap_s : tap_s;
-                        if (CTA2) tma2_load_4d(sa, &P.tmA, fbc, cc * BK, w0 + sft, h0 + r, img);
-                        else tma_load_4d(sa, &P.tmA, fb, cc * BK, w0 + sft, h0 + r, img);
+                        if (CTA2) tma2_load_4d(sa, tmA, fbc, cc * BK, w0 + sft, h0 + r, img);
+                        else tma_load_4d(sa, tmA, fb, cc * BK, w0 + sft, h0 + r, img);
                         if (++cc == P.cin_chunks) { cc = 0; if (++tap_s == P.taps_s) { tap_s = 0; ++tap_r; } }
                     }
                     if (P.mode != GM_CONV_WGRAD) {
                         if (!b_mn) {
                             if (P.epi == EPI_GEGLU) {
-                                if (CTA2) tma2_load_2d(sb, &P.tmB, fbc, k0, g_row0);
+                                if (CTA2) tma2_load_2d(sb, tmB, fbc, k0, g_row0);
                                 else {
-                                    tma_load_2d(sb, &P.tmB, fb, k0, g_row0);
-                                    tma_load_2d(sb + (BN / 2) * 128, &P.tmB, fb, k0, P.geglu_half + g_row0);
+                                    tma_load_2d(sb, tmB, fb, k0, g_row0);
+                                    tma_load_2d(sb + (BN / 2) * 128, tmB, fb, k0, P.geglu_half + g_row0);
                                 }
                             } else {
-                                if (CTA2) tma2_load_2d(sb, &P.tmB, fbc, k0, n_row0); else tma_load_2d(sb, &P.tmB, fb, k0, n_row0);
+                                if (CTA2) tma2_load_2d(sb, tmB, fbc, k0, n_row0); else tma_load_2d(sb, tmB, fb, k0, n_row0);
                             }
                         } else {
                             for (int jj = 0; jj < b_chunks; ++jj) {
-                                if (CTA2) tma2_load_2d(sb + jj * 8192, &P.tmB, fbc, n_row0 + jj * 64, k0);
-                                else tma_load_2d(sb + jj * 8192, &P.tmB, fb, n_row0 + jj * 64, k0);
+                                if (CTA2) tma2_load_2d(sb + jj * 8192, tmB, fbc, n_row0 + jj * 64, k0);
+                                else tma_load_2d(sb + jj * 8192, tmB, fb, n_row0 + jj * 64, k0);
                             }
                         }
                     } else {   // GM_CONV_WGRAD: K iteration = one 8x8 pixel tile of dy; both operands MN-major
                         const int hh = p_th * P.TH, ww = p_tw * P.TW;
 #pragma unroll
                         for (int jj = 0; jj < BM / 64; ++jj) {
-                            if (CTA2) tma2_load_4d(sa + jj * 8192, &P.tmA, fbc, m_row0 + jj * 64, ww, hh, p_im);
-                            else tma_load_4d(sa + jj * 8192, &P.tmA, fb, m_row0 + jj * 64, ww, hh, p_im);
+                            if (CTA2) tma2_load_4d(sa + jj * 8192, tmA, fbc, m_row0 + jj * 64, ww, hh, p_im);
+                            else tma_load_4d(sa + jj * 8192, tmA, fb, m_row0 + jj * 64, ww, hh, p_im);
                         }
                         for (int jj = 0; jj < b_chunks; ++jj) {
-                            if (CTA2) tma2_load_4d(sb + jj * 8192, &P.tmB, fbc, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
-                            else tma_load_4d(sb + jj * 8192, &P.tmB, fb, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
+                            if (CTA2) tma2_load_4d(sb + jj * 8192, tmB, fbc, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
+                            else tma_load_4d(sb + jj * 8192, tmB, fb, wg_c0 + jj * 64, ww * P.stride + wg_dw, hh * P.stride + wg_dh, p_im);
                         }
                         if (++p_tw == P.tiles_w) { p_tw = 0; if (++p_th == P.tiles_h) { p_th = 0; ++p_im; } }
                     }
@@ -445,10 +477,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         uint32_t acc = 0, acc_phase = 0;
         for (int work = unit; work < total_work; work += n_units) {
             const WorkItem wi = decode_work(P, work, k_per_split);
-            const int tile = wi.tile, split = wi.split;
-            const int m_blk = (tile % P.m_tiles) * m_sub + (int)rank, n_blk = tile / P.m_tiles;
+            const int split = wi.split;
+            const Prob pr = select_prob(P, wi.tile);
+            const int m_blk = (pr.ltile % pr.m_tiles) * m_sub + (int)rank, n_blk = pr.ltile / pr.m_tiles;
             const bool empty_split = wi.k_end <= wi.k_begin;
-            const RowMap rm = map_row(P, m_blk, row_in_tile);
+            const RowMap rm = map_row(P, pr.M, m_blk, row_in_tile);
             const long long row = rm.row;
             const bool row_ok = rm.ok;
             const int group = rm.group;
@@ -466,7 +499,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 col_limit = P.geglu_half;
             } else {
                 col0 = n_blk * BN;
-                col_limit = P.N;
+                col_limit = pr.N;
             }
 
             mbar_wait(&tfull_bar[acc], acc_phase);
@@ -480,7 +513,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
                 RowMap rmap[4];
 #pragma unroll
-                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, m_blk, q * 32 + st * 8 + (lane >> 2));
+                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
 #pragma unroll 1
                 for (int c = half * 32; c < BN / 2; c += 64) {
                     uint32_t rv[32], rg[32];
@@ -575,7 +608,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             } else {
                 RowMap rmap[4];
 #pragma unroll
-                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, m_blk, q * 32 + st * 8 + (lane >> 2));
+                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
                     if (col0 + c >= col_limit) break;          // warp-uniform
@@ -594,7 +627,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     for (int st = 0; st < 4; ++st) {
                         float f[8];
                         unstage8(stg, lane, st, f);
-                        if (rmap[st].ok && col < col_limit) epi_store8(P, rmap[st].row, rmap[st].group, col, col_limit, f);
+                        if (rmap[st].ok && col < col_limit) epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, col, col_limit, f);
                     }
                     __syncwarp();
                 }
@@ -632,13 +665,13 @@ tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
     const int rblk = b & 3; b >>= 2;
     const int sub = b % m_sub;
     const int t = b / m_sub;
-    const int tile = P.full_work + t;                       // tail split implies splits == 1
-    const int m_blk = (tile % P.m_tiles) * m_sub + sub, n_blk = tile / P.m_tiles;
+    const Prob pr = select_prob(P, P.full_work + t);        // tail split implies splits == 1
+    const int m_blk = (pr.ltile % pr.m_tiles) * m_sub + sub, n_blk = pr.ltile / pr.m_tiles;
     const int row_in_tile = rblk * 32 + (threadIdx.x >> 2);
     const int cq = (threadIdx.x & 3) * 8;                   // this lane's 8 columns inside the 32-column block
-    const RowMap rm = map_row(P, m_blk, row_in_tile);
+    const RowMap rm = map_row(P, pr.M, m_blk, row_in_tile);
     const int col = n_blk * P.bn + chunk * 32 + cq;
-    if (!rm.ok || col >= P.N) return;
+    if (!rm.ok || col >= pr.N) return;
     float acc[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) acc[j] = 0.f;
@@ -651,7 +684,7 @@ tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
         acc[0] += v0.x; acc[1] += v0.y; acc[2] += v0.z; acc[3] += v0.w;
         acc[4] += v1.x; acc[5] += v1.y; acc[6] += v1.z; acc[7] += v1.w;
     }
-    epi_store8(P, rm.row, rm.group, col, P.N, acc);
+    epi_store8(P, pr.C, pr.ldc, rm.row, rm.group, col, pr.N, acc);
 }
 
 // ---- split-K reduction: sum fp32 partials, optional accumulate into existing bf16, optional OIHW permute ----
@@ -787,39 +820,40 @@ struct TilePlan { int bn; bool pair; int n_tiles; double cycles; int tail_tiles,
 
 // `allow_tail`: the caller's epilogue is EPI_STORE with splits == 1, so the last (partial) wave may be cut along K instead
 // (decode_work / tail_fixup_kernel): 80 tiles on 74 CTA pairs then cost ~1.1 tile times instead of 2.
-static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, int splits, bool b_mn, bool geglu, int n_groups /*taps*/,
-                           bool allow_tail = false) {
+// core: `units_of(pair, bn, &n_tiles)` = number of work units (tiles x splits) for a candidate tile shape
+template <class UnitsFn>
+static TilePlan plan_tiles_core(UnitsFn units_of, bool can_pair, int k_iters_per_unit, int splits, bool b_mn, bool geglu, bool allow_tail) {
     TilePlan best{128, false, 0, 1e300, 0, 1}, best_tail{128, false, 0, 1e300, 0, 1};
     const int sms = sm_count();
     const int step = b_mn ? 64 : 32;
     for (int pair = 0; pair <= 1; ++pair) {
-        if (pair && (g_pair_mode == 0 || m_tiles128 < 2)) continue;
-        if (!pair && g_pair_mode == 2 && m_tiles128 >= 2) continue;
+        if (pair && (g_pair_mode == 0 || !can_pair)) continue;
+        if (!pair && g_pair_mode == 2 && can_pair) continue;
         for (int bn = 64; bn <= 256; bn += step) {
             if (g_force_bn > 0 && bn != g_force_bn) continue;
             if (geglu && bn != 256 && bn != 128) continue;
             if (pair && (bn % (2 * step))) continue;
-            const int n_out = geglu ? bn / 2 : bn;
-            const int n_tiles = n_groups * ceil_div(n_extent, n_out);
-            const long long units = (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * n_tiles * splits;
+            int n_tiles = 0;
+            const long long units = units_of(pair != 0, bn, &n_tiles);
             const int slots = pair ? sms / 2 : sms;
             const double rounds = (double)((units + slots - 1) / slots);
             // cycles per K iteration, calibrated on B200 (tools/gemm_sweep.py, profiles/r01_gemm_sweep.json): a ~540-cycle
             // floor per iteration, then growth with the tile width; a CTA pair shares B and grows more slowly
             const double cyc = pair ? fmax(535.0, 535.0 + (bn - 64) * 0.30 + fmax(0.0, bn - 128.0) * 0.85)
                                     : fmax(535.0, 535.0 + (bn - 64) * 0.60 + fmax(0.0, bn - 160.0) * 1.95);
-            const double epi = (geglu ? 20.0 : 9.0) * bn + 400.0;
+            const double epi = (geglu ? 12.0 : 6.0) * bn + 400.0;
             const double main_loop = k_iters_per_unit * cyc;
             const double total = rounds * fmax(main_loop, epi) + epi + 3000.0;
             if (total < best.cycles) best = TilePlan{bn, pair != 0, n_tiles, total, 0, 1};
             // the same tiles with the last wave cut along K
             const int r = (int)(units % slots);
             if (allow_tail && g_tail_mode > 0 && splits == 1 && !geglu && r > 0 && g_tail_ws) {
-                int ts = slots / r;
-                if (ts > k_iters_per_unit / 2) ts = k_iters_per_unit / 2;
-                if (ts > 16) ts = 16;
-                const long long ws_bytes = (long long)r * ts * (pair ? 2 : 1) * BM * bn * 4;
-                if (ts >= 2 && ws_bytes <= g_tail_bytes) {
+                int ts_max = slots / r;
+                if (ts_max > k_iters_per_unit / 2) ts_max = k_iters_per_unit / 2;
+                if (ts_max > 16) ts_max = 16;
+                for (int ts = 2; ts <= ts_max; ++ts) {
+                    const long long ws_bytes = (long long)r * ts * (pair ? 2 : 1) * BM * bn * 4;
+                    if (ws_bytes > g_tail_bytes) break;
                     const double full_rounds = (double)(units / slots);
                     const double slice = ceil_div(k_iters_per_unit, ts) * cyc;
                     const double fix = 6000.0 + (double)ws_bytes * 2.0 / 3000.0;         // extra launch + partial write / read
@@ -831,6 +865,18 @@ static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, i
     }
     if (best_tail.tail_tiles > 0 && (g_tail_mode == 2 || best_tail.cycles < best.cycles)) return best_tail;
     return best;
+}
+
+// `allow_tail`: the caller's epilogue is EPI_STORE with splits == 1, so the last (partial) wave may be cut along K instead
+// (decode_work / tail_fixup_kernel): 80 tiles on 74 CTA pairs then cost ~1.1 tile times instead of 2.
+static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, int splits, bool b_mn, bool geglu, int n_groups /*taps*/,
+                           bool allow_tail = false) {
+    auto units_of = [&](bool pair, int bn, int* n_tiles) -> long long {
+        const int n_out = geglu ? bn / 2 : bn;
+        *n_tiles = n_groups * ceil_div(n_extent, n_out);
+        return (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * (*n_tiles) * splits;
+    };
+    return plan_tiles_core(units_of, m_tiles128 >= 2, k_iters_per_unit, splits, b_mn, geglu, allow_tail);
 }
 
 // split-K factor for un-fused GEMMs: trades wave quantisation against fp32 partial traffic.  `store_direct`: with one split
@@ -975,6 +1021,69 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
     }
     return AOZ_OK;
+}
+
+// Grouped GEMM: C_g[M_g, N_g] = op(A_g) op(B_g) for g in [0, n), n <= 8, ONE persistent launch.  All problems share K, the
+// operand majors and the tile shape; plain bf16 store (no bias / residual / split-K).  Built for the weight gradients of
+// one transformer block (dW = dy^T x for to_q/k/v, to_out, ff.*: ~900 tiles that fill 148 SMs in ~6 full waves).
+// A_ptrs / B_ptrs / C_ptrs: HOST arrays of n device pointers (uint64); lda / ldb / ldc: HOST int64[n]; M / N: HOST int32[n].
+int aoz_gemm_grouped_bf16(int n, const void* A_ptrs, const void* lda, const void* B_ptrs, const void* ldb, const void* C_ptrs,
+                          const void* ldc, const void* M, const void* N, int K, int a_mn, int b_mn, void* stream) {
+    AOZ_CHECK_ARG(n >= 1 && n <= MAX_GROUPS, "aoz_gemm_grouped_bf16: 1..%d problems per launch (got %d)", MAX_GROUPS, n);
+    AOZ_CHECK_ARG(A_ptrs && B_ptrs && C_ptrs && lda && ldb && ldc && M && N && K > 0, "aoz_gemm_grouped_bf16: bad arguments");
+    const uint64_t* Ap = (const uint64_t*)A_ptrs; const uint64_t* Bp = (const uint64_t*)B_ptrs; const uint64_t* Cp = (const uint64_t*)C_ptrs;
+    const long long* la = (const long long*)lda; const long long* lb = (const long long*)ldb; const long long* lc = (const long long*)ldc;
+    const int* Ms = (const int*)M; const int* Ns = (const int*)N;
+    GemmParams P;
+    memset(&P, 0, sizeof(P));
+    P.mode = GM_LINEAR; P.epi = EPI_STORE; P.a_mn = a_mn; P.b_mn = b_mn;
+    P.K = K; P.k_iters = ceil_div(K, BK);
+    P.splits = 1;
+    P.n_groups = n;
+    bool can_pair = true, aligned = true;
+    for (int g = 0; g < n; ++g) {
+        AOZ_CHECK_ARG(Ap[g] && Bp[g] && Cp[g] && Ms[g] > 0 && Ns[g] > 0, "aoz_gemm_grouped_bf16: problem %d is empty", g);
+        AOZ_CHECK_ARG((la[g] % 8) == 0 && (lb[g] % 8) == 0 && ((Ap[g] | Bp[g]) & 15) == 0, "aoz_gemm_grouped_bf16: problem %d operand alignment", g);
+        if (Ms[g] <= BM) can_pair = false;
+        if ((Cp[g] & 15) || (lc[g] % 8)) aligned = false;
+    }
+    auto units_of = [&](bool pair, int bn, int* n_tiles) -> long long {
+        long long u = 0;
+        for (int g = 0; g < n; ++g) u += (long long)ceil_div(Ms[g], pair ? 2 * BM : BM) * ceil_div(Ns[g], bn);
+        *n_tiles = 1;
+        return u;
+    };
+    const TilePlan tp = plan_tiles_core(units_of, can_pair, P.k_iters, 1, b_mn != 0, false, /*allow_tail=*/true);
+    const int bn = tp.bn;
+    const bool pair = tp.pair;
+    P.bn = bn;
+    P.vec_ok = aligned;
+    int rc, tile_start = 0;
+    for (int g = 0; g < n; ++g) {
+        GroupDesc& d = P.grp[g];
+        d.C = (__nv_bfloat16*)Cp[g]; d.ldc = lc[g]; d.M = Ms[g]; d.N = Ns[g];
+        d.m_tiles = ceil_div(Ms[g], pair ? 2 * BM : BM);
+        d.tile_start = tile_start;
+        tile_start += d.m_tiles * ceil_div(Ns[g], bn);
+        {
+            uint64_t dims[2], strides[1]; uint32_t box[2];
+            if (!a_mn) { dims[0] = K; dims[1] = Ms[g]; box[0] = 64; box[1] = BM; }
+            else       { dims[0] = Ms[g]; dims[1] = K; box[0] = 64; box[1] = BK; }
+            strides[0] = (uint64_t)la[g] * 2;
+            if ((rc = make_tmap_bf16(&d.tmA, (const void*)Ap[g], 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+        }
+        {
+            uint64_t dims[2], strides[1]; uint32_t box[2];
+            if (!b_mn) { dims[0] = K; dims[1] = Ns[g]; box[0] = 64; box[1] = (uint32_t)(pair ? bn / 2 : bn); }
+            else       { dims[0] = Ns[g]; dims[1] = K; box[0] = 64; box[1] = BK; }
+            strides[0] = (uint64_t)lb[g] * 2;
+            if ((rc = make_tmap_bf16(&d.tmB, (const void*)Bp[g], 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+        }
+    }
+    // launch_gemm_t takes the tile count as m_tiles * n_tiles
+    P.m_tiles = tile_start; P.n_tiles = 1;
+    P.tail_tiles = tp.tail_tiles; P.tail_splits = tp.tail_splits;
+    return pair ? launch_gemm_t<true>(P, (cudaStream_t)stream) : launch_gemm_t<false>(P, (cudaStream_t)stream);
 }
 
 // Implicit-GEMM convolution forward over NHWC bf16 (also used for dgrad with a flipped, transposed weight pack).

@@ -345,7 +345,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
         const float mu = mean[row], rs = rstd[row];
-        uint4 xpk[VPL], dpk[VPL];
+        uint4 xpk[VPL], dpk[VPL], rpk[VPL];
         float s1 = 0.f, s2 = 0.f;
 #pragma unroll
         for (int i = 0; i < VPL; ++i) {
@@ -353,6 +353,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             if (v < nv) {
                 xpk[i] = ld_stream(x + row * C + v * 8);
                 dpk[i] = ld_stream(dy + row * C + v * 8);
+                if (dres) rpk[i] = ld_stream(dres + row * C + v * 8);      // residual gradient: fetched with the rest, used last
             }
         }
 #pragma unroll
@@ -384,7 +385,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
                 for (int e = 0; e < 8; ++e) o[e] = rs * (fd[e] * gm[e] - s1 - (fx[e] - mu) * rs * s2);
                 if (dres) {
                     float fr[8];
-                    unpack8(ld_stream(dres + row * C + v * 8), fr);
+                    unpack8(rpk[i], fr);
 #pragma unroll
                     for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
                 }

@@ -109,6 +109,48 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bia
     return out
 
 
+def gemm_grouped(problems, *, a_mn, b_mn):
+    """One persistent launch for up to 8 GEMMs that share K and the operand majors (plain bf16 store, no epilogue fusion):
+    ``problems`` = [(a, b, out_or_None), ...] with the operand conventions of :func:`gemm`.  Returns the outputs."""
+    import ctypes
+    n = len(problems)
+    if n == 0:
+        return []
+    if n > 8:
+        return gemm_grouped(problems[:8], a_mn=a_mn, b_mn=b_mn) + gemm_grouped(problems[8:], a_mn=a_mn, b_mn=b_mn)
+    Ks, Ms, Ns, outs = set(), [], [], []
+    for a, b, out in problems:
+        _chk(a, "gemm_grouped a", contiguous=False)
+        _chk(b, "gemm_grouped b", contiguous=False)
+        if a.dim() != 2 or b.dim() != 2 or a.stride(1) != 1 or b.stride(1) != 1:
+            raise _lib.AozoraError("gemm_grouped: operands must be 2-D with unit inner stride")
+        (M, K) = (a.shape[1], a.shape[0]) if a_mn else (a.shape[0], a.shape[1])
+        (N, Kb) = (b.shape[1], b.shape[0]) if b_mn else (b.shape[0], b.shape[1])
+        if K != Kb:
+            raise _lib.AozoraError(f"gemm_grouped: K mismatch {K} vs {Kb}")
+        Ks.add(K)
+        if out is None:
+            out = torch.empty((M, N), dtype=BF16, device=a.device)
+        _chk(out, "gemm_grouped out", contiguous=False)
+        Ms.append(M)
+        Ns.append(N)
+        outs.append(out)
+    if len(Ks) != 1:
+        raise _lib.AozoraError(f"gemm_grouped: all problems must share K (got {sorted(Ks)})")
+    _ensure_gemm_scratch(problems[0][0].device)
+    u64, i64, i32 = ctypes.c_uint64 * n, ctypes.c_longlong * n, ctypes.c_int * n
+    ap, bp, cp = u64(*[p[0].data_ptr() for p in problems]), u64(*[p[1].data_ptr() for p in problems]), u64(*[o.data_ptr() for o in outs])
+    la, lb, lc = i64(*[p[0].stride(0) for p in problems]), i64(*[p[1].stride(0) for p in problems]), i64(*[o.stride(0) for o in outs])
+    ms, ns = i32(*Ms), i32(*Ns)
+    K = Ks.pop()
+    if trace is not None:
+        trace.append(("grouped", sum(Ms), max(Ns), K, int(a_mn), int(b_mn), 0, 1, 2.0 * K * sum(m * nn for m, nn in zip(Ms, Ns))))
+    _lib.call("aoz_gemm_grouped_bf16", n, ctypes.addressof(ap), ctypes.addressof(la), ctypes.addressof(bp), ctypes.addressof(lb),
+              ctypes.addressof(cp), ctypes.addressof(lc), ctypes.addressof(ms), ctypes.addressof(ns), K, int(a_mn), int(b_mn), _stream())
+    _count()
+    return outs
+
+
 def pack_conv_weight(w, need_dgrad=True):
     """OIHW bf16 -> (wf [Cout, taps*CinPad], wd [Cin, taps*CoutPad]) with channel pads to multiples of 64."""
     _chk(w, "pack_conv_weight w")

@@ -165,6 +165,36 @@ class GradSink:
     def __init__(self):
         self.grads = {}
         self.on_grad = None        # optional callback(param, grad): data-parallel bucket scheduling during the sweep
+        self.pending = []          # deferred Linear weight gradients: (params stacked by rows, dy, x)
+
+    def wgrad(self, params, dy, x, defer=False):
+        """dW = dyᵀ x for ``params`` (one parameter, or several stacked by rows).  ``defer``: queue it; ``flush`` then runs
+        every queued gradient that shares the token count as ONE grouped persistent GEMM launch (a transformer block's
+        six weight gradients = ~900 tiles = ~6 full waves on 148 SMs, instead of six ragged launches + split-K reduces)."""
+        if defer:
+            self.pending.append((params, dy, x))
+        else:
+            self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True))
+
+    def _hand_out(self, params, dw):
+        r = 0
+        for p in params:
+            self.add(p, dw[r:r + p.shape[0]])
+            r += p.shape[0]
+
+    def flush(self):
+        jobs, self.pending = self.pending, []
+        by_k = {}
+        for job in jobs:
+            by_k.setdefault(job[2].shape[0], []).append(job)
+        for group in by_k.values():
+            if len(group) == 1:
+                params, dy, x = group[0]
+                self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True))
+                continue
+            outs = ops.gemm_grouped([(dy, x, None) for _, dy, x in group], a_mn=True, b_mn=True)
+            for (params, _, _), dw in zip(group, outs):
+                self._hand_out(params, dw)
 
     def add(self, p, g):
         g = g.view_as(p)
@@ -193,15 +223,19 @@ class _PackCache:
         return wf, wd
 
 
-def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None):
+def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None, defer=False):
     """y = x Wᵀ + b (+ residual); returns (y, bwd) with bwd(dy, out=None, accumulate=False) -> dx.
-    ``w_param``: the parameter ``w`` is a reshaped view of (1x1 conv weights used as a matrix)."""
+    ``w_param``: the parameter ``w`` is a reshaped view of (1x1 conv weights used as a matrix).
+    ``defer``: queue the weight gradient for a grouped launch (``G.flush()``)."""
     y = ops.gemm(x, w, bias=b, residual=residual)
     wp = w if w_param is None else w_param
 
     def bwd(dy, out=None, accumulate=False):
         if wp.requires_grad:
-            G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
+            if w_param is None:
+                G.wgrad((wp,), dy, x, defer=defer)
+            else:
+                G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
         if b is not None and b.requires_grad:
             G.add(b, ops.colsum(dy))
         if not need_dx:
@@ -211,14 +245,14 @@ def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None):
     return y, bwd
 
 
-def _geglu(x, w, b, G):
+def _geglu(x, w, b, G, defer=False):
     aux = torch.empty((x.shape[0], w.shape[0]), dtype=BF16, device=x.device)
     y = ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
 
     def bwd(dy):
         daux = ops.geglu_bwd(dy, aux)
         if w.requires_grad:
-            G.add(w, ops.gemm(daux, x, a_mn=True, b_mn=True))
+            G.wgrad((w,), daux, x, defer=defer)
         if b.requires_grad:
             G.add(b, ops.colsum(daux))
         return ops.gemm(daux, w, b_mn=True)
@@ -315,18 +349,14 @@ def _stacked(params):
     return torch.as_strided(w0.detach(), (rows, K), (K, 1))
 
 
-def _linear_stacked(x, wcat, params, G, *, need_dx=True):
+def _linear_stacked(x, wcat, params, G, *, need_dx=True, defer=False):
     """y = x [W_0; W_1; ...]ᵀ for bias-free projections sharing the input; returns (y [M, sum rows], bwd).
     bwd(dy [M, sum rows]) -> dx; the weight gradient is produced by one GEMM and handed out as row blocks."""
     y = ops.gemm(x, wcat)
 
     def bwd(dy):
         if params[0].requires_grad:
-            dw = ops.gemm(dy, x, a_mn=True, b_mn=True)
-            r = 0
-            for p in params:
-                G.add(p, dw[r:r + p.shape[0]])
-                r += p.shape[0]
+            G.wgrad(params, dy, x, defer=defer)
         if not need_dx:
             return None
         return ops.gemm(dy, wcat, b_mn=True)
@@ -343,16 +373,16 @@ def _basic_block(blk, x, ctx, B, T, Tc, G):
     p_qkv = (a1.to_q.weight, a1.to_k.weight, a1.to_v.weight)
     w_qkv = _stacked(p_qkv)
     if w_qkv is not None:
-        qkv, b_qkv = _linear_stacked(n1, w_qkv, p_qkv, G)
+        qkv, b_qkv = _linear_stacked(n1, w_qkv, p_qkv, G, defer=True)
         q, k, v = qkv[:, :C], qkv[:, C:2 * C], qkv[:, 2 * C:]
     else:
-        q, b_q = _linear(n1, a1.to_q.weight, None, G)
-        k, b_k = _linear(n1, a1.to_k.weight, None, G)
-        v, b_v = _linear(n1, a1.to_v.weight, None, G)
+        q, b_q = _linear(n1, a1.to_q.weight, None, G, defer=True)
+        k, b_k = _linear(n1, a1.to_k.weight, None, G, defer=True)
+        v, b_v = _linear(n1, a1.to_v.weight, None, G, defer=True)
     o1, b_at1 = _attention(q, k, v, B, T, T)
-    x1, b_o1 = _linear(o1, a1.to_out[0].weight, a1.to_out[0].bias, G, residual=x)
+    x1, b_o1 = _linear(o1, a1.to_out[0].weight, a1.to_out[0].bias, G, residual=x, defer=True)
     n2, b_n2 = _layernorm(x1, blk.norm2, G)
-    q2, b_q2 = _linear(n2, a2.to_q.weight, None, G)
+    q2, b_q2 = _linear(n2, a2.to_q.weight, None, G, defer=True)
     p_kv = (a2.to_k.weight, a2.to_v.weight)
     w_kv = _stacked(p_kv)
     if w_kv is not None:
@@ -362,10 +392,10 @@ def _basic_block(blk, x, ctx, B, T, Tc, G):
         k2, b_k2 = _linear(ctx, a2.to_k.weight, None, G, need_dx=False)
         v2, b_v2 = _linear(ctx, a2.to_v.weight, None, G, need_dx=False)
     o2, b_at2 = _attention(q2, k2, v2, B, T, Tc)
-    x2, b_o2 = _linear(o2, a2.to_out[0].weight, a2.to_out[0].bias, G, residual=x1)
+    x2, b_o2 = _linear(o2, a2.to_out[0].weight, a2.to_out[0].bias, G, residual=x1, defer=True)
     n3, b_n3 = _layernorm(x2, blk.norm3, G)
-    g, b_g = _geglu(n3, ff.net[0].proj.weight, ff.net[0].proj.bias, G)
-    x3, b_f2 = _linear(g, ff.net[2].weight, ff.net[2].bias, G, residual=x2)
+    g, b_g = _geglu(n3, ff.net[0].proj.weight, ff.net[0].proj.bias, G, defer=True)
+    x3, b_f2 = _linear(g, ff.net[2].weight, ff.net[2].bias, G, residual=x2, defer=True)
     M, Mc = x.shape[0], ctx.shape[0]
     del n1, q, k, v, o1, n2, q2, k2, v2, o2, n3, g
 
@@ -395,6 +425,7 @@ def _basic_block(blk, x, ctx, B, T, Tc, G):
             dn1 = b_q(dq)
             b_k(dk, out=dn1, accumulate=True)
             b_v(dv, out=dn1, accumulate=True)
+        G.flush()                      # this block's queued weight gradients: one grouped launch
         return b_n1(dn1, dres=dx1)
 
     return x3, bwd
@@ -655,6 +686,7 @@ class UNet2DConditionModel(nn.Module):
             b_ae1(ops.silu_bwd(da1s, a1))
             de1s = b_te2(demb)
             b_te1(ops.silu_bwd(de1s, e1))
+            G.flush()
             return G.grads
 
         assert len(skips) == 0 and n_skips >= 0

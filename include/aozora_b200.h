@@ -61,6 +61,11 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
                   int M, int N, int K, const void* bias, const void* rowgroup_bias, int rows_per_group, long long ld_rgb,
                   const void* residual, long long ldr, int epi, void* aux, long long ld_aux, int accumulate, int splits,
                   void* workspace, void* stream);
+/* Grouped GEMM (one persistent launch for up to 8 problems sharing K, operand majors and tile shape; plain bf16 store):
+ * the weight gradients dW = dy^T x of one BasicTransformerBlock [3P].  A_ptrs/B_ptrs/C_ptrs: HOST arrays of n device
+ * pointers (uint64); lda/ldb/ldc: HOST int64[n]; M/N: HOST int32[n]. */
+int aoz_gemm_grouped_bf16(int n, const void* A_ptrs, const void* lda, const void* B_ptrs, const void* ldb, const void* C_ptrs,
+                          const void* ldc, const void* M, const void* N, int K, int a_mn, int b_mn, void* stream);
 int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const void* wpack, int Cout, int ks, int stride,
                       int pad, int flip, void* y, const void* bias, const void* rowgroup_bias, const void* residual,
                       int accumulate, void* stream);

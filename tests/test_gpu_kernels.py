@@ -96,6 +96,42 @@ def test_gemm_tail_split_matches_plain_tiles(pair_mode, M, N, K, b_mn):
         _lib.call("aoz_gemm_set_tail_mode", 1)
 
 
+@pytest.mark.parametrize("pair_mode,tail_mode", [(0, 0), (2, 0), (1, 1), (0, 2), (2, 2)])
+def test_grouped_weight_gradient_gemm(pair_mode, tail_mode):
+    """One persistent launch for several dW = dy^T x problems sharing the token count (a transformer block's weight
+    gradients); every problem must match its own plain fp32 reference, for every tile / tail configuration."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(13)
+    T = 1000                                                   # tokens: not a multiple of the 64-row K step
+    shapes = [(768, 256), (256, 256), (256, 256), (2048, 256), (256, 1024), (200, 136)]      # (out features, in features)
+    probs, refs = [], []
+    for of, inf in shapes:
+        dy = torch.randn(T, of, device="cuda", generator=g).to(BF16)
+        x = torch.randn(T, inf, device="cuda", generator=g).to(BF16)
+        probs.append((dy, x, None))
+        refs.append(dy.float().t() @ x.float())
+    try:
+        _lib.call("aoz_gemm_set_pair_mode", pair_mode)
+        _lib.call("aoz_gemm_set_tail_mode", tail_mode)
+        l0 = _lib.query("aoz_launch_count")
+        outs = ops.gemm_grouped(probs, a_mn=True, b_mn=True)
+        assert _lib.query("aoz_launch_count") - l0 <= 2          # one GEMM (+ at most the tail fix-up)
+        for o, r in zip(outs, refs):
+            check(o, r)
+        # strided output views (row blocks of a stacked gradient) and > 8 problems (split into two launches)
+        big = torch.zeros(1024, 256, device="cuda", dtype=BF16)
+        more = [(probs[1][0], probs[1][1], big[i * 256:(i + 1) * 256]) for i in range(4)] + probs[:5]
+        outs = ops.gemm_grouped(more, a_mn=True, b_mn=True)
+        for i in range(4):
+            check(big[i * 256:(i + 1) * 256], refs[1])
+        for o, r in zip(outs[4:], refs[:5]):
+            check(o, r)
+    finally:
+        _lib.call("aoz_gemm_set_pair_mode", 1)
+        _lib.call("aoz_gemm_set_tail_mode", 1)
+
+
 def test_conv_tail_split_with_time_embedding_and_residual():
     from aozora_sdxl_training_b200 import _lib
     ops = _ops()
