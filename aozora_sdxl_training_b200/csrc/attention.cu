@@ -116,7 +116,8 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
     uint64_t* s_ready = bars + 5;
     uint64_t* p_ready = bars + 6;
     uint64_t* o_ready = bars + 7;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 8);
+    uint64_t* p_free = bars + 8;        // P V of the previous tile has retired: the P tile in smem (and O in TMEM) may be touched again
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (P.Tq + TILE - 1) / TILE;
@@ -129,7 +130,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(p_ready, 256); mbar_init(o_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(p_ready, 256); mbar_init(o_ready, 1); mbar_init(p_free, 1);
         fence_mbar_init();
     }
     if (warp == 9) tmem_alloc(tmem_slot, 256);
@@ -168,10 +169,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                 const int s = j & 1;
                 mbar_wait(p_ready, j & 1);
                 tc_fence_after();
-#pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tO, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
-                umma_commit(&kv_empty[s]);
+                // S of the next tile first (the softmax warps are idle until it lands), then this tile's P V
                 if (j + 1 < nkv) {
                     const int s2 = (j + 1) & 1;
                     mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
@@ -180,9 +178,13 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                     for (int k = 0; k < 4; ++k)
                         umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s2 * TILE_BYTES, k), idesc_qk, k > 0);
                     umma_commit(s_ready);
-                } else {
-                    umma_commit(o_ready);
                 }
+#pragma unroll
+                for (int k = 0; k < 8; ++k)
+                    umma_bf16(tO, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                umma_commit(p_free);
+                if (j + 1 == nkv) umma_commit(o_ready);
             }
         }
         __syncwarp();
@@ -198,7 +200,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
         float m_ref = -INFINITY, l = 0.f;
         // exp2(s * sl2 - m_ref) of this thread's 64 columns -> bf16 P tile in shared memory; returns the partial row sum and
         // (through mx) the raw maximum.  ONE pass over TMEM: reading S is the scarce resource (64 B/clk/SM), not the math.
-        auto softmax_pass = [&](int kvalid, bool full, float& mx) -> float {
+        auto softmax_pass = [&](int kvalid, bool full, float& mx, int wait_parity) -> float {
             float lsum = 0.f;
 #pragma unroll 1
             for (int c = hf * 2; c < hf * 2 + 2; ++c) {
@@ -228,6 +230,8 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                         w[e >> 1] = pack_bf16(p0, p1);
                     }
                 }
+                // the previous tile's P V reads the P tile until p_free (its MMAs are issued AFTER this tile's Q K^T)
+                if (c == hf * 2 && wait_parity >= 0) { mbar_wait(p_free, (uint32_t)wait_parity); tc_fence_after(); }
                 store_p_chunk(sP, r, c * 32, w);
             }
             return lsum;
@@ -255,11 +259,11 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                 m_ref = fmaxf(mx, __bfloat162float(xmax[(hf ^ 1) * 128 + r]));
                 named_bar_sync(1, 256);                          // xmax is reused by the next tile
                 float dummy = -3.0e38f;
-                l = softmax_pass(kvalid, full, dummy);
+                l = softmax_pass(kvalid, full, dummy, -1);
             } else {
                 // optimistic single pass against the running reference; redo only if the row maximum jumped by > 2^8
                 float mx = -3.0e38f;
-                float lsum = softmax_pass(kvalid, full, mx);
+                float lsum = softmax_pass(kvalid, full, mx, (j - 1) & 1);       // also orders the O rescale below after P V (j-1)
                 mx = bf16_ceil(mx * sl2);
                 xmax[hf * 128 + r] = __float2bfloat16_rn(mx);
                 named_bar_sync(1, 256);
@@ -278,7 +282,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                     l *= alpha;
                     m_ref = m_new;
                     float dummy = -3.0e38f;
-                    lsum = softmax_pass(kvalid, full, dummy);    // P of this tile again, against the new reference
+                    lsum = softmax_pass(kvalid, full, dummy, -1);    // P of this tile again, against the new reference
                 }
                 l += lsum;
                 named_bar_sync(1, 256);                          // xmax is reused by the next tile
@@ -359,12 +363,17 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const _
 // ================================================================================================
 // backward: dK, dV  (CTA = one KV tile; loop over Q tiles)
 // ================================================================================================
+// Ring depth of the streamed operand tiles in the backward kernels.  A slot is refilled only after the accumulating MMAs of
+// the tile that used it have retired, and a TMA round trip is ~2000 cycles: with 2 slots the score MMAs of tile i+1
+// waited for their operands every iteration (20 % of the dQ kernel's samples at s_ready, ncu r01); 3 slots hide it.
+constexpr int BWD_STAGES = 3;
+
 struct KvSmem {
     static constexpr int K = 0;
     static constexpr int V = K + TILE_BYTES;
-    static constexpr int Q = V + TILE_BYTES;             // 2 stages
-    static constexpr int DO = Q + 2 * TILE_BYTES;        // 2 stages
-    static constexpr int PT = DO + 2 * TILE_BYTES;       // 32 KB
+    static constexpr int Q = V + TILE_BYTES;             // BWD_STAGES stages
+    static constexpr int DO = Q + BWD_STAGES * TILE_BYTES;   // BWD_STAGES stages
+    static constexpr int PT = DO + BWD_STAGES * TILE_BYTES;  // 32 KB
     static constexpr int DST = PT + 2 * TILE_BYTES;      // 32 KB
     static constexpr int VEC = DST + 2 * TILE_BYTES;     // lse2[2][128], D[2][128] floats
     static constexpr int BAR = VEC + 2048;
@@ -377,14 +386,14 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + KvSmem::BAR);
     uint64_t* kv_once = bars;           // 1
-    uint64_t* q_full = bars + 1;        // 2
-    uint64_t* q_empty = bars + 3;       // 2
-    uint64_t* s_ready = bars + 5;
-    uint64_t* pds_ready = bars + 6;
-    uint64_t* acc_ready = bars + 7;
-    uint64_t* st_free = bars + 8;       // compute warps have moved S^T / dP^T into registers: next tile's MMAs may overwrite TMEM
-    uint64_t* pd_free = bars + 9;       // dV / dK MMAs that read the P^T / dS^T smem tiles have completed
-    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+    uint64_t* q_full = bars + 1;        // BWD_STAGES
+    uint64_t* q_empty = bars + 5;       // BWD_STAGES
+    uint64_t* s_ready = bars + 9;
+    uint64_t* pds_ready = bars + 10;
+    uint64_t* acc_ready = bars + 11;
+    uint64_t* st_free = bars + 12;      // compute warps have moved S^T / dP^T into registers: next tile's MMAs may overwrite TMEM
+    uint64_t* pd_free = bars + 13;      // dV / dK MMAs that read the P^T / dS^T smem tiles have completed
+    uint32_t* tmem_slot = (uint32_t*)(bars + 14);
     float* vec = (float*)(smem + KvSmem::VEC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -397,7 +406,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
 
     if (threadIdx.x == 0) {
         mbar_init(kv_once, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
         mbar_init(s_ready, 1); mbar_init(pds_ready, BWD_CT); mbar_init(acc_ready, 1);
         mbar_init(st_free, BWD_CT); mbar_init(pd_free, 1);
         fence_mbar_init();
@@ -416,8 +425,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             tma_load_4d(smem + KvSmem::K, &P.tmK, kv_once, 0, h, k0, b);
             tma_load_4d(smem + KvSmem::V, &P.tmV, kv_once, 0, h, k0, b);
             for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
-                mbar_wait(&q_empty[s], ((i >> 1) & 1) ^ 1);
+                const int s = i % BWD_STAGES;
+                mbar_wait(&q_empty[s], ((i / BWD_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(&q_full[s], 2 * TILE_BYTES);
                 tma_load_4d(smem + KvSmem::Q + s * TILE_BYTES, &P.tmQ, &q_full[s], 0, h, i * TILE, b);
                 tma_load_4d(smem + KvSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
@@ -433,8 +442,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
             const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
             auto issue_scores = [&](int i) {
-                const int s = i & 1;
-                mbar_wait(&q_full[s], (i >> 1) & 1);
+                const int s = i % BWD_STAGES;
+                mbar_wait(&q_full[s], (i / BWD_STAGES) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tSt, desc_kmajor(sK, k), desc_kmajor(sQ + s * TILE_BYTES, k), idesc_s, k > 0);
@@ -445,7 +454,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(kv_once, 0);
             issue_scores(0);
             for (int i = 0; i < nq; ++i) {
-                const int s = i & 1;
+                const int s = i % BWD_STAGES;
                 if (i + 1 < nq) {
                     mbar_wait(st_free, i & 1);
                     tc_fence_after();
@@ -580,9 +589,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
 struct DqSmem {
     static constexpr int Q = 0;
     static constexpr int DO = Q + TILE_BYTES;
-    static constexpr int K = DO + TILE_BYTES;            // 2 stages
-    static constexpr int V = K + 2 * TILE_BYTES;         // 2 stages
-    static constexpr int DS = V + 2 * TILE_BYTES;        // 32 KB
+    static constexpr int K = DO + TILE_BYTES;            // BWD_STAGES stages
+    static constexpr int V = K + BWD_STAGES * TILE_BYTES;    // BWD_STAGES stages
+    static constexpr int DS = V + BWD_STAGES * TILE_BYTES;   // 32 KB
     static constexpr int BAR = DS + 2 * TILE_BYTES;
     static constexpr int TOTAL = BAR + 256 + 1024;
 };
@@ -593,14 +602,14 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t* bars = (uint64_t*)(smem + DqSmem::BAR);
     uint64_t* q_once = bars;
-    uint64_t* kv_full = bars + 1;       // 2
-    uint64_t* kv_empty = bars + 3;      // 2
-    uint64_t* s_ready = bars + 5;
-    uint64_t* ds_ready = bars + 6;
-    uint64_t* acc_ready = bars + 7;
-    uint64_t* st_free = bars + 8;
-    uint64_t* ds_free = bars + 9;
-    uint32_t* tmem_slot = (uint32_t*)(bars + 10);
+    uint64_t* kv_full = bars + 1;       // BWD_STAGES
+    uint64_t* kv_empty = bars + 5;      // BWD_STAGES
+    uint64_t* s_ready = bars + 9;
+    uint64_t* ds_ready = bars + 10;
+    uint64_t* acc_ready = bars + 11;
+    uint64_t* st_free = bars + 12;
+    uint64_t* ds_free = bars + 13;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 14);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (P.Tq + TILE - 1) / TILE;
@@ -612,7 +621,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
 
     if (threadIdx.x == 0) {
         mbar_init(q_once, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        for (int i = 0; i < BWD_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
         mbar_init(s_ready, 1); mbar_init(ds_ready, BWD_CT); mbar_init(acc_ready, 1);
         mbar_init(st_free, BWD_CT); mbar_init(ds_free, 1);
         fence_mbar_init();
@@ -631,8 +640,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             tma_load_4d(smem + DqSmem::Q, &P.tmQ, q_once, 0, h, q0, b);
             tma_load_4d(smem + DqSmem::DO, &P.tmDO, q_once, 0, h, q0, b);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
-                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                const int s = j % BWD_STAGES;
+                mbar_wait(&kv_empty[s], ((j / BWD_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
                 tma_load_4d(smem + DqSmem::K + s * TILE_BYTES, &P.tmK, &kv_full[s], 0, h, j * TILE, b);
                 tma_load_4d(smem + DqSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
@@ -646,8 +655,8 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             const uint32_t sK = smem_u32(smem + DqSmem::K), sV = smem_u32(smem + DqSmem::V);
             const uint32_t sDS = smem_u32(smem + DqSmem::DS);
             auto issue_scores = [&](int j) {
-                const int s = j & 1;
-                mbar_wait(&kv_full[s], (j >> 1) & 1);
+                const int s = j % BWD_STAGES;
+                mbar_wait(&kv_full[s], (j / BWD_STAGES) & 1);
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s * TILE_BYTES, k), idesc_s, k > 0);
@@ -658,7 +667,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(q_once, 0);
             issue_scores(0);
             for (int j = 0; j < nkv; ++j) {
-                const int s = j & 1;
+                const int s = j % BWD_STAGES;
                 if (j + 1 < nkv) {
                     mbar_wait(st_free, j & 1);
                     tc_fence_after();
