@@ -63,6 +63,11 @@ def load():
         fn.restype = _CTYPES[ret]
         fn.argtypes = [_CTYPES[a] for a in args]
     _lib = lib
+    # experiment switches (tools / A-B runs): AOZ_PDL=0 disables programmatic dependent launch, AOZ_AUTOTUNE=1 times tile plans
+    if os.environ.get("AOZ_PDL") is not None:
+        lib.aoz_set_pdl(int(os.environ["AOZ_PDL"]))
+    if os.environ.get("AOZ_AUTOTUNE") is not None:
+        lib.aoz_gemm_set_autotune(int(os.environ["AOZ_AUTOTUNE"]))
     return lib
 
 

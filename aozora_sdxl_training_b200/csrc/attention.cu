@@ -53,6 +53,11 @@ __device__ __forceinline__ float fast_exp2(float x) {
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
     asm volatile("bar.sync %0, %1;" :: "r"(id), "r"(nthreads) : "memory");
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {       // explicit shared-space load (a generic LD costs ~2x the latency)
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr));
+    return v;
+}
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
     asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
 }
@@ -139,6 +144,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tO = tmem + 128;
+    pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
     if (warp == 8) {
         if (lane == 0) {
@@ -336,6 +342,7 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
                      long long lddo, int B, int H, int Tq, float* __restrict__ D) {
+    pdl_enter();
     const long long total = (long long)B * Tq * H * 8;                    // one work item = 8 elements of one row
     const long long bound = (total + 31) & ~31LL;                         // whole warps stay in the loop (full-mask shuffles)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += (long long)gridDim.x * blockDim.x) {
@@ -417,6 +424,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+    pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
     if (warp == BWD_CW) {
         if (lane == 0) {
@@ -500,6 +508,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             }
             named_bar_sync(1, BWD_CT);
             if (hf == 0 && i + 1 < nq) fetch_vec(i + 1);
+            const uint32_t lse2_s = smem_u32(lse2);              // dv = lse2 + 128 floats
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
             // This thread's 64 columns of S^T and dP^T in four 16-column chunks, software-pipelined: the tcgen05.ld of chunk
@@ -526,8 +535,8 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
 #pragma unroll
                 for (int e = 0; e < 16; e += 4) {
                     const int qa = hf * 32 + c * 16 + e;
-                    const float4 ls = *reinterpret_cast<const float4*>(lse2 + qa);      // broadcast reads
-                    const float4 dd = *reinterpret_cast<const float4*>(dv + qa);
+                    const float4 ls = ld_shared_f4(lse2_s + qa * 4);                    // broadcast reads
+                    const float4 dd = ld_shared_f4(lse2_s + 512 + qa * 4);
                     float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -ls.x));
                     float p1 = fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -ls.y));
                     float p2 = fast_exp2(fmaf(__uint_as_float(cs[e + 2]), sl2, -ls.z));
@@ -632,6 +641,7 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const uint32_t tS = tmem, tdP = tmem + 128, tdQ = tmem + 256;
+    pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
     if (warp == BWD_CW) {
         if (lane == 0) {
@@ -796,7 +806,7 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     static bool attr = false;
     if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL); attr = true; }
     const int grid = B * H * ((Tq + TILE - 1) / TILE);
-    attn_fwd_kernel<<<grid, ATT_FWD_THREADS, FwdSmem::TOTAL, (cudaStream_t)stream>>>(P);
+    launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
     return AOZ_OK;
 }
@@ -826,7 +836,7 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         const long long items = (long long)B * Tq * H * 8;
         long long blocks = (items + 255) / 256;
         if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-        attn_bwd_prep_kernel<<<(int)blocks, 256, 0, s>>>((const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace);
+        launch_k(attn_bwd_prep_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace);
         AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");
     }
     static bool attr = false;
@@ -835,9 +845,9 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL);
         attr = true;
     }
-    attn_bwd_dkv_kernel<<<B * H * ((Tk + TILE - 1) / TILE), ATT_BWD_THREADS, KvSmem::TOTAL, s>>>(P);
+    launch_k(attn_bwd_dkv_kernel, dim3(B * H * ((Tk + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(KvSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-    attn_bwd_dq_kernel<<<B * H * ((Tq + TILE - 1) / TILE), ATT_BWD_THREADS, DqSmem::TOTAL, s>>>(P);
+    launch_k(attn_bwd_dq_kernel, dim3(B * H * ((Tq + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(DqSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dq_kernel");
     return AOZ_OK;
 }

@@ -9,6 +9,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <string.h>
 
 namespace aoz {
 
@@ -42,9 +43,36 @@ extern long long g_launch_count;      // kernels launched by this library (api.c
     } while (0)
 
 int sm_count();
+
+// ---------------------------------------------------------------------------------------------
+// programmatic dependent launch (PDL): consecutive kernels of the training step are chained with
+// cudaLaunchAttributeProgrammaticStreamSerialization, so a kernel's CTAs are scheduled (and run their prologue: barrier
+// init, TMEM allocation, descriptor prefetch) while the previous kernel's last wave drains.  Contract: every kernel
+// launched through launch_k executes pdl_enter() before its first global-memory access -- griddepcontrol.wait returns only
+// when the preceding grid has completed and its writes are visible, so no ordering is lost.  Off by default
+// (aoz_set_pdl(1) / AOZ_PDL=1 enables it): under CUDA-graph replay the step measured 150.0 ms with it and 148.7 ms without.
+// ---------------------------------------------------------------------------------------------
+extern int g_pdl;
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args... args) {
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
 // bf16 tensor map with 128-byte swizzle and zero OOB fill (api.cu)
 int make_tmap_bf16(CUtensorMap* out, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
                    const uint32_t* box, const uint32_t* elem_strides);
+
+// device side of PDL: let the next kernel in the stream start launching, then wait for the previous one to finish
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_enter() { pdl_trigger(); pdl_wait(); }
 
 // ---------------------------------------------------------------------------------------------
 // small math helpers

@@ -131,6 +131,7 @@ __global__ void mse_finalize_kernel(const float* __restrict__ per_sample, const 
 // ---- GEGLU backward: out = h * gelu(g); aux = [h | g] (bf16) -----------------------------------------------
 __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux, long long M,
                                  int half, __nv_bfloat16* __restrict__ daux) {
+    pdl_enter();
     const int vec = half / 8;
     const long long total = M * vec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -154,8 +155,93 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __n
     }
 }
 
+// GEGLU backward + bias gradient in one pass.  grid (column blocks of 256 of the `half` columns, row chunks); a thread
+// owns 8 value and 8 gate columns and walks its row lane: daux is written as before, and the column sums of dh / dg
+// (= d bias of ff.net.0.proj, otherwise a second 84 MB read of daux) fall out of the same registers.  Partials
+// [chunk][2*half] go to the workspace; the last block of a column block (atomicInc ticket) sums them in fixed order.
+__device__ unsigned int g_geglu_tickets[1024];
+
+__global__ void __launch_bounds__(256)
+geglu_bwd_bias_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux, long long M, int half,
+                      __nv_bfloat16* __restrict__ daux, float* __restrict__ partial, __nv_bfloat16* __restrict__ dbias) {
+    pdl_enter();
+    __shared__ float sm[8][512];
+    __shared__ unsigned int s_last;
+    const int lane32 = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int vcol = blockIdx.x * 32 + lane32;                 // vector column (8 channels) inside `half`
+    const int chunks = gridDim.y;
+    const long long rows_per_chunk = (M + chunks - 1) / chunks;
+    const long long r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+    float sh[8] = {0, 0, 0, 0, 0, 0, 0, 0}, sg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (vcol * 8 < half) {
+        auto one_row = [&](long long row, const uint4& pd, const uint4& ph, const uint4& pg) {
+            float d[8], h[8], g[8], dh[8], dg[8];
+            unpack8e(pd, d); unpack8e(ph, h); unpack8e(pg, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float ex;                                           // exp(-g^2 / 2), shared by the CDF and the density
+                const float cdf = gelu_cdf(g[e], ex);
+                const float pdf = 0.39894228040143267794f * ex;
+                const float gelu = round_bf16(g[e] * cdf);          // forward rounded gelu(g) to bf16
+                dh[e] = round_bf16(d[e] * gelu);
+                dg[e] = round_bf16(round_bf16(d[e] * h[e]) * (cdf + g[e] * pdf));
+                sh[e] += dh[e];                                     // sums of the bf16 values the GEMMs will see
+                sg[e] += dg[e];
+            }
+            st_stream(daux + row * 2 * half + vcol * 8, pack8e(dh));
+            st_stream(daux + row * 2 * half + half + vcol * 8, pack8e(dg));
+        };
+        long long row = r0 + rl;
+        for (; row + 24 < r1; row += 32) {                          // four rows (12 x 16-byte loads) in flight per thread
+            uint4 pd[4], ph[4], pg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                const long long rr = row + 8 * u;
+                pd[u] = ld_stream(dy + rr * half + vcol * 8);
+                ph[u] = ld_stream(aux + rr * 2 * half + vcol * 8);
+                pg[u] = ld_stream(aux + rr * 2 * half + half + vcol * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one_row(row + 8 * u, pd[u], ph[u], pg[u]);
+        }
+        for (; row < r1; row += 8)
+            one_row(row, ld_stream(dy + row * half + vcol * 8), ld_stream(aux + row * 2 * half + vcol * 8),
+                    ld_stream(aux + row * 2 * half + half + vcol * 8));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { sm[rl][lane32 * 8 + e] = sh[e]; sm[rl][256 + lane32 * 8 + e] = sg[e]; }
+    __syncthreads();
+    // thread c sums value column c and gate column c of this block over the 8 row lanes
+    const int c = threadIdx.x;
+    float a = 0.f, b = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { a += sm[k][c]; b += sm[k][256 + c]; }
+    const int col = blockIdx.x * 256 + c;
+    float* prow = partial + (long long)blockIdx.y * 2 * half;
+    if (col < half) { prow[col] = a; prow[half + col] = b; }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicInc(&g_geglu_tickets[blockIdx.x & 1023], (unsigned int)chunks - 1);
+        s_last = (t == (unsigned int)chunks - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (col < half) {
+        float ta = 0.f, tb = 0.f;
+        for (int k = 0; k < chunks; ++k) {
+            ta += __ldcg(partial + (long long)k * 2 * half + col);
+            tb += __ldcg(partial + (long long)k * 2 * half + half + col);
+        }
+        dbias[col] = __float2bfloat16_rn(ta);
+        dbias[half + col] = __float2bfloat16_rn(tb);
+    }
+}
+
 // ---- SiLU fwd / bwd, add, scale (small tensors: embeddings) --------------------------------------------------
 __global__ void silu_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long n, __nv_bfloat16* __restrict__ y) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = __bfloat162float(x[i]);
         y[i] = __float2bfloat16_rn(v * sigm(v));
@@ -163,6 +249,7 @@ __global__ void silu_fwd_kernel(const __nv_bfloat16* __restrict__ x, long long n
 }
 __global__ void silu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x, long long n,
                                 __nv_bfloat16* __restrict__ dx) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const float v = __bfloat162float(x[i]), s = sigm(v);
         dx[i] = __float2bfloat16_rn(__bfloat162float(dy[i]) * s * (1.0f + v * (1.0f - s)));
@@ -170,6 +257,7 @@ __global__ void silu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
 }
 __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloat16* __restrict__ b, long long n8,
                            long long n, __nv_bfloat16* __restrict__ y) {
+    pdl_enter();
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (long long)gridDim.x * blockDim.x) {
         float fa[8], fb[8];
         unpack8e(ld_stream(a + i * 8), fa);
@@ -185,6 +273,7 @@ __global__ void add_kernel(const __nv_bfloat16* __restrict__ a, const __nv_bfloa
 
 // ---- nearest 2x upsample (NHWC) fwd and its adjoint --------------------------------------------------------
 __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C, __nv_bfloat16* __restrict__ y) {
+    pdl_enter();
     const int vec = C / 8;
     const long long total = (long long)NB * 2 * H * 2 * W * vec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -198,6 +287,7 @@ __global__ void upsample2x_fwd_kernel(const __nv_bfloat16* __restrict__ x, int N
     }
 }
 __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int NB, int H, int W, int C, __nv_bfloat16* __restrict__ dx) {
+    pdl_enter();
     const int vec = C / 8;
     const long long total = (long long)NB * H * W * vec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -223,6 +313,7 @@ __global__ void upsample2x_bwd_kernel(const __nv_bfloat16* __restrict__ dy, int 
 // y[n, 2h, 2w] = x[n, h, w], zero elsewhere; y is [NB, Hout, Wout, C] (adjoint helper for stride-2 conv dgrad)
 __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ x, int NB, int H, int W, int C, int Hout, int Wout,
                                      __nv_bfloat16* __restrict__ y) {
+    pdl_enter();
     const int vec = C / 8;
     const long long total = (long long)NB * Hout * Wout * vec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -242,6 +333,7 @@ __global__ void zero_insert2x_kernel(const __nv_bfloat16* __restrict__ x, int NB
 __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, long long src_ld, int src_off,
                                      __nv_bfloat16* __restrict__ dst, long long dst_ld, int dst_off, long long rows, int ch,
                                      int accumulate) {
+    pdl_enter();
     const int vec = ch / 8;
     const long long total = rows * vec;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
@@ -270,6 +362,7 @@ __device__ unsigned int g_colsum_tickets[4096];     // zero at module load; atom
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
               float* __restrict__ partial0, __nv_bfloat16* __restrict__ out0, int accumulate) {
+    pdl_enter();
     __shared__ float sm[8][256];
     __shared__ unsigned int s_last;
     const __nv_bfloat16* x = x0 + (long long)blockIdx.z * group_stride;
@@ -332,6 +425,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
 __global__ void __launch_bounds__(256)
 pack_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, int Cout, int Cin, int taps, int CinPad,
                         int CoutPad, __nv_bfloat16* __restrict__ wf, __nv_bfloat16* __restrict__ wd) {
+    pdl_enter();
     __shared__ __nv_bfloat16 sm[32][32 * 9 + 2];          // [co][ci * taps + tap], +2: odd word stride (conflict-free column reads)
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
     const int run = 32 * taps;
@@ -459,10 +553,26 @@ int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_s
     return AOZ_OK;
 }
 
-int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* stream) {
+long long aoz_geglu_bwd_workspace_floats(int half) { return 64LL * 2 * half; }
+
+// dbias (optional, [2*half] bf16 = d bias of the GEGLU projection) needs `workspace` (aoz_geglu_bwd_workspace_floats)
+int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* dbias, void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && aux && daux && half % 8 == 0, "aoz_geglu_bwd: bad arguments");
     if (M <= 0) return AOZ_OK;
-    geglu_bwd_kernel<<<grid_for(M * (half / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, M, half,
+    if (dbias) {
+        AOZ_CHECK_ARG(workspace != nullptr, "aoz_geglu_bwd: the bias gradient needs a workspace");
+        const int colblocks = (half + 255) / 256;
+        AOZ_CHECK_ARG(colblocks <= 1024, "aoz_geglu_bwd: half=%d too wide", half);
+        int chunks = (sm_count() * 4 + colblocks - 1) / colblocks;
+        if (chunks > 64) chunks = 64;
+        if ((long long)chunks > (M + 7) / 8) chunks = (int)((M + 7) / 8);
+        if (chunks < 1) chunks = 1;
+        launch_k(geglu_bwd_bias_kernel, dim3(colblocks, chunks), dim3(256), (size_t)(0), (cudaStream_t)stream, 
+            (const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, M, half, (__nv_bfloat16*)daux, (float*)workspace, (__nv_bfloat16*)dbias);
+        AOZ_CHECK_LAUNCH("geglu_bwd_bias_kernel");
+        return AOZ_OK;
+    }
+    launch_k(geglu_bwd_kernel, dim3(grid_for(M * (half / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, M, half,
                                                                                       (__nv_bfloat16*)daux);
     AOZ_CHECK_LAUNCH("geglu_bwd_kernel");
     return AOZ_OK;
@@ -471,14 +581,14 @@ int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* 
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream) {
     AOZ_CHECK_ARG(x && y, "aoz_silu_fwd: null pointer");
     if (n <= 0) return AOZ_OK;
-    silu_fwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, n, (__nv_bfloat16*)y);
+    launch_k(silu_fwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, n, (__nv_bfloat16*)y);
     AOZ_CHECK_LAUNCH("silu_fwd_kernel");
     return AOZ_OK;
 }
 int aoz_silu_bwd(const void* dy, const void* x, long long n, void* dx, void* stream) {
     AOZ_CHECK_ARG(dy && x && dx, "aoz_silu_bwd: null pointer");
     if (n <= 0) return AOZ_OK;
-    silu_bwd_kernel<<<grid_for(n, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, n, (__nv_bfloat16*)dx);
+    launch_k(silu_bwd_kernel, dim3(grid_for(n, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, n, (__nv_bfloat16*)dx);
     AOZ_CHECK_LAUNCH("silu_bwd_kernel");
     return AOZ_OK;
 }
@@ -487,7 +597,7 @@ int aoz_add(const void* a, const void* b, long long n, void* y, void* stream) {
     AOZ_CHECK_ARG(a && b && y, "aoz_add: null pointer");
     AOZ_CHECK_ARG((((uintptr_t)a | (uintptr_t)b | (uintptr_t)y) & 15) == 0, "aoz_add: pointers must be 16-byte aligned");
     if (n <= 0) return AOZ_OK;
-    add_kernel<<<grid_for(n / 8 + 1, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n / 8, n, (__nv_bfloat16*)y);
+    launch_k(add_kernel, dim3(grid_for(n / 8 + 1, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)a, (const __nv_bfloat16*)b, n / 8, n, (__nv_bfloat16*)y);
     AOZ_CHECK_LAUNCH("add_kernel");
     return AOZ_OK;
 }
@@ -496,7 +606,7 @@ int aoz_upsample2x_fwd(const void* x, int NB, int H, int W, int C, void* y, void
     AOZ_CHECK_ARG(x && y && C % 8 == 0, "aoz_upsample2x_fwd: bad arguments");
     const long long total = (long long)NB * 4 * H * W * (C / 8);
     if (total == 0) return AOZ_OK;
-    upsample2x_fwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C, (__nv_bfloat16*)y);
+    launch_k(upsample2x_fwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, NB, H, W, C, (__nv_bfloat16*)y);
     AOZ_CHECK_LAUNCH("upsample2x_fwd_kernel");
     return AOZ_OK;
 }
@@ -504,7 +614,7 @@ int aoz_upsample2x_bwd(const void* dy, int NB, int H, int W, int C, void* dx, vo
     AOZ_CHECK_ARG(dy && dx && C % 8 == 0, "aoz_upsample2x_bwd: bad arguments");
     const long long total = (long long)NB * H * W * (C / 8);
     if (total == 0) return AOZ_OK;
-    upsample2x_bwd_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)dy, NB, H, W, C, (__nv_bfloat16*)dx);
+    launch_k(upsample2x_bwd_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)dy, NB, H, W, C, (__nv_bfloat16*)dx);
     AOZ_CHECK_LAUNCH("upsample2x_bwd_kernel");
     return AOZ_OK;
 }
@@ -513,7 +623,7 @@ int aoz_zero_insert2x(const void* x, int NB, int H, int W, int C, int Hout, int 
     AOZ_CHECK_ARG(x && y && C % 8 == 0, "aoz_zero_insert2x: bad arguments");
     const long long total = (long long)NB * Hout * Wout * (C / 8);
     if (total == 0) return AOZ_OK;
-    zero_insert2x_kernel<<<grid_for(total, 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, NB, H, W, C, Hout, Wout, (__nv_bfloat16*)y);
+    launch_k(zero_insert2x_kernel, dim3(grid_for(total, 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, NB, H, W, C, Hout, Wout, (__nv_bfloat16*)y);
     AOZ_CHECK_LAUNCH("zero_insert2x_kernel");
     return AOZ_OK;
 }
@@ -525,7 +635,7 @@ int aoz_copy_channels(const void* src, long long src_ld, int src_off, void* dst,
     AOZ_CHECK_ARG(ch % 8 == 0 && src_off % 8 == 0 && dst_off % 8 == 0 && src_ld % 8 == 0 && dst_ld % 8 == 0,
                   "aoz_copy_channels: extents must be multiples of 8");
     if (rows <= 0 || ch <= 0) return AOZ_OK;
-    copy_channels_kernel<<<grid_for(rows * (ch / 8), 256), 256, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)src, src_ld, src_off, (__nv_bfloat16*)dst,
+    launch_k(copy_channels_kernel, dim3(grid_for(rows * (ch / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)src, src_ld, src_off, (__nv_bfloat16*)dst,
                                                                                           dst_ld, dst_off, rows, ch, accumulate);
     AOZ_CHECK_LAUNCH("copy_channels_kernel");
     return AOZ_OK;
@@ -546,7 +656,7 @@ int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long
     if ((long long)chunks > (M + 7) / 8) chunks = (int)((M + 7) / 8);
     if (chunks < 1) chunks = 1;
     AOZ_CHECK_ARG((long long)colblocks * groups <= 4096, "aoz_colsum: too many column blocks (%d x %d)", colblocks, groups);
-    colsum_kernel<<<dim3(colblocks, chunks, groups), 256, 0, s>>>((const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace,
+    launch_k(colsum_kernel, dim3(colblocks, chunks, groups), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace,
                                                                  (__nv_bfloat16*)out, accumulate);
     AOZ_CHECK_LAUNCH("colsum_kernel");
     return AOZ_OK;
@@ -558,7 +668,7 @@ int aoz_pack_conv_weight(const void* w, int Cout, int Cin, int ks, int CinPad, i
     const int taps = ks * ks;
     AOZ_CHECK_ARG(taps <= 9, "aoz_pack_conv_weight: kernel size %d unsupported", ks);
     const int cmax = CoutPad > Cout ? CoutPad : Cout;
-    pack_conv_weight_kernel<<<dim3((CinPad + 31) / 32, (cmax + 31) / 32), 256, 0, (cudaStream_t)stream>>>(
+    launch_k(pack_conv_weight_kernel, dim3((CinPad + 31) / 32, (cmax + 31) / 32), dim3(256), (size_t)(0), (cudaStream_t)stream, 
         (const __nv_bfloat16*)w, Cout, Cin, taps, CinPad, CoutPad, (__nv_bfloat16*)wf, (__nv_bfloat16*)wd);
     AOZ_CHECK_LAUNCH("pack_conv_weight_kernel");
     return AOZ_OK;

@@ -19,6 +19,9 @@
 // exactly the conv's zero padding.
 #include "common.cuh"
 #include <cstring>
+#include <string>
+#include <unordered_map>
+#include <vector>
 
 namespace aoz {
 
@@ -308,6 +311,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_enter();          // prologue done (barriers, TMEM, descriptors): only now wait for the previous kernel's results
 
     const int total_work = P.full_work + P.tail_tiles * P.tail_splits;      // (m_tiles counts 256-row pair tiles when CTA2)
     const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
@@ -659,6 +663,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 // writes 8 x 64-byte output segments.
 __global__ void __launch_bounds__(128)
 tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
+    pdl_enter();
     const int chunks = P.bn / 32;
     int b = blockIdx.x;
     const int chunk = b % chunks; b /= chunks;
@@ -695,6 +700,7 @@ tail_fixup_kernel(const __grid_constant__ GemmParams P, int m_sub) {
 __global__ void __launch_bounds__(256)
 splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, long long cols,
                      __nv_bfloat16* __restrict__ out, long long ld_out, int permute_taps, int Cin, int cin_real, int accumulate) {
+    pdl_enter();
     const long long total = rows * cols;
     if ((cols & 3) == 0 && (ld_out & 3) == 0 && ((((uintptr_t)out) & 7) == 0)) {
         const long long quads = total >> 2;
@@ -732,6 +738,7 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long ro
 __global__ void __launch_bounds__(128)
 wgrad_permute_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, int Cin, int cin_real, int taps,
                             __nv_bfloat16* __restrict__ out, int accumulate) {
+    pdl_enter();
     __shared__ float sm[128 * 9];
     const long long row = blockIdx.y;
     const int c0 = blockIdx.x * 128, c = c0 + threadIdx.x;
@@ -789,24 +796,26 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     if (!CTA2) {
         const int grid = total_work < sm_count() ? total_work : sm_count();
-        gemm_bf16_kernel<false><<<grid, GEMM_THREADS, GEMM_SMEM_TOTAL, stream>>>(P);
+        launch_k(gemm_bf16_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)(GEMM_SMEM_TOTAL), stream, P);
     } else {
         const int pairs = sm_count() / 2;
         const int grid = 2 * (total_work < pairs ? total_work : pairs);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
         cfg.gridDim = dim3(grid); cfg.blockDim = dim3(GEMM_THREADS); cfg.dynamicSmemBytes = GEMM_SMEM_TOTAL; cfg.stream = stream;
-        cudaLaunchAttribute at[1];
+        cudaLaunchAttribute at[2];
         at[0].id = cudaLaunchAttributeClusterDimension;
         at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-        cfg.attrs = at; cfg.numAttrs = 1;
+        at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[1].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at; cfg.numAttrs = g_pdl ? 2 : 1;
         cudaError_t e = cudaLaunchKernelEx(&cfg, gemm_bf16_kernel<true>, P);
         if (e != cudaSuccess) { set_error("gemm_bf16_kernel<pair> launch: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
     }
     AOZ_CHECK_LAUNCH("gemm_bf16_kernel");
     if (P.tail_tiles > 0) {
         const int m_sub = CTA2 ? 2 : 1;
-        tail_fixup_kernel<<<P.tail_tiles * m_sub * 4 * (P.bn / 32), 128, 0, stream>>>(P, m_sub);
+        launch_k(tail_fixup_kernel, dim3(P.tail_tiles * m_sub * 4 * (P.bn / 32)), dim3(128), (size_t)(0), stream, P, m_sub);
         AOZ_CHECK_LAUNCH("tail_fixup_kernel");
     }
     return AOZ_OK;
@@ -879,6 +888,76 @@ static TilePlan plan_tiles(int m_tiles128, int n_extent, int k_iters_per_unit, i
     return plan_tiles_core(units_of, m_tiles128 >= 2, k_iters_per_unit, splits, b_mn, geglu, allow_tail);
 }
 
+// ---- measured plan selection ------------------------------------------------------------------------------------
+// The cycle model above is off by up to ~60 % on mid-size shapes (the L2 -> SM feed rate depends on how many SMs pull at
+// once), so the first EAGER call of every distinct problem times the candidate plans on the caller's own operands and
+// remembers the fastest (cuBLASLt-style).  Nothing is timed during CUDA-graph capture (the model decides for shapes never
+// seen eagerly), with accumulate epilogues (re-running would change the result) or while a tile / pair / tail mode is forced.
+static int g_autotune = 0;      // off by default: plans timed on L2-warm operands mis-rank the in-step (cold weight) behaviour
+static std::unordered_map<std::string, TilePlan> g_tuned;
+
+template <class UnitsFn>
+static std::vector<TilePlan> enumerate_plans(UnitsFn units_of, bool can_pair, int k_iters_per_unit, bool b_mn, bool geglu, bool allow_tail) {
+    std::vector<TilePlan> out;
+    const int sms = sm_count();
+    const int step = b_mn ? 64 : 32;
+    for (int pair = 0; pair <= 1; ++pair) {
+        if (pair && !can_pair) continue;
+        for (int bn = 64; bn <= 256; bn += step) {
+            if (geglu && bn != 256 && bn != 128) continue;
+            if (pair && (bn % (2 * step))) continue;
+            int n_tiles = 0;
+            const long long units = units_of(pair != 0, bn, &n_tiles);
+            const int slots = pair ? sms / 2 : sms;
+            if (units > 24LL * slots && bn < 128) continue;          // many waves of narrow tiles never win
+            out.push_back(TilePlan{bn, pair != 0, n_tiles, 0.0, 0, 1});
+            const int r = (int)(units % slots);
+            if (!allow_tail || geglu || r == 0 || !g_tail_ws) continue;
+            int ts_max = slots / r;
+            if (ts_max > k_iters_per_unit / 2) ts_max = k_iters_per_unit / 2;
+            if (ts_max > 16) ts_max = 16;
+            int last = 0;
+            const int tries[4] = {2, 4, 8, ts_max};
+            for (int t = 0; t < 4; ++t) {
+                const int ts = tries[t] < ts_max ? tries[t] : ts_max;
+                if (ts < 2 || ts == last) continue;
+                last = ts;
+                if ((long long)r * ts * (pair ? 2 : 1) * BM * bn * 4 > g_tail_bytes) continue;
+                out.push_back(TilePlan{bn, pair != 0, n_tiles, 0.0, r, ts});
+            }
+        }
+    }
+    return out;
+}
+
+static bool tuning_allowed(cudaStream_t stream) {
+    if (!g_autotune || g_force_bn > 0 || g_pair_mode != 1 || g_tail_mode != 1 || g_dbg) return false;
+    cudaStreamCaptureStatus st = cudaStreamCaptureStatusNone;
+    if (cudaStreamIsCapturing(stream, &st) != cudaSuccess || st != cudaStreamCaptureStatusNone) return false;
+    return true;
+}
+
+// run(plan) launches the problem with that plan; returns the fastest candidate (or `fallback` if anything fails)
+template <class RunFn>
+static TilePlan tune_plan(const std::string& key, const std::vector<TilePlan>& cands, const TilePlan& fallback, RunFn run, cudaStream_t stream) {
+    static cudaEvent_t e0 = nullptr, e1 = nullptr;
+    if (!e0) { cudaEventCreate(&e0); cudaEventCreate(&e1); }
+    TilePlan best = fallback;
+    float best_ms = 1e30f;
+    for (const TilePlan& c : cands) {
+        if (run(c) != AOZ_OK) return fallback;                       // warm (tensor maps, instruction cache)
+        cudaEventRecord(e0, stream);
+        if (run(c) != AOZ_OK || run(c) != AOZ_OK) return fallback;
+        cudaEventRecord(e1, stream);
+        if (cudaEventSynchronize(e1) != cudaSuccess) return fallback;
+        float ms = 0.f;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (ms < best_ms) { best_ms = ms; best = c; }
+    }
+    g_tuned[key] = best;
+    return best;
+}
+
 // split-K factor for un-fused GEMMs: trades wave quantisation against fp32 partial traffic.  `store_direct`: with one split
 // the result is stored straight from the epilogue (Linear layers), so the tail split is available as an alternative to
 // split-K; conv weight gradients always go through fp32 partials + the permuting reduce.
@@ -923,6 +1002,10 @@ int aoz_gemm_set_scratch(void* ptr, long long bytes) {
     g_tail_bytes = ptr ? bytes : 0;
     return AOZ_OK;
 }
+
+// 1: time candidate plans on the first eager call of every distinct problem; 0 (default): cost model only
+int aoz_gemm_set_autotune(int on) { g_autotune = on; return AOZ_OK; }
+int aoz_gemm_tuned_plans(void) { return (int)g_tuned.size(); }
 
 int aoz_gemm_force_bn(int bn) { g_force_bn = bn; return AOZ_OK; }
 int aoz_gemm_debug_flags(int flags) { g_dbg = flags; return AOZ_OK; }
@@ -974,53 +1057,81 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         AOZ_CHECK_ARG((N % 2) == 0 && !b_mn && splits == 1, "aoz_gemm_bf16: GEGLU needs even N, K-major B, no split");
         P.geglu_half = N / 2;
     }
-    const TilePlan tp = plan_tiles(P.m_tiles, geglu ? N / 2 : N, ceil_div(P.k_iters, splits), splits, b_mn != 0, geglu, 1,
-                                   /*allow_tail=*/splits == 1 && !geglu);
-    const int bn = tp.bn;
-    const bool pair = tp.pair;
-    P.bn = bn;
-    P.n_tiles = tp.n_tiles;
-    P.splits = splits;
-    P.tail_tiles = tp.tail_tiles; P.tail_splits = tp.tail_splits;
-    P.vec_ok = ((((uintptr_t)C | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (ldc % 8) == 0 &&
-               (ld_rgb % 8) == 0 && (ldr % 8) == 0;
+    const int m_tiles128 = P.m_tiles;
+    const bool allow_tail = splits == 1 && !geglu;
+    const int kit = ceil_div(P.k_iters, splits);
     if (splits > 1) {
         AOZ_CHECK_ARG(workspace != nullptr, "aoz_gemm_bf16: split-K needs a workspace");
         AOZ_CHECK_ARG(!bias && !residual && !rowgroup_bias, "aoz_gemm_bf16: split-K does not fuse bias/residual");
-        P.epi = EPI_PARTIAL;
-        P.partial = (float*)workspace;
     }
-    P.C = (__nv_bfloat16*)C; P.ldc = ldc;
-    P.bias = (const __nv_bfloat16*)bias;
-    P.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; P.rows_per_group = rows_per_group; P.ld_rgb = ld_rgb;
-    P.residual = (const __nv_bfloat16*)residual; P.ldr = ldr;
-    P.aux = (__nv_bfloat16*)aux; P.ld_aux = ld_aux;
-    P.accumulate = accumulate;
-    int rc;
-    {   // A map
-        uint64_t dims[2], strides[1]; uint32_t box[2];
-        if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = BM; }
-        else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
-        strides[0] = (uint64_t)lda * 2;
-        if ((rc = make_tmap_bf16(&P.tmA, A, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+    const GemmParams base = P;
+    auto run = [&](const TilePlan& tp) -> int {
+        GemmParams Q = base;
+        const int bn = tp.bn;
+        const bool pair = tp.pair;
+        Q.bn = bn;
+        Q.n_tiles = tp.n_tiles;
+        Q.splits = splits;
+        Q.tail_tiles = tp.tail_tiles; Q.tail_splits = tp.tail_splits;
+        Q.vec_ok = ((((uintptr_t)C | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (ldc % 8) == 0 &&
+                   (ld_rgb % 8) == 0 && (ldr % 8) == 0;
+        if (splits > 1) {
+            Q.epi = EPI_PARTIAL;
+            Q.partial = (float*)workspace;
+        }
+        Q.C = (__nv_bfloat16*)C; Q.ldc = ldc;
+        Q.bias = (const __nv_bfloat16*)bias;
+        Q.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; Q.rows_per_group = rows_per_group; Q.ld_rgb = ld_rgb;
+        Q.residual = (const __nv_bfloat16*)residual; Q.ldr = ldr;
+        Q.aux = (__nv_bfloat16*)aux; Q.ld_aux = ld_aux;
+        Q.accumulate = accumulate;
+        int rc;
+        {   // A map
+            uint64_t dims[2], strides[1]; uint32_t box[2];
+            if (!a_mn) { dims[0] = K; dims[1] = M; box[0] = 64; box[1] = BM; }
+            else       { dims[0] = M; dims[1] = K; box[0] = 64; box[1] = BK; }
+            strides[0] = (uint64_t)lda * 2;
+            if ((rc = make_tmap_bf16(&Q.tmA, A, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+        }
+        {   // B map
+            uint64_t dims[2], strides[1]; uint32_t box[2];
+            const int b_rows = pair ? bn / 2 : bn;
+            if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = (uint32_t)((geglu && !pair) ? bn / 2 : b_rows); }
+            else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
+            strides[0] = (uint64_t)ldb * 2;
+            if ((rc = make_tmap_bf16(&Q.tmB, B, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+        }
+        if ((rc = launch_gemm(Q, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
+        if (splits > 1) {
+            const long long total = ((long long)M * N + 3) / 4;
+            int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
+            launch_k(splitk_reduce_kernel, dim3(grid), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)workspace, splits, M, N, (__nv_bfloat16*)C,
+                                                                        ldc, 0, 0, 0, accumulate);
+            AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
+        }
+        return AOZ_OK;
+    };
+    auto units_of = [&](bool pair, int bn, int* n_tiles) -> long long {
+        const int n_out = geglu ? bn / 2 : bn;
+        *n_tiles = ceil_div(geglu ? N / 2 : N, n_out);
+        return (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * (*n_tiles) * splits;
+    };
+    TilePlan tp = plan_tiles(m_tiles128, geglu ? N / 2 : N, kit, splits, b_mn != 0, geglu, 1, allow_tail);
+    if (!accumulate && tuning_allowed((cudaStream_t)stream)) {
+        char key[160];
+        snprintf(key, sizeof(key), "L %d %d %d %d %d e%d s%d f%d%d%d a%d", M, N, K, a_mn, b_mn, epi, splits, bias != nullptr, residual != nullptr,
+                 rowgroup_bias != nullptr, aux != nullptr);
+        auto it = g_tuned.find(key);
+        if (it != g_tuned.end()) tp = it->second;
+        else tp = tune_plan(key, enumerate_plans(units_of, m_tiles128 >= 2, kit, b_mn != 0, geglu, allow_tail), tp, run, (cudaStream_t)stream);
+    } else if (g_autotune && !accumulate && g_force_bn == 0 && g_pair_mode == 1 && g_tail_mode == 1) {
+        char key[160];                                              // capturing: reuse a plan measured earlier, never time
+        snprintf(key, sizeof(key), "L %d %d %d %d %d e%d s%d f%d%d%d a%d", M, N, K, a_mn, b_mn, epi, splits, bias != nullptr, residual != nullptr,
+                 rowgroup_bias != nullptr, aux != nullptr);
+        auto it = g_tuned.find(key);
+        if (it != g_tuned.end()) tp = it->second;
     }
-    {   // B map
-        uint64_t dims[2], strides[1]; uint32_t box[2];
-        const int b_rows = pair ? bn / 2 : bn;
-        if (!b_mn) { dims[0] = K; dims[1] = N; box[0] = 64; box[1] = (uint32_t)((geglu && !pair) ? bn / 2 : b_rows); }
-        else       { dims[0] = N; dims[1] = K; box[0] = 64; box[1] = BK; }
-        strides[0] = (uint64_t)ldb * 2;
-        if ((rc = make_tmap_bf16(&P.tmB, B, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
-    }
-    if ((rc = launch_gemm(P, pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
-    if (splits > 1) {
-        const long long total = ((long long)M * N + 3) / 4;
-        int grid = (int)((total + 255) / 256); if (grid > sm_count() * 16) grid = sm_count() * 16;
-        splitk_reduce_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>((const float*)workspace, splits, M, N, (__nv_bfloat16*)C,
-                                                                    ldc, 0, 0, 0, accumulate);
-        AOZ_CHECK_LAUNCH("splitk_reduce_kernel");
-    }
-    return AOZ_OK;
+    return run(tp);
 }
 
 // Grouped GEMM: C_g[M_g, N_g] = op(A_g) op(B_g) for g in [0, n), n <= 8, ONE persistent launch.  All problems share K, the
@@ -1111,34 +1222,53 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
     P.k_iters = ks * ks * P.cin_chunks;
     P.M = NB * H * W; P.N = Cout; P.K = P.k_iters * 64;
     P.m_tiles = NB * P.tiles_h * P.tiles_w;
-    const TilePlan tp = plan_tiles(P.m_tiles, Cout, P.k_iters, 1, false, false, 1, /*allow_tail=*/true);
-    const int bn = tp.bn;
-    const bool pair = tp.pair;
-    P.bn = bn;
-    P.n_tiles = tp.n_tiles;
-    P.splits = 1;
-    P.tail_tiles = tp.tail_tiles; P.tail_splits = tp.tail_splits;
-    P.vec_ok = ((((uintptr_t)y | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (Cout % 8) == 0;
-    P.C = (__nv_bfloat16*)y; P.ldc = Cout;
-    P.bias = (const __nv_bfloat16*)bias;
-    P.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; P.ld_rgb = Cout;
-    P.residual = (const __nv_bfloat16*)residual; P.ldr = Cout;
-    P.accumulate = accumulate;
-    int rc;
-    {
-        uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
-        uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
-        uint32_t box[4] = {64, (uint32_t)(P.TW * stride), (uint32_t)(P.TH * stride), 1};
-        uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
-        if ((rc = make_tmap_bf16(&P.tmA, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
+    const int m_tiles128 = P.m_tiles;
+    const GemmParams base = P;
+    auto run = [&](const TilePlan& tp) -> int {
+        GemmParams Q = base;
+        const int bn = tp.bn;
+        const bool pair = tp.pair;
+        Q.bn = bn;
+        Q.n_tiles = tp.n_tiles;
+        Q.splits = 1;
+        Q.tail_tiles = tp.tail_tiles; Q.tail_splits = tp.tail_splits;
+        Q.vec_ok = ((((uintptr_t)y | (uintptr_t)bias | (uintptr_t)rowgroup_bias | (uintptr_t)residual) & 15) == 0) && (Cout % 8) == 0;
+        Q.C = (__nv_bfloat16*)y; Q.ldc = Cout;
+        Q.bias = (const __nv_bfloat16*)bias;
+        Q.rowgroup_bias = (const __nv_bfloat16*)rowgroup_bias; Q.ld_rgb = Cout;
+        Q.residual = (const __nv_bfloat16*)residual; Q.ldr = Cout;
+        Q.accumulate = accumulate;
+        int rc;
+        {
+            uint64_t dims[4] = {(uint64_t)Cin, (uint64_t)Win, (uint64_t)Hin, (uint64_t)NB};
+            uint64_t strides[3] = {(uint64_t)Cin * 2, (uint64_t)Win * Cin * 2, (uint64_t)Hin * Win * Cin * 2};
+            uint32_t box[4] = {64, (uint32_t)(Q.TW * stride), (uint32_t)(Q.TH * stride), 1};
+            uint32_t es[4] = {1, (uint32_t)stride, (uint32_t)stride, 1};
+            if ((rc = make_tmap_bf16(&Q.tmA, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
+        }
+        {
+            uint64_t dims[2] = {(uint64_t)Q.K, (uint64_t)Cout};
+            uint64_t strides[1] = {(uint64_t)Q.K * 2};
+            uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
+            if ((rc = make_tmap_bf16(&Q.tmB, wpack, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
+        }
+        return launch_gemm(Q, pair, (cudaStream_t)stream);
+    };
+    auto units_of = [&](bool pair, int bn, int* n_tiles) -> long long {
+        *n_tiles = ceil_div(Cout, bn);
+        return (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * (*n_tiles);
+    };
+    TilePlan tp = plan_tiles(m_tiles128, Cout, P.k_iters, 1, false, false, 1, /*allow_tail=*/true);
+    if (!accumulate && g_autotune && g_force_bn == 0 && g_pair_mode == 1 && g_tail_mode == 1) {
+        char key[160];
+        snprintf(key, sizeof(key), "C %d %d %d %d %d k%d s%d p%d f%d%d%d%d", NB, Hin, Win, Cin, Cout, ks, stride, pad, flip, bias != nullptr,
+                 rowgroup_bias != nullptr, residual != nullptr);
+        auto it = g_tuned.find(key);
+        if (it != g_tuned.end()) tp = it->second;
+        else if (tuning_allowed((cudaStream_t)stream))
+            tp = tune_plan(key, enumerate_plans(units_of, m_tiles128 >= 2, P.k_iters, false, false, true), tp, run, (cudaStream_t)stream);
     }
-    {
-        uint64_t dims[2] = {(uint64_t)P.K, (uint64_t)Cout};
-        uint64_t strides[1] = {(uint64_t)P.K * 2};
-        uint32_t box[2] = {64, (uint32_t)(pair ? bn / 2 : bn)};
-        if ((rc = make_tmap_bf16(&P.tmB, wpack, 2, dims, strides, box, nullptr)) != AOZ_OK) return rc;
-    }
-    return launch_gemm(P, pair, (cudaStream_t)stream);
+    return run(tp);
 }
 
 // Convolution weight gradient: dW[cout][tap][cin] = sum_pixels dy[pix][cout] * x[pix*stride + tap - pad][cin].
@@ -1185,7 +1315,7 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
     if ((rc = launch_gemm(P, tp.pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
-    wgrad_permute_reduce_kernel<<<dim3(ceil_div(Cin, 128), Cout), 128, 0, (cudaStream_t)stream>>>(
+    launch_k(wgrad_permute_reduce_kernel, dim3(ceil_div(Cin, 128), Cout), dim3(128), (size_t)(0), (cudaStream_t)stream, 
         (const float*)workspace, splits, Cout, Cin, cin_real, taps, (__nv_bfloat16*)grad_w, accumulate);
     AOZ_CHECK_LAUNCH("wgrad_permute_reduce_kernel");
     return AOZ_OK;

@@ -31,6 +31,7 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
 gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __restrict__ partial) {
+    pdl_enter();
     extern __shared__ float sm[];          // [2][C] per-channel sums
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int vec_per_row = C / 8;
@@ -75,6 +76,7 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
                 const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int HW, int C,
                 float eps, int silu, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
                 float* __restrict__ rstd_out) {
+    pdl_enter();
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
@@ -120,6 +122,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, int HW, int C, int silu,
                     float* __restrict__ partial) {
+    pdl_enter();
     extern __shared__ float sm[];          // [2][C]
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
@@ -171,6 +174,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 __global__ void __launch_bounds__(128)
 gn_bwd_group_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma, int chunks, int C,
                     float* __restrict__ chansum, float* __restrict__ group_terms) {
+    pdl_enter();
     __shared__ float s_db[128], s_ds[128];
     const int g = blockIdx.x, n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
@@ -213,6 +217,7 @@ gn_bwd_group_kernel(const float* __restrict__ partial, const __nv_bfloat16* __re
 // pass 2b: dgamma / dbeta = sum over images of the per-channel sums
 __global__ void gn_bwd_param_kernel(const float* __restrict__ chansum, int NB, int C, __nv_bfloat16* __restrict__ dgamma,
                                     __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    pdl_enter();
     const int c = blockIdx.x * blockDim.x + threadIdx.x;
     if (c >= C) return;
     float a = 0.f, b = 0.f;
@@ -228,6 +233,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
                     const float* __restrict__ mean, const float* __restrict__ rstd, const float* __restrict__ group_terms,
                     int HW, int C, int silu, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx) {
+    pdl_enter();
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS], s_db[GN_GROUPS], s_ds[GN_GROUPS];
     const int n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
@@ -281,6 +287,7 @@ __global__ void __launch_bounds__(LN_WARPS * 32)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ beta, long long rows, int C, float eps, __nv_bfloat16* __restrict__ y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
+    pdl_enter();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = C / 8;
     for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
@@ -331,6 +338,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
               float* __restrict__ partial) {
+    pdl_enter();
     extern __shared__ float sm[];      // [LN_WARPS][2][C] per-warp partials, reduced at the end
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = C / 8;
@@ -419,6 +427,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 __global__ void __launch_bounds__(256)
 ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
                        __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+    pdl_enter();
     __shared__ float sm[8][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + cx;
@@ -450,7 +459,7 @@ static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const
         cudaFuncSetAttribute(ln_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         attr = smem;
     }
-    ln_bwd_kernel<VPL><<<blocks, LN_WARPS * 32, smem, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+    launch_k(ln_bwd_kernel<VPL>, dim3(blocks), dim3(LN_WARPS * 32), (size_t)(smem), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                           (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
                                                           (__nv_bfloat16*)dx, (float*)workspace);
     AOZ_CHECK_LAUNCH("ln_bwd_kernel");
@@ -483,14 +492,14 @@ int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB
     AOZ_CHECK_ARG(2 * C * (int)sizeof(float) <= 48 * 1024, "aoz_groupnorm_fwd: C=%d too large", C);
     cudaStream_t s = (cudaStream_t)stream;
     const int chunks = gn_chunks(NB, HW);
-    gn_stats_kernel<<<dim3(chunks, NB), GN_THREADS, 2 * C * sizeof(float), s>>>((const __nv_bfloat16*)x, HW, C, (float*)workspace);
+    launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(GN_THREADS), (size_t)(2 * C * sizeof(float)), s, (const __nv_bfloat16*)x, HW, C, (float*)workspace);
     AOZ_CHECK_LAUNCH("gn_stats_kernel");
     long long vecs = (long long)HW * (C / 8);
     int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
     const int cap = (sm_count() * 8 + NB - 1) / NB;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    gn_apply_kernel<<<dim3(gx, NB), GN_THREADS, 0, s>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
+    launch_k(gn_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
                                                        (const float*)workspace, chunks, HW, C, eps, silu, (__nv_bfloat16*)y,
                                                        (float*)mean, (float*)rstd);
     AOZ_CHECK_LAUNCH("gn_apply_kernel");
@@ -506,16 +515,16 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     const int chunks = gn_chunks(NB, HW);
     float* partial = (float*)workspace;
     float* group_terms = partial + (size_t)NB * GN_MAX_CHUNKS * 2 * C;
-    gn_bwd_stats_kernel<<<dim3(chunks, NB), GN_THREADS, 2 * C * sizeof(float), s>>>(
+    launch_k(gn_bwd_stats_kernel, dim3(chunks, NB), dim3(GN_THREADS), (size_t)(2 * C * sizeof(float)), s, 
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
         (const float*)mean, (const float*)rstd, HW, C, silu, partial);
     AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
     float* chansum = group_terms + (size_t)NB * GN_GROUPS * 2 + 64;
     cudaMemsetAsync(chansum, 0, (size_t)NB * 2 * C * sizeof(float), s);
-    gn_bwd_group_kernel<<<dim3(GN_GROUPS, NB), 128, 0, s>>>(partial, (const __nv_bfloat16*)gamma, chunks, C, chansum, group_terms);
+    launch_k(gn_bwd_group_kernel, dim3(GN_GROUPS, NB), dim3(128), (size_t)(0), s, partial, (const __nv_bfloat16*)gamma, chunks, C, chansum, group_terms);
     AOZ_CHECK_LAUNCH("gn_bwd_group_kernel");
     if (dgamma) {
-        gn_bwd_param_kernel<<<(C + 255) / 256, 256, 0, s>>>(chansum, NB, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
+        launch_k(gn_bwd_param_kernel, dim3((C + 255) / 256), dim3(256), (size_t)(0), s, chansum, NB, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
         AOZ_CHECK_LAUNCH("gn_bwd_param_kernel");
     }
     long long vecs = (long long)HW * (C / 8);
@@ -523,7 +532,7 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     const int cap = (sm_count() * 8 + NB - 1) / NB;
     if (gx > cap) gx = cap;
     if (gx < 1) gx = 1;
-    gn_bwd_apply_kernel<<<dim3(gx, NB), GN_THREADS, 0, s>>>((const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+    launch_k(gn_bwd_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                            (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd,
                                                            group_terms, HW, C, silu, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx);
     AOZ_CHECK_LAUNCH("gn_bwd_apply_kernel");
@@ -537,7 +546,7 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
     if (rows <= 0) return AOZ_OK;
     long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
     if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    ln_fwd_kernel<<<(int)blocks, LN_WARPS * 32, 0, (cudaStream_t)stream>>>((const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+    launch_k(ln_fwd_kernel, dim3((int)blocks), dim3(LN_WARPS * 32), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                                           (const __nv_bfloat16*)beta, rows, C, eps, (__nv_bfloat16*)y,
                                                                           (float*)mean, (float*)rstd);
     AOZ_CHECK_LAUNCH("ln_fwd_kernel");
@@ -565,7 +574,7 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         default: rc = launch_ln_bwd<8>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
     }
     if (rc != AOZ_OK) return rc;
-    ln_bwd_finalize_kernel<<<(2 * C + 31) / 32, 256, 0, s>>>((const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
+    launch_k(ln_bwd_finalize_kernel, dim3((2 * C + 31) / 32), dim3(256), (size_t)(0), s, (const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
                                                                (__nv_bfloat16*)dbeta, accumulate);
     AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");
     return AOZ_OK;

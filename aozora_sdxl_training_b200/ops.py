@@ -381,15 +381,21 @@ def mse_loss(pred, target_nchw, tickets, table, denom, grad_scale=1.0, *, pred_n
     return loss, per, dpred
 
 
-def geglu_bwd(dy, aux):
+def geglu_bwd(dy, aux, need_bias_grad=False):
+    """d(aux) of out = h * gelu(g), aux = [h | g].  ``need_bias_grad``: also return the column sums of d(aux) (the gradient
+    of the GEGLU projection bias) from the same pass -> (daux, dbias)."""
     _chk(dy, "geglu_bwd dy")
     _chk(aux, "geglu_bwd aux")
     half = dy.shape[-1]
     M = dy.numel() // half
     daux = torch.empty_like(aux)
-    _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _stream())
+    dbias = ws = None
+    if need_bias_grad:
+        dbias = torch.empty((2 * half,), dtype=BF16, device=dy.device)
+        ws = workspace(_lib.query("aoz_geglu_bwd_workspace_floats", half), dy.device)
+    _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _p(dbias), _p(ws), _stream())
     _count()
-    return daux
+    return (daux, dbias) if need_bias_grad else daux
 
 
 def silu_fwd(x):

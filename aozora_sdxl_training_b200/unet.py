@@ -250,11 +250,13 @@ def _geglu(x, w, b, G, defer=False):
     y = ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
 
     def bwd(dy):
-        daux = ops.geglu_bwd(dy, aux)
+        if b.requires_grad:
+            daux, db = ops.geglu_bwd(dy, aux, need_bias_grad=True)      # bias gradient from the same pass over daux
+            G.add(b, db)
+        else:
+            daux = ops.geglu_bwd(dy, aux)
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
-        if b.requires_grad:
-            G.add(b, ops.colsum(daux))
         return ops.gemm(daux, w, b_mn=True)
 
     return y, bwd

@@ -304,8 +304,9 @@ def main():
         return ms.item()
 
     from aozora_sdxl_training_b200 import _lib
+    r = step.step(dev_batch)                                   # first eager step: also times the GEMM tile plans (autotune)
     l0 = _lib.query("aoz_launch_count")                        # counted inside the library at every kernel launch site
-    r = step.step(dev_batch)                                   # first step runs eagerly: its launches are what the graph replays
+    r = step.step(dev_batch)                                   # second eager step: its launches are what the graph replays
     per_step_launches = _lib.query("aoz_launch_count") - l0
     for _ in range(max(3, args.warmup) + 1):
         r = step.step(dev_batch)

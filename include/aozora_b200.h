@@ -26,6 +26,7 @@ extern "C" {
 const char* aoz_last_error(void);
 int aoz_abi_version(void);
 int aoz_sm_count(void);
+int aoz_set_pdl(int on);               /* programmatic dependent launch between consecutive kernels (default off: no gain under graph replay) */
 long long aoz_launch_count(void);      /* kernels launched by this library so far (every launch site counts itself) */
 
 /* ---- optimizer: RavenAdamW.step / TitanAdamW.step (training_utils/optimizers/raven.py:89-149,
@@ -52,6 +53,11 @@ int aoz_gemm_force_bn(int bn);
  * scratch, finished by a fix-up kernel).  mode 0 = off, 1 = cost model decides (default), 2 = whenever possible.
  * The scratch (>= 20 MB covers every shape) is used stream-ordered: all GEMM / conv calls must share one stream. */
 int aoz_gemm_set_tail_mode(int mode);
+/* measured plan selection: the first EAGER call of every distinct GEMM / conv problem times the candidate tile plans on the
+ * caller's operands and caches the fastest (never during CUDA-graph capture, never for accumulate epilogues).  Off by
+ * default: on B200 the L2-warm timings mis-ranked the plans for the in-step (cold-weight) launches (profiles/r01 notes). */
+int aoz_gemm_set_autotune(int on);
+int aoz_gemm_tuned_plans(void);
 int aoz_gemm_set_scratch(void* ptr, long long bytes);
 int aoz_gemm_debug_flags(int flags);
 int aoz_gemm_auto_splits(int M, int N, int K, int b_mn);
@@ -109,7 +115,9 @@ int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_s
                  const void* table, int table_len, int NB, int C, int HW, float denom, const void* grad_scale_ptr, float grad_scale,
                  void* per_sample, void* weights, void* loss_out, void* dpred, long long d_sn, long long d_sc, long long d_shw,
                  void* stream);
-int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* stream);
+long long aoz_geglu_bwd_workspace_floats(int half);
+/* dbias (optional): [2*half] bf16 gradient of the GEGLU projection bias, produced in the same pass (needs workspace) */
+int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* dbias, void* workspace, void* stream);
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream);
 int aoz_silu_bwd(const void* dy, const void* x, long long n, void* dx, void* stream);
 int aoz_add(const void* a, const void* b, long long n, void* y, void* stream);
