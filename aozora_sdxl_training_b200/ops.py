@@ -256,13 +256,17 @@ def groupnorm_fwd(x, gamma, beta, eps, silu):
     return y, mean, rstd
 
 
-def groupnorm_bwd(dy, x, gamma, beta, mean, rstd, silu, need_param_grads=True, dres=None):
+def groupnorm_bwd(dy, x, gamma, beta, mean, rstd, silu, need_param_grads=True, dres=None, dgamma=None, dbeta=None):
+    """``dgamma`` / ``dbeta``: optional destinations (e.g. slices of a flat gradient buffer)."""
     _chk(dy, "groupnorm dy")
     NB, C = x.shape[0], x.shape[-1]
     HW = x.numel() // (NB * C)
     dx = torch.empty_like(x)
-    dgamma = torch.empty_like(gamma) if need_param_grads else None
-    dbeta = torch.empty_like(beta) if need_param_grads else None
+    if need_param_grads:
+        dgamma = torch.empty_like(gamma) if dgamma is None else dgamma
+        dbeta = torch.empty_like(beta) if dbeta is None else dbeta
+    else:
+        dgamma = dbeta = None
     ws = workspace(_lib.query("aoz_groupnorm_workspace_floats", NB, HW, C), x.device)
     _lib.call("aoz_groupnorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), beta.data_ptr(), mean.data_ptr(),
               rstd.data_ptr(), NB, HW, C, int(silu), _p(dres), dx.data_ptr(), _p(dgamma), _p(dbeta), 0, ws.data_ptr(), _stream())
@@ -283,13 +287,14 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None):
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
+    """``dgamma`` / ``dbeta``: optional destinations (e.g. slices of a flat gradient buffer)."""
     _chk(dy, "layernorm dy")
     C = x.shape[-1]
     rows = x.numel() // C
     dx = torch.empty_like(x)
-    dgamma = torch.empty_like(gamma)
-    dbeta = torch.empty_like(gamma)
+    dgamma = torch.empty_like(gamma) if dgamma is None else dgamma
+    dbeta = torch.empty_like(gamma) if dbeta is None else dbeta
     ws = workspace(_lib.query("aoz_layernorm_bwd_workspace_floats", C), x.device)
     _lib.call("aoz_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
               _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0, ws.data_ptr(), _stream())

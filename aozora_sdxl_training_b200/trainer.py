@@ -60,6 +60,9 @@ class SDXLTrainStep:
         if self.global_batch % self.world:
             raise ValueError("BATCH_SIZE (global) must be divisible by the number of ranks")
         self.local_batch = self.global_batch // self.world
+        if dp is not None and self.grad_accum != 1:
+            raise ValueError("data-parallel training reduces every micro-step: GRADIENT_ACCUMULATION_STEPS must be 1 "
+                             "(raise the per-GPU batch instead; 180 GB of HBM holds b=16 at 1024x1024)")
         if not hasattr(config, "is_rectified_flow"):
             config.is_rectified_flow = self.is_rf
         self.sampler = host.TimestepSampler(config, self.device)
@@ -110,8 +113,10 @@ class SDXLTrainStep:
         denom = float(b * self.world)
         loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
                                        grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
-        hook = self.dp.grad_ready if self.dp is not None else None
-        grads = bwd(dpred8) if hook is None else bwd(dpred8, on_grad=hook)
+        if self.dp is None:
+            grads = bwd(dpred8)
+        else:       # gradients are written straight into the flat buffer; each bucket is reduced as soon as it is complete
+            grads = bwd(dpred8, on_grad=self.dp.grad_ready, dest=self.dp.grad_view)
         return loss, grads
 
     def _host_inputs(self, batch, noise, jitter):

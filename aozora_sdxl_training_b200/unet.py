@@ -166,6 +166,30 @@ class GradSink:
         self.grads = {}
         self.on_grad = None        # optional callback(param, grad): data-parallel bucket scheduling during the sweep
         self.pending = []          # deferred Linear weight gradients: (params stacked by rows, dy, x)
+        self.dest = None           # optional callback(param) -> tensor the gradient must be written to (data-parallel flat buffer)
+
+    def out_for(self, params):
+        """Destination for the gradient of ``params`` (one parameter, or several stacked by rows): a view of the caller's
+        gradient storage when it provides one and the row blocks are contiguous there, else None (fresh tensor)."""
+        if self.dest is None:
+            return None
+        if not isinstance(params, (tuple, list)):
+            return None if params in self.grads else self.dest(params)
+        if any(p in self.grads for p in params):
+            return None
+        d0 = self.dest(params[0])
+        if d0 is None:
+            return None
+        if len(params) == 1:
+            return d0
+        K = params[0].shape[1]
+        rows = 0
+        for p in params:
+            d = self.dest(p)
+            if d is None or d.data_ptr() != d0.data_ptr() + rows * K * d0.element_size():
+                return None
+            rows += p.shape[0]
+        return torch.as_strided(d0, (rows, K), (K, 1))
 
     def wgrad(self, params, dy, x, defer=False):
         """dW = dyᵀ x for ``params`` (one parameter, or several stacked by rows).  ``defer``: queue it; ``flush`` then runs
@@ -174,7 +198,7 @@ class GradSink:
         if defer:
             self.pending.append((params, dy, x))
         else:
-            self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True))
+            self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True, out=self.out_for(params)))
 
     def _hand_out(self, params, dw):
         r = 0
@@ -190,9 +214,9 @@ class GradSink:
         for group in by_k.values():
             if len(group) == 1:
                 params, dy, x = group[0]
-                self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True))
+                self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True, out=self.out_for(params)))
                 continue
-            outs = ops.gemm_grouped([(dy, x, None) for _, dy, x in group], a_mn=True, b_mn=True)
+            outs = ops.gemm_grouped([(dy, x, self.out_for(params)) for params, dy, x in group], a_mn=True, b_mn=True)
             for (params, _, _), dw in zip(group, outs):
                 self._hand_out(params, dw)
 
@@ -237,7 +261,7 @@ def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None, defer=Fals
             else:
                 G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
         if b is not None and b.requires_grad:
-            G.add(b, ops.colsum(dy))
+            G.add(b, ops.colsum(dy, out=G.out_for(b)))
         if not need_dx:
             return None
         return ops.gemm(dy, w, b_mn=True, out=out, accumulate=accumulate, splits=1 if accumulate else None)
@@ -272,10 +296,12 @@ def _conv(x, mod, G, packs, *, stride=1, rowgroup_bias=None, residual=None, need
     def bwd(dy):
         # dy may carry zero-padded output channels (conv_out: 4 real channels of 8)
         if w.requires_grad:
-            dw = ops.conv_wgrad(dy, x, ks, stride=stride, pad=ks // 2, cin_real=cin_real)
+            gw = G.out_for(w) if dy.shape[-1] == cout else None           # padded output channels: slice a temporary instead
+            dw = ops.conv_wgrad(dy, x, ks, stride=stride, pad=ks // 2, cin_real=cin_real, grad_w=gw)
             G.add(w, dw[:cout])
         if b.requires_grad:
-            G.add(b, ops.colsum(dy.view(-1, dy.shape[-1]))[:cout])
+            gb = G.out_for(b) if dy.shape[-1] == cout else None
+            G.add(b, ops.colsum(dy.view(-1, dy.shape[-1]), out=gb)[:cout])
         if not need_dx:
             return None
         cin = x.shape[-1]
@@ -292,7 +318,9 @@ def _groupnorm(x, mod, G, silu):
 
     def bwd(dy, dres=None):
         need = mod.weight.requires_grad or mod.bias.requires_grad
-        dx, dg, db = ops.groupnorm_bwd(dy, x, mod.weight, mod.bias, mean, rstd, silu, need_param_grads=need, dres=dres)
+        both = mod.weight.requires_grad and mod.bias.requires_grad
+        dx, dg, db = ops.groupnorm_bwd(dy, x, mod.weight, mod.bias, mean, rstd, silu, need_param_grads=need, dres=dres,
+                                       dgamma=G.out_for(mod.weight) if both else None, dbeta=G.out_for(mod.bias) if both else None)
         if mod.weight.requires_grad:
             G.add(mod.weight, dg)
         if mod.bias.requires_grad:
@@ -306,7 +334,9 @@ def _layernorm(x, mod, G):
     y, mean, rstd = ops.layernorm_fwd(x, mod.weight, mod.bias, mod.eps)
 
     def bwd(dy, dres=None):
-        dx, dg, db = ops.layernorm_bwd(dy, x, mod.weight, mean, rstd, dres=dres)
+        both = mod.weight.requires_grad and mod.bias.requires_grad
+        dx, dg, db = ops.layernorm_bwd(dy, x, mod.weight, mean, rstd, dres=dres, dgamma=G.out_for(mod.weight) if both else None,
+                                       dbeta=G.out_for(mod.bias) if both else None)
         if mod.weight.requires_grad:
             G.add(mod.weight, dg)
         if mod.bias.requires_grad:
@@ -644,8 +674,9 @@ class UNet2DConditionModel(nn.Module):
         del hn, x
         n_skips = 3 * len(self.up_blocks)
 
-        def bwd(dpred8, on_grad=None):
+        def bwd(dpred8, on_grad=None, dest=None):
             G.on_grad = on_grad
+            G.dest = dest
             dsemb = None
 
             def acc_semb(d):

@@ -277,8 +277,8 @@ def main():
     else:
         opt = RavenAdamW([{"params": [p for p in unet.parameters() if p.requires_grad], "lr_scale": 1.0}], lr=8e-7,
                          momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
-    # data-parallel runs issue kernels eagerly (NCCL collectives interleave with the reverse sweep); single GPU replays a graph
-    use_graph = (not args.no_graph) and world == 1
+    # the device side of the step (NCCL reduce-scatter / all-gather included) is captured once and replayed
+    use_graph = not args.no_graph
     step = SDXLTrainStep(unet, opt, cfg, device=dev, dp=dp, use_cuda_graph=use_graph)
 
     host_batch = synth_batch(args.batch, args.res, 100 + rank, pin=True)
@@ -374,7 +374,9 @@ def main():
         print(json.dumps(line))
     if world > 1:
         torch.distributed.barrier()
-        torch.distributed.destroy_process_group()
+        torch.cuda.synchronize()
+        sys.stdout.flush()
+        os._exit(0)           # CUDA graphs holding captured NCCL kernels make destroy_process_group hang; nothing is left to do
 
 
 if __name__ == "__main__":

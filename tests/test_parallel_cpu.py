@@ -81,9 +81,16 @@ def _worker(rank, world, port, q):
             grads_all = [[torch.randn(s, generator=torch.Generator().manual_seed(1000 * step + 10 * r + i)) for i, s in enumerate(shapes)]
                          for r in range(world)]
             # reverse order, as the sweep produces them
+            versions = [p._version for p in dp.params]
             for i in reversed(range(len(shapes))):
-                dp.grad_ready(dp.params[i], grads_all[rank][i])
+                if i % 2 == 0:
+                    dp.grad_ready(dp.params[i], grads_all[rank][i])            # staged by copy
+                else:
+                    dp.grad_view(dp.params[i]).copy_(grads_all[rank][i])       # produced in place (what the GEMM kernels do)
+                    dp.grad_ready(dp.params[i], dp.grad_view(dp.params[i]))
             out = dp.reduce_clip_step(opt, 0.5)
+            # parameters changed behind autograd's back: version counters must move (the UNet's packed conv weights key on them)
+            assert all(p._version > v for p, v in zip(dp.params, versions))
             summed = [sum(grads_all[r][i] for r in range(world)) for i in range(len(shapes))]
             norm = torch.sqrt(sum((g.double() ** 2).sum() for g in summed)).item()
             coef = min(1.0, 0.5 / (norm + 1e-6))
