@@ -581,6 +581,13 @@ class UNet2DConditionModel(nn.Module):
                         r += p.shape[0]
         self._fused_storage_ok = True
 
+    # ---- reference boundary: UNet2DConditionModel.from_single_file (train.py:1458-1464) -------------------
+    @classmethod
+    def from_single_file(cls, path, torch_dtype=None, low_cpu_mem_usage=True, in_channels=None, out_channels=None, device="cpu", **_):
+        """Load the UNet of an SDXL single-file ``.safetensors`` checkpoint (LDM key names) -- see ``checkpoint.py``."""
+        from .checkpoint import load_unet_single_file
+        return load_unet_single_file(path, torch_dtype=torch_dtype or BF16, device=device, in_channels=in_channels, out_channels=out_channels)
+
     # ---- reference boundary no-ops (train.py:199-229, 2660) ----------------------------------------------
     def enable_gradient_checkpointing(self):
         self.gradient_checkpointing = True        # accepted; nothing is recomputed on B200 (see module docstring)

@@ -125,6 +125,8 @@ def main():
     out["key_map"] = dict(n=len(names), sha256_names=hashlib.sha256("\n".join(names).encode()).hexdigest(),
                           sha256_ldm=hashlib.sha256("\n".join(mapping[k] for k in names).encode()).hexdigest(),
                           samples={k: mapping[k] for k in names[::97]})
+    # digest of the whole {diffusers key -> LDM key} table, in state_dict order (tests/test_checkpoint.py)
+    out["unet_key_mapping_sha256"] = hashlib.sha256("\n".join(f"{k} -> {v}" for k, v in mapping.items()).encode()).hexdigest()
 
     # ---- Raven / Titan trajectories (raven.py:89-149, titan.py:237-296) -------------------
     traj = {}
