@@ -1,0 +1,85 @@
+"""The reference's training loop (train.py:2558-2828 ``main``) over the B200 pieces: cached dataset -> bucketed batch
+schedule -> pinned-memory feeder -> ``SDXLTrainStep`` (noise, UNet, loss, reverse sweep, clip, Raven) -> periodic export.
+
+Only what the loop needs is here (no GUI reporter, no caching pass, no VAE): it exists so that a run can be started,
+checkpointed and resumed with the reference's files -- same cache directory, same ``.safetensors`` / ``.pt`` outputs, same
+schedule and ticket positions after a resume (train.py:2566-2582, 2700-2712).
+"""
+from __future__ import annotations
+
+from pathlib import Path
+
+import torch
+
+from . import checkpoint, data, host
+from .optimizers import RavenAdamW
+from .trainer import SDXLTrainStep
+
+
+def build_optimizer(config, unet, dp=None):
+    """RavenAdamW over the trainable parameters in ``unet.parameters()`` order, one group with ``lr_scale`` 1.0
+    (train.py:2669-2679, 2265-2270); the LR curve's maximum is the constructor lr as in ``create_optimizer`` (2256-2262)."""
+    host.apply_exclusion(unet, list(getattr(config, "UNET_EXCLUDE_TARGETS", []) or []))
+    curve = getattr(config, "LR_CUSTOM_CURVE", None) or []
+    lr = max(p[1] for p in curve) if curve else getattr(config, "LEARNING_RATE", 1e-6)
+    kw = dict(getattr(config, "RAVEN_PARAMS", {}) or {})
+    kw.setdefault("betas", (0.9, 0.999))
+    if dp is not None:
+        return dp.make_optimizer(lr=lr, **kw)
+    params = [p for p in unet.parameters() if p.requires_grad]
+    return RavenAdamW([{"params": params, "lr_scale": 1.0}], lr=lr, momentum_dtype=getattr(config, "MOMENTUM_DTYPE", torch.bfloat16), **kw)
+
+
+def run_training(config, unet, *, device="cuda", dp=None, optimizer=None, resume_state_path=None, base_checkpoint_path=None,
+                 use_cuda_graph=False, on_step=None):
+    """Train for ``config.MAX_TRAIN_STEPS`` micro-steps (or resume).  Returns {"losses", "micro_step", "saved"}.
+
+    ``config`` carries the reference's flat keys: SEED, BATCH_SIZE (global), MAX_TRAIN_STEPS, GRADIENT_ACCUMULATION_STEPS,
+    INSTANCE_DATASETS, PREDICTION_TYPE, LR_CUSTOM_CURVE, CLIP_GRAD_NORM, SAVE_EVERY_N_STEPS, OUTPUT_DIR, OUTPUT_NAME ...
+    ``base_checkpoint_path``: the single-file checkpoint whose non-UNet tensors an export carries along; without it only the
+    training-state file is written."""
+    if not hasattr(config, "is_rectified_flow"):
+        config.is_rectified_flow = getattr(config, "PREDICTION_TYPE", "epsilon") == "rectified_flow"
+    world = 1 if dp is None else dp.world
+    rank = 0 if dp is None else dp.rank
+    optimizer = optimizer or build_optimizer(config, unet, dp)
+    step = SDXLTrainStep(unet, optimizer, config, device=device, dp=dp, use_cuda_graph=use_cuda_graph)
+    dataset = data.CachedLatentDataset(config)
+    schedule = data.pack_sample_schedule(
+        data.epoch_shuffle_batch_schedule(dataset.bucket_keys, int(config.MAX_TRAIN_STEPS), int(config.BATCH_SIZE), step.seed),
+        int(config.BATCH_SIZE))
+    start = 0
+    if resume_state_path is not None:
+        st = checkpoint.load_training_state(resume_state_path, optimizer=optimizer, timestep_sampler=step.sampler,
+                                            grad_accum=step.grad_accum)
+        start = int(st["micro_step"])
+        step.micro_step = start
+        step.optimizer_steps = int(st["optimizer_step"])
+    feeder = data.BatchFeeder(dataset, schedule, rank=rank, world=world, start_step=start)
+    save_every = int(getattr(config, "SAVE_EVERY_N_STEPS", 0) or 0)
+    out_dir = Path(getattr(config, "OUTPUT_DIR", "."))
+    stem = getattr(config, "OUTPUT_NAME", "aozora_b200")
+    losses, saved = [], []
+    for batch in feeder:
+        if step.micro_step >= int(config.MAX_TRAIN_STEPS):
+            break
+        if not batch:                              # every item of the batch failed to load: the reference skips it too
+            continue
+        res = step.step(batch)
+        losses.append(res)
+        if on_step is not None:
+            on_step(step.micro_step, res)
+        if save_every and res.did_optimizer_step and step.optimizer_steps % save_every == 0:
+            gs = step.optimizer_steps
+            state_path = out_dir / f"{stem}_training_state_step_{gs}.pt"
+            # under data parallel every rank takes part in the gather inside save_cpu_state; rank 0 writes
+            st = checkpoint.save_training_state(state_path if rank == 0 else out_dir / f".rank{rank}_{stem}_state.pt", global_step=gs,
+                                                micro_step=step.micro_step, optimizer=optimizer, sampler_seed=step.seed,
+                                                sampler_epoch=step.micro_step, timestep_sampler=step.sampler)
+            del st
+            if rank == 0:
+                if base_checkpoint_path is not None:
+                    checkpoint.save_model(out_dir / f"{stem}_step_{gs}.safetensors", unet, base_checkpoint_path,
+                                          getattr(config, "compute_dtype", torch.bfloat16))
+                saved.append(state_path)
+    return dict(losses=[r.loss_value() for r in losses], micro_step=step.micro_step, saved=saved, step=step)

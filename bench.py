@@ -131,7 +131,10 @@ def gemm_roofline(torch, peaks, iters=20):
     flops = 2.0 * M * N * K
     ach = flops / (ms * 1e-3) / 1e12
     return dict(bound="tensor", kernel="gemm_bf16_kernel<256> (GEGLU epilogue) M=4096 K=1280 N=10240", achieved=round(ach, 1),
-                peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4), traffic=None,
+                peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4),
+                # dram__bytes_read.sum + dram__bytes_write.sum of this exact launch from the committed `ncu --set full` capture
+                # (36.86 MB read + 77.51 MB written; algorithmic bytes: 36.7 MB operands + 125.8 MB outputs, part still in L2)
+                traffic=114366464, traffic_source="profiles/r01_gemm_geglu_ncu_v2.txt",
                 peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
                 flops_per_launch=flops)
 

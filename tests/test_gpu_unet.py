@@ -246,3 +246,61 @@ def test_stacked_projections_match_separate_projections():
     assert [k for k, _ in prod.named_parameters()] == [k for k, _ in ref.named_parameters()]
     for (k, v), (_, r) in zip(prod.state_dict().items(), ref.state_dict().items()):
         assert torch.equal(v.float().cpu(), r), k
+
+
+def _training_cache(root):
+    """Small cache in the reference's on-disk format with latent sizes the three-level UNet accepts (multiples of 4)."""
+    import os
+    g = torch.Generator().manual_seed(77)
+    cdir = os.path.join(root, "set", ".precomputed_embeddings_cache_standard_sdxl")
+    os.makedirs(cdir)
+    files = []
+    for i in range(10):
+        w, h = [(1024, 1024), (1536, 1024), (1024, 1536)][i % 3]
+        lat, te = os.path.join(cdir, f"im{i}_lat.pt"), os.path.join(cdir, f"im{i}_te.pt")
+        torch.save({"latents": (torch.randn(4, h // 64, w // 64, generator=g) * 0.8).to(BF16)}, lat)
+        torch.save({"embeds": torch.randn(77, 128, generator=g).to(BF16), "pooled": torch.randn(64, generator=g).to(BF16)}, te)
+        files.append({"lat_path": lat, "te_path": te, "original_size": (w, h), "target_size": (w, h), "relative_path": f"im{i}.png"})
+    torch.save({"files": files}, os.path.join(cdir, "dataset_index.pt"))
+    return [{"path": os.path.join(root, "set"), "repeats": 1}]
+
+
+def test_training_loop_from_cache_checkpoint_and_resume(tmp_path):
+    """Cached dataset -> schedule -> feeder -> fused step -> training-state file; a run resumed from the step-4 state must
+    continue with the same batches, tickets, noise and LR as the uninterrupted run (identical losses for steps 5..8)."""
+    from aozora_sdxl_training_b200.train_loop import run_training
+
+    def cfg(out):
+        return type("C", (Cfg,), dict(BATCH_SIZE=2, MAX_TRAIN_STEPS=8, PREDICTION_TYPE="epsilon", INSTANCE_DATASETS=_training_cache(str(tmp_path / out)),
+                                      SAVE_EVERY_N_STEPS=4, OUTPUT_DIR=str(tmp_path / out), OUTPUT_NAME="t", MOMENTUM_DTYPE=torch.float32,
+                                      LR_CUSTOM_CURVE=[[0.0, 1e-5], [1.0, 2e-6]], is_rectified_flow=False))
+    prod, _ = build_pair()
+    full = run_training(cfg("a"), prod, device="cuda")
+    assert full["micro_step"] == 8 and len(full["losses"]) == 8 and len(full["saved"]) == 2
+    assert all(torch.isfinite(torch.tensor(full["losses"])))
+    # restart: fresh model stepped to the saved point is not available without a model file, so replay 4 steps then resume 4
+    prod2, _ = build_pair()
+    first = run_training(type("C4", (cfg("b"),), dict(MAX_TRAIN_STEPS=8)), prod2, device="cuda", on_step=None)
+    # resume a THIRD model that was trained 4 steps in a separate loop object, from the step-4 state of run "a"
+    prod3, _ = build_pair()
+    c3 = cfg("c")
+    c3.MAX_TRAIN_STEPS = 8
+    warm = type("W", (c3,), dict(SAVE_EVERY_N_STEPS=0))
+    # bring the weights to step 4 deterministically (same data, same seeds), stopping the loop there
+    class Halt(Exception):
+        pass
+
+    def halt_at_4(ms, res):
+        if ms == 4:
+            raise Halt
+
+    try:
+        run_training(warm, prod3, device="cuda", on_step=halt_at_4)
+    except Halt:
+        pass
+    resumed = run_training(c3, prod3, device="cuda", resume_state_path=full["saved"][0])
+    assert resumed["micro_step"] == 8 and len(resumed["losses"]) == 4
+    for a, b in zip(resumed["losses"], full["losses"][4:]):
+        assert abs(a - b) <= 2e-3 * abs(b), (resumed["losses"], full["losses"])
+    for a, b in zip(first["losses"], full["losses"]):           # and the loop itself is reproducible run to run
+        assert abs(a - b) <= 1e-4 * abs(b)
