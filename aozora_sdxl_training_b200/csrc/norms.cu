@@ -27,6 +27,19 @@ __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __ex
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics: x [NB, HW, C] -> partial [NB][chunks][GROUPS][2] (sum, sumsq)
+// Row-lane partials are added to the per-channel shared-memory sums ONE LANE AT A TIME (plain adds between barriers): float
+// atomics would make the summation order, and with it the low bits of every statistic and gradient, differ run to run.
+// When there is more than one row lane every thread owns exactly one vector column (cols == vec_per_row).
+__device__ __forceinline__ void gn_ordered_accumulate(float* sm, int C, int v, int tr, int row_lanes, bool active, const float* s, const float* q) {
+    for (int l = 0; l < row_lanes; ++l) {
+        if (active && tr == l) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { sm[v * 8 + e] += s[e]; sm[C + v * 8 + e] += q[e]; }
+        }
+        __syncthreads();
+    }
+}
+
 // grid (chunks, NB).  Each thread owns one 8-channel vector column and walks pixels.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
@@ -44,9 +57,9 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __res
     const int cols = min(vec_per_row, GN_THREADS);
     const int row_lanes = GN_THREADS / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    float s[8], q[8];
     if (tr < row_lanes) {
         for (int v = tc; v < vec_per_row; v += cols) {
-            float s[8], q[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
             for (int r = r0 + tr; r < r1; r += row_lanes) {
@@ -55,12 +68,15 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __res
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
             }
+            if (row_lanes == 1) {                                  // single writer per channel
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], s[e]); atomicAdd(&sm[C + v * 8 + e], q[e]); }
+                for (int e = 0; e < 8; ++e) { sm[v * 8 + e] = s[e]; sm[C + v * 8 + e] = q[e]; }
+            }
         }
     }
+    if (row_lanes > 1) gn_ordered_accumulate(sm, C, tc, tr, row_lanes, tr < row_lanes && tc < vec_per_row, s, q);
     __syncthreads();
-    // channels -> groups (fixed order: deterministic given the smem atomics are over <= row_lanes addends)
+    // channels -> groups (fixed order)
     const int cpg = C / GN_GROUPS;
     if (threadIdx.x < 2 * GN_GROUPS) {
         const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
@@ -137,9 +153,10 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     const int cols = min(vec_per_row, GN_THREADS);
     const int row_lanes = GN_THREADS / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    float a[8], b[8];
     if (tr < row_lanes) {
         for (int v = tc; v < vec_per_row; v += cols) {
-            float gm[8], bt[8], a[8], b[8], mu[8], rs[8];
+            float gm[8], bt[8], mu[8], rs[8];
             unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
             unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
 #pragma unroll
@@ -160,10 +177,13 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     a[e] += dz; b[e] = fmaf(dz, xh, b[e]);
                 }
             }
+            if (row_lanes == 1) {                                  // single writer per channel
 #pragma unroll
-            for (int e = 0; e < 8; ++e) { atomicAdd(&sm[v * 8 + e], a[e]); atomicAdd(&sm[C + v * 8 + e], b[e]); }
+                for (int e = 0; e < 8; ++e) { sm[v * 8 + e] = a[e]; sm[C + v * 8 + e] = b[e]; }
+            }
         }
     }
+    if (row_lanes > 1) gn_ordered_accumulate(sm, C, tc, tr, row_lanes, tr < row_lanes && tc < vec_per_row, a, b);
     __syncthreads();
     float* out = partial + ((size_t)n * chunks + chunk) * 2 * C;
     for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) out[i] = sm[i];
@@ -175,7 +195,7 @@ __global__ void __launch_bounds__(128)
 gn_bwd_group_kernel(const float* __restrict__ partial, const __nv_bfloat16* __restrict__ gamma, int chunks, int C,
                     float* __restrict__ chansum, float* __restrict__ group_terms) {
     pdl_enter();
-    __shared__ float s_db[128], s_ds[128];
+    __shared__ float s_db[128], s_ds[128], s_a[128], s_b[128];
     const int g = blockIdx.x, n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
     float db = 0.f, ds = 0.f;
@@ -195,12 +215,22 @@ gn_bwd_group_kernel(const float* __restrict__ partial, const __nv_bfloat16* __re
                 chansum[((size_t)n * 2 + 1) * C + c] = b;
                 const float gm = __bfloat162float(gamma[c]);
                 db = fmaf(gm, a, db); ds = fmaf(gm, b, ds);
-            } else {
-                atomicAdd(&chansum[((size_t)n * 2 + 0) * C + c], a);
-                atomicAdd(&chansum[((size_t)n * 2 + 1) * C + c], b);
-                const float gm = __bfloat162float(gamma[c]);
-                db = fmaf(gm, a, db); ds = fmaf(gm, b, ds);
+            } else {                                   // cpg < 128: one channel per (cl), chunk lanes combined in fixed order below
+                s_a[kl * cpg + cl] = a;
+                s_b[kl * cpg + cl] = b;
             }
+        }
+    }
+    if (lanes > 1) {
+        __syncthreads();
+        if (threadIdx.x < cpg) {
+            const int c = g * cpg + threadIdx.x;
+            float a = 0.f, b = 0.f;
+            for (int k = 0; k < lanes; ++k) { a += s_a[k * cpg + threadIdx.x]; b += s_b[k * cpg + threadIdx.x]; }
+            chansum[((size_t)n * 2 + 0) * C + c] = a;
+            chansum[((size_t)n * 2 + 1) * C + c] = b;
+            const float gm = __bfloat162float(gamma[c]);
+            db = gm * a; ds = gm * b;
         }
     }
     s_db[threadIdx.x] = db; s_ds[threadIdx.x] = ds;
@@ -520,7 +550,6 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         (const float*)mean, (const float*)rstd, HW, C, silu, partial);
     AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
     float* chansum = group_terms + (size_t)NB * GN_GROUPS * 2 + 64;
-    cudaMemsetAsync(chansum, 0, (size_t)NB * 2 * C * sizeof(float), s);
     launch_k(gn_bwd_group_kernel, dim3(GN_GROUPS, NB), dim3(128), (size_t)(0), s, partial, (const __nv_bfloat16*)gamma, chunks, C, chansum, group_terms);
     AOZ_CHECK_LAUNCH("gn_bwd_group_kernel");
     if (dgamma) {

@@ -362,3 +362,237 @@ class BatchFeeder:
             if isinstance(item, Exception):
                 raise item
             yield item
+
+
+# ------------------------------------------------------------------------------------------------------------
+# bucket ladder (train.py:894-999): which (width, height) a source image is cached at
+# ------------------------------------------------------------------------------------------------------------
+SDXL_BUCKETS = [(1024, 1024), (1152, 896), (896, 1152), (1216, 832), (832, 1216), (1344, 768), (768, 1344), (1440, 720), (720, 1440),
+                (1536, 640), (640, 1536), (1600, 512), (512, 1600), (896, 896), (768, 768)]
+LOW_RES_BUCKETS = [(1152, 512), (512, 1152), (1024, 576), (576, 1024), (960, 640), (640, 960), (896, 704), (704, 896), (768, 768)]
+MAX_BUCKET_CHOICES = (896, 1024, 1152, 1536)
+
+
+def resolve_max_bucket_resolution(value=None):
+    """Largest ladder tier not above ``value`` (an edge length; values above 4096 are read as a pixel area)."""
+    try:
+        n = 1024 if value is None else int(float(value))
+    except (TypeError, ValueError):
+        return 1024
+    if n > 4096:
+        n = int(round(math.sqrt(max(1, n))))
+    fits = [c for c in MAX_BUCKET_CHOICES if c <= n]
+    return fits[-1] if fits else MAX_BUCKET_CHOICES[0]
+
+
+def bucket_ladder(max_bucket_resolution=None):
+    """All cache resolutions for a maximum tier: the 1024 ladder as listed, other tiers by scaling it to multiples of 64;
+    sorted by (area, width, height)."""
+    top = resolve_max_bucket_resolution(max_bucket_resolution)
+    tiers = [top] if top < 1024 else [1024] + [t for t in (1152, 1536) if t <= top]
+    base = SDXL_BUCKETS + LOW_RES_BUCKETS
+    out = set()
+    for tier in tiers:
+        if tier == 1024:
+            out.update(base)
+        else:
+            k = tier / 1024
+            out.update((max(64, int(round(w * k / 64)) * 64), max(64, int(round(h * k / 64)) * 64)) for w, h in base)
+    return sorted(out, key=lambda b: (b[0] * b[1], b[0], b[1]))
+
+
+def _bucket_cost(bucket, aspect, area):
+    """10 x relative aspect error + |log(area ratio)| (train.py:958-963)."""
+    w, h = bucket
+    ar_err = abs(w / max(h, 1) - aspect) / max(aspect, 0.01)
+    return ar_err * 10.0 + (abs(math.log(w * h / area)) if w * h > 0 else 100.0)
+
+
+def optimal_bucket(orig_w, orig_h, target_area=None, stride=64, should_upscale=False):
+    """Best ladder entry for an image; without upscaling, the largest entry that fits inside the image (or, if none fits, the
+    best of the smallest-area entries)."""
+    aspect = orig_w / max(orig_h, 1)
+    top = resolve_max_bucket_resolution(target_area)
+    ladder = bucket_ladder(top)
+    area = top * top
+    best = min(ladder, key=lambda b: _bucket_cost(b, aspect, area))
+    if not should_upscale and (best[0] > orig_w or best[1] > orig_h):
+        fitting = [b for b in ladder if b[0] <= orig_w and b[1] <= orig_h]
+        if fitting:
+            return max(fitting, key=lambda b: b[0] * b[1])
+        floor = min(b[0] * b[1] for b in ladder)
+        return min((b for b in ladder if b[0] * b[1] <= floor * 1.1), key=lambda b: _bucket_cost(b, aspect, area))
+    return best
+
+
+def multi_bucket_resolutions(orig_w, orig_h, target_area=None, should_upscale=False, max_extra=0):
+    """Primary bucket plus up to ``max_extra`` next-best alternatives (multi-bucket caching)."""
+    primary = optimal_bucket(orig_w, orig_h, target_area, 64, should_upscale)
+    if max_extra <= 0:
+        return [primary]
+    aspect = orig_w / max(orig_h, 1)
+    top = resolve_max_bucket_resolution(target_area)
+    ranked = sorted(((_bucket_cost(b, aspect, top * top), b) for b in bucket_ladder(top)
+                     if b != primary and (should_upscale or (b[0] <= orig_w and b[1] <= orig_h))), key=lambda t: t[0])
+    return [primary] + [b for _, b in ranked[:max_extra]]
+
+
+# ------------------------------------------------------------------------------------------------------------
+# timestep-spread schedules (train.py:565-575, 688-889): besides shuffling, steer which image meets which timestep bin so
+# that an image does not see the same bin again within its last few visits
+# ------------------------------------------------------------------------------------------------------------
+def timestep_bin_ids(timesteps, bin_ranges):
+    """Bin number of every ticket (first range with start <= t < end; 0 when none matches)."""
+    import numpy as np
+    ids = np.zeros(len(timesteps), dtype=np.int32)
+    for i, t in enumerate(timesteps):
+        t = int(t)
+        for b, (lo, hi) in enumerate(bin_ranges):
+            if lo <= t < hi:
+                ids[i] = b
+                break
+    return ids
+
+
+def epoch_shuffle_image_schedule(total_images, total_steps, seed):
+    """One image per step: seeded permutations (``torch.Generator(seed + epoch)``) laid end to end (train.py:688-700)."""
+    import numpy as np
+    out = np.empty(total_steps, dtype=np.uint32)
+    filled = epoch = 0
+    while filled < total_steps:
+        g = torch.Generator()
+        g.manual_seed(seed + epoch)
+        order = torch.randperm(total_images, generator=g).numpy().astype(np.uint32, copy=False)
+        take = min(total_images, total_steps - filled)
+        out[filled:filled + take] = order[:take]
+        filled += take
+        epoch += 1
+    return out
+
+
+class _BinHistory:
+    """Which timestep bins each image met on its last ``depth`` visits, plus the per-epoch 'not used yet' flags and the
+    lazily created candidate queues.  ``pick`` is the selection rule shared by the image and the batch schedule: walk the
+    queue of this (scope, bin) from where it stopped and take the first image that is still unused this epoch and has not
+    met the bin recently; if the queue runs dry, take -- at random among ties -- the unused image of the fallback pool that
+    met the bin least often."""
+
+    def __init__(self, total_images, bin_count, visits_per_image):
+        import numpy as np
+        self.np = np
+        self.depth = max(1, min(bin_count, visits_per_image))
+        wide = bin_count >= 255
+        self.recent = np.full((total_images, self.depth), 65535 if wide else 255, dtype=np.uint16 if wide else np.uint8)
+        self.cursor = np.zeros(total_images, dtype=np.uint16)
+        self.total_images = total_images
+
+    def new_epoch(self, seed, epoch):
+        np = self.np
+        self.unused = np.ones(self.total_images, dtype=np.bool_)
+        self.queues, self.where = {}, {}
+        self.rng = np.random.Generator(np.random.PCG64(seed + 104729 + epoch))
+
+    def pick(self, key, bin_id, make_queue, fallback_pool):
+        np = self.np
+        q = self.queues.get(key)
+        if q is None:
+            q = self.queues[key] = make_queue(self.rng)
+            self.where[key] = 0
+        pos, chosen = self.where[key], None
+        while pos < len(q):
+            cand = int(q[pos])
+            pos += 1
+            if self.unused[cand] and not np.any(self.recent[cand] == bin_id):
+                chosen = cand
+                break
+        self.where[key] = pos
+        if chosen is None:
+            pool = fallback_pool(self.unused)
+            if pool.size == 0:
+                return None
+            seen = np.count_nonzero(self.recent[pool] == bin_id, axis=1)
+            ties = pool[seen == seen.min()]
+            chosen = int(ties[int(self.rng.integers(0, len(ties)))])
+        self.unused[chosen] = False
+        slot = int(self.cursor[chosen] % self.depth)
+        self.recent[chosen, slot] = bin_id
+        self.cursor[chosen] = (self.cursor[chosen] + 1) % self.depth
+        return chosen
+
+
+def spread_image_schedule(total_images, total_steps, seed, bin_ids, bin_count):
+    """``build_spread_image_schedule`` (train.py:703-764): batch size 1, one candidate queue per bin over all images."""
+    import numpy as np
+    if total_images <= 0 or total_steps <= 0:
+        return np.empty(0, dtype=np.uint32)
+    if bin_count <= 1:
+        return epoch_shuffle_image_schedule(total_images, total_steps, seed)
+    hist = _BinHistory(total_images, bin_count, math.ceil(total_steps / total_images))
+    out = np.empty(total_steps, dtype=np.uint32)
+    done = epoch = 0
+    while done < total_steps:
+        hist.new_epoch(seed, epoch)
+        for step in range(done, done + min(total_images, total_steps - done)):
+            b = int(bin_ids[step])
+            chosen = hist.pick(b, b, lambda rng: rng.permutation(total_images).astype(np.uint32, copy=False), lambda unused: np.flatnonzero(unused))
+            if chosen is None:
+                break
+            out[step] = chosen
+        done += min(total_images, total_steps - done)
+        epoch += 1
+    return out
+
+
+def spread_batch_schedule(bucket_keys, total_steps, batch_size, seed, timesteps, bin_ranges):
+    """``build_spread_batch_schedule`` (train.py:781-881): the bucketed epoch order decides WHICH bucket and how many samples
+    each step takes; the members are then re-picked inside that bucket by the bin-history rule, one candidate queue per
+    (bucket, bin)."""
+    import numpy as np
+    total_images = len(bucket_keys)
+    if total_images <= 0 or total_steps <= 0:
+        return []
+    if batch_size == 1:
+        ids = timestep_bin_ids(timesteps, bin_ranges)
+        return [[int(i)] for i in spread_image_schedule(total_images, total_steps, seed, ids, len(bin_ranges)).tolist()]
+    bin_ids = timestep_bin_ids(timesteps, bin_ranges)
+    samples = min(len(timesteps), total_steps * batch_size)
+    hist = _BinHistory(total_images, max(1, len(bin_ranges)), math.ceil(samples / total_images))
+    members = defaultdict(list)
+    for i, key in enumerate(bucket_keys):
+        members[key].append(i)
+    schedule, offset, epoch = [], 0, 0
+    while len(schedule) < total_steps and offset < len(bin_ids):
+        hist.new_epoch(seed, epoch)
+        for base in bucket_epoch_batches(bucket_keys, batch_size, seed, epoch):
+            if len(schedule) >= total_steps:
+                break
+            key = bucket_keys[base[0]]
+            pool = members[key]
+            batch = []
+            for j in range(len(base)):
+                if offset + j >= len(bin_ids):
+                    break
+                b = int(bin_ids[offset + j])
+
+                def make_queue(rng, pool=pool):
+                    q = np.array(pool, dtype=np.uint32)
+                    rng.shuffle(q)
+                    return q
+                chosen = hist.pick((key, b), b, make_queue, lambda unused, pool=pool: np.array([i for i in pool if unused[i]], dtype=np.int64))
+                if chosen is None:
+                    break
+                batch.append(chosen)
+            if batch:
+                schedule.append(batch)
+                offset += len(batch)
+            if offset >= len(bin_ids):
+                break
+        epoch += 1
+    return schedule
+
+
+def image_batch_schedule(bucket_keys, total_steps, batch_size, seed, timesteps, bin_ranges, force_spread):
+    """``build_image_batch_schedule`` (train.py:884-887)."""
+    if not force_spread:
+        return epoch_shuffle_batch_schedule(bucket_keys, total_steps, batch_size, seed)
+    return spread_batch_schedule(bucket_keys, total_steps, batch_size, seed, timesteps, bin_ranges)

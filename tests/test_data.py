@@ -21,7 +21,7 @@ from oracle import ref_shim  # noqa: E402
 
 GOLD = json.load(open(os.path.join(HERE, "golden", "data_golden.json")))
 sys.path.insert(0, os.path.join(HERE, "golden"))
-from make_data_golden import VARIANTS, run  # noqa: E402
+from make_data_golden import SPREAD_CASES, VARIANTS, run, run_buckets, run_spread  # noqa: E402
 
 
 def product_schedule(ds, total_steps, batch_size, seed):
@@ -83,3 +83,15 @@ def test_time_ids_and_feeder(tmp_path):
         assert parts[0] + parts[1] == b and len(parts[0]) >= len(parts[1])
     r1 = list(data.BatchFeeder(ds, sched, rank=1, world=2, pin=False))
     assert all((not x) or len(x["latents"]) <= 2 for x in r1)
+
+
+def test_spread_schedules_and_bucket_ladder_match_reference_golden():
+    """Timestep-spread batch schedules (train.py:703-887) and the bucket ladder (train.py:894-999), against digests made by
+    running the reference's functions."""
+    from aozora_sdxl_training_b200 import host
+    got = [run_spread(host.build_timestep_ticket_pool,
+                      lambda keys, steps, bs, seed, pool, ranges: data.image_batch_schedule(keys, steps, bs, seed, pool, ranges, True), c)
+           for c in SPREAD_CASES]
+    assert got == GOLD["spread"]
+    assert run_buckets(data.optimal_bucket, data.multi_bucket_resolutions, data.bucket_ladder) == GOLD["buckets"]
+    assert data.resolve_max_bucket_resolution("abc") == 1024 and data.resolve_max_bucket_resolution(2359296) == 1536
