@@ -34,7 +34,7 @@ constexpr int EPI_STAGE_BYTES = 8 * 4096;               // 8 epilogue warps x (3
 constexpr int GEMM_SMEM_TOTAL = SMEM_TILE_BYTES + 1024 + EPI_STAGE_BYTES + 1024;   // + barriers + staging + alignment slack (226 KB)
 
 enum GemmMode : int { GM_LINEAR = 0, GM_CONV_FWD = 1, GM_CONV_WGRAD = 2 };
-constexpr int MAX_GROUPS = 8;
+constexpr int MAX_GROUPS = 10;     // 10 x 320 B of descriptors + the base parameters stay under the 4 KB kernel-parameter limit
 
 // one problem of a grouped launch (GM_LINEAR, EPI_STORE, same K / operand majors / tile shape for all problems): the
 // weight gradients of one transformer block run as ONE persistent launch, so ~900 tiles fill the 148 SMs in ~6 full
@@ -77,6 +77,8 @@ struct GemmParams {
     int n_groups;                   // > 0: grouped launch, tile indices run over grp[0..n_groups) back to back
     GroupDesc grp[MAX_GROUPS];
 };
+
+static_assert(sizeof(GemmParams) <= 4096, "GemmParams must fit the kernel parameter space");
 
 // erf GELU (torch F.gelu default), fp32: x * Phi(x)
 __device__ __forceinline__ float gelu_erf(float x) { float e; return x * gelu_cdf(x, e); }
@@ -1134,7 +1136,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
     return run(tp);
 }
 
-// Grouped GEMM: C_g[M_g, N_g] = op(A_g) op(B_g) for g in [0, n), n <= 8, ONE persistent launch.  All problems share K, the
+// Grouped GEMM: C_g[M_g, N_g] = op(A_g) op(B_g) for g in [0, n), n <= 10, ONE persistent launch.  All problems share K, the
 // operand majors and the tile shape; plain bf16 store (no bias / residual / split-K).  Built for the weight gradients of
 // one transformer block (dW = dy^T x for to_q/k/v, to_out, ff.*: ~900 tiles that fill 148 SMs in ~6 full waves).
 // A_ptrs / B_ptrs / C_ptrs: HOST arrays of n device pointers (uint64); lda / ldb / ldc: HOST int64[n]; M / N: HOST int32[n].

@@ -109,15 +109,18 @@ def gemm(a, b, *, a_mn=False, b_mn=False, bias=None, residual=None, rowgroup_bia
     return out
 
 
+MAX_GROUPED = 10
+
+
 def gemm_grouped(problems, *, a_mn, b_mn):
-    """One persistent launch for up to 8 GEMMs that share K and the operand majors (plain bf16 store, no epilogue fusion):
+    """One persistent launch for up to 10 GEMMs that share K and the operand majors (plain bf16 store, no epilogue fusion):
     ``problems`` = [(a, b, out_or_None), ...] with the operand conventions of :func:`gemm`.  Returns the outputs."""
     import ctypes
     n = len(problems)
     if n == 0:
         return []
-    if n > 8:
-        return gemm_grouped(problems[:8], a_mn=a_mn, b_mn=b_mn) + gemm_grouped(problems[8:], a_mn=a_mn, b_mn=b_mn)
+    if n > MAX_GROUPED:
+        return gemm_grouped(problems[:MAX_GROUPED], a_mn=a_mn, b_mn=b_mn) + gemm_grouped(problems[MAX_GROUPED:], a_mn=a_mn, b_mn=b_mn)
     Ks, Ms, Ns, outs = set(), [], [], []
     for a, b, out in problems:
         _chk(a, "gemm_grouped a", contiguous=False)
@@ -386,21 +389,15 @@ def mse_loss(pred, target_nchw, tickets, table, denom, grad_scale=1.0, *, pred_n
     return loss, per, dpred
 
 
-def geglu_bwd(dy, aux, need_bias_grad=False):
-    """d(aux) of out = h * gelu(g), aux = [h | g].  ``need_bias_grad``: also return the column sums of d(aux) (the gradient
-    of the GEGLU projection bias) from the same pass -> (daux, dbias)."""
+def geglu_bwd(dy, aux):
     _chk(dy, "geglu_bwd dy")
     _chk(aux, "geglu_bwd aux")
     half = dy.shape[-1]
     M = dy.numel() // half
     daux = torch.empty_like(aux)
-    dbias = ws = None
-    if need_bias_grad:
-        dbias = torch.empty((2 * half,), dtype=BF16, device=dy.device)
-        ws = workspace(_lib.query("aoz_geglu_bwd_workspace_floats", half), dy.device)
-    _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _p(dbias), _p(ws), _stream())
+    _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _stream())
     _count()
-    return (daux, dbias) if need_bias_grad else daux
+    return daux
 
 
 def silu_fwd(x):

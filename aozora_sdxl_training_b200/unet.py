@@ -166,6 +166,7 @@ class GradSink:
         self.grads = {}
         self.on_grad = None        # optional callback(param, grad): data-parallel bucket scheduling during the sweep
         self.pending = []          # deferred Linear weight gradients: (params stacked by rows, dy, x)
+        self.pending_late = []     # the same, flushed once per Transformer2DModel (cross-attention k/v: K = text tokens)
         self.dest = None           # optional callback(param) -> tensor the gradient must be written to (data-parallel flat buffer)
 
     def out_for(self, params):
@@ -195,7 +196,9 @@ class GradSink:
         """dW = dyᵀ x for ``params`` (one parameter, or several stacked by rows).  ``defer``: queue it; ``flush`` then runs
         every queued gradient that shares the token count as ONE grouped persistent GEMM launch (a transformer block's
         six weight gradients = ~900 tiles = ~6 full waves on 148 SMs, instead of six ragged launches + split-K reduces)."""
-        if defer:
+        if defer == "late":
+            self.pending_late.append((params, dy, x))
+        elif defer:
             self.pending.append((params, dy, x))
         else:
             self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True, out=self.out_for(params)))
@@ -206,8 +209,11 @@ class GradSink:
             self.add(p, dw[r:r + p.shape[0]])
             r += p.shape[0]
 
-    def flush(self):
-        jobs, self.pending = self.pending, []
+    def flush(self, late=False):
+        if late:
+            jobs, self.pending_late = self.pending_late, []
+        else:
+            jobs, self.pending = self.pending, []
         by_k = {}
         for job in jobs:
             by_k.setdefault(job[2].shape[0], []).append(job)
@@ -274,13 +280,11 @@ def _geglu(x, w, b, G, defer=False):
     y = ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
 
     def bwd(dy):
-        if b.requires_grad:
-            daux, db = ops.geglu_bwd(dy, aux, need_bias_grad=True)      # bias gradient from the same pass over daux
-            G.add(b, db)
-        else:
-            daux = ops.geglu_bwd(dy, aux)
+        daux = ops.geglu_bwd(dy, aux)
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
+        if b.requires_grad:
+            G.add(b, ops.colsum(daux, out=G.out_for(b)))
         return ops.gemm(daux, w, b_mn=True)
 
     return y, bwd
@@ -396,7 +400,22 @@ def _linear_stacked(x, wcat, params, G, *, need_dx=True, defer=False):
     return y, bwd
 
 
-def _basic_block(blk, x, ctx, B, T, Tc, G):
+def _cross_kv(blocks, ctx, G):
+    """attn2 key/value projections of every block of a Transformer2DModel in ONE grouped launch: they all read the same text
+    embedding (M = B x 77 rows) and do not depend on the blocks before them, so ten 15-microsecond GEMMs that each fill a
+    fraction of the GPU become one.  Returns {block index: kv [B*Tc, 2C]} for the blocks whose k/v weights are stacked."""
+    idx, probs = [], []
+    for i, blk in enumerate(blocks):
+        w = _stacked((blk.attn2.to_k.weight, blk.attn2.to_v.weight))
+        if w is not None:
+            idx.append(i)
+            probs.append((ctx, w, None))
+    if len(probs) < 2:
+        return {}
+    return dict(zip(idx, ops.gemm_grouped(probs, a_mn=False, b_mn=False)))
+
+
+def _basic_block(blk, x, ctx, B, T, Tc, G, kv_pre=None):
     """Pre-LN self-attention, cross-attention and GEGLU feed-forward, each with a residual fused into the
     producing GEMM's epilogue.  x: [B*T, C]; ctx: [B*Tc, ctx_dim]."""
     a1, a2, ff = blk.attn1, blk.attn2, blk.ff
@@ -417,7 +436,14 @@ def _basic_block(blk, x, ctx, B, T, Tc, G):
     q2, b_q2 = _linear(n2, a2.to_q.weight, None, G, defer=True)
     p_kv = (a2.to_k.weight, a2.to_v.weight)
     w_kv = _stacked(p_kv)
-    if w_kv is not None:
+    if w_kv is not None and kv_pre is not None:
+        kv2 = kv_pre                                 # computed with the other blocks' (see _cross_kv); gradient flushed "late"
+
+        def b_kv2(dkv):
+            if p_kv[0].requires_grad:
+                G.wgrad(p_kv, dkv, ctx, defer="late")
+        k2, v2 = kv2[:, :C], kv2[:, C:]
+    elif w_kv is not None:
         kv2, b_kv2 = _linear_stacked(ctx, w_kv, p_kv, G, need_dx=False)
         k2, v2 = kv2[:, :C], kv2[:, C:]
     else:
@@ -471,9 +497,11 @@ def _transformer(tr, x, ctx, Tc, G):
     h, b_pi = _linear(hn.view(B * T, C), tr.proj_in.weight, tr.proj_in.bias, G)
     del hn
     blocks = []
-    for blk in tr.transformer_blocks:
-        h, b_blk = _basic_block(blk, h, ctx, B, T, Tc, G)
+    kv_pre = _cross_kv(tr.transformer_blocks, ctx, G)
+    for i, blk in enumerate(tr.transformer_blocks):
+        h, b_blk = _basic_block(blk, h, ctx, B, T, Tc, G, kv_pre=kv_pre.get(i))
         blocks.append(b_blk)
+    del kv_pre
     y, b_po = _linear(h, tr.proj_out.weight, tr.proj_out.bias, G, residual=x.view(B * T, C))
     del h
 
@@ -482,6 +510,7 @@ def _transformer(tr, x, ctx, Tc, G):
         dh = b_po(dy2)
         while blocks:
             dh = blocks.pop()(dh)
+        G.flush(late=True)             # cross-attention k/v weight gradients of all blocks: one grouped launch
         dhn = b_pi(dh)
         return b_gn(dhn.view(B, H, W, C), dres=dy)
 
@@ -727,6 +756,7 @@ class UNet2DConditionModel(nn.Module):
             de1s = b_te2(demb)
             b_te1(ops.silu_bwd(de1s, e1))
             G.flush()
+            G.flush(late=True)
             return G.grads
 
         assert len(skips) == 0 and n_skips >= 0

@@ -67,7 +67,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
                   int M, int N, int K, const void* bias, const void* rowgroup_bias, int rows_per_group, long long ld_rgb,
                   const void* residual, long long ldr, int epi, void* aux, long long ld_aux, int accumulate, int splits,
                   void* workspace, void* stream);
-/* Grouped GEMM (one persistent launch for up to 8 problems sharing K, operand majors and tile shape; plain bf16 store):
+/* Grouped GEMM (one persistent launch for up to 10 problems sharing K, operand majors and tile shape; plain bf16 store):
  * the weight gradients dW = dy^T x of one BasicTransformerBlock [3P].  A_ptrs/B_ptrs/C_ptrs: HOST arrays of n device
  * pointers (uint64); lda/ldb/ldc: HOST int64[n]; M/N: HOST int32[n]. */
 int aoz_gemm_grouped_bf16(int n, const void* A_ptrs, const void* lda, const void* B_ptrs, const void* ldb, const void* C_ptrs,
@@ -115,9 +115,7 @@ int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_s
                  const void* table, int table_len, int NB, int C, int HW, float denom, const void* grad_scale_ptr, float grad_scale,
                  void* per_sample, void* weights, void* loss_out, void* dpred, long long d_sn, long long d_sc, long long d_shw,
                  void* stream);
-long long aoz_geglu_bwd_workspace_floats(int half);
-/* dbias (optional): [2*half] bf16 gradient of the GEGLU projection bias, produced in the same pass (needs workspace) */
-int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* dbias, void* workspace, void* stream);
+int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* stream);
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream);
 int aoz_silu_bwd(const void* dy, const void* x, long long n, void* dx, void* stream);
 int aoz_add(const void* a, const void* b, long long n, void* y, void* stream);

@@ -176,9 +176,6 @@ def test_geglu_fused_epilogue_and_backward(M, C):
     hh, gg = pr.chunk(2, dim=-1)
     (hh * torch.nn.functional.gelu(gg)).backward(dy.float())
     check(ops.geglu_bwd(dy, aux), pr.grad, rel=8e-3)
-    daux, dbias = ops.geglu_bwd(dy, aux, need_bias_grad=True)
-    check(daux, pr.grad, rel=8e-3)
-    check(dbias, daux.float().sum(0), rel=8e-3)
 
 
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,ks,stride", [
