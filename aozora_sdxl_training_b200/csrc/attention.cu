@@ -387,6 +387,16 @@ struct KvSmem {
     static constexpr int TOTAL = BAR + 256 + 1024;
 };
 
+// [128 q, 128 k] bf16 tile (two 64-column blocks, 16 KB apart) read as an MN-major A operand: contraction over its ROWS
+// (queries), M = its 128 columns (keys).  k16 selects 16 query rows.
+__device__ __forceinline__ uint64_t desc_ptile_rows_as_k(uint32_t p_addr, int k16) {
+    return make_sdesc_sw128(p_addr + k16 * 2048, TILE_BYTES, 1024);
+}
+
+// Scores are computed query-major here exactly as in the dQ kernel (S = Q K^T, dP = dO V^T: one thread = one query row, its
+// LSE and D are two registers), and P / dS are written once as [q, k] tiles; dV += P^T dO and dK += dS^T Q then read those
+// tiles as MN-major A operands (contraction over the query rows), so no transposed score tile, no per-column LSE / D
+// broadcast loads and no per-tile block barrier are needed.
 __global__ void __launch_bounds__(ATT_BWD_THREADS, 1)
 attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -398,10 +408,9 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     uint64_t* s_ready = bars + 9;
     uint64_t* pds_ready = bars + 10;
     uint64_t* acc_ready = bars + 11;
-    uint64_t* st_free = bars + 12;      // compute warps have moved S^T / dP^T into registers: next tile's MMAs may overwrite TMEM
-    uint64_t* pd_free = bars + 13;      // dV / dK MMAs that read the P^T / dS^T smem tiles have completed
+    uint64_t* st_free = bars + 12;      // compute warps have moved S / dP into registers: next tile's MMAs may overwrite TMEM
+    uint64_t* pd_free = bars + 13;      // dV / dK MMAs that read the P / dS smem tiles have completed
     uint32_t* tmem_slot = (uint32_t*)(bars + 14);
-    float* vec = (float*)(smem + KvSmem::VEC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kv_tiles = (P.Tk + TILE - 1) / TILE;
@@ -423,7 +432,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tSt = tmem, tdPt = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
     pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
     if (warp == BWD_CW) {
@@ -441,22 +450,22 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             }
         }
     } else if (warp == BWD_CW + 1) {
-        // Software pipeline: S^T / dP^T of Q tile i+1 are issued as soon as the compute warps have pulled tile i's S^T / dP^T
-        // into registers, so the tensor pipe works on tile i+1 while they do the exp / dS math of tile i.
+        // Software pipeline: S / dP of Q tile i+1 are issued as soon as the compute warps have pulled tile i's S / dP into
+        // registers, so the tensor pipe works on tile i+1 while they do the exp / dS math of tile i.
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);           // A = P / dS read MN-major, B = dO / Q read MN-major
             const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
             const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
-            const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
+            const uint32_t sP = smem_u32(smem + KvSmem::PT), sDS = smem_u32(smem + KvSmem::DST);
             auto issue_scores = [&](int i) {
                 const int s = i % BWD_STAGES;
                 mbar_wait(&q_full[s], (i / BWD_STAGES) & 1);
                 tc_fence_after();
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tSt, desc_kmajor(sK, k), desc_kmajor(sQ + s * TILE_BYTES, k), idesc_s, k > 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ + s * TILE_BYTES, k), desc_kmajor(sK, k), idesc_s, k > 0);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tdPt, desc_kmajor(sV, k), desc_kmajor(sDO + s * TILE_BYTES, k), idesc_s, k > 0);
+                for (int k = 0; k < 4; ++k) umma_bf16(tdP, desc_kmajor(sDO + s * TILE_BYTES, k), desc_kmajor(sV, k), idesc_s, k > 0);
                 umma_commit(s_ready);
             };
             mbar_wait(kv_once, 0);
@@ -472,10 +481,10 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 tc_fence_after();
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16(tdV, desc_ptile(sPT, k), desc_rows_as_k(sDO + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tdV, desc_ptile_rows_as_k(sP, k), desc_rows_as_k(sDO + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
-                    umma_bf16(tdK, desc_ptile(sDST, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                    umma_bf16(tdK, desc_ptile_rows_as_k(sDS, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
                 umma_commit(&q_empty[s]);
                 umma_commit(pd_free);
                 if (i == nq - 1) umma_commit(acc_ready);
@@ -483,78 +492,71 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         }
         __syncwarp();
     } else {
-        // compute warps: quarter = warp & 3 (TMEM lanes), hf = warp >> 2 selects which 32 of the 128 query columns
+        // compute warps: quarter = warp & 3 (TMEM lanes = query rows), hf = warp >> 2 selects 32 of the tile's 128 key columns
         const int qtr = warp & 3, hf = warp >> 2;
-        const int r = qtr * 32 + lane;                       // key row inside the tile
+        const int r = qtr * 32 + lane;                       // query row inside the tile
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-        const uint32_t sPT = smem_u32(smem + KvSmem::PT), sDST = smem_u32(smem + KvSmem::DST);
+        const uint32_t sP = smem_u32(smem + KvSmem::PT), sDS = smem_u32(smem + KvSmem::DST);
         const float sl2 = P.scale * LOG2E;
-        const bool key_ok = (k0 + r) < P.Tk;
+        const int kvalid = P.Tk - k0;                        // keys >= kvalid of this tile are padding
         // per-query LSE / D of the NEXT Q tile are fetched one tile ahead (their global-load latency hides behind this tile's math)
         float nx_lse = INFINITY, nx_d = 0.f;
         auto fetch_vec = [&](int i) {
             const int q = i * TILE + r;
             const long long idx = ((long long)b * P.H + h) * P.Tq + q;
-            nx_lse = q < P.Tq ? P.lse[idx] : INFINITY;                   // +inf -> P = 0 for padded queries (scaled by
-            nx_d = q < P.Tq ? P.Dvec[idx] : 0.f;                         // log2 e when consumed: no use of the loads here)
+            nx_lse = q < P.Tq ? P.lse[idx] : INFINITY;       // +inf -> P = 0 for padded queries
+            nx_d = q < P.Tq ? P.Dvec[idx] : 0.f;
         };
-        if (hf == 0) fetch_vec(0);
+        fetch_vec(0);
         for (int i = 0; i < nq; ++i) {
-            float* lse2 = vec + (i & 1) * 256;
-            float* dv = lse2 + 128;
-            if (hf == 0) {
-                lse2[r] = nx_lse * LOG2E;
-                dv[r] = nx_d;
-            }
-            named_bar_sync(1, BWD_CT);
-            if (hf == 0 && i + 1 < nq) fetch_vec(i + 1);
-            const uint32_t lse2_s = smem_u32(lse2);              // dv = lse2 + 128 floats
+            const float lse2 = nx_lse * LOG2E, dvec = nx_d;
+            if (i + 1 < nq) fetch_vec(i + 1);
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
-            // This thread's 64 columns of S^T and dP^T in four 16-column chunks, software-pipelined: the tcgen05.ld of chunk
-            // c+1 is in flight while chunk c goes through the exp / dS math, so the TMEM read port (the scarce resource at
-            // 64 B/clk/SM) and the MUFU / FMA pipes work at the same time.  TMEM is released for the next tile's score MMAs
-            // as soon as the last chunk has landed in registers.
+            // two 16-column chunks, software-pipelined: the tcgen05.ld of chunk 1 is in flight during chunk 0's math
             uint32_t vs[2][16], vp[2][16], hp[2][8], hd[2][8];
-            tmem_ld16(tSt + lane_off + hf * 32, vs[0]);
-            tmem_ld16(tdPt + lane_off + hf * 32, vp[0]);
+            tmem_ld16(tS + lane_off + hf * 32, vs[0]);
+            tmem_ld16(tdP + lane_off + hf * 32, vp[0]);
 #pragma unroll
             for (int c = 0; c < 2; ++c) {
                 tc_wait_ld();
                 if (c + 1 < 2) {
-                    tmem_ld16(tSt + lane_off + hf * 32 + (c + 1) * 16, vs[(c + 1) & 1]);
-                    tmem_ld16(tdPt + lane_off + hf * 32 + (c + 1) * 16, vp[(c + 1) & 1]);
+                    tmem_ld16(tS + lane_off + hf * 32 + (c + 1) * 16, vs[(c + 1) & 1]);
+                    tmem_ld16(tdP + lane_off + hf * 32 + (c + 1) * 16, vp[(c + 1) & 1]);
                 } else {
                     tc_fence_before();
-                    mbar_arrive(st_free);
+                    mbar_arrive(st_free);                    // TMEM S / dP may be overwritten by the next tile's MMAs
                 }
                 uint32_t* wp = hp[c & 1];
                 uint32_t* wd = hd[c & 1];
                 const uint32_t* cs = vs[c & 1];
                 const uint32_t* cp = vp[c & 1];
+                if (kvalid >= TILE) {
 #pragma unroll
-                for (int e = 0; e < 16; e += 4) {
-                    const int qa = hf * 32 + c * 16 + e;
-                    const float4 ls = ld_shared_f4(lse2_s + qa * 4);                    // broadcast reads
-                    const float4 dd = ld_shared_f4(lse2_s + 512 + qa * 4);
-                    float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -ls.x));
-                    float p1 = fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -ls.y));
-                    float p2 = fast_exp2(fmaf(__uint_as_float(cs[e + 2]), sl2, -ls.z));
-                    float p3 = fast_exp2(fmaf(__uint_as_float(cs[e + 3]), sl2, -ls.w));
-                    if (!key_ok) { p0 = 0.f; p1 = 0.f; p2 = 0.f; p3 = 0.f; }
-                    wp[e >> 1] = pack_bf16(p0, p1);
-                    wp[(e >> 1) + 1] = pack_bf16(p2, p3);
-                    wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dd.x), p1 * (__uint_as_float(cp[e + 1]) - dd.y));
-                    wd[(e >> 1) + 1] = pack_bf16(p2 * (__uint_as_float(cp[e + 2]) - dd.z), p3 * (__uint_as_float(cp[e + 3]) - dd.w));
+                    for (int e = 0; e < 16; e += 2) {
+                        const float p0 = fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -lse2));
+                        const float p1 = fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -lse2));
+                        wp[e >> 1] = pack_bf16(p0, p1);
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dvec), p1 * (__uint_as_float(cp[e + 1]) - dvec));
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const int ka = hf * 32 + c * 16 + e;
+                        const float p0 = (ka < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e]), sl2, -lse2)) : 0.f;
+                        const float p1 = (ka + 1 < kvalid) ? fast_exp2(fmaf(__uint_as_float(cs[e + 1]), sl2, -lse2)) : 0.f;
+                        wp[e >> 1] = pack_bf16(p0, p1);
+                        wd[e >> 1] = pack_bf16(p0 * (__uint_as_float(cp[e]) - dvec), p1 * (__uint_as_float(cp[e + 1]) - dvec));
+                    }
                 }
-                // chunks 0 and 1 wait in registers: the previous tile's dV / dK MMAs (issued when that tile's P^T / dS^T were
-                // complete) still read these smem tiles for the first few hundred cycles of this tile
+                // chunk 0 waits in registers: the previous tile's dV / dK MMAs (issued when that tile's P / dS were complete)
+                // still read these smem tiles for the first few hundred cycles of this tile
                 if (c == 1) {
                     if (i > 0) mbar_wait(pd_free, (i - 1) & 1);
-                    store_p_16(sPT, r, hf * 32, hp[0]);
-                    store_p_16(sDST, r, hf * 32, hd[0]);
-                    store_p_16(sPT, r, hf * 32 + 16, hp[1]);
-                    store_p_16(sDST, r, hf * 32 + 16, hd[1]);
+                    store_p_16(sP, r, hf * 32, hp[0]);
+                    store_p_16(sDS, r, hf * 32, hd[0]);
+                    store_p_16(sP, r, hf * 32 + 16, hp[1]);
+                    store_p_16(sDS, r, hf * 32 + 16, hd[1]);
                 }
             }
             fence_proxy_async_smem();
@@ -563,7 +565,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         }
         mbar_wait(acc_ready, 0);
         tc_fence_after();
-        const int key = k0 + r;
+        const int key = k0 + r;                              // accumulator rows are keys
         {
             const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
             const uint32_t tacc = which == 0 ? tdV : tdK;

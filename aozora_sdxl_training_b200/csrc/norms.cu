@@ -62,7 +62,20 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __res
         for (int v = tc; v < vec_per_row; v += cols) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
-            for (int r = r0 + tr; r < r1; r += row_lanes) {
+            int r = r0 + tr;
+            for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {           // four rows in flight
+                uint4 px[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) px[u] = ld_stream(xb + (size_t)(r + u * row_lanes) * C + v * 8);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    float f[8];
+                    unpack8(px[u], f);
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
+                }
+            }
+            for (; r < r1; r += row_lanes) {
                 float f[8];
                 unpack8(ld_stream(xb + (size_t)r * C + v * 8), f);
 #pragma unroll
@@ -110,24 +123,47 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
         if (blockIdx.x == 0) { mean_out[n * GN_GROUPS + threadIdx.x] = mean; rstd_out[n * GN_GROUPS + threadIdx.x] = rstd; }
     }
     __syncthreads();
+    // A thread owns one 8-channel vector column (its gamma / beta / mean / rstd stay in registers: no per-element group
+    // division or shared-memory lookup in the loop) and walks its row lane of this block's pixel chunk, four rows in flight.
     const int vec_per_row = C / 8;
-    const size_t total_vec = (size_t)HW * vec_per_row;
+    const int cols = min(vec_per_row, GN_THREADS);
+    const int row_lanes = GN_THREADS / cols;
+    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    const int rows_per_chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
     const __nv_bfloat16* xb = x + (size_t)n * HW * C;
     __nv_bfloat16* yb = y + (size_t)n * HW * C;
-    for (size_t i = (size_t)blockIdx.x * GN_THREADS + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * GN_THREADS) {
-        const int v = (int)(i % vec_per_row);
-        float f[8], gm[8], bt[8];
-        unpack8(ld_stream(xb + i * 8), f);
+    if (tr >= row_lanes) return;
+    for (int v = tc; v < vec_per_row; v += cols) {
+        float gm[8], bt[8], sc[8], sh[8];
         unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
         unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
+        for (int e = 0; e < 8; ++e) {                          // z = x * sc + sh
             const int g = (v * 8 + e) / cpg;
-            float z = (f[e] - s_mean[g]) * s_rstd[g] * gm[e] + bt[e];
-            if (silu) z = z * sigmoidf_(z);
-            f[e] = z;
+            sc[e] = s_rstd[g] * gm[e];
+            sh[e] = bt[e] - s_mean[g] * sc[e];
         }
-        st_stream(yb + i * 8, pack8(f));
+        auto one = [&](const uint4& px, int r) {
+            float f[8];
+            unpack8(px, f);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float z = fmaf(f[e], sc[e], sh[e]);
+                if (silu) z = z * sigmoidf_(z);
+                f[e] = z;
+            }
+            st_stream(yb + (size_t)r * C + v * 8, pack8(f));
+        };
+        int r = r0 + tr;
+        for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {
+            uint4 px[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) px[u] = ld_stream(xb + (size_t)(r + u * row_lanes) * C + v * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one(px[u], r + u * row_lanes);
+        }
+        for (; r < r1; r += row_lanes) one(ld_stream(xb + (size_t)r * C + v * 8), r);
     }
 }
 
@@ -161,10 +197,10 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
             unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
 #pragma unroll
             for (int e = 0; e < 8; ++e) { a[e] = 0.f; b[e] = 0.f; const int g = (v * 8 + e) / cpg; mu[e] = s_mean[g]; rs[e] = s_rstd[g]; }
-            for (int r = r0 + tr; r < r1; r += row_lanes) {
+            auto acc_row = [&](const uint4& px, const uint4& pd) {
                 float fx[8], fd[8];
-                unpack8(ld_stream(x + base + (size_t)r * C + v * 8), fx);
-                unpack8(ld_stream(dy + base + (size_t)r * C + v * 8), fd);
+                unpack8(px, fx);
+                unpack8(pd, fd);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
                     const float xh = (fx[e] - mu[e]) * rs[e];
@@ -176,7 +212,15 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                     }
                     a[e] += dz; b[e] = fmaf(dz, xh, b[e]);
                 }
+            };
+            int r = r0 + tr;
+            for (; r + row_lanes < r1; r += 2 * row_lanes) {               // two rows (four loads) in flight
+                const size_t o0 = base + (size_t)r * C + v * 8, o1 = base + (size_t)(r + row_lanes) * C + v * 8;
+                const uint4 x0 = ld_stream(x + o0), d0 = ld_stream(dy + o0), x1 = ld_stream(x + o1), d1 = ld_stream(dy + o1);
+                acc_row(x0, d0);
+                acc_row(x1, d1);
             }
+            for (; r < r1; r += row_lanes) acc_row(ld_stream(x + base + (size_t)r * C + v * 8), ld_stream(dy + base + (size_t)r * C + v * 8));
             if (row_lanes == 1) {                                  // single writer per channel
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { sm[v * 8 + e] = a[e]; sm[C + v * 8 + e] = b[e]; }
@@ -276,34 +320,63 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     }
     __syncthreads();
     const int vec_per_row = C / 8;
-    const size_t total_vec = (size_t)HW * vec_per_row;
+    const int cols = min(vec_per_row, GN_THREADS);
+    const int row_lanes = GN_THREADS / cols;
+    const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
+    const int rows_per_chunk = (HW + gridDim.x - 1) / gridDim.x;
+    const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
     const size_t base = (size_t)n * HW * C;
-    for (size_t i = (size_t)blockIdx.x * GN_THREADS + threadIdx.x; i < total_vec; i += (size_t)gridDim.x * GN_THREADS) {
-        const int v = (int)(i % vec_per_row);
-        float fx[8], fd[8], gm[8], bt[8];
-        unpack8(ld_stream(x + base + i * 8), fx);
-        unpack8(ld_stream(dy + base + i * 8), fd);
+    if (tr >= row_lanes) return;
+    for (int v = tc; v < vec_per_row; v += cols) {             // column-owner loop, see gn_apply_kernel
+        float gm[8], bt[8], mu[8], rs[8], gdb[8], gds[8];
         unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
         unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             const int g = (v * 8 + e) / cpg;
-            const float xh = (fx[e] - s_mean[g]) * s_rstd[g];
-            float dz = fd[e];
-            if (silu) {
-                const float z = xh * gm[e] + bt[e];
-                const float sg = sigmoidf_(z);
-                dz *= sg * (1.0f + z * (1.0f - sg));
-            }
-            fx[e] = s_rstd[g] * (dz * gm[e] - s_db[g] - xh * s_ds[g]);
+            mu[e] = s_mean[g]; rs[e] = s_rstd[g]; gdb[e] = s_db[g]; gds[e] = s_ds[g];
         }
-        if (dres) {
-            float fr[8];
-            unpack8(ld_stream(dres + base + i * 8), fr);
+        auto one = [&](const uint4& px, const uint4& pd, const uint4& pr, int r) {
+            float fx[8], fd[8];
+            unpack8(px, fx);
+            unpack8(pd, fd);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) fx[e] = round_bf16(fx[e]) + fr[e];
+            for (int e = 0; e < 8; ++e) {
+                const float xh = (fx[e] - mu[e]) * rs[e];
+                float dz = fd[e];
+                if (silu) {
+                    const float z = xh * gm[e] + bt[e];
+                    const float sg = sigmoidf_(z);
+                    dz *= sg * (1.0f + z * (1.0f - sg));
+                }
+                fx[e] = rs[e] * (dz * gm[e] - gdb[e] - xh * gds[e]);
+            }
+            if (dres) {
+                float fr[8];
+                unpack8(pr, fr);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) fx[e] = round_bf16(fx[e]) + fr[e];
+            }
+            st_stream(dx + base + (size_t)r * C + v * 8, pack8(fx));
+        };
+        const uint4 zero4 = make_uint4(0, 0, 0, 0);
+        int r = r0 + tr;
+        for (; r + row_lanes < r1; r += 2 * row_lanes) {        // two rows (up to six 16-byte loads) in flight
+            uint4 px[2], pd[2], pr[2];
+#pragma unroll
+            for (int u = 0; u < 2; ++u) {
+                const size_t off = base + (size_t)(r + u * row_lanes) * C + v * 8;
+                px[u] = ld_stream(x + off);
+                pd[u] = ld_stream(dy + off);
+                pr[u] = dres ? ld_stream(dres + off) : zero4;
+            }
+#pragma unroll
+            for (int u = 0; u < 2; ++u) one(px[u], pd[u], pr[u], r + u * row_lanes);
         }
-        st_stream(dx + base + i * 8, pack8(fx));
+        for (; r < r1; r += row_lanes) {
+            const size_t off = base + (size_t)r * C + v * 8;
+            one(ld_stream(x + off), ld_stream(dy + off), dres ? ld_stream(dres + off) : zero4, r);
+        }
     }
 }
 
@@ -507,6 +580,18 @@ static int gn_chunks(int NB, int HW) {
     return chunks;
 }
 
+// pixel chunks (grid.x) of the apply kernels: enough blocks to fill the GPU a few times over, at least 8 rows per thread
+static int gn_apply_chunks(int NB, int HW, int C) {
+    const int vec = C / 8;
+    const int cols = vec < GN_THREADS ? vec : GN_THREADS;
+    const int row_lanes = GN_THREADS / cols;
+    int chunks = (HW + row_lanes * 8 - 1) / (row_lanes * 8);
+    const int cap = (sm_count() * 8 + NB - 1) / NB;
+    if (chunks > cap) chunks = cap;
+    if (chunks < 1) chunks = 1;
+    return chunks;
+}
+
 // workspace floats needed by the GroupNorm forward / backward (upper bound)
 long long aoz_groupnorm_workspace_floats(int NB, int HW, int C) {
     const long long chunks = GN_MAX_CHUNKS;
@@ -524,11 +609,7 @@ int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB
     const int chunks = gn_chunks(NB, HW);
     launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(GN_THREADS), (size_t)(2 * C * sizeof(float)), s, (const __nv_bfloat16*)x, HW, C, (float*)workspace);
     AOZ_CHECK_LAUNCH("gn_stats_kernel");
-    long long vecs = (long long)HW * (C / 8);
-    int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
-    const int cap = (sm_count() * 8 + NB - 1) / NB;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
+    int gx = gn_apply_chunks(NB, HW, C);
     launch_k(gn_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
                                                        (const float*)workspace, chunks, HW, C, eps, silu, (__nv_bfloat16*)y,
                                                        (float*)mean, (float*)rstd);
@@ -556,11 +637,7 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         launch_k(gn_bwd_param_kernel, dim3((C + 255) / 256), dim3(256), (size_t)(0), s, chansum, NB, C, (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
         AOZ_CHECK_LAUNCH("gn_bwd_param_kernel");
     }
-    long long vecs = (long long)HW * (C / 8);
-    int gx = (int)((vecs + GN_THREADS * 4 - 1) / (GN_THREADS * 4));
-    const int cap = (sm_count() * 8 + NB - 1) / NB;
-    if (gx > cap) gx = cap;
-    if (gx < 1) gx = 1;
+    int gx = gn_apply_chunks(NB, HW, C);
     launch_k(gn_bwd_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                            (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd,
                                                            group_terms, HW, C, silu, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx);
