@@ -207,16 +207,21 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
         // exp2(s * sl2 - m_ref) of this thread's 64 columns -> bf16 P tile in shared memory; returns the partial row sum and
         // (through mx) the raw maximum.  ONE pass over TMEM: reading S is the scarce resource (64 B/clk/SM), not the math.
         auto softmax_pass = [&](int kvalid, bool full, float& mx, int wait_parity) -> float {
+            // four 16-column chunks, software-pipelined: the tcgen05.ld of chunk c+1 is in flight during chunk c's exp math
             float lsum = 0.f;
-#pragma unroll 1
-            for (int c = hf * 2; c < hf * 2 + 2; ++c) {
-                uint32_t v[32], w[16];
-                tmem_ld32(tS + lane_off + c * 32, v);
+            uint32_t v[2][16];
+            const int col0 = hf * 64;
+            tmem_ld16(tS + lane_off + col0, v[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
                 tc_wait_ld();
+                if (c + 1 < 4) tmem_ld16(tS + lane_off + col0 + (c + 1) * 16, v[(c + 1) & 1]);
+                const uint32_t* cv = v[c & 1];
+                uint32_t w[8];
                 if (full) {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+                    for (int e = 0; e < 16; e += 2) {
+                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
                         mx = fmaxf(mx, fmaxf(s0, s1));
                         const float p0 = fast_exp2(fmaf(s0, sl2, -m_ref));
                         const float p1 = fast_exp2(fmaf(s1, sl2, -m_ref));
@@ -225,9 +230,10 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                     }
                 } else {
 #pragma unroll
-                    for (int e = 0; e < 32; e += 2) {
-                        const bool ok0 = c * 32 + e < kvalid, ok1 = c * 32 + e + 1 < kvalid;
-                        const float s0 = __uint_as_float(v[e]), s1 = __uint_as_float(v[e + 1]);
+                    for (int e = 0; e < 16; e += 2) {
+                        const int ka = col0 + c * 16 + e;
+                        const bool ok0 = ka < kvalid, ok1 = ka + 1 < kvalid;
+                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
                         if (ok0) mx = fmaxf(mx, s0);
                         if (ok1) mx = fmaxf(mx, s1);
                         const float p0 = ok0 ? fast_exp2(fmaf(s0, sl2, -m_ref)) : 0.f;
@@ -237,8 +243,8 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
                     }
                 }
                 // the previous tile's P V reads the P tile until p_free (its MMAs are issued AFTER this tile's Q K^T)
-                if (c == hf * 2 && wait_parity >= 0) { mbar_wait(p_free, (uint32_t)wait_parity); tc_fence_after(); }
-                store_p_chunk(sP, r, c * 32, w);
+                if (c == 0 && wait_parity >= 0) { mbar_wait(p_free, (uint32_t)wait_parity); tc_fence_after(); }
+                store_p_16(sP, r, col0 + c * 16, w);
             }
             return lsum;
         };
