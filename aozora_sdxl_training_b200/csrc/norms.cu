@@ -13,8 +13,10 @@
 namespace aoz {
 
 constexpr int GN_GROUPS = 32;
-constexpr int GN_THREADS = 256;
-constexpr int GN_MAX_CHUNKS = 64;
+constexpr int GN_THREADS = 512;            // upper bound; blocks are launched with cols * row_lanes threads (gn_block_threads)
+constexpr int GN_MAX_CHUNKS = 160;         // pixel chunks per image of the backward statistics (per-channel partial rows)
+constexpr int GN_FWD_MAX_CHUNKS = 256;     // forward statistics: a partial row is only [32 groups][2]
+__device__ unsigned int g_gn_tickets[1024];     // zero at module load; atomicInc wraps back to zero after every use
 
 __device__ __forceinline__ void unpack8(const uint4& a, float* f) {
     f[0] = bf16lo(a.x); f[1] = bf16hi(a.x); f[2] = bf16lo(a.y); f[3] = bf16hi(a.y);
@@ -43,19 +45,23 @@ __device__ __forceinline__ void gn_ordered_accumulate(float* sm, int C, int v, i
 // grid (chunks, NB).  Each thread owns one 8-channel vector column and walks pixels.
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __restrict__ partial) {
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float eps, float* __restrict__ partial,
+                float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     pdl_enter();
     extern __shared__ float sm[];          // [2][C] per-channel sums
+    __shared__ float s_fin[4][2][GN_GROUPS];
+    __shared__ unsigned int s_last;
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
+    const int nthreads = blockDim.x;
     const int vec_per_row = C / 8;
     const int rows_per_chunk = (HW + chunks - 1) / chunks;
     const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
-    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * C; i += nthreads) sm[i] = 0.f;
     __syncthreads();
     const __nv_bfloat16* xb = x + (size_t)n * HW * C;
-    // threads are laid out as (row lane, vector column): column = tid % vec_cols_per_pass
-    const int cols = min(vec_per_row, GN_THREADS);
-    const int row_lanes = GN_THREADS / cols;
+    // threads are laid out as (row lane, vector column): column = tid % cols
+    const int cols = min(vec_per_row, nthreads);
+    const int row_lanes = nthreads / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
     float s[8], q[8];
     if (tr < row_lanes) {
@@ -97,37 +103,54 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float* __res
         for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
         partial[(((size_t)n * chunks + chunk) * GN_GROUPS + g) * 2 + which] = a;
     }
+    // the LAST block of this image (self-resetting ticket) turns the chunk partials into mean / rstd, in fixed order
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicInc(&g_gn_tickets[n & 1023], (unsigned int)chunks - 1);
+        s_last = (t == (unsigned int)chunks - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (threadIdx.x < 256) {                                       // blocks always have >= 256 threads (gn_block_threads)
+        const int g = threadIdx.x & 31, which = (threadIdx.x >> 5) & 1, kl = threadIdx.x >> 6;
+        float a = 0.f;
+        for (int k = kl; k < chunks; k += 4) a += __ldcg(partial + (((size_t)n * chunks + k) * GN_GROUPS + g) * 2 + which);
+        s_fin[kl][which][g] = a;
+    }
+    __syncthreads();
+    if (threadIdx.x < GN_GROUPS) {
+        const int g = threadIdx.x;
+        const float sum = (s_fin[0][0][g] + s_fin[1][0][g]) + (s_fin[2][0][g] + s_fin[3][0][g]);
+        const float sq = (s_fin[0][1][g] + s_fin[1][1][g]) + (s_fin[2][1][g] + s_fin[3][1][g]);
+        const float cnt = (float)HW * (float)cpg;
+        const float mean = sum / cnt;
+        const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+        mean_out[n * GN_GROUPS + g] = mean;
+        rstd_out[n * GN_GROUPS + g] = rsqrtf(var + eps);
+    }
 }
 
 // GroupNorm apply: y = silu?((x - mean) * rstd * gamma + beta); also writes mean/rstd [NB][GROUPS] (chunk 0 block)
 __global__ void __launch_bounds__(GN_THREADS)
 gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
-                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ partial, int stat_chunks, int HW, int C,
-                float eps, int silu, __nv_bfloat16* __restrict__ y, float* __restrict__ mean_out,
-                float* __restrict__ rstd_out) {
+                const __nv_bfloat16* __restrict__ beta, const float* __restrict__ mean, const float* __restrict__ rstd,
+                int HW, int C, int silu, __nv_bfloat16* __restrict__ y) {
     pdl_enter();
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int n = blockIdx.y;
     const int cpg = C / GN_GROUPS;
     if (threadIdx.x < GN_GROUPS) {
-        float s = 0.f, q = 0.f;
-        for (int k = 0; k < stat_chunks; ++k) {
-            const float* p = partial + (((size_t)n * stat_chunks + k) * GN_GROUPS + threadIdx.x) * 2;
-            s += p[0]; q += p[1];
-        }
-        const float cnt = (float)HW * (float)cpg;
-        const float mean = s / cnt;
-        const float var = fmaxf(q / cnt - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + eps);
-        s_mean[threadIdx.x] = mean; s_rstd[threadIdx.x] = rstd;
-        if (blockIdx.x == 0) { mean_out[n * GN_GROUPS + threadIdx.x] = mean; rstd_out[n * GN_GROUPS + threadIdx.x] = rstd; }
+        s_mean[threadIdx.x] = mean[n * GN_GROUPS + threadIdx.x];
+        s_rstd[threadIdx.x] = rstd[n * GN_GROUPS + threadIdx.x];
     }
     __syncthreads();
     // A thread owns one 8-channel vector column (its gamma / beta / mean / rstd stay in registers: no per-element group
     // division or shared-memory lookup in the loop) and walks its row lane of this block's pixel chunk, four rows in flight.
     const int vec_per_row = C / 8;
-    const int cols = min(vec_per_row, GN_THREADS);
-    const int row_lanes = GN_THREADS / cols;
+    const int cols = min(vec_per_row, (int)blockDim.x);
+    const int row_lanes = (int)blockDim.x / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
     const int rows_per_chunk = (HW + gridDim.x - 1) / gridDim.x;
     const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
@@ -180,14 +203,14 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int cpg = C / GN_GROUPS;
     if (threadIdx.x < GN_GROUPS) { s_mean[threadIdx.x] = mean[n * GN_GROUPS + threadIdx.x]; s_rstd[threadIdx.x] = rstd[n * GN_GROUPS + threadIdx.x]; }
-    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) sm[i] = 0.f;
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     const int vec_per_row = C / 8;
     const int rows_per_chunk = (HW + chunks - 1) / chunks;
     const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
     const size_t base = (size_t)n * HW * C;
-    const int cols = min(vec_per_row, GN_THREADS);
-    const int row_lanes = GN_THREADS / cols;
+    const int cols = min(vec_per_row, (int)blockDim.x);
+    const int row_lanes = (int)blockDim.x / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
     float a[8], b[8];
     if (tr < row_lanes) {
@@ -214,11 +237,16 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                 }
             };
             int r = r0 + tr;
-            for (; r + row_lanes < r1; r += 2 * row_lanes) {               // two rows (four loads) in flight
-                const size_t o0 = base + (size_t)r * C + v * 8, o1 = base + (size_t)(r + row_lanes) * C + v * 8;
-                const uint4 x0 = ld_stream(x + o0), d0 = ld_stream(dy + o0), x1 = ld_stream(x + o1), d1 = ld_stream(dy + o1);
-                acc_row(x0, d0);
-                acc_row(x1, d1);
+            for (; r + 3 * row_lanes < r1; r += 4 * row_lanes) {           // four rows (eight 16-byte loads) in flight
+                uint4 px[4], pd[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                    const size_t o = base + (size_t)(r + u * row_lanes) * C + v * 8;
+                    px[u] = ld_stream(x + o);
+                    pd[u] = ld_stream(dy + o);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) acc_row(px[u], pd[u]);
             }
             for (; r < r1; r += row_lanes) acc_row(ld_stream(x + base + (size_t)r * C + v * 8), ld_stream(dy + base + (size_t)r * C + v * 8));
             if (row_lanes == 1) {                                  // single writer per channel
@@ -230,7 +258,7 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     if (row_lanes > 1) gn_ordered_accumulate(sm, C, tc, tr, row_lanes, tr < row_lanes && tc < vec_per_row, a, b);
     __syncthreads();
     float* out = partial + ((size_t)n * chunks + chunk) * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += GN_THREADS) out[i] = sm[i];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
 }
 
 // pass 2a: one block per (group, image): reduce the chunk partials of the group's channels, write the per-channel
@@ -320,8 +348,8 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
     }
     __syncthreads();
     const int vec_per_row = C / 8;
-    const int cols = min(vec_per_row, GN_THREADS);
-    const int row_lanes = GN_THREADS / cols;
+    const int cols = min(vec_per_row, (int)blockDim.x);
+    const int row_lanes = (int)blockDim.x / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
     const int rows_per_chunk = (HW + gridDim.x - 1) / gridDim.x;
     const int r0 = blockIdx.x * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
@@ -381,168 +409,225 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
 }
 
 // ---------------------------------------------------------------------------------------------
-// LayerNorm: one warp per row, C % 8 == 0, C <= 2048
+// LayerNorm, C % 8 == 0, C <= 2048
 // ---------------------------------------------------------------------------------------------
+// forward : one warp per R consecutive rows.  Every 16-byte load of the R rows is issued before the first reduction, so a
+//           warp's whole life is ONE memory round trip (the old one-row-at-a-time loop was a chain of 2..7 of them and
+//           ran at ~2.4 TB/s); x stays packed in registers between the mean, variance and output passes.
+// backward: "column owner" layout.  A thread owns ONE 8-channel vector column and T rows of a tile, so the dgamma / dbeta
+//           accumulators are 16 registers per thread (the warp-per-row kernel needed 2*C/32 = 80 and fit one row in flight per
+//           warp); the two per-row sums cross the block through warp shuffles + a small shared-memory table.
 constexpr int LN_MAXV = 8;     // vectors of 8 per lane -> C <= 2048
-constexpr int LN_WARPS = 8;
+constexpr int LN_FWD_WARPS = 4;
 
-__global__ void __launch_bounds__(LN_WARPS * 32)
+template <int VPL, int R>
+__global__ void __launch_bounds__(LN_FWD_WARPS * 32, (VPL <= 5 ? 4 : 2))       // <= 128 registers for the SDXL widths (640, 1280)
 ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ gamma,
               const __nv_bfloat16* __restrict__ beta, long long rows, int C, float eps, __nv_bfloat16* __restrict__ y,
               float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     pdl_enter();
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int nv = C / 8;
-    for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-        float f[LN_MAXV][8];
-        float s = 0.f;
+    const float inv_c = 1.0f / (float)C;
+    const long long stride = (long long)gridDim.x * LN_FWD_WARPS * R;
+    for (long long r0 = ((long long)blockIdx.x * LN_FWD_WARPS + warp) * R; r0 < rows; r0 += stride) {
+        float f[R][VPL][8];
+        {
+            uint4 xp[R][VPL];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) {
+                    const int v = lane + 32 * i;
+                    xp[j][i] = (v < nv && r0 + j < rows) ? ld_stream(x + (r0 + j) * C + v * 8) : make_uint4(0, 0, 0, 0);
+                }
+#pragma unroll
+            for (int j = 0; j < R; ++j)
+#pragma unroll
+                for (int i = 0; i < VPL; ++i) unpack8(xp[j][i], f[j][i]);
+        }
+        float mean[R], rstd[R];
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float s = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i)
+#pragma unroll
+                for (int e = 0; e < 8; ++e) s += f[j][i][e];
+            mean[j] = s;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) mean[j] = warp_sum(mean[j]) * inv_c;
+#pragma unroll
+        for (int j = 0; j < R; ++j) {
+            float q = 0.f;
+#pragma unroll
+            for (int i = 0; i < VPL; ++i) {
+                if (lane + 32 * i < nv) {                       // padding lanes hold zeros, not (0 - mean)
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) { const float d = f[j][i][e] - mean[j]; q = fmaf(d, d, q); }
+                }
+            }
+            rstd[j] = q;
+        }
+#pragma unroll
+        for (int j = 0; j < R; ++j) rstd[j] = rsqrtf(warp_sum(rstd[j]) * inv_c + eps);
+#pragma unroll
+        for (int i = 0; i < VPL; ++i) {
             const int v = lane + 32 * i;
             if (v < nv) {
-                unpack8(ld_stream(x + row * C + v * 8), f[i]);
+                float gm[8], bt[8];                              // L1-resident after the first warp touched them
+                unpack8(__ldg(reinterpret_cast<const uint4*>(gamma + v * 8)), gm);
+                unpack8(__ldg(reinterpret_cast<const uint4*>(beta + v * 8)), bt);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) s += f[i][e];
+                for (int j = 0; j < R; ++j) {
+                    if (r0 + j < rows) {
+                        float o[8];
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) o[e] = (f[j][i][e] - mean[j]) * rstd[j] * gm[e] + bt[e];
+                        st_stream(y + (r0 + j) * C + v * 8, pack8(o));
+                    }
+                }
             }
         }
-        const float mean = warp_sum(s) / (float)C;
-        float q = 0.f;
+        if (lane < R && r0 + lane < rows) {
+            float m = mean[0], rsd = rstd[0];
 #pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
-            const int v = lane + 32 * i;
-            if (v < nv) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) { const float d = f[i][e] - mean; q = fmaf(d, d, q); }
-            }
+            for (int j = 1; j < R; ++j) if (lane == j) { m = mean[j]; rsd = rstd[j]; }
+            mean_out[r0 + lane] = m; rstd_out[r0 + lane] = rsd;
         }
-        const float rstd = rsqrtf(warp_sum(q) / (float)C + eps);
-#pragma unroll
-        for (int i = 0; i < LN_MAXV; ++i) {
-            const int v = lane + 32 * i;
-            if (v < nv) {
-                float gm[8], bt[8];
-                unpack8(*reinterpret_cast<const uint4*>(gamma + v * 8), gm);
-                unpack8(*reinterpret_cast<const uint4*>(beta + v * 8), bt);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) f[i][e] = (f[i][e] - mean) * rstd * gm[e] + bt[e];
-                st_stream(y + row * C + v * 8, pack8(f[i]));
-            }
-        }
-        if (lane == 0) { mean_out[row] = mean; rstd_out[row] = rstd; }
     }
 }
 
-// backward: dx per row (one warp per row); dgamma/dbeta partials per block -> partial [gridDim.x][2][C].
-// VPL = 16-byte vectors per lane (C <= 256*VPL).  x and dy stay packed (uint4) in registers between the two passes so
-// the per-thread footprint is ~ 20*VPL registers of data + 16*VPL of dgamma/dbeta accumulators: no spills at VPL = 5.
-template <int VPL>
-__global__ void __launch_bounds__(LN_WARPS * 32)
+// backward.  blockDim = cols_pad * RL: cols_pad = vector columns rounded up to a warp multiple (a warp never straddles two
+// row lanes), RL row lanes.  A tile is RL*T rows: thread (tc, rl) takes rows base + t*RL + rl.  Per tile: all loads issued,
+// per-row partial sums of the thread's 8 channels -> warp_sum -> red[rl][t][warp-in-lane][2] -> barrier -> every thread adds
+// the cols_pad/32 entries of its rows in fixed order (deterministic) -> dx.  dgamma / dbeta: 16 accumulators per thread,
+// combined over the row lanes through shared memory at the end -> partial [gridDim.x][2][C].
+constexpr int LNB_T = 4;
+constexpr int LNB_MAX_THREADS = 512;
+
+__global__ void __launch_bounds__(LNB_MAX_THREADS, 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
-              float* __restrict__ partial) {
+              float* __restrict__ partial, int cols_pad, int RL, long long rows_per_block) {
     pdl_enter();
-    extern __shared__ float sm[];      // [LN_WARPS][2][C] per-warp partials, reduced at the end
-    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    extern __shared__ float sm[];      // red [RL][T][W][2] during the sweep, then [RL][2][C]
+    const int tc = threadIdx.x % cols_pad, rl = threadIdx.x / cols_pad;
+    const int lane = threadIdx.x & 31, wcol = tc >> 5, W = cols_pad >> 5;
     const int nv = C / 8;
-    uint4 gpk[VPL];
-    float ag[VPL][8], ab[VPL][8];
+    const bool active = tc < nv;
+    const float inv_c = 1.0f / (float)C;
+    float gm[8], ag[8], ab[8];
+    {
+        const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + tc * 8) : make_uint4(0, 0, 0, 0);
+        unpack8(g4, gm);
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) { ag[i][e] = 0.f; ab[i][e] = 0.f; }
-        gpk[i] = v < nv ? *reinterpret_cast<const uint4*>(gamma + v * 8) : make_uint4(0, 0, 0, 0);
+        for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; }
     }
-    for (long long row = (long long)blockIdx.x * LN_WARPS + warp; row < rows; row += (long long)gridDim.x * LN_WARPS) {
-        const float mu = mean[row], rs = rstd[row];
-        uint4 xpk[VPL], dpk[VPL], rpk[VPL];
-        float s1 = 0.f, s2 = 0.f;
+    const long long rb0 = (long long)blockIdx.x * rows_per_block;
+    const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
+    const uint4 zero4 = make_uint4(0, 0, 0, 0);
+    for (long long base = rb0; base < rb1; base += (long long)RL * LNB_T) {
+        uint4 xp[LNB_T], dp[LNB_T], rp[LNB_T];
+        float mu[LNB_T], rs[LNB_T], p1[LNB_T], p2[LNB_T];
+        bool ok[LNB_T];
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int v = lane + 32 * i;
-            if (v < nv) {
-                xpk[i] = ld_stream(x + row * C + v * 8);
-                dpk[i] = ld_stream(dy + row * C + v * 8);
-                if (dres) rpk[i] = ld_stream(dres + row * C + v * 8);      // residual gradient: fetched with the rest, used last
-            }
+        for (int t = 0; t < LNB_T; ++t) {
+            const long long row = base + (long long)t * RL + rl;
+            ok[t] = active && row < rb1;
+            const long long off = row * C + tc * 8;
+            xp[t] = ok[t] ? ld_stream(x + off) : zero4;
+            dp[t] = ok[t] ? ld_stream(dy + off) : zero4;
+            rp[t] = (ok[t] && dres) ? ld_stream(dres + off) : zero4;
+            mu[t] = ok[t] ? __ldg(mean + row) : 0.f;
+            rs[t] = ok[t] ? __ldg(rstd + row) : 0.f;
         }
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int v = lane + 32 * i;
-            if (v < nv) {
-                float fx[8], fd[8], gm[8];
-                unpack8(xpk[i], fx); unpack8(dpk[i], fd); unpack8(gpk[i], gm);
+        for (int t = 0; t < LNB_T; ++t) {
+            float fx[8], fd[8];
+            unpack8(xp[t], fx); unpack8(dp[t], fd);
+            float a = 0.f, b = 0.f;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float xh = (fx[e] - mu) * rs;
-                    const float dg = fd[e] * gm[e];
-                    s1 += dg;
-                    s2 = fmaf(dg, xh, s2);
-                    ag[i][e] = fmaf(fd[e], xh, ag[i][e]);
-                    ab[i][e] += fd[e];
-                }
+            for (int e = 0; e < 8; ++e) {
+                const float xh = (fx[e] - mu[t]) * rs[t];
+                const float dg = fd[e] * gm[e];
+                a += dg;
+                b = fmaf(dg, xh, b);
+                ag[e] = fmaf(fd[e], xh, ag[e]);
+                ab[e] += fd[e];
+            }
+            p1[t] = a; p2[t] = b;
+        }
+#pragma unroll
+        for (int t = 0; t < LNB_T; ++t) { p1[t] = warp_sum(p1[t]); p2[t] = warp_sum(p2[t]); }
+        if (lane == 0) {
+#pragma unroll
+            for (int t = 0; t < LNB_T; ++t) {
+                float* d = sm + ((size_t)(rl * LNB_T + t) * W + wcol) * 2;
+                d[0] = p1[t]; d[1] = p2[t];
             }
         }
-        s1 = warp_sum(s1) / (float)C;
-        s2 = warp_sum(s2) / (float)C;
+        __syncthreads();
 #pragma unroll
-        for (int i = 0; i < VPL; ++i) {
-            const int v = lane + 32 * i;
-            if (v < nv) {
-                float fx[8], fd[8], gm[8], o[8];
-                unpack8(xpk[i], fx); unpack8(dpk[i], fd); unpack8(gpk[i], gm);
+        for (int t = 0; t < LNB_T; ++t) {
+            if (!ok[t]) continue;
+            const float2* srow = reinterpret_cast<const float2*>(sm + (size_t)(rl * LNB_T + t) * W * 2);
+            float s1 = 0.f, s2 = 0.f;
+            for (int w = 0; w < W; ++w) { const float2 v = srow[w]; s1 += v.x; s2 += v.y; }
+            s1 *= inv_c; s2 *= inv_c;
+            float fx[8], fd[8], o[8];
+            unpack8(xp[t], fx); unpack8(dp[t], fd);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = rs * (fd[e] * gm[e] - s1 - (fx[e] - mu) * rs * s2);
-                if (dres) {
-                    float fr[8];
-                    unpack8(rpk[i], fr);
+            for (int e = 0; e < 8; ++e) o[e] = rs[t] * (fd[e] * gm[e] - s1 - (fx[e] - mu[t]) * rs[t] * s2);
+            if (dres) {
+                float fr[8];
+                unpack8(rp[t], fr);
 #pragma unroll
-                    for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
-                }
-                st_stream(dx + row * C + v * 8, pack8(o));
+                for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
             }
+            const long long row = base + (long long)t * RL + rl;
+            st_stream(dx + row * C + tc * 8, pack8(o));
         }
+        __syncthreads();               // the table is rewritten by the next tile
     }
-    // per-warp partials -> smem (no atomics), then a column-parallel sum over the warps
-    float* mine = sm + (size_t)warp * 2 * C;
+    // accumulators -> [RL][2][C] -> fixed-order sum over the row lanes -> this block's partial row
+    if (active) {
 #pragma unroll
-    for (int i = 0; i < VPL; ++i) {
-        const int v = lane + 32 * i;
-        if (v < nv) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { mine[v * 8 + e] = ag[i][e]; mine[C + v * 8 + e] = ab[i][e]; }
+        for (int e = 0; e < 8; ++e) {
+            sm[(size_t)(rl * 2 + 0) * C + tc * 8 + e] = ag[e];
+            sm[(size_t)(rl * 2 + 1) * C + tc * 8 + e] = ab[e];
         }
     }
     __syncthreads();
     float* out = partial + (size_t)blockIdx.x * 2 * C;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         float a = 0.f;
-#pragma unroll
-        for (int w = 0; w < LN_WARPS; ++w) a += sm[(size_t)w * 2 * C + i];
+        for (int l = 0; l < RL; ++l) a += sm[(size_t)l * 2 * C + i];
         out[i] = a;
     }
 }
 
 // reduce [blocks][2][C] -> dgamma (first C), dbeta (second C)
-// block = 32 columns x 8 row lanes: lane (cx, ry) sums partial rows ry, ry+8, ... of its column (a warp reads 128
-// contiguous bytes per row), then the 8 row lanes are combined through shared memory
-__global__ void __launch_bounds__(256)
+// block = 32 columns x 32 row lanes: lane (cx, ry) sums partial rows ry, ry+32, ... of its column (a warp reads 128
+// contiguous bytes per row), then the 32 row lanes are combined through shared memory in fixed order
+__global__ void __launch_bounds__(1024)
 ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
                        __nv_bfloat16* __restrict__ dbeta, int accumulate) {
     pdl_enter();
-    __shared__ float sm[8][33];
+    __shared__ float sm[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + cx;
     float s = 0.f;
     if (i < 2 * C)
-        for (int b = ry; b < blocks; b += 8) s += partial[(size_t)b * 2 * C + i];
+        for (int b = ry; b < blocks; b += 32) s += partial[(size_t)b * 2 * C + i];
     sm[ry][cx] = s;
     __syncthreads();
     if (ry == 0 && i < 2 * C) {
         float t = 0.f;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) t += sm[k][cx];
+        for (int k = 0; k < 32; ++k) t += sm[k][cx];
         __nv_bfloat16* dst = i < C ? dgamma + i : dbeta + (i - C);
         if (accumulate) t = round_bf16(t) + __bfloat162float(*dst);
         *dst = __float2bfloat16_rn(t);
@@ -553,40 +638,47 @@ ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __n
 
 using namespace aoz;
 
-template <int VPL>
-static int launch_ln_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
-                         const void* dres, void* dx, void* workspace, int blocks, cudaStream_t s) {
-    const size_t smem = (size_t)LN_WARPS * 2 * C * sizeof(float);
-    static size_t attr = 0;
-    if (smem > 48 * 1024 && smem > attr) {
-        cudaFuncSetAttribute(ln_bwd_kernel<VPL>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        attr = smem;
-    }
-    launch_k(ln_bwd_kernel<VPL>, dim3(blocks), dim3(LN_WARPS * 32), (size_t)(smem), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
-                                                          (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
-                                                          (__nv_bfloat16*)dx, (float*)workspace);
-    AOZ_CHECK_LAUNCH("ln_bwd_kernel");
+template <int VPL, int R>
+static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, long long rows, int C, float eps, void* y, void* mean,
+                         void* rstd, cudaStream_t s) {
+    const long long warps = (rows + R - 1) / R;
+    long long blocks = (warps + LN_FWD_WARPS - 1) / LN_FWD_WARPS;
+    if (blocks > sm_count() * 12) blocks = sm_count() * 12;
+    launch_k(ln_fwd_kernel<VPL, R>, dim3((int)blocks), dim3(LN_FWD_WARPS * 32), (size_t)(0), s, (const __nv_bfloat16*)x,
+             (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta, rows, C, eps, (__nv_bfloat16*)y, (float*)mean, (float*)rstd);
+    AOZ_CHECK_LAUNCH("ln_fwd_kernel");
     return AOZ_OK;
 }
 
-
 extern "C" {
 
-static int gn_chunks(int NB, int HW) {
-    int chunks = (sm_count() * 2 + NB - 1) / NB;
-    if (chunks > GN_MAX_CHUNKS) chunks = GN_MAX_CHUNKS;
-    if (chunks > HW) chunks = HW;
+// block shape: one thread per 16-byte vector column (C/8 of them) times as many row lanes as fit 512 threads; always >= 256
+static int gn_block_threads(int C, int* row_lanes_out = nullptr) {
+    const int vec = C / 8;
+    const int cols = vec < GN_THREADS ? vec : GN_THREADS;
+    const int row_lanes = GN_THREADS / cols;
+    if (row_lanes_out) *row_lanes_out = row_lanes;
+    return cols * row_lanes;
+}
+
+// pixel chunks (grid.x) of the statistics kernels: ~4 blocks per SM over the whole batch, at least `min_rows` rows per thread
+static int gn_chunks(int NB, int HW, int C, int max_chunks, int min_rows) {
+    int row_lanes = 1;
+    gn_block_threads(C, &row_lanes);
+    int chunks = (sm_count() * 4 + NB - 1) / NB;
+    const int by_rows = HW / (row_lanes * min_rows);
+    if (chunks > by_rows) chunks = by_rows;
+    if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
     return chunks;
 }
 
 // pixel chunks (grid.x) of the apply kernels: enough blocks to fill the GPU a few times over, at least 8 rows per thread
 static int gn_apply_chunks(int NB, int HW, int C) {
-    const int vec = C / 8;
-    const int cols = vec < GN_THREADS ? vec : GN_THREADS;
-    const int row_lanes = GN_THREADS / cols;
+    int row_lanes = 1;
+    gn_block_threads(C, &row_lanes);
     int chunks = (HW + row_lanes * 8 - 1) / (row_lanes * 8);
-    const int cap = (sm_count() * 8 + NB - 1) / NB;
+    const int cap = (sm_count() * 6 + NB - 1) / NB;
     if (chunks > cap) chunks = cap;
     if (chunks < 1) chunks = 1;
     return chunks;
@@ -595,7 +687,9 @@ static int gn_apply_chunks(int NB, int HW, int C) {
 // workspace floats needed by the GroupNorm forward / backward (upper bound)
 long long aoz_groupnorm_workspace_floats(int NB, int HW, int C) {
     const long long chunks = GN_MAX_CHUNKS;
-    return (long long)NB * chunks * 2 * C + (long long)NB * GN_GROUPS * 2 + 64 + (long long)NB * 2 * C + 64;
+    const long long bwd = (long long)NB * chunks * 2 * C + (long long)NB * GN_GROUPS * 2 + 64 + (long long)NB * 2 * C + 64;
+    const long long fwd = (long long)NB * GN_FWD_MAX_CHUNKS * GN_GROUPS * 2;
+    return bwd > fwd ? bwd : fwd;
 }
 
 // y = silu?(GroupNorm32(x)); x, y: [NB, HW, C] bf16 channels-last; mean/rstd out: [NB, 32] fp32
@@ -606,13 +700,15 @@ int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB
     AOZ_CHECK_ARG(NB > 0 && HW > 0, "aoz_groupnorm_fwd: empty input");
     AOZ_CHECK_ARG(2 * C * (int)sizeof(float) <= 48 * 1024, "aoz_groupnorm_fwd: C=%d too large", C);
     cudaStream_t s = (cudaStream_t)stream;
-    const int chunks = gn_chunks(NB, HW);
-    launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(GN_THREADS), (size_t)(2 * C * sizeof(float)), s, (const __nv_bfloat16*)x, HW, C, (float*)workspace);
+    const int chunks = gn_chunks(NB, HW, C, GN_FWD_MAX_CHUNKS, 4);
+    const int threads = gn_block_threads(C);
+    AOZ_CHECK_ARG(NB <= 1024, "aoz_groupnorm_fwd: NB=%d > 1024", NB);
+    launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(threads), (size_t)(2 * C * sizeof(float)), s, (const __nv_bfloat16*)x, HW, C, eps,
+             (float*)workspace, (float*)mean, (float*)rstd);
     AOZ_CHECK_LAUNCH("gn_stats_kernel");
     int gx = gn_apply_chunks(NB, HW, C);
-    launch_k(gn_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-                                                       (const float*)workspace, chunks, HW, C, eps, silu, (__nv_bfloat16*)y,
-                                                       (float*)mean, (float*)rstd);
+    launch_k(gn_apply_kernel, dim3(gx, NB), dim3(threads), (size_t)(0), s, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+             (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd, HW, C, silu, (__nv_bfloat16*)y);
     AOZ_CHECK_LAUNCH("gn_apply_kernel");
     return AOZ_OK;
 }
@@ -623,10 +719,11 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     AOZ_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && workspace, "aoz_groupnorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_bwd: C=%d must be a multiple of 32", C);
     cudaStream_t s = (cudaStream_t)stream;
-    const int chunks = gn_chunks(NB, HW);
+    const int chunks = gn_chunks(NB, HW, C, GN_MAX_CHUNKS, 8);
+    const int threads = gn_block_threads(C);
     float* partial = (float*)workspace;
     float* group_terms = partial + (size_t)NB * GN_MAX_CHUNKS * 2 * C;
-    launch_k(gn_bwd_stats_kernel, dim3(chunks, NB), dim3(GN_THREADS), (size_t)(2 * C * sizeof(float)), s, 
+    launch_k(gn_bwd_stats_kernel, dim3(chunks, NB), dim3(threads), (size_t)(2 * C * sizeof(float)), s, 
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
         (const float*)mean, (const float*)rstd, HW, C, silu, partial);
     AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
@@ -638,7 +735,7 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
         AOZ_CHECK_LAUNCH("gn_bwd_param_kernel");
     }
     int gx = gn_apply_chunks(NB, HW, C);
-    launch_k(gn_bwd_apply_kernel, dim3(gx, NB), dim3(GN_THREADS), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
+    launch_k(gn_bwd_apply_kernel, dim3(gx, NB), dim3(threads), (size_t)(0), s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
                                                            (const __nv_bfloat16*)beta, (const float*)mean, (const float*)rstd,
                                                            group_terms, HW, C, silu, (const __nv_bfloat16*)dres, (__nv_bfloat16*)dx);
     AOZ_CHECK_LAUNCH("gn_bwd_apply_kernel");
@@ -650,13 +747,17 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
     AOZ_CHECK_ARG(x && gamma && beta && y && mean && rstd, "aoz_layernorm_fwd: null pointer");
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_fwd: C=%d unsupported (multiple of 8, <= 2048)", C);
     if (rows <= 0) return AOZ_OK;
-    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-    if (blocks > sm_count() * 8) blocks = sm_count() * 8;
-    launch_k(ln_fwd_kernel, dim3((int)blocks), dim3(LN_WARPS * 32), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma,
-                                                                          (const __nv_bfloat16*)beta, rows, C, eps, (__nv_bfloat16*)y,
-                                                                          (float*)mean, (float*)rstd);
-    AOZ_CHECK_LAUNCH("ln_fwd_kernel");
-    return AOZ_OK;
+    cudaStream_t s = (cudaStream_t)stream;
+    switch ((C / 8 + 31) / 32) {            // 16-byte vectors per lane; fewer vectors -> more rows in flight per warp
+        case 1: return launch_ln_fwd<1, 4>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 2: return launch_ln_fwd<2, 4>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 3: return launch_ln_fwd<3, 3>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 4: return launch_ln_fwd<4, 2>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 5: return launch_ln_fwd<5, 2>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 6: return launch_ln_fwd<6, 1>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        case 7: return launch_ln_fwd<7, 1>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+        default: return launch_ln_fwd<8, 1>(x, gamma, beta, rows, C, eps, y, mean, rstd, s);
+    }
 }
 
 long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 2 * 2 * C; }
@@ -666,22 +767,23 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     AOZ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "aoz_layernorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
     if (rows <= 0) return AOZ_OK;
-    long long blocks = (rows + LN_WARPS - 1) / LN_WARPS;
-    if (blocks > sm_count() * 2) blocks = sm_count() * 2;
     cudaStream_t s = (cudaStream_t)stream;
-    const int vpl = (C / 8 + 31) / 32;
-    int rc;
-    switch (vpl) {
-        case 1: rc = launch_ln_bwd<1>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-        case 2: rc = launch_ln_bwd<2>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-        case 3: rc = launch_ln_bwd<3>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-        case 4: rc = launch_ln_bwd<4>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-        case 5: rc = launch_ln_bwd<5>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-        default: rc = launch_ln_bwd<8>(dy, x, gamma, mean, rstd, rows, C, dres, dx, workspace, (int)blocks, s); break;
-    }
-    if (rc != AOZ_OK) return rc;
-    launch_k(ln_bwd_finalize_kernel, dim3((2 * C + 31) / 32), dim3(256), (size_t)(0), s, (const float*)workspace, (int)blocks, C, (__nv_bfloat16*)dgamma,
-                                                               (__nv_bfloat16*)dbeta, accumulate);
+    const int cols_pad = ((C / 8 + 31) / 32) * 32;
+    int RL = LNB_MAX_THREADS / cols_pad;
+    if (RL > 16) RL = 16;
+    const int tile = RL * LNB_T;
+    long long blocks = (rows + tile - 1) / tile;
+    if (blocks > sm_count()) blocks = sm_count();
+    const long long rows_per_block = (rows + blocks - 1) / blocks;
+    blocks = (rows + rows_per_block - 1) / rows_per_block;
+    const size_t red = (size_t)RL * LNB_T * (cols_pad / 32) * 2, fin = (size_t)RL * 2 * C;
+    const size_t smem = (red > fin ? red : fin) * sizeof(float);
+    launch_k(ln_bwd_kernel, dim3((int)blocks), dim3(cols_pad * RL), smem, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
+             (const __nv_bfloat16*)gamma, (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
+             (__nv_bfloat16*)dx, (float*)workspace, cols_pad, RL, rows_per_block);
+    AOZ_CHECK_LAUNCH("ln_bwd_kernel");
+    launch_k(ln_bwd_finalize_kernel, dim3((2 * C + 31) / 32), dim3(1024), (size_t)(0), s, (const float*)workspace, (int)blocks, C,
+             (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
     AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");
     return AOZ_OK;
 }

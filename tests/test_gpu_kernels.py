@@ -264,7 +264,8 @@ def test_groupnorm_silu_fwd_bwd(NB, HW, C, silu):
     check(dx2, xr.grad.to(BF16).float() + dres.float())
 
 
-@pytest.mark.parametrize("rows,C", [(300, 640), (1000, 1280), (7, 64), (4096, 2048)])
+@pytest.mark.parametrize("rows,C", [(300, 640), (1000, 1280), (7, 64), (4096, 2048), (16384, 640), (4096, 1280), (33, 320), (1, 8),
+                                    (2049, 1536), (613, 1024)])
 def test_layernorm_fwd_bwd(rows, C):
     ops = _ops()
     g = gen(8)
@@ -276,12 +277,19 @@ def test_layernorm_fwd_bwd(rows, C):
     gr, br = ga.float().requires_grad_(True), be.float().requires_grad_(True)
     yr = torch.nn.functional.layer_norm(xr, (C,), gr, br, 1e-5)
     check(y, yr)
+    xf = x.float()
+    torch.testing.assert_close(mean, xf.mean(1), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close(rstd, torch.rsqrt(xf.var(1, unbiased=False) + 1e-5), rtol=1e-4, atol=1e-5)
     dy = torch.randn(y.shape, device="cuda", generator=g).to(BF16)
     yr.backward(dy.float())
     dx, dg, db = ops.layernorm_bwd(dy, x, ga, mean, rstd)
     check(dx, xr.grad)
     check(dg, gr.grad)
     check(db, br.grad)
+    dres = torch.randn(rows, C, device="cuda", generator=g).to(BF16)      # residual-stream gradient added in the same pass
+    dx2, dg2, db2 = ops.layernorm_bwd(dy, x, ga, mean, rstd, dres=dres)
+    check(dx2, xr.grad.to(BF16).float() + dres.float())
+    assert torch.equal(dg2, dg) and torch.equal(db2, db)                  # fixed summation order: bit-reproducible
 
 
 def test_glue_kernels():

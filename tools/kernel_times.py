@@ -34,6 +34,9 @@ def prof(name, fn, flops=None, n=5):
 
 
 def main():
+    only = sys.argv[1] if len(sys.argv) > 1 else ""
+    if only == "norms":
+        return norms()
     for name, NB, H, Cin, Cout in [("conv_1280", 4, 32, 1280, 1280), ("conv_640", 4, 64, 640, 640), ("conv_320", 4, 128, 320, 320),
                                    ("conv_2560_1280", 4, 32, 2560, 1280), ("conv_960_320", 4, 128, 960, 320)]:
         x = torch.randn(NB, H, H, Cin, device="cuda").to(BF)
@@ -75,12 +78,22 @@ def main():
         prof(f"attn_{name}_fwd", lambda: ops.attn_fwd(q, k, v, 0.125), f)
         o, lse = ops.attn_fwd(q, k, v, 0.125)
         prof(f"attn_{name}_bwd", lambda: ops.attn_bwd(q, k, v, o, do, lse, 0.125), 2.5 * f)
+    norms()
+
+
+def norms():
     for rows, C in [(4096, 1280), (16384, 640)]:
         x = torch.randn(rows, C, device="cuda").to(BF)
         g, bb = torch.ones(C, device="cuda", dtype=BF), torch.zeros(C, device="cuda", dtype=BF)
         y, mean, rstd = ops.layernorm_fwd(x, g, bb)
         prof(f"ln_fwd_{C}", lambda: ops.layernorm_fwd(x, g, bb))
         prof(f"ln_bwd_{C}", lambda: ops.layernorm_bwd(x, x, g, mean, rstd, dres=x))
+    for NB, HW, C in [(4, 1024, 1280), (4, 4096, 640), (4, 16384, 320), (4, 16384, 960), (4, 1024, 2560)]:
+        x = torch.randn(NB, HW, C, device="cuda").to(BF)
+        g, bb = torch.ones(C, device="cuda", dtype=BF), torch.zeros(C, device="cuda", dtype=BF)
+        y, mean, rstd = ops.groupnorm_fwd(x, g, bb, 1e-5, True)
+        prof(f"gn_silu_fwd_{C}x{HW}", lambda: ops.groupnorm_fwd(x, g, bb, 1e-5, True))
+        prof(f"gn_silu_bwd_{C}x{HW}", lambda: ops.groupnorm_bwd(x, x, g, bb, mean, rstd, True, dres=x))
 
 
 if __name__ == "__main__":

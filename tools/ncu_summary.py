@@ -24,7 +24,16 @@ def main(path):
         for k in WANT:
             if k in d:
                 print(f"  {k:80s} {d[k]:>16s} {units[hdr.index(k)]}")
-        rd, wr = d.get("dram__bytes_read.sum"), d.get("dram__bytes_write.sum")
+        try:                                      # derived: achieved DRAM bandwidth of this launch
+            def val(k):
+                v, u = float(d[k].replace(",", "")), units[hdr.index(k)].lower()
+                scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9, "ns": 1e-9, "us": 1e-6, "ms": 1e-3,
+                         "usecond": 1e-6, "nsecond": 1e-9, "msecond": 1e-3, "second": 1.0, "s": 1.0}.get(u, 1.0)
+                return v * scale
+            byts = val("dram__bytes_read.sum") + val("dram__bytes_write.sum")
+            print(f"  {'derived: DRAM read+write / duration':80s} {byts / val('gpu__time_duration.sum') / 1e9:16.1f} GB/s")
+        except (KeyError, ValueError, ZeroDivisionError):
+            pass
         print()
 
 
