@@ -28,44 +28,37 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
 
 // ---------------------------------------------------------------------------------------------
-// GroupNorm statistics: x [NB, HW, C] -> partial [NB][chunks][GROUPS][2] (sum, sumsq)
-// Row-lane partials are added to the per-channel shared-memory sums ONE LANE AT A TIME (plain adds between barriers): float
-// atomics would make the summation order, and with it the low bits of every statistic and gradient, differ run to run.
-// When there is more than one row lane every thread owns exactly one vector column (cols == vec_per_row).
-__device__ __forceinline__ void gn_ordered_accumulate(float* sm, int C, int v, int tr, int row_lanes, bool active, const float* s, const float* q) {
-    for (int l = 0; l < row_lanes; ++l) {
-        if (active && tr == l) {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) { sm[v * 8 + e] += s[e]; sm[C + v * 8 + e] += q[e]; }
-        }
-        __syncthreads();
-    }
+// GroupNorm statistics: x [NB, HW, C] -> partial [NB][chunks][GROUPS][2] (sum, sumsq) -> mean / rstd [NB][GROUPS]
+// grid (chunks, NB) ~ one block per SM; block = `cols` vector columns x `row_lanes` row lanes (<= 1024 threads, rounded up to
+// whole warps).  A thread owns one 8-channel vector column and walks its row lane of the chunk with four rows in flight.
+// No float atomics anywhere (they would make the low bits of every statistic and gradient differ run to run): the row-lane
+// partials go to shared memory [row_lanes][2][C], ONE barrier, then 16 threads per (group, sum|sumsq) add the group's
+// row_lanes * C/32 entries in a fixed order.  The last block of an image (self-resetting ticket) reduces the chunk partials
+// the same way and writes mean / rstd, so the apply kernel starts streaming immediately.
+__device__ __forceinline__ float half_warp_sum_fixed(float v) {
+    v += __shfl_xor_sync(0xffffffffu, v, 8);
+    v += __shfl_xor_sync(0xffffffffu, v, 4);
+    v += __shfl_xor_sync(0xffffffffu, v, 2);
+    v += __shfl_xor_sync(0xffffffffu, v, 1);
+    return v;
 }
 
-// grid (chunks, NB).  Each thread owns one 8-channel vector column and walks pixels.
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(GN_THREADS)
-gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float eps, float* __restrict__ partial,
+__global__ void __launch_bounds__(1024)
+gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float eps, int cols, int row_lanes, float* __restrict__ partial,
                 float* __restrict__ mean_out, float* __restrict__ rstd_out) {
     pdl_enter();
-    extern __shared__ float sm[];          // [2][C] per-channel sums
-    __shared__ float s_fin[4][2][GN_GROUPS];
+    extern __shared__ float sm[];          // [row_lanes][2][C]
+    __shared__ float s_fin[2][GN_GROUPS];
     __shared__ unsigned int s_last;
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
-    const int nthreads = blockDim.x;
     const int vec_per_row = C / 8;
     const int rows_per_chunk = (HW + chunks - 1) / chunks;
     const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
-    for (int i = threadIdx.x; i < 2 * C; i += nthreads) sm[i] = 0.f;
-    __syncthreads();
     const __nv_bfloat16* xb = x + (size_t)n * HW * C;
-    // threads are laid out as (row lane, vector column): column = tid % cols
-    const int cols = min(vec_per_row, nthreads);
-    const int row_lanes = nthreads / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
-    float s[8], q[8];
     if (tr < row_lanes) {
-        for (int v = tc; v < vec_per_row; v += cols) {
+        for (int v = tc; v < vec_per_row; v += cols) {             // one trip unless C/8 exceeds the block (then row_lanes == 1)
+            float s[8], q[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) { s[e] = 0.f; q[e] = 0.f; }
             int r = r0 + tr;
@@ -87,23 +80,27 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float eps, f
 #pragma unroll
                 for (int e = 0; e < 8; ++e) { s[e] += f[e]; q[e] = fmaf(f[e], f[e], q[e]); }
             }
-            if (row_lanes == 1) {                                  // single writer per channel
+            float* d = sm + (size_t)tr * 2 * C + v * 8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sm[v * 8 + e] = s[e]; sm[C + v * 8 + e] = q[e]; }
-            }
+            for (int e = 0; e < 8; ++e) { d[e] = s[e]; d[C + e] = q[e]; }
         }
     }
-    if (row_lanes > 1) gn_ordered_accumulate(sm, C, tc, tr, row_lanes, tr < row_lanes && tc < vec_per_row, s, q);
     __syncthreads();
-    // channels -> groups (fixed order)
+    // (group, which) pairs: 16 threads each, fixed summation order
     const int cpg = C / GN_GROUPS;
-    if (threadIdx.x < 2 * GN_GROUPS) {
-        const int g = threadIdx.x % GN_GROUPS, which = threadIdx.x / GN_GROUPS;
+    const int sub = threadIdx.x & 15;
+    const int count = row_lanes * cpg;
+    for (int p = threadIdx.x >> 4; p < 2 * GN_GROUPS; p += blockDim.x >> 4) {
+        const int g = p & (GN_GROUPS - 1), which = p >> 5;
         float a = 0.f;
-        for (int c = g * cpg; c < (g + 1) * cpg; ++c) a += sm[which * C + c];
-        partial[(((size_t)n * chunks + chunk) * GN_GROUPS + g) * 2 + which] = a;
+        for (int idx = sub; idx < count; idx += 16) {
+            const int l = idx / cpg, c = idx - l * cpg;
+            a += sm[(size_t)(l * 2 + which) * C + g * cpg + c];
+        }
+        a = half_warp_sum_fixed(a);
+        if (sub == 0) partial[(((size_t)n * chunks + chunk) * GN_GROUPS + g) * 2 + which] = a;
     }
-    // the LAST block of this image (self-resetting ticket) turns the chunk partials into mean / rstd, in fixed order
+    // the LAST block of this image turns the chunk partials into mean / rstd
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -113,20 +110,19 @@ gn_stats_kernel(const __nv_bfloat16* __restrict__ x, int HW, int C, float eps, f
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    if (threadIdx.x < 256) {                                       // blocks always have >= 256 threads (gn_block_threads)
-        const int g = threadIdx.x & 31, which = (threadIdx.x >> 5) & 1, kl = threadIdx.x >> 6;
+    for (int p = threadIdx.x >> 4; p < 2 * GN_GROUPS; p += blockDim.x >> 4) {
+        const int g = p & (GN_GROUPS - 1), which = p >> 5;
         float a = 0.f;
-        for (int k = kl; k < chunks; k += 4) a += __ldcg(partial + (((size_t)n * chunks + k) * GN_GROUPS + g) * 2 + which);
-        s_fin[kl][which][g] = a;
+        for (int k = sub; k < chunks; k += 16) a += __ldcg(partial + (((size_t)n * chunks + k) * GN_GROUPS + g) * 2 + which);
+        a = half_warp_sum_fixed(a);
+        if (sub == 0) s_fin[which][g] = a;
     }
     __syncthreads();
     if (threadIdx.x < GN_GROUPS) {
         const int g = threadIdx.x;
-        const float sum = (s_fin[0][0][g] + s_fin[1][0][g]) + (s_fin[2][0][g] + s_fin[3][0][g]);
-        const float sq = (s_fin[0][1][g] + s_fin[1][1][g]) + (s_fin[2][1][g] + s_fin[3][1][g]);
         const float cnt = (float)HW * (float)cpg;
-        const float mean = sum / cnt;
-        const float var = fmaxf(sq / cnt - mean * mean, 0.f);
+        const float mean = s_fin[0][g] / cnt;
+        const float var = fmaxf(s_fin[1][g] / cnt - mean * mean, 0.f);
         mean_out[n * GN_GROUPS + g] = mean;
         rstd_out[n * GN_GROUPS + g] = rsqrtf(var + eps);
     }
@@ -192,25 +188,22 @@ gn_apply_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __rest
 
 // GroupNorm backward pass 1: per-channel sums of dz and dz*xhat over a pixel chunk.
 // partial [NB][chunks][2][C]
-__global__ void __launch_bounds__(GN_THREADS)
+__global__ void __launch_bounds__(GN_THREADS, 1)
 gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
                     const __nv_bfloat16* __restrict__ gamma, const __nv_bfloat16* __restrict__ beta,
-                    const float* __restrict__ mean, const float* __restrict__ rstd, int HW, int C, int silu,
-                    float* __restrict__ partial) {
+                    const float* __restrict__ mean, const float* __restrict__ rstd, int HW, int C, int silu, int cols,
+                    int row_lanes, float* __restrict__ partial) {
     pdl_enter();
-    extern __shared__ float sm[];          // [2][C]
+    extern __shared__ float sm[];          // [row_lanes][2][C]
     __shared__ float s_mean[GN_GROUPS], s_rstd[GN_GROUPS];
     const int n = blockIdx.y, chunk = blockIdx.x, chunks = gridDim.x;
     const int cpg = C / GN_GROUPS;
     if (threadIdx.x < GN_GROUPS) { s_mean[threadIdx.x] = mean[n * GN_GROUPS + threadIdx.x]; s_rstd[threadIdx.x] = rstd[n * GN_GROUPS + threadIdx.x]; }
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) sm[i] = 0.f;
     __syncthreads();
     const int vec_per_row = C / 8;
     const int rows_per_chunk = (HW + chunks - 1) / chunks;
     const int r0 = chunk * rows_per_chunk, r1 = min(HW, r0 + rows_per_chunk);
     const size_t base = (size_t)n * HW * C;
-    const int cols = min(vec_per_row, (int)blockDim.x);
-    const int row_lanes = (int)blockDim.x / cols;
     const int tc = threadIdx.x % cols, tr = threadIdx.x / cols;
     float a[8], b[8];
     if (tr < row_lanes) {
@@ -249,16 +242,18 @@ gn_bwd_stats_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                 for (int u = 0; u < 4; ++u) acc_row(px[u], pd[u]);
             }
             for (; r < r1; r += row_lanes) acc_row(ld_stream(x + base + (size_t)r * C + v * 8), ld_stream(dy + base + (size_t)r * C + v * 8));
-            if (row_lanes == 1) {                                  // single writer per channel
+            float* d = sm + (size_t)tr * 2 * C + v * 8;
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { sm[v * 8 + e] = a[e]; sm[C + v * 8 + e] = b[e]; }
-            }
+            for (int e = 0; e < 8; ++e) { d[e] = a[e]; d[C + e] = b[e]; }
         }
     }
-    if (row_lanes > 1) gn_ordered_accumulate(sm, C, tc, tr, row_lanes, tr < row_lanes && tc < vec_per_row, a, b);
     __syncthreads();
     float* out = partial + ((size_t)n * chunks + chunk) * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) out[i] = sm[i];
+    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {        // fixed-order sum over the row lanes
+        float t = 0.f;
+        for (int l = 0; l < row_lanes; ++l) t += sm[(size_t)l * 2 * C + i];
+        out[i] = t;
+    }
 }
 
 // pass 2a: one block per (group, image): reduce the chunk partials of the group's channels, write the per-channel
@@ -530,7 +525,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
     const uint4 zero4 = make_uint4(0, 0, 0, 0);
     for (long long base = rb0; base < rb1; base += (long long)RL * LNB_T) {
-        uint4 xp[LNB_T], dp[LNB_T], rp[LNB_T];
+        uint4 xp[LNB_T], dp[LNB_T];
         float mu[LNB_T], rs[LNB_T], p1[LNB_T], p2[LNB_T];
         bool ok[LNB_T];
 #pragma unroll
@@ -540,7 +535,6 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             const long long off = row * C + tc * 8;
             xp[t] = ok[t] ? ld_stream(x + off) : zero4;
             dp[t] = ok[t] ? ld_stream(dy + off) : zero4;
-            rp[t] = (ok[t] && dres) ? ld_stream(dres + off) : zero4;
             mu[t] = ok[t] ? __ldg(mean + row) : 0.f;
             rs[t] = ok[t] ? __ldg(rstd + row) : 0.f;
         }
@@ -569,9 +563,13 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
                 d[0] = p1[t]; d[1] = p2[t];
             }
         }
+        // the residual gradient is fetched one row ahead of its use (it is L2-resident: the kernel before this one wrote it)
+        uint4 rp = (ok[0] && dres) ? ld_stream(dres + (base + rl) * C + tc * 8) : zero4;
         __syncthreads();
 #pragma unroll
         for (int t = 0; t < LNB_T; ++t) {
+            const uint4 rcur = rp;
+            if (t + 1 < LNB_T) rp = (ok[t + 1] && dres) ? ld_stream(dres + (base + (long long)(t + 1) * RL + rl) * C + tc * 8) : zero4;
             if (!ok[t]) continue;
             const float2* srow = reinterpret_cast<const float2*>(sm + (size_t)(rl * LNB_T + t) * W * 2);
             float s1 = 0.f, s2 = 0.f;
@@ -583,7 +581,7 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             for (int e = 0; e < 8; ++e) o[e] = rs[t] * (fd[e] * gm[e] - s1 - (fx[e] - mu[t]) * rs[t] * s2);
             if (dres) {
                 float fr[8];
-                unpack8(rp[t], fr);
+                unpack8(rcur, fr);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
             }
@@ -652,21 +650,21 @@ static int launch_ln_fwd(const void* x, const void* gamma, const void* beta, lon
 
 extern "C" {
 
-// block shape: one thread per 16-byte vector column (C/8 of them) times as many row lanes as fit 512 threads; always >= 256
-static int gn_block_threads(int C, int* row_lanes_out = nullptr) {
+// block shape: one thread per 16-byte vector column (C/8 of them) times as many row lanes as fit `max_threads`
+static int gn_block_threads(int C, int* row_lanes_out = nullptr, int* cols_out = nullptr, int max_threads = GN_THREADS) {
     const int vec = C / 8;
-    const int cols = vec < GN_THREADS ? vec : GN_THREADS;
-    const int row_lanes = GN_THREADS / cols;
+    const int cols = vec < max_threads ? vec : max_threads;
+    const int row_lanes = max_threads / cols;
     if (row_lanes_out) *row_lanes_out = row_lanes;
+    if (cols_out) *cols_out = cols;
     return cols * row_lanes;
 }
 
-// pixel chunks (grid.x) of the statistics kernels: ~4 blocks per SM over the whole batch, at least `min_rows` rows per thread
-static int gn_chunks(int NB, int HW, int C, int max_chunks, int min_rows) {
-    int row_lanes = 1;
-    gn_block_threads(C, &row_lanes);
-    int chunks = (sm_count() * 4 + NB - 1) / NB;
-    const int by_rows = HW / (row_lanes * min_rows);
+// pixel chunks (grid.x) of the statistics kernels: one block per SM over the whole batch (fewer partials to combine, every
+// load of the tensor in flight at once), at least four rows per thread
+static int gn_chunks(int NB, int HW, int row_lanes, int max_chunks) {
+    int chunks = sm_count() / NB;
+    const int by_rows = HW / (row_lanes * 4);
     if (chunks > by_rows) chunks = by_rows;
     if (chunks > max_chunks) chunks = max_chunks;
     if (chunks < 1) chunks = 1;
@@ -698,12 +696,20 @@ int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB
     AOZ_CHECK_ARG(x && gamma && beta && y && mean && rstd && workspace, "aoz_groupnorm_fwd: null pointer");
     AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_fwd: C=%d must be a multiple of 32", C);
     AOZ_CHECK_ARG(NB > 0 && HW > 0, "aoz_groupnorm_fwd: empty input");
-    AOZ_CHECK_ARG(2 * C * (int)sizeof(float) <= 48 * 1024, "aoz_groupnorm_fwd: C=%d too large", C);
+    AOZ_CHECK_ARG(C <= 16384, "aoz_groupnorm_fwd: C=%d too large", C);
     cudaStream_t s = (cudaStream_t)stream;
-    const int chunks = gn_chunks(NB, HW, C, GN_FWD_MAX_CHUNKS, 4);
+    int cols = 1, row_lanes = 1;
+    const int st_threads = (gn_block_threads(C, &row_lanes, &cols, 1024) + 31) & ~31;
+    const int chunks = gn_chunks(NB, HW, row_lanes, GN_FWD_MAX_CHUNKS);
     const int threads = gn_block_threads(C);
     AOZ_CHECK_ARG(NB <= 1024, "aoz_groupnorm_fwd: NB=%d > 1024", NB);
-    launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(threads), (size_t)(2 * C * sizeof(float)), s, (const __nv_bfloat16*)x, HW, C, eps,
+    const size_t st_smem = (size_t)row_lanes * 2 * C * sizeof(float);
+    static size_t st_attr = 48 * 1024;
+    if (st_smem > st_attr) {
+        cudaFuncSetAttribute(gn_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem);
+        st_attr = st_smem;
+    }
+    launch_k(gn_stats_kernel, dim3(chunks, NB), dim3(st_threads), st_smem, s, (const __nv_bfloat16*)x, HW, C, eps, cols, row_lanes,
              (float*)workspace, (float*)mean, (float*)rstd);
     AOZ_CHECK_LAUNCH("gn_stats_kernel");
     int gx = gn_apply_chunks(NB, HW, C);
@@ -719,13 +725,21 @@ int aoz_groupnorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     AOZ_CHECK_ARG(dy && x && gamma && beta && mean && rstd && dx && workspace, "aoz_groupnorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % GN_GROUPS == 0 && C % 8 == 0, "aoz_groupnorm_bwd: C=%d must be a multiple of 32", C);
     cudaStream_t s = (cudaStream_t)stream;
-    const int chunks = gn_chunks(NB, HW, C, GN_MAX_CHUNKS, 8);
-    const int threads = gn_block_threads(C);
+    int cols = 1, row_lanes = 1;
+    const int threads = gn_block_threads(C, &row_lanes, &cols);
+    const int st_threads = (threads + 31) & ~31;
+    const int chunks = gn_chunks(NB, HW, row_lanes, GN_MAX_CHUNKS);
     float* partial = (float*)workspace;
     float* group_terms = partial + (size_t)NB * GN_MAX_CHUNKS * 2 * C;
-    launch_k(gn_bwd_stats_kernel, dim3(chunks, NB), dim3(threads), (size_t)(2 * C * sizeof(float)), s, 
+    const size_t st_smem = (size_t)row_lanes * 2 * C * sizeof(float);
+    static size_t st_attr = 48 * 1024;
+    if (st_smem > st_attr) {
+        cudaFuncSetAttribute(gn_bwd_stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)st_smem);
+        st_attr = st_smem;
+    }
+    launch_k(gn_bwd_stats_kernel, dim3(chunks, NB), dim3(st_threads), st_smem, s,
         (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x, (const __nv_bfloat16*)gamma, (const __nv_bfloat16*)beta,
-        (const float*)mean, (const float*)rstd, HW, C, silu, partial);
+        (const float*)mean, (const float*)rstd, HW, C, silu, cols, row_lanes, partial);
     AOZ_CHECK_LAUNCH("gn_bwd_stats_kernel");
     float* chansum = group_terms + (size_t)NB * GN_GROUPS * 2 + 64;
     launch_k(gn_bwd_group_kernel, dim3(GN_GROUPS, NB), dim3(128), (size_t)(0), s, partial, (const __nv_bfloat16*)gamma, chunks, C, chansum, group_terms);

@@ -1,11 +1,12 @@
-"""One launch of every hot kernel family at its SDXL shape, for ONE `ncu --set full` capture (profiles/rNN_kernels_ncu.txt):
+"""One launch of every hot kernel family at its SDXL shape, for ONE ncu capture (profiles/rNN_kernels_ncu.txt):
 
-    ncu --set full --clock-control none --import-source on --profile-from-start off -o gpurun_out/kernels \
-        python tools/ncu_kernels.py
+    ncu --section SpeedOfLight --section MemoryWorkloadAnalysis --section LaunchStats --section Occupancy \
+        --metrics $(python tools/ncu_summary.py --metrics) --clock-control none --profile-from-start off \
+        -o gpurun_out/kernels python tools/ncu_kernels.py
     python tools/ncu_summary.py gpurun_out/kernels.ncu-rep > profiles/r01_kernels_ncu_v1.txt
 
 Each op is warmed up outside the profiled range (cudaProfilerStart/Stop bracket exactly one call), so the report holds one
-launch per kernel: attention forward / dK,dV / dQ (self 4096 tokens x 10 heads, self 1024 x 20, cross 77 keys), the 3x3
+launch per kernel: attention forward / dK,dV / dQ (self 4096 tokens x 10 heads, cross 77 keys), the 3x3
 implicit-GEMM convolution (1280 -> 1280 at 32x32: forward, dgrad, wgrad), the GEGLU projection GEMM, GroupNorm+SiLU
 (1280 channels, forward and backward), LayerNorm (forward and backward), the timestep-embedding MLP (M = batch), the
 weighted-MSE loss, the noising kernel, the gradient-norm reduction and the Raven update."""
@@ -35,7 +36,7 @@ def once(fn, warm=2):
 def main():
     B = 4
     # attention
-    for H, T, Tk in [(10, 4096, 4096), (20, 1024, 1024), (10, 4096, 77)]:
+    for H, T, Tk in [(10, 4096, 4096), (10, 4096, 77)]:
         q, do = [torch.randn(B, T, H, 64, device=dev).to(BF) for _ in range(2)]
         k, v = [torch.randn(B, Tk, H, 64, device=dev).to(BF) for _ in range(2)]
         o, lse = ops.attn_fwd(q, k, v, 0.125)
@@ -62,14 +63,14 @@ def main():
     dg = torch.randn(M, 4 * C, device=dev).to(BF)
     once(lambda: ops.geglu_bwd(dg, aux))
     # GroupNorm + SiLU, 1280 channels at 32x32 (BASELINE config 5) and 320 channels at 128x128
-    for HW, Cg in [(1024, 1280), (16384, 320)]:
+    for HW, Cg in [(1024, 1280), (16384, 320)][:int(os.environ.get('NCU_GN_SHAPES', '2'))]:
         xg = torch.randn(B, HW, Cg, device=dev).to(BF)
         ga, be = torch.ones(Cg, device=dev, dtype=BF), torch.zeros(Cg, device=dev, dtype=BF)
         yg, mean, rstd = ops.groupnorm_fwd(xg, ga, be, 1e-5, True)
         once(lambda: ops.groupnorm_fwd(xg, ga, be, 1e-5, True))
         once(lambda: ops.groupnorm_bwd(xg, xg, ga, be, mean, rstd, True, dres=xg))
     # LayerNorm
-    for rows, Cl in [(4096, 1280), (16384, 640)]:
+    for rows, Cl in [(4096, 1280)]:
         xl = torch.randn(rows, Cl, device=dev).to(BF)
         ga, be = torch.ones(Cl, device=dev, dtype=BF), torch.zeros(Cl, device=dev, dtype=BF)
         yl, mean, rstd = ops.layernorm_fwd(xl, ga, be)
@@ -89,9 +90,9 @@ def main():
     pred = torch.randn(B, 128, 128, 8, device=dev).to(BF)
     table = torch.ones(1000, device=dev)
     once(lambda: ops.mse_loss(pred, lat.float(), tickets, table, float(B)))
-    # Raven step + gradient norm over 2^28 parameters (bf16 p, g, m, v: 14 B / parameter -> 3.8 GB per launch)
+    # Raven step + gradient norm over 2^27 parameters (bf16 p, g, m, v: 14 B / parameter -> 1.9 GB per launch)
     from aozora_sdxl_training_b200.optimizers import RavenAdamW
-    n = 1 << 22
+    n = 1 << 21
     params = [torch.nn.Parameter(torch.randn(n, device=dev).to(BF)) for _ in range(64)]
     for p in params:
         p.grad = torch.randn_like(p) * 1e-3

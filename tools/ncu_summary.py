@@ -38,4 +38,7 @@ def main(path):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1])
+    if sys.argv[1] == "--metrics":           # the metric list as an `ncu --metrics` argument (lighter than --set full)
+        print(",".join(w for w in WANT if not w.startswith("launch__")))
+    else:
+        main(sys.argv[1])
