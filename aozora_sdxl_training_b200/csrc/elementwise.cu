@@ -291,15 +291,19 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
     float acc[8] = {0, 0, 0, 0, 0, 0, 0, 0};
     if (vcol * 8 < N) {
         long long r = r0 + rl;
-        for (; r + 8 < r1; r += 16) {                          // two rows in flight per thread
-            float f[8], g[8];
-            const uint4 a = ld_stream(x + r * ld + vcol * 8);
-            const uint4 b = ld_stream(x + (r + 8) * ld + vcol * 8);
-            unpack8e(a, f); unpack8e(b, g);
+        for (; r + 24 < r1; r += 32) {                         // four rows in flight per thread
+            uint4 q[4];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) acc[e] += f[e] + g[e];
+            for (int u = 0; u < 4; ++u) q[u] = ld_stream(x + (r + 8 * u) * ld + vcol * 8);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                float f[8];
+                unpack8e(q[u], f);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) acc[e] += f[e];
+            }
         }
-        if (r < r1) {
+        for (; r < r1; r += 8) {
             float f[8];
             unpack8e(ld_stream(x + r * ld + vcol * 8), f);
 #pragma unroll
@@ -326,8 +330,14 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
     if (!s_last) return;
     __threadfence();
     if (col < N) {
+        // every chunk partial of this column in flight at once (chunks <= 64), then a fixed-order sum: the serial
+        // load -> add chain of the plain loop cost ~16 L2 round trips, most of a small launch's time
+        float v[64];
+#pragma unroll
+        for (int k = 0; k < 64; ++k) v[k] = k < chunks ? __ldcg(partial + (long long)k * N + col) : 0.f;
         float t = 0.f;
-        for (int k = 0; k < chunks; ++k) t += __ldcg(partial + (long long)k * N + col);
+#pragma unroll
+        for (int k = 0; k < 64; ++k) t += v[k];
         __nv_bfloat16* out = out0 + (long long)blockIdx.z * N;
         if (accumulate) t = round_bf16(t) + __bfloat162float(out[col]);
         out[col] = __float2bfloat16_rn(t);
@@ -346,10 +356,22 @@ pack_conv_weight_kernel(const __nv_bfloat16* __restrict__ w, int Cout, int Cin, 
     const int ci0 = blockIdx.x * 32, co0 = blockIdx.y * 32;
     const int run = 32 * taps;
     const __nv_bfloat16 zero = __float2bfloat16_rn(0.f);
-    for (int i = threadIdx.x; i < 32 * run; i += 256) {
-        const int co = i / run, k = i - co * run;         // k = ci_local * taps + tap
-        const int ci = ci0 + k / taps;
-        sm[co][k] = (co0 + co < Cout && ci < Cin) ? w[((long long)(co0 + co) * Cin + ci0) * taps + k] : zero;
+    if (ci0 + 32 <= Cin && (Cin & 7) == 0 && ((32 * taps) & 7) == 0) {
+        // full block of input channels: every output-channel row is one 16-byte-aligned run of 32*taps elements
+        const int vec_per_row = run >> 3;
+        for (int i = threadIdx.x; i < 32 * vec_per_row; i += 256) {
+            const int co = i / vec_per_row, v = i - co * vec_per_row;
+            uint4 q = make_uint4(0, 0, 0, 0);
+            if (co0 + co < Cout) q = ld_stream(w + ((long long)(co0 + co) * Cin + ci0) * taps + v * 8);
+            uint32_t* d = reinterpret_cast<uint32_t*>(&sm[co][v * 8]);       // rows are 4-byte aligned (odd word stride)
+            d[0] = q.x; d[1] = q.y; d[2] = q.z; d[3] = q.w;
+        }
+    } else {
+        for (int i = threadIdx.x; i < 32 * run; i += 256) {
+            const int co = i / run, k = i - co * run;         // k = ci_local * taps + tap
+            const int ci = ci0 + k / taps;
+            sm[co][k] = (co0 + co < Cout && ci < Cin) ? w[((long long)(co0 + co) * Cin + ci0) * taps + k] : zero;
+        }
     }
     __syncthreads();
     // wf: rows co (< Cout only), for every tap a 32-element run along ci, written as four 16-byte vectors

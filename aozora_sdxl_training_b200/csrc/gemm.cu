@@ -737,27 +737,32 @@ splitk_reduce_kernel(const float* __restrict__ partial, int splits, long long ro
 // conv weight-gradient finish: partial [splits][rows][taps*Cin] fp32 -> OIHW bf16 [rows][cin_real][taps].
 // One block = one output row x 128 input channels: per tap the 128 threads read 512 contiguous bytes of every split,
 // the [cin][tap] block is transposed through shared memory (stride 9: conflict-free) and leaves as one contiguous run.
+template <int TAPS>
 __global__ void __launch_bounds__(128)
-wgrad_permute_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, int Cin, int cin_real, int taps,
+wgrad_permute_reduce_kernel(const float* __restrict__ partial, int splits, long long rows, int Cin, int cin_real,
                             __nv_bfloat16* __restrict__ out, int accumulate) {
     pdl_enter();
-    __shared__ float sm[128 * 9];
+    __shared__ float sm[128 * TAPS];
     const long long row = blockIdx.y;
     const int c0 = blockIdx.x * 128, c = c0 + threadIdx.x;
-    const long long cols = (long long)taps * Cin, total = rows * cols;
+    const long long cols = (long long)TAPS * Cin, total = rows * cols;
     if (c < Cin) {
-        for (int tap = 0; tap < taps; ++tap) {
-            const float* src = partial + row * cols + (long long)tap * Cin + c;
-            float sum = 0.f;
-            for (int k = 0; k < splits; ++k) sum += src[(long long)k * total];
-            sm[threadIdx.x * taps + tap] = sum;
+        float sum[TAPS];
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) sum[tap] = 0.f;
+        const float* src = partial + row * cols + c;
+        for (int k = 0; k < splits; ++k) {                      // all taps of a split in flight at once
+#pragma unroll
+            for (int tap = 0; tap < TAPS; ++tap) sum[tap] += __ldcs(src + (long long)k * total + (long long)tap * Cin);
         }
+#pragma unroll
+        for (int tap = 0; tap < TAPS; ++tap) sm[threadIdx.x * TAPS + tap] = sum[tap];
     }
     __syncthreads();
     const int nch = min(128, cin_real - c0);
     if (nch <= 0) return;
-    __nv_bfloat16* o = out + (row * cin_real + c0) * taps;
-    for (int i = threadIdx.x; i < nch * taps; i += 128) {
+    __nv_bfloat16* o = out + (row * cin_real + c0) * TAPS;
+    for (int i = threadIdx.x; i < nch * TAPS; i += 128) {
         float v = sm[i];
         if (accumulate) v = round_bf16(v) + __bfloat162float(o[i]);
         o[i] = __float2bfloat16_rn(v);
@@ -1317,8 +1322,12 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
         if ((rc = make_tmap_bf16(&P.tmB, x, 4, dims, strides, box, es)) != AOZ_OK) return rc;
     }
     if ((rc = launch_gemm(P, tp.pair, (cudaStream_t)stream)) != AOZ_OK) return rc;
-    launch_k(wgrad_permute_reduce_kernel, dim3(ceil_div(Cin, 128), Cout), dim3(128), (size_t)(0), (cudaStream_t)stream, 
-        (const float*)workspace, splits, Cout, Cin, cin_real, taps, (__nv_bfloat16*)grad_w, accumulate);
+    if (taps == 9)
+        launch_k(wgrad_permute_reduce_kernel<9>, dim3(ceil_div(Cin, 128), Cout), dim3(128), (size_t)(0), (cudaStream_t)stream,
+                 (const float*)workspace, splits, (long long)Cout, Cin, cin_real, (__nv_bfloat16*)grad_w, accumulate);
+    else
+        launch_k(wgrad_permute_reduce_kernel<1>, dim3(ceil_div(Cin, 128), Cout), dim3(128), (size_t)(0), (cudaStream_t)stream,
+                 (const float*)workspace, splits, (long long)Cout, Cin, cin_real, (__nv_bfloat16*)grad_w, accumulate);
     AOZ_CHECK_LAUNCH("wgrad_permute_reduce_kernel");
     return AOZ_OK;
 }
