@@ -7,6 +7,7 @@
 // reached through train.py:2760.  All kernels stream bf16 with 16-byte accesses where the shape allows and
 // are bound by HBM bandwidth (or, for the [B]-sized ones, by launch latency -- stated in DESIGN.md).
 #include "common.cuh"
+#include <cstring>
 
 namespace aoz {
 
@@ -275,14 +276,12 @@ __global__ void copy_channels_kernel(const __nv_bfloat16* __restrict__ src, long
 // sums the chunk partials in fixed order (deterministic) and writes the bf16 result.  No second launch.
 __device__ unsigned int g_colsum_tickets[4096];     // zero at module load; atomicInc wraps back to zero after every use
 
-__global__ void __launch_bounds__(256)
-colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
-              float* __restrict__ partial0, __nv_bfloat16* __restrict__ out0, int accumulate) {
-    pdl_enter();
+// body shared by the single-tensor / per-image launch (colsum_kernel) and the batched launch (colsum_batch_kernel):
+// x, partial [gridDim.y][N] and out [N] already point at this block's problem; `ticket` = its (problem, column block) slot
+__device__ __forceinline__ void colsum_body(const __nv_bfloat16* __restrict__ x, long long M, int N, long long ld,
+                                            float* __restrict__ partial, __nv_bfloat16* __restrict__ out, int accumulate, int ticket) {
     __shared__ float sm[8][256];
     __shared__ unsigned int s_last;
-    const __nv_bfloat16* x = x0 + (long long)blockIdx.z * group_stride;
-    float* partial = partial0 + (long long)blockIdx.z * gridDim.y * N;
     const int vcol = blockIdx.x * 32 + (threadIdx.x & 31);     // vector column (8 channels)
     const int rl = threadIdx.x >> 5;                           // 8 row lanes
     const int chunks = gridDim.y;
@@ -323,7 +322,7 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        const unsigned int t = atomicInc(&g_colsum_tickets[(blockIdx.z * gridDim.x + blockIdx.x) & 4095], (unsigned int)chunks - 1);
+        const unsigned int t = atomicInc(&g_colsum_tickets[ticket & 4095], (unsigned int)chunks - 1);
         s_last = (t == (unsigned int)chunks - 1);
     }
     __syncthreads();
@@ -338,10 +337,31 @@ colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long lon
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 64; ++k) t += v[k];
-        __nv_bfloat16* out = out0 + (long long)blockIdx.z * N;
         if (accumulate) t = round_bf16(t) + __bfloat162float(out[col]);
         out[col] = __float2bfloat16_rn(t);
     }
+}
+
+__global__ void __launch_bounds__(256)
+colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
+              float* __restrict__ partial0, __nv_bfloat16* __restrict__ out0, int accumulate) {
+    pdl_enter();
+    colsum_body(x0 + (long long)blockIdx.z * group_stride, M, N, ld, partial0 + (long long)blockIdx.z * gridDim.y * N,
+                out0 + (long long)blockIdx.z * N, accumulate, blockIdx.z * gridDim.x + blockIdx.x);
+}
+
+// Batched column sums: up to 8 independent [M_i, N_i] tensors in ONE launch (grid.z = tensor).  A transformer block's bias
+// gradients (attn1.to_out, attn2.to_out, ff.net.0.proj, ff.net.2) are four latency-bound 6..18 us launches otherwise.
+constexpr int COLSUM_BATCH = 8;
+struct ColsumProb { const __nv_bfloat16* x; long long M; long long ld; float* partial; __nv_bfloat16* out; int N; int colblocks; };
+struct ColsumBatch { ColsumProb p[COLSUM_BATCH]; int accumulate; int col_block_base[COLSUM_BATCH]; };
+
+__global__ void __launch_bounds__(256)
+colsum_batch_kernel(const __grid_constant__ ColsumBatch B) {
+    pdl_enter();
+    const ColsumProb& p = B.p[blockIdx.z];
+    if ((int)blockIdx.x >= p.colblocks) return;           // block-uniform: this tensor has fewer column blocks than the widest
+    colsum_body(p.x, p.M, p.N, p.ld, p.partial, p.out, B.accumulate, B.col_block_base[blockIdx.z] + blockIdx.x);
 }
 
 // ---- conv weight packing: OIHW -> [Cout][taps][CinPad] (forward) and [Cin][taps][CoutPad] (dgrad) -------------
@@ -583,6 +603,43 @@ int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long
     launch_k(colsum_kernel, dim3(colblocks, chunks, groups), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)x, M, N, ld, group_stride, (float*)workspace,
                                                                  (__nv_bfloat16*)out, accumulate);
     AOZ_CHECK_LAUNCH("colsum_kernel");
+    return AOZ_OK;
+}
+
+// Batched form of aoz_colsum: out_i[c] (+)= sum_r x_i[r, c] for i in [0, n), n <= 8, ONE launch.  x_ptrs / out_ptrs: HOST arrays
+// of n device pointers (uint64); Ms / lds: HOST int64[n]; Ns: HOST int32[n]; workspace >= 64 * sum(N_i) floats.
+int aoz_colsum_batch(int n, const void* x_ptrs, const void* Ms, const void* Ns, const void* lds, const void* out_ptrs, int accumulate,
+                     void* workspace, void* stream) {
+    AOZ_CHECK_ARG(n >= 1 && n <= COLSUM_BATCH, "aoz_colsum_batch: 1..%d tensors per launch (got %d)", COLSUM_BATCH, n);
+    AOZ_CHECK_ARG(x_ptrs && Ms && Ns && lds && out_ptrs && workspace, "aoz_colsum_batch: bad arguments");
+    const uint64_t* xp = (const uint64_t*)x_ptrs; const uint64_t* op = (const uint64_t*)out_ptrs;
+    const long long* M = (const long long*)Ms; const long long* ld = (const long long*)lds; const int* N = (const int*)Ns;
+    ColsumBatch B;
+    memset(&B, 0, sizeof(B));
+    B.accumulate = accumulate;
+    int max_colblocks = 0, total_colblocks = 0;
+    long long max_m = 0;
+    for (int i = 0; i < n; ++i) {
+        AOZ_CHECK_ARG(xp[i] && op[i] && M[i] > 0 && N[i] > 0, "aoz_colsum_batch: tensor %d is empty", i);
+        AOZ_CHECK_ARG(N[i] % 8 == 0 && ld[i] % 8 == 0 && (xp[i] & 15) == 0, "aoz_colsum_batch: tensor %d: N, ld multiples of 8, 16-byte aligned", i);
+        const int cb = (N[i] + 255) / 256;
+        B.col_block_base[i] = total_colblocks;
+        total_colblocks += cb;
+        if (cb > max_colblocks) max_colblocks = cb;
+        if (M[i] > max_m) max_m = M[i];
+    }
+    AOZ_CHECK_ARG(total_colblocks <= 4096, "aoz_colsum_batch: too many column blocks (%d)", total_colblocks);
+    int chunks = (sm_count() * 4 + total_colblocks - 1) / total_colblocks;
+    if (chunks > 64) chunks = 64;
+    if ((long long)chunks > (max_m + 7) / 8) chunks = (int)((max_m + 7) / 8);
+    if (chunks < 1) chunks = 1;
+    float* ws = (float*)workspace;
+    for (int i = 0; i < n; ++i) {
+        B.p[i] = ColsumProb{(const __nv_bfloat16*)xp[i], M[i], ld[i], ws, (__nv_bfloat16*)op[i], N[i], (N[i] + 255) / 256};
+        ws += (long long)64 * N[i];
+    }
+    launch_k(colsum_batch_kernel, dim3(max_colblocks, chunks, n), dim3(256), (size_t)(0), (cudaStream_t)stream, B);
+    AOZ_CHECK_LAUNCH("colsum_batch_kernel");
     return AOZ_OK;
 }
 

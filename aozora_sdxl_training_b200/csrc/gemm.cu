@@ -221,8 +221,9 @@ __device__ __forceinline__ RowMap map_row(const GemmParams& P, int M, int m_blk,
 
 // EPI_STORE for 8 consecutive output columns [col, col+8) of output row `row`: bias -> per-image time embedding -> residual
 // -> accumulate, each with the bf16 rounding point the op-by-op autocast path has, then one 16-byte store.
+// `has_pre` / `pre`: the residual vector of this segment when the caller fetched it ahead of time (vector path only).
 __device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C, long long ldc, long long row, int group, int col,
-                                           int col_limit, float* f) {
+                                           int col_limit, float* f, bool has_pre = false, uint4 pre = make_uint4(0u, 0u, 0u, 0u)) {
     __nv_bfloat16* dst = C + row * ldc + col;
     const __nv_bfloat16* res = P.residual ? P.residual + row * P.ldr + col : nullptr;
     const __nv_bfloat16* rgb = P.rowgroup_bias ? P.rowgroup_bias + (long long)group * P.ld_rgb + col : nullptr;
@@ -243,7 +244,7 @@ __device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C
             }
         }
         if (res) {
-            const uint4 rr = *reinterpret_cast<const uint4*>(res);
+            const uint4 rr = has_pre ? pre : *reinterpret_cast<const uint4*>(res);
             const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
@@ -508,18 +509,35 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 col_limit = pr.N;
             }
 
+            // EPI_STORE with a residual: the residual rows do not depend on the accumulator, so the 64-byte row segments of the
+            // first chunk are requested BEFORE waiting for the MMAs and every later chunk's one chunk ahead (a load placed next
+            // to its use cost ~0.6 us of L2 latency per 8 rows: the epilogue, not the main loop, bounded the K <= 1280 GEMMs)
+            const int lcol = (lane & 3) * 8;               // this lane's 8 columns inside a 32-column chunk (transposed layout)
+            const bool pre_res = P.residual != nullptr && P.vec_ok && P.epi == EPI_STORE && wi.tail_slot < 0 && P.mode != GM_CONV_WGRAD;
+            RowMap rmap[4];
+            uint4 rnext[4];
+#pragma unroll
+            for (int st = 0; st < 4; ++st) {
+                rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
+                rnext[st] = make_uint4(0u, 0u, 0u, 0u);
+            }
+            auto fetch_res = [&](int c) {
+                const int col = col0 + c + lcol;
+#pragma unroll
+                for (int st = 0; st < 4; ++st)
+                    if (rmap[st].ok && col + 7 < col_limit)
+                        rnext[st] = *reinterpret_cast<const uint4*>(P.residual + rmap[st].row * P.ldr + col);
+            };
+            if (pre_res && col0 + half * 32 < col_limit) fetch_res(half * 32);
+
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
             if (P.dbg & 1) goto epilogue_done;
             {
             const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
-            const int lcol = (lane & 3) * 8;               // this lane's 8 columns inside a 32-column chunk (transposed layout)
 
             if (P.epi == EPI_GEGLU) {
                 // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
-                RowMap rmap[4];
-#pragma unroll
-                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
 #pragma unroll 1
                 for (int c = half * 32; c < BN / 2; c += 64) {
                     uint32_t rv[32], rg[32];
@@ -612,12 +630,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     }
                 }
             } else {
-                RowMap rmap[4];
-#pragma unroll
-                for (int st = 0; st < 4; ++st) rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
                     if (col0 + c >= col_limit) break;          // warp-uniform
+                    uint4 rcur[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) rcur[st] = rnext[st];
+                    if (pre_res && c + 64 < OUT_COLS && col0 + c + 64 < col_limit) fetch_res(c + 64);
                     uint32_t r[32];
                     if (!empty_split) {
                         tmem_ld32(taddr + c, r);
@@ -633,7 +652,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     for (int st = 0; st < 4; ++st) {
                         float f[8];
                         unstage8(stg, lane, st, f);
-                        if (rmap[st].ok && col < col_limit) epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, col, col_limit, f);
+                        if (rmap[st].ok && col < col_limit)
+                            epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, col, col_limit, f, pre_res, rcur[st]);
                     }
                     __syncwarp();
                 }

@@ -167,6 +167,7 @@ class GradSink:
         self.on_grad = None        # optional callback(param, grad): data-parallel bucket scheduling during the sweep
         self.pending = []          # deferred Linear weight gradients: (params stacked by rows, dy, x)
         self.pending_late = []     # the same, flushed once per Transformer2DModel (cross-attention k/v: K = text tokens)
+        self.pending_bias = []     # deferred Linear bias gradients: (bias, dy) -> one batched column-sum launch per flush
         self.dest = None           # optional callback(param) -> tensor the gradient must be written to (data-parallel flat buffer)
 
     def out_for(self, params):
@@ -203,6 +204,13 @@ class GradSink:
         else:
             self._hand_out(params, ops.gemm(dy, x, a_mn=True, b_mn=True, out=self.out_for(params)))
 
+    def bias_grad(self, b, dy, defer=False):
+        """db = column sums of dy.  ``defer``: queue it; ``flush`` sums every queued tensor in ONE launch."""
+        if defer:
+            self.pending_bias.append((b, dy))
+        else:
+            self.add(b, ops.colsum(dy, out=self.out_for(b)))
+
     def _hand_out(self, params, dw):
         r = 0
         for p in params:
@@ -214,6 +222,11 @@ class GradSink:
             jobs, self.pending_late = self.pending_late, []
         else:
             jobs, self.pending = self.pending, []
+            if self.pending_bias:
+                bjobs, self.pending_bias = self.pending_bias, []
+                outs = ops.colsum_batch([(dy, self.out_for(b)) for b, dy in bjobs])
+                for (b, _), db in zip(bjobs, outs):
+                    self.add(b, db)
         by_k = {}
         for job in jobs:
             by_k.setdefault(job[2].shape[0], []).append(job)
@@ -267,7 +280,7 @@ def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None, defer=Fals
             else:
                 G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
         if b is not None and b.requires_grad:
-            G.add(b, ops.colsum(dy, out=G.out_for(b)))
+            G.bias_grad(b, dy, defer=bool(defer))
         if not need_dx:
             return None
         return ops.gemm(dy, w, b_mn=True, out=out, accumulate=accumulate, splits=1 if accumulate else None)
@@ -284,7 +297,7 @@ def _geglu(x, w, b, G, defer=False):
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
         if b.requires_grad:
-            G.add(b, ops.colsum(daux, out=G.out_for(b)))
+            G.bias_grad(b, daux, defer=bool(defer))
         return ops.gemm(daux, w, b_mn=True)
 
     return y, bwd

@@ -127,6 +127,11 @@ int aoz_copy_channels(const void* src, long long src_ld, int src_off, void* dst,
 long long aoz_colsum_workspace_floats(int groups, int N);
 int aoz_colsum(const void* x, int groups, long long M, int N, long long ld, long long group_stride, void* out, int accumulate,
                void* workspace, void* stream);
+/* Batched column sums (train.py:2765 autograd: the bias gradients of one BasicTransformerBlock's Linear layers): n <= 8
+ * tensors x_i [M_i, N_i] bf16 (row stride ld_i) -> out_i [N_i] bf16 in ONE launch.  x_ptrs / out_ptrs: HOST uint64[n] device
+ * pointers; Ms / lds: HOST int64[n]; Ns: HOST int32[n]; workspace >= 64 * sum(N_i) floats. */
+int aoz_colsum_batch(int n, const void* x_ptrs, const void* Ms, const void* Ns, const void* lds, const void* out_ptrs, int accumulate,
+                     void* workspace, void* stream);
 int aoz_timestep_embedding(const void* t, int n, int dim, void* out, void* stream);
 
 #ifdef __cplusplus
