@@ -280,7 +280,7 @@ def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None, defer=Fals
             else:
                 G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
         if b is not None and b.requires_grad:
-            G.bias_grad(b, dy, defer=bool(defer))
+            G.bias_grad(b, dy)          # right away: dy is still L2-resident (deferring it to the block's flush measured slower)
         if not need_dx:
             return None
         return ops.gemm(dy, w, b_mn=True, out=out, accumulate=accumulate, splits=1 if accumulate else None)
@@ -297,7 +297,7 @@ def _geglu(x, w, b, G, defer=False):
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
         if b.requires_grad:
-            G.bias_grad(b, daux, defer=bool(defer))
+            G.bias_grad(b, daux)
         return ops.gemm(daux, w, b_mn=True)
 
     return y, bwd
