@@ -495,10 +495,13 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 }
 
 // backward.  blockDim = cols_pad * RL: cols_pad = vector columns rounded up to a warp multiple (a warp never straddles two
-// row lanes), RL row lanes.  A tile is RL*T rows: thread (tc, rl) takes rows base + t*RL + rl.  Per tile: all loads issued,
-// per-row partial sums of the thread's 8 channels -> warp_sum -> red[rl][t][warp-in-lane][2] -> barrier -> every thread adds
-// the cols_pad/32 entries of its rows in fixed order (deterministic) -> dx.  dgamma / dbeta: 16 accumulators per thread,
-// combined over the row lanes through shared memory at the end -> partial [gridDim.x][2][C].
+// row lanes), RL row lanes.  A tile is RL*T consecutive rows = ONE contiguous range of x, dy and the residual gradient, so a
+// tile is fetched by three 1-D TMA bulk copies (cp.async.bulk, <= 32 KB each) into a two-deep shared-memory ring, completion
+// on an mbarrier: the next tile streams in while this one is reduced, and no fetched row is held in registers.
+// Thread (tc, rl) takes rows base + t*RL + rl.  Per tile: per-row partial sums of the thread's 8 channels -> warp_sum ->
+// red[row][warp-in-lane][2] -> barrier -> every thread adds the cols_pad/32 entries of its rows in fixed order
+// (deterministic) -> dx.  dgamma / dbeta: 16 accumulators per thread, combined over the row lanes through shared memory at
+// the end -> partial [gridDim.x][2][C].
 constexpr int LNB_T = 4;
 constexpr int LNB_MAX_THREADS = 512;
 
@@ -508,12 +511,17 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
               long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
               float* __restrict__ partial, int cols_pad, int RL, long long rows_per_block) {
     pdl_enter();
-    extern __shared__ float sm[];      // red [RL][T][W][2] during the sweep, then [RL][2][C]
+    extern __shared__ __align__(128) uint8_t lnb_smem[];
     const int tc = threadIdx.x % cols_pad, rl = threadIdx.x / cols_pad;
     const int lane = threadIdx.x & 31, wcol = tc >> 5, W = cols_pad >> 5;
     const int nv = C / 8;
     const bool active = tc < nv;
     const float inv_c = 1.0f / (float)C;
+    const int tile_rows = RL * LNB_T;
+    const uint32_t tensor_bytes = (uint32_t)tile_rows * (uint32_t)C * 2u;      // one tensor's rows of a tile
+    uint8_t* ring = lnb_smem;                                                  // [2 slots][x | dy | dres][tensor_bytes]
+    float* red = reinterpret_cast<float*>(lnb_smem + 6 * (size_t)tensor_bytes);   // [tile_rows][W][2]
+    uint64_t* bars = reinterpret_cast<uint64_t*>(red + (size_t)tile_rows * W * 2);
     float gm[8], ag[8], ab[8];
     {
         const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + tc * 8) : make_uint4(0, 0, 0, 0);
@@ -523,34 +531,56 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     }
     const long long rb0 = (long long)blockIdx.x * rows_per_block;
     const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
-    const uint4 zero4 = make_uint4(0, 0, 0, 0);
-    for (long long base = rb0; base < rb1; base += (long long)RL * LNB_T) {
-        uint4 xp[LNB_T], dp[LNB_T];
+    const int ntiles = rb1 > rb0 ? (int)((rb1 - rb0 + tile_rows - 1) / tile_rows) : 0;
+    if (threadIdx.x == 0) {
+        mbar_init(&bars[0], 1); mbar_init(&bars[1], 1);
+        fence_mbar_init();
+    }
+    __syncthreads();
+    auto issue = [&](int i) {                                   // one thread: arm the slot's barrier, start the three copies
+        const long long base = rb0 + (long long)i * tile_rows;
+        const long long left = rb1 - base;
+        const uint32_t bytes = (uint32_t)(left < tile_rows ? left : tile_rows) * (uint32_t)C * 2u;
+        uint8_t* slot = ring + (size_t)(i & 1) * 3 * tensor_bytes;
+        mbar_arrive_expect_tx(&bars[i & 1], bytes * (dres ? 3u : 2u));
+        bulk_load_1d(slot, x + base * C, bytes, &bars[i & 1]);
+        bulk_load_1d(slot + tensor_bytes, dy + base * C, bytes, &bars[i & 1]);
+        if (dres) bulk_load_1d(slot + 2 * (size_t)tensor_bytes, dres + base * C, bytes, &bars[i & 1]);
+    };
+    if (threadIdx.x == 0) {
+        if (ntiles > 0) issue(0);
+        if (ntiles > 1) issue(1);
+    }
+    for (int i = 0; i < ntiles; ++i) {
+        const long long base = rb0 + (long long)i * tile_rows;
+        const uint8_t* slot = ring + (size_t)(i & 1) * 3 * tensor_bytes;
         float mu[LNB_T], rs[LNB_T], p1[LNB_T], p2[LNB_T];
         bool ok[LNB_T];
 #pragma unroll
         for (int t = 0; t < LNB_T; ++t) {
             const long long row = base + (long long)t * RL + rl;
             ok[t] = active && row < rb1;
-            const long long off = row * C + tc * 8;
-            xp[t] = ok[t] ? ld_stream(x + off) : zero4;
-            dp[t] = ok[t] ? ld_stream(dy + off) : zero4;
             mu[t] = ok[t] ? __ldg(mean + row) : 0.f;
             rs[t] = ok[t] ? __ldg(rstd + row) : 0.f;
         }
+        mbar_wait(&bars[i & 1], (uint32_t)((i >> 1) & 1));
 #pragma unroll
         for (int t = 0; t < LNB_T; ++t) {
-            float fx[8], fd[8];
-            unpack8(xp[t], fx); unpack8(dp[t], fd);
             float a = 0.f, b = 0.f;
+            if (ok[t]) {
+                const size_t off = ((size_t)(t * RL + rl) * C + (size_t)tc * 8) * 2;
+                float fx[8], fd[8];
+                unpack8(*reinterpret_cast<const uint4*>(slot + off), fx);
+                unpack8(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) {
-                const float xh = (fx[e] - mu[t]) * rs[t];
-                const float dg = fd[e] * gm[e];
-                a += dg;
-                b = fmaf(dg, xh, b);
-                ag[e] = fmaf(fd[e], xh, ag[e]);
-                ab[e] += fd[e];
+                for (int e = 0; e < 8; ++e) {
+                    const float xh = (fx[e] - mu[t]) * rs[t];
+                    const float dg = fd[e] * gm[e];
+                    a += dg;
+                    b = fmaf(dg, xh, b);
+                    ag[e] = fmaf(fd[e], xh, ag[e]);
+                    ab[e] += fd[e];
+                }
             }
             p1[t] = a; p2[t] = b;
         }
@@ -559,50 +589,50 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         if (lane == 0) {
 #pragma unroll
             for (int t = 0; t < LNB_T; ++t) {
-                float* d = sm + ((size_t)(rl * LNB_T + t) * W + wcol) * 2;
+                float* d = red + ((size_t)(rl * LNB_T + t) * W + wcol) * 2;
                 d[0] = p1[t]; d[1] = p2[t];
             }
         }
-        // the residual gradient is fetched one row ahead of its use (it is L2-resident: the kernel before this one wrote it)
-        uint4 rp = (ok[0] && dres) ? ld_stream(dres + (base + rl) * C + tc * 8) : zero4;
         __syncthreads();
 #pragma unroll
         for (int t = 0; t < LNB_T; ++t) {
-            const uint4 rcur = rp;
-            if (t + 1 < LNB_T) rp = (ok[t + 1] && dres) ? ld_stream(dres + (base + (long long)(t + 1) * RL + rl) * C + tc * 8) : zero4;
             if (!ok[t]) continue;
-            const float2* srow = reinterpret_cast<const float2*>(sm + (size_t)(rl * LNB_T + t) * W * 2);
+            const float2* srow = reinterpret_cast<const float2*>(red + (size_t)(rl * LNB_T + t) * W * 2);
             float s1 = 0.f, s2 = 0.f;
             for (int w = 0; w < W; ++w) { const float2 v = srow[w]; s1 += v.x; s2 += v.y; }
             s1 *= inv_c; s2 *= inv_c;
+            const size_t off = ((size_t)(t * RL + rl) * C + (size_t)tc * 8) * 2;
             float fx[8], fd[8], o[8];
-            unpack8(xp[t], fx); unpack8(dp[t], fd);
+            unpack8(*reinterpret_cast<const uint4*>(slot + off), fx);
+            unpack8(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
 #pragma unroll
             for (int e = 0; e < 8; ++e) o[e] = rs[t] * (fd[e] * gm[e] - s1 - (fx[e] - mu[t]) * rs[t] * s2);
             if (dres) {
                 float fr[8];
-                unpack8(rcur, fr);
+                unpack8(*reinterpret_cast<const uint4*>(slot + 2 * (size_t)tensor_bytes + off), fr);
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
             }
             const long long row = base + (long long)t * RL + rl;
             st_stream(dx + row * C + tc * 8, pack8(o));
         }
-        __syncthreads();               // the table is rewritten by the next tile
+        __syncthreads();               // slot and table are free: refill the slot with the tile after next
+        if (threadIdx.x == 0 && i + 2 < ntiles) issue(i + 2);
     }
-    // accumulators -> [RL][2][C] -> fixed-order sum over the row lanes -> this block's partial row
+    // accumulators -> [RL][2][C] (over the idle ring) -> fixed-order sum over the row lanes -> this block's partial row
+    float* fin = reinterpret_cast<float*>(lnb_smem);
     if (active) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            sm[(size_t)(rl * 2 + 0) * C + tc * 8 + e] = ag[e];
-            sm[(size_t)(rl * 2 + 1) * C + tc * 8 + e] = ab[e];
+            fin[(size_t)(rl * 2 + 0) * C + tc * 8 + e] = ag[e];
+            fin[(size_t)(rl * 2 + 1) * C + tc * 8 + e] = ab[e];
         }
     }
     __syncthreads();
     float* out = partial + (size_t)blockIdx.x * 2 * C;
     for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
         float a = 0.f;
-        for (int l = 0; l < RL; ++l) a += sm[(size_t)l * 2 * C + i];
+        for (int l = 0; l < RL; ++l) a += fin[(size_t)l * 2 * C + i];
         out[i] = a;
     }
 }
@@ -790,8 +820,14 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     if (blocks > sm_count()) blocks = sm_count();
     const long long rows_per_block = (rows + blocks - 1) / blocks;
     blocks = (rows + rows_per_block - 1) / rows_per_block;
-    const size_t red = (size_t)RL * LNB_T * (cols_pad / 32) * 2, fin = (size_t)RL * 2 * C;
-    const size_t smem = (red > fin ? red : fin) * sizeof(float);
+    // ring: 2 slots x (x, dy, dres) x tile rows; + the row-sum table + 2 mbarriers.  The final [RL][2][C] fp32 staging reuses the ring
+    // (RL*2*C*4 = tile bytes of two tensors).
+    const size_t smem = 6 * (size_t)tile * C * 2 + (size_t)tile * (cols_pad / 32) * 2 * sizeof(float) + 16;
+    static size_t attr = 48 * 1024;
+    if (smem > attr) {
+        cudaFuncSetAttribute(ln_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        attr = smem;
+    }
     launch_k(ln_bwd_kernel, dim3((int)blocks), dim3(cols_pad * RL), smem, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
              (const __nv_bfloat16*)gamma, (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
              (__nv_bfloat16*)dx, (float*)workspace, cols_pad, RL, rows_per_block);
