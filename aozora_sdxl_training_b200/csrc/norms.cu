@@ -502,7 +502,7 @@ ln_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restri
 // red[row][warp-in-lane][2] -> barrier -> every thread adds the cols_pad/32 entries of its rows in fixed order
 // (deterministic) -> dx.  dgamma / dbeta: 16 accumulators per thread, combined over the row lanes through shared memory at
 // the end -> partial [gridDim.x][2][C].
-constexpr int LNB_T = 4;
+constexpr int LNB_T = 4;                   // the reduce-scatter below is written for exactly 2 x 4 values
 constexpr int LNB_MAX_THREADS = 512;
 
 __global__ void __launch_bounds__(LNB_MAX_THREADS, 1)
@@ -584,13 +584,25 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             }
             p1[t] = a; p2[t] = b;
         }
+        // eight warp sums as a reduce-scatter (9 shuffles instead of 8 x 5): after the xor-16 / 8 / 4 steps every lane owns ONE
+        // of the eight values, two plain butterfly steps finish it.  Value v = which * 4 + t ends up in the lanes whose bits
+        // 4..2 spell v; fixed exchange pattern = fixed summation order.
+        {
+            const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4;
+            float w4[4], w2[2];
 #pragma unroll
-        for (int t = 0; t < LNB_T; ++t) { p1[t] = warp_sum(p1[t]); p2[t] = warp_sum(p2[t]); }
-        if (lane == 0) {
+            for (int k = 0; k < 4; ++k) {
+                const float lo = p1[k], hi = p2[k];
+                w4[k] = (b4 ? hi : lo) + __shfl_xor_sync(0xffffffffu, b4 ? lo : hi, 16);
+            }
 #pragma unroll
-            for (int t = 0; t < LNB_T; ++t) {
-                float* d = red + ((size_t)(rl * LNB_T + t) * W + wcol) * 2;
-                d[0] = p1[t]; d[1] = p2[t];
+            for (int k = 0; k < 2; ++k) w2[k] = (b3 ? w4[k + 2] : w4[k]) + __shfl_xor_sync(0xffffffffu, b3 ? w4[k] : w4[k + 2], 8);
+            float z = (b2 ? w2[1] : w2[0]) + __shfl_xor_sync(0xffffffffu, b2 ? w2[0] : w2[1], 4);
+            z += __shfl_xor_sync(0xffffffffu, z, 2);
+            z += __shfl_xor_sync(0xffffffffu, z, 1);
+            if ((lane & 3) == 0) {
+                const int v = lane >> 2, which = v >> 2, t = v & 3;
+                red[((size_t)(rl * LNB_T + t) * W + wcol) * 2 + which] = z;
             }
         }
         __syncthreads();
