@@ -173,10 +173,37 @@ def kernel_table(torch, peaks):
     ms = timeit(lambda: opt.step(), n=5)
     out["raven_step_gbs"] = round(14.0 * n / ms / 1e6, 1)
     out["raven_frac_of_hbm"] = round(out["raven_step_gbs"] / peaks["hbm"], 4)
-    x = torch.randn(4, 32 * 32, 1280, device="cuda").to(torch.bfloat16)
+    def timeit_graph(fn, n=10):
+        """Device time of small kernels: n calls captured in a CUDA graph and replayed (an eager Python loop measures the host:
+        three allocations + a ctypes call cost more than a 10-microsecond kernel)."""
+        for _ in range(2):
+            fn()
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for _ in range(n):
+                fn()
+        g.replay()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / n
+
+    # GroupNorm+SiLU forward, 4 B / element: 1280 channels at 32x32 (BASELINE config 5; a 10 MB tensor: latency, not bandwidth)
+    # and 320 channels at 128x128 (42 MB per tensor, the size class that holds most of the step's GroupNorm bytes)
+    for name, hw, c in (("groupnorm_silu_gbs", 32 * 32, 1280), ("groupnorm_silu_320x128x128_gbs", 128 * 128, 320)):
+        x = torch.randn(4, hw, c, device="cuda").to(torch.bfloat16)
+        ga, be = torch.ones(c, device="cuda", dtype=torch.bfloat16), torch.zeros(c, device="cuda", dtype=torch.bfloat16)
+        ms = timeit_graph(lambda: ops.groupnorm_fwd(x, ga, be, 1e-5, True))
+        out[name] = round(4.0 * x.numel() / ms / 1e6, 1)
+    x = torch.randn(4096, 1280, device="cuda").to(torch.bfloat16)
     ga, be = torch.ones(1280, device="cuda", dtype=torch.bfloat16), torch.zeros(1280, device="cuda", dtype=torch.bfloat16)
-    ms = timeit(lambda: ops.groupnorm_fwd(x, ga, be, 1e-5, True))
-    out["groupnorm_silu_gbs"] = round(4.0 * x.numel() / ms / 1e6, 1)
+    y, mean, rstd = ops.layernorm_fwd(x, ga, be)
+    out["layernorm_fwd_gbs"] = round(4.0 * x.numel() / timeit_graph(lambda: ops.layernorm_fwd(x, ga, be)) / 1e6, 1)
+    out["layernorm_bwd_gbs"] = round(6.0 * x.numel() / timeit_graph(lambda: ops.layernorm_bwd(y, x, ga, mean, rstd)) / 1e6, 1)
     return out
 
 

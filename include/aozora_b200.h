@@ -93,6 +93,9 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
 
 /* ---- normalisation [3P]: GroupNorm(32)(+SiLU) in ResnetBlock2D / Transformer2DModel.norm / conv_norm_out,
  *      LayerNorm in BasicTransformerBlock ------------------------------------------------------------------- */
+/* experiment switch: 1 = single-launch slab kernels where a (image, group) slab fits in shared memory (default), 0 = always
+ * the statistics + apply kernels */
+int aoz_groupnorm_set_slab(int on);
 long long aoz_groupnorm_workspace_floats(int NB, int HW, int C);
 int aoz_groupnorm_fwd(const void* x, const void* gamma, const void* beta, int NB, int HW, int C, float eps, int silu,
                       void* y, void* mean, void* rstd, void* workspace, void* stream);

@@ -240,7 +240,8 @@ def test_attention_fwd_bwd(B, H, Tq, Tk):
 
 
 @pytest.mark.parametrize("NB,HW,C,silu", [(2, 64, 320, True), (2, 256, 1280, False), (1, 100, 960, True), (4, 4096, 320, True),
-                                           (1, 16, 2560, True), (2, 1, 64, False)])
+                                           (1, 16, 2560, True), (2, 1, 64, False), (4, 1024, 1280, True), (2, 1024, 2560, True),
+                                           (3, 1000, 1280, False), (2, 4096, 640, True), (1, 16384, 960, True)])
 def test_groupnorm_silu_fwd_bwd(NB, HW, C, silu):
     ops = _ops()
     g = gen(7)
@@ -262,6 +263,36 @@ def test_groupnorm_silu_fwd_bwd(NB, HW, C, silu):
     check(db, br.grad)
     dx2, _, _ = ops.groupnorm_bwd(dy, x, ga, be, mean, rstd, silu, dres=dres)
     check(dx2, xr.grad.to(BF16).float() + dres.float())
+
+
+def test_groupnorm_slab_kernels_agree_with_the_two_pass_path():
+    """The single-launch slab kernels (a group's pixels held in shared memory) against the statistics + apply kernels on the
+    same inputs: same math, different summation order -> equal within fp32 reduction noise after the bf16 rounding."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(17)
+    NB, HW, C = 4, 1024, 1280
+    x = (torch.randn(NB, HW, C, device="cuda", generator=g) * 2 + 0.5).to(BF16)
+    dy = torch.randn(NB, HW, C, device="cuda", generator=g).to(BF16)
+    dres = torch.randn(NB, HW, C, device="cuda", generator=g).to(BF16)
+    ga = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).to(BF16)
+    be = (0.1 * torch.randn(C, device="cuda", generator=g)).to(BF16)
+    res = {}
+    try:
+        for slab in (1, 0):
+            _lib.call("aoz_groupnorm_set_slab", slab)
+            y, mean, rstd = ops.groupnorm_fwd(x, ga, be, 1e-5, True)
+            dx, dg, db = ops.groupnorm_bwd(dy, x, ga, be, mean, rstd, True, dres=dres)
+            res[slab] = (y, mean, rstd, dx, dg, db)
+    finally:
+        _lib.call("aoz_groupnorm_set_slab", 1)
+    torch.testing.assert_close(res[1][1], res[0][1], rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(res[1][2], res[0][2], rtol=1e-5, atol=1e-6)
+    for i in (0, 3, 4, 5):
+        check(res[1][i], res[0][i], rel=2e-3)
+    # run-to-run reproducible
+    y2, _, _ = ops.groupnorm_fwd(x, ga, be, 1e-5, True)
+    assert torch.equal(y2, res[1][0])
 
 
 @pytest.mark.parametrize("rows,C", [(300, 640), (1000, 1280), (7, 64), (4096, 2048), (16384, 640), (4096, 1280), (33, 320), (1, 8),
