@@ -43,6 +43,7 @@ struct AttnParams {
     __nv_bfloat16* dQ; long long lddq;
     __nv_bfloat16* dK; long long lddk;
     __nv_bfloat16* dV; long long lddv;
+    int fuse_dq;                // dK/dV kernel, one KV tile (cross-attention): dQ = dS K of every Q tile is computed there too
 };
 
 __device__ __forceinline__ float fast_exp2(float x) {
@@ -438,7 +439,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;
     pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
     if (warp == BWD_CW) {
@@ -461,6 +462,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         if (lane == 0) {
             const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
             const uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);           // A = P / dS read MN-major, B = dO / Q read MN-major
+            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);            // A = dS read K-major (over keys), B = K read MN-major
             const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
             const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
             const uint32_t sP = smem_u32(smem + KvSmem::PT), sDS = smem_u32(smem + KvSmem::DST);
@@ -491,6 +493,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
 #pragma unroll
                 for (int k = 0; k < 8; ++k)
                     umma_bf16(tdK, desc_ptile_rows_as_k(sDS, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                if (P.fuse_dq) {
+                    // the only KV tile: dQ(i) = dS(i) K is complete after this tile (the compute warps drain it during tile i+1)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) umma_bf16(tdQ, desc_ptile(sDS, k), desc_rows_as_k(sK, k), idesc_dq, k > 0 ? 1u : 0u);
+                }
                 umma_commit(&q_empty[s]);
                 umma_commit(pd_free);
                 if (i == nq - 1) umma_commit(acc_ready);
@@ -512,6 +519,26 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             const long long idx = ((long long)b * P.H + h) * P.Tq + q;
             nx_lse = q < P.Tq ? P.lse[idx] : INFINITY;       // +inf -> P = 0 for padded queries
             nx_d = q < P.Tq ? P.Dvec[idx] : 0.f;
+        };
+        // fused dQ (cross-attention): each of the four warps of a lane quarter stores 16 of the 64 columns of Q tile `i`
+        auto drain_dq = [&](int i) {
+            uint32_t v[16];
+            tmem_ld16(tdQ + lane_off + hf * 16, v);
+            tc_wait_ld();
+            const int q = i * TILE + r;
+            if (q < P.Tq) {
+                __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD + hf * 16;
+                const float mul = P.scale;
+#pragma unroll
+                for (int e = 0; e < 16; e += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
         };
         fetch_vec(0);
         for (int i = 0; i < nq; ++i) {
@@ -558,7 +585,11 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
                 // chunk 0 waits in registers: the previous tile's dV / dK MMAs (issued when that tile's P / dS were complete)
                 // still read these smem tiles for the first few hundred cycles of this tile
                 if (c == 1) {
-                    if (i > 0) mbar_wait(pd_free, (i - 1) & 1);
+                    if (i > 0) {
+                        mbar_wait(pd_free, (i - 1) & 1);
+                        // dQ(i-1) retired with those MMAs; dQ(i) is issued only after every compute thread arrived at pds_ready(i)
+                        if (P.fuse_dq) { tc_fence_after(); drain_dq(i - 1); }
+                    }
                     store_p_16(sP, r, hf * 32, hp[0]);
                     store_p_16(sDS, r, hf * 32, hd[0]);
                     store_p_16(sP, r, hf * 32 + 16, hp[1]);
@@ -571,6 +602,7 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
         }
         mbar_wait(acc_ready, 0);
         tc_fence_after();
+        if (P.fuse_dq) drain_dq(nq - 1);
         const int key = k0 + r;                              // accumulator rows are keys
         {
             const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
@@ -821,6 +853,10 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
 
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
 
+static int g_fuse_cross_dq = 1;
+// experiment switch: 1 = cross-attention (Tk <= 128) backward runs as ONE kernel (default), 0 = always dK/dV + dQ kernels
+int aoz_attn_set_fused_cross_bwd(int on) { g_fuse_cross_dq = on ? 1 : 0; return AOZ_OK; }
+
 int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
                  long long ldo, const void* d_o, long long lddo, const void* lse, void* dq, long long lddq, void* dk,
                  long long lddk, void* dv, long long lddv, int B, int H, int Tq, int Tk, float scale, void* workspace,
@@ -853,8 +889,12 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         cudaFuncSetAttribute(attn_bwd_dq_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, DqSmem::TOTAL);
         attr = true;
     }
+    // one KV tile (cross-attention, 77 text tokens): the dK/dV kernel's dS tile is all dQ needs, so it computes dQ as well and
+    // the dQ launch (one prologue-bound CTA per Q tile: 24..44 us for a few GFLOP) disappears
+    P.fuse_dq = (Tk <= TILE && g_fuse_cross_dq) ? 1 : 0;
     launch_k(attn_bwd_dkv_kernel, dim3(B * H * ((Tk + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(KvSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dkv_kernel");
+    if (P.fuse_dq) return AOZ_OK;
     launch_k(attn_bwd_dq_kernel, dim3(B * H * ((Tq + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(DqSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dq_kernel");
     return AOZ_OK;

@@ -638,7 +638,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     for (int st = 0; st < 4; ++st) rcur[st] = rnext[st];
                     if (pre_res && c + 64 < OUT_COLS && col0 + c + 64 < col_limit) fetch_res(c + 64);
                     uint32_t r[32];
-                    if (!empty_split) {
+                    if (!empty_split && !(P.dbg & 16)) {          // dbg 16 (experiments): epilogue without the TMEM read
                         tmem_ld32(taddr + c, r);
                         tc_wait_ld();
                     } else {
@@ -652,6 +652,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     for (int st = 0; st < 4; ++st) {
                         float f[8];
                         unstage8(stg, lane, st, f);
+                        if ((P.dbg & 8) && f[0] != 12345.678f) continue;      // dbg 8 (experiments): epilogue without the global stores
                         if (rmap[st].ok && col < col_limit)
                             epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, col, col_limit, f, pre_res, rcur[st]);
                     }

@@ -218,7 +218,8 @@ def test_conv_fused_time_embedding_and_residual():
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk", [(1, 2, 128, 128), (2, 5, 1024, 1024), (1, 3, 1008, 1008), (2, 10, 1024, 77),
-                                        (1, 5, 988, 154), (1, 2, 64, 64), (1, 1, 16, 77)])
+                                        (1, 5, 988, 154), (1, 2, 64, 64), (1, 1, 16, 77), (1, 10, 4096, 77), (2, 3, 200, 77),
+                                        (1, 2, 300, 128)])
 def test_attention_fwd_bwd(B, H, Tq, Tk):
     ops = _ops()
     g = gen(6)
@@ -237,6 +238,26 @@ def test_attention_fwd_bwd(B, H, Tq, Tk):
     check(dq, qr.grad.permute(0, 2, 1, 3), rel=8e-3)
     check(dk, kr.grad.permute(0, 2, 1, 3), rel=8e-3)
     check(dv, vr.grad.permute(0, 2, 1, 3), rel=8e-3)
+
+
+def test_cross_attention_backward_one_kernel_equals_two_kernels():
+    """With one KV tile (77 text tokens) the dK/dV kernel also produces dQ; same dS tile, same MMA chain as the dQ kernel."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(16)
+    B, H, Tq, Tk = 2, 20, 1024, 77
+    q, do = [torch.randn(B, Tq, H, 64, device="cuda", generator=g).to(BF16) for _ in range(2)]
+    k, v = [torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(BF16) for _ in range(2)]
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    res = {}
+    try:
+        for fused in (1, 0):
+            _lib.call("aoz_attn_set_fused_cross_bwd", fused)
+            res[fused] = [t.clone() for t in ops.attn_bwd(q, k, v, o, do, lse, 0.125)]
+    finally:
+        _lib.call("aoz_attn_set_fused_cross_bwd", 1)
+    for a, b in zip(res[1], res[0]):
+        assert torch.equal(a, b)
 
 
 @pytest.mark.parametrize("NB,HW,C,silu", [(2, 64, 320, True), (2, 256, 1280, False), (1, 100, 960, True), (4, 4096, 320, True),

@@ -36,9 +36,10 @@ def kernel_us(fn, n=6, interleave=None):
 
 def main():
     M, N = 4096, 1280
+    parts_only = len(sys.argv) > 1 and sys.argv[1] == "parts"
     big = torch.empty(64 << 20, device="cuda", dtype=torch.float32)           # 256 MB: L2 flush between launches
     flush = lambda: big.zero_()
-    for label, pair, bn in [("single_bn160", 0, 160), ("pair_bn256", 2, 256), ("single_bn256", 0, 256)]:
+    for label, pair, bn in ([] if parts_only else [("single_bn160", 0, 160), ("pair_bn256", 2, 256), ("single_bn256", 0, 256)]):
         _lib.call("aoz_gemm_set_pair_mode", pair)
         _lib.call("aoz_gemm_force_bn", bn)
         _lib.call("aoz_gemm_set_tail_mode", 0)
@@ -64,6 +65,17 @@ def main():
         out = torch.empty(Mx, Nx, device="cuda", dtype=BF)
         row[f"{Mx}x{Nx}"] = round(kernel_us(lambda: ops.gemm(x, w, out=out, splits=1)), 1)
     print("K64_single_bn128_by_grid", row, flush=True)
+    # what the epilogue of a tile is made of: K = 64 (main loop = one iteration), 320 tiles of 128 x 128 = 3 rounds per CTA.
+    # flags: 1 = no epilogue at all, 8 = everything but the global stores, 16 = everything but the TMEM read, 24 = staging only
+    x = torch.randn(4096, 64, device="cuda").to(BF)
+    w = (torch.randn(1280, 64, device="cuda") * 0.02).to(BF)
+    out = torch.empty(4096, 1280, device="cuda", dtype=BF)
+    row = {}
+    for flags in (0, 1, 8, 16, 24):
+        _lib.call("aoz_gemm_debug_flags", flags)
+        row[f"dbg{flags}"] = round(kernel_us(lambda: ops.gemm(x, w, out=out, splits=1)), 1)
+    _lib.call("aoz_gemm_debug_flags", 0)
+    print("K64_4096x1280_bn128_epilogue_parts", row, flush=True)
     _lib.call("aoz_gemm_set_pair_mode", 1); _lib.call("aoz_gemm_force_bn", 0); _lib.call("aoz_gemm_set_tail_mode", 1)
 
 
