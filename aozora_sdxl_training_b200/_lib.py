@@ -63,11 +63,16 @@ def load():
         fn.restype = _CTYPES[ret]
         fn.argtypes = [_CTYPES[a] for a in args]
     _lib = lib
-    # experiment switches (tools / A-B runs): AOZ_PDL=0 disables programmatic dependent launch, AOZ_AUTOTUNE=1 times tile plans
+    # experiment switches (tools / A-B runs): AOZ_PDL=0 disables programmatic dependent launch, AOZ_AUTOTUNE=1 times tile plans,
+    # AOZ_FUSED_CROSS_BWD=0 / AOZ_GN_SLAB=0 select the multi-kernel cross-attention backward / GroupNorm paths
     if os.environ.get("AOZ_PDL") is not None:
         lib.aoz_set_pdl(int(os.environ["AOZ_PDL"]))
     if os.environ.get("AOZ_AUTOTUNE") is not None:
         lib.aoz_gemm_set_autotune(int(os.environ["AOZ_AUTOTUNE"]))
+    if os.environ.get("AOZ_FUSED_CROSS_BWD") is not None:
+        lib.aoz_attn_set_fused_cross_bwd(int(os.environ["AOZ_FUSED_CROSS_BWD"]))
+    if os.environ.get("AOZ_GN_SLAB") is not None:
+        lib.aoz_groupnorm_set_slab(int(os.environ["AOZ_GN_SLAB"]))
     return lib
 
 
