@@ -853,8 +853,11 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
 
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
 
-static int g_fuse_cross_dq = 1;
-// experiment switch: 1 = cross-attention (Tk <= 128) backward runs as ONE kernel (default), 0 = always dK/dV + dQ kernels
+// Measured (profiles/r01_cross_bwd_ab.txt): alone the fused kernel wins (1024 queries x 77 keys x 20 heads: 48.1 -> 30.6 us) and the
+// per-kernel times inside the step drop by 1.2 ms, but the event-timed training step is 1.5 ms SLOWER (139.3 vs 137.8 ms, two
+// runs each): one 80-CTA kernel per layer leaves 68 SMs idle for 25 us where the 640-CTA dQ kernel filled them.  Off by default.
+static int g_fuse_cross_dq = 0;
+// experiment switch: 1 = cross-attention (Tk <= 128) backward runs as ONE kernel, 0 = dK/dV + dQ kernels (default)
 int aoz_attn_set_fused_cross_bwd(int on) { g_fuse_cross_dq = on ? 1 : 0; return AOZ_OK; }
 
 int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,

@@ -86,7 +86,7 @@ int aoz_pack_conv_weight(const void* w, int Cout, int Cin, int ks, int CinPad, i
 int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                  void* lse, int B, int H, int Tq, int Tk, float scale, void* stream);
 /* experiment switch: 1 = with a single KV tile (cross-attention, Tk <= 128) the dK/dV kernel also produces dQ and the dQ
- * launch is skipped (default), 0 = always two kernels */
+ * launch is skipped, 0 = always two kernels (default: the fused form measured slower inside the training step) */
 int aoz_attn_set_fused_cross_bwd(int on);
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq);
 int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,

@@ -255,7 +255,7 @@ def test_cross_attention_backward_one_kernel_equals_two_kernels():
             _lib.call("aoz_attn_set_fused_cross_bwd", fused)
             res[fused] = [t.clone() for t in ops.attn_bwd(q, k, v, o, do, lse, 0.125)]
     finally:
-        _lib.call("aoz_attn_set_fused_cross_bwd", 1)
+        _lib.call("aoz_attn_set_fused_cross_bwd", 0)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
 
