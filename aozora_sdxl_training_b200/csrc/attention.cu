@@ -99,8 +99,8 @@ struct FwdSmem {
     static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
     static constexpr int P = V + 2 * TILE_BYTES;        // 32 KB
     static constexpr int BAR = P + 2 * TILE_BYTES;      // 256 B of mbarriers
-    static constexpr int XCH = BAR + 256;               // 512 B: row-max / row-sum exchange between the two column halves
-    static constexpr int TOTAL = XCH + 512;             // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
+    static constexpr int XCH = BAR + 256;               // 2 KB: row-max / row-sum exchange between the two column halves
+    static constexpr int TOTAL = XCH + 2048;            // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
 };
 
 constexpr int ATT_FWD_THREADS = 320;                    // 8 softmax warps + producer + issuer
@@ -335,6 +335,240 @@ attn_fwd_kernel(const __grid_constant__ AttnParams P) {
             }
         }
         if (hf == 0 && q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+}
+
+// Forward, split-statistics form (default).  The two threads that share a query row (key columns 0..63 / 64..127 of every tile) keep
+// SEPARATE running maxima and row sums and accumulate into SEPARATE O tiles in TMEM (P V is issued as two K = 64 MMA groups), so the
+// per-tile maximum exchange through shared memory and its two 256-thread named barriers disappear from the loop; the halves are
+// merged once after the last tile.  TMEM: S 128 + O_a 64 + O_b 64 = the same 256 columns as the single-O kernel.
+__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
+attn_fwd_split_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = (uint64_t*)(smem + FwdSmem::BAR);
+    uint64_t* q_full = bars;            // 1
+    uint64_t* kv_full = bars + 1;       // 2
+    uint64_t* kv_empty = bars + 3;      // 2
+    uint64_t* s_ready = bars + 5;
+    uint64_t* p_ready = bars + 6;
+    uint64_t* o_ready = bars + 7;
+    uint64_t* p_free = bars + 8;        // P V of the previous tile has retired: the P tile in smem (and O in TMEM) may be touched again
+    uint32_t* tmem_slot = (uint32_t*)(bars + 9);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (P.Tq + TILE - 1) / TILE;
+    const int qt = blockIdx.x % q_tiles;
+    const int bh = blockIdx.x / q_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int q0 = qt * TILE;
+    const int nkv = (P.Tk + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(p_ready, 256); mbar_init(o_ready, 1); mbar_init(p_free, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tOa = tmem + 128, tOb = tmem + 192;      // O accumulators of the two key halves
+    pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV);
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_4d(smem + FwdSmem::Q, &P.tmQ, q_full, 0, h, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(&kv_empty[s], ((j >> 1) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_4d(smem + FwdSmem::K + s * TILE_BYTES, &P.tmK, &kv_full[s], 0, h, j * TILE, b);
+                tma_load_4d(smem + FwdSmem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
+            }
+        }
+    } else if (warp == 9) {
+        if (lane == 0) {
+            const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+            const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+            const uint32_t sQ = smem_u32(smem + FwdSmem::Q), sK = smem_u32(smem + FwdSmem::K);
+            const uint32_t sV = smem_u32(smem + FwdSmem::V), sP = smem_u32(smem + FwdSmem::P);
+            mbar_wait(q_full, 0);
+            mbar_wait(&kv_full[0], 0);
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK, k), idesc_qk, k > 0);
+            umma_commit(s_ready);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j & 1;
+                mbar_wait(p_ready, j & 1);
+                tc_fence_after();
+                // S of the next tile first (the softmax warps are idle until it lands), then this tile's P V
+                if (j + 1 < nkv) {
+                    const int s2 = (j + 1) & 1;
+                    mbar_wait(&kv_full[s2], ((j + 1) >> 1) & 1);
+                    tc_fence_after();
+#pragma unroll
+                    for (int k = 0; k < 4; ++k)
+                        umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s2 * TILE_BYTES, k), idesc_qk, k > 0);
+                    umma_commit(s_ready);
+                }
+#pragma unroll
+                for (int k = 0; k < 4; ++k)          // keys 0..63 of the tile -> O_a, keys 64..127 -> O_b (each half has its own running max)
+                    umma_bf16(tOa, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+                for (int k = 4; k < 8; ++k)
+                    umma_bf16(tOb, desc_ptile(sP, k), desc_rows_as_k(sV + s * TILE_BYTES, k), idesc_pv, (j > 0 || k > 4) ? 1u : 0u);
+                umma_commit(&kv_empty[s]);
+                umma_commit(p_free);
+                if (j + 1 == nkv) umma_commit(o_ready);
+            }
+        }
+        __syncwarp();
+    } else {
+        // ---- softmax warps 0..7: two threads per query row, each owns 64 of the 128 key columns of a tile ----
+        const int qtr = warp & 3, hf = warp >> 2;
+        const int r = qtr * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+        const uint32_t sP = smem_u32(smem + FwdSmem::P);
+        float* xm = (float*)(smem + FwdSmem::XCH);                       // [2][128] running max of each half, exchanged once at the end
+        float* xl = xm + 256;                                            // [2][128] row sums
+        const float sl2 = P.scale * LOG2E;
+        float m_ref = -INFINITY, l = 0.f;
+        // exp2(s * sl2 - m_ref) of this thread's 64 columns -> bf16 P tile in shared memory; returns the partial row sum and
+        // (through mx) the raw maximum.  ONE pass over TMEM: reading S is the scarce resource (64 B/clk/SM), not the math.
+        auto softmax_pass = [&](int kvalid, bool full, float& mx, int wait_parity) -> float {
+            // four 16-column chunks, software-pipelined: the tcgen05.ld of chunk c+1 is in flight during chunk c's exp math
+            float lsum = 0.f;
+            uint32_t v[2][16];
+            const int col0 = hf * 64;
+            tmem_ld16(tS + lane_off + col0, v[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tc_wait_ld();
+                if (c + 1 < 4) tmem_ld16(tS + lane_off + col0 + (c + 1) * 16, v[(c + 1) & 1]);
+                const uint32_t* cv = v[c & 1];
+                uint32_t w[8];
+                if (full) {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
+                        mx = fmaxf(mx, fmaxf(s0, s1));
+                        const float p0 = fast_exp2(fmaf(s0, sl2, -m_ref));
+                        const float p1 = fast_exp2(fmaf(s1, sl2, -m_ref));
+                        lsum += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
+                } else {
+#pragma unroll
+                    for (int e = 0; e < 16; e += 2) {
+                        const int ka = col0 + c * 16 + e;
+                        const bool ok0 = ka < kvalid, ok1 = ka + 1 < kvalid;
+                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
+                        if (ok0) mx = fmaxf(mx, s0);
+                        if (ok1) mx = fmaxf(mx, s1);
+                        const float p0 = ok0 ? fast_exp2(fmaf(s0, sl2, -m_ref)) : 0.f;
+                        const float p1 = ok1 ? fast_exp2(fmaf(s1, sl2, -m_ref)) : 0.f;
+                        lsum += p0 + p1;
+                        w[e >> 1] = pack_bf16(p0, p1);
+                    }
+                }
+                // the previous tile's P V reads the P tile until p_free (its MMAs are issued AFTER this tile's Q K^T)
+                if (c == 0 && wait_parity >= 0) { mbar_wait(p_free, (uint32_t)wait_parity); tc_fence_after(); }
+                store_p_16(sP, r, col0 + c * 16, w);
+            }
+            return lsum;
+        };
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_ready, j & 1);
+            tc_fence_after();
+            const int kvalid = P.Tk - j * TILE;              // keys >= kvalid are padding
+            const bool full = kvalid >= TILE;                // warp-uniform: full tiles skip every per-element predicate
+            if (j == 0) {
+                // first tile: a max-only pass over this thread's 64 columns seeds ITS reference (no exchange with the other half)
+                float mx = -3.0e38f;
+#pragma unroll 1
+                for (int c = hf * 2; c < hf * 2 + 2; ++c) {
+                    uint32_t v[32];
+                    tmem_ld32(tS + lane_off + c * 32, v);
+                    tc_wait_ld();
+#pragma unroll
+                    for (int e = 0; e < 32; ++e)
+                        if (full || c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+                }
+                m_ref = mx * sl2;
+                float dummy = -3.0e38f;
+                l = softmax_pass(kvalid, full, dummy, -1);
+            } else {
+                // optimistic single pass against the running reference; redo only if the row maximum jumped by > 2^8
+                float mx = -3.0e38f;
+                float lsum = softmax_pass(kvalid, full, mx, (j - 1) & 1);       // also orders the O rescale below after P V (j-1)
+                const float m_new = fmaxf(m_ref, mx * sl2);
+                const bool need = (m_new - m_ref) > 8.0f;
+                if (__any_sync(0xffffffffu, need)) {
+                    const float alpha = fast_exp2(m_ref - m_new);
+                    const uint32_t tOx = hf == 0 ? tOa : tOb;                  // this half's own accumulator: all 64 columns
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tOx + lane_off + c * 32, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                        tmem_st32(tOx + lane_off + c * 32, v);
+                        tc_wait_st();
+                    }
+                    l *= alpha;
+                    m_ref = m_new;
+                    float dummy = -3.0e38f;
+                    lsum = softmax_pass(kvalid, full, dummy, -1);    // P of this tile again, against the new reference
+                }
+                l += lsum;
+            }
+            fence_proxy_async_smem();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        mbar_wait(o_ready, 0);
+        tc_fence_after();
+        // combine the two halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
+        xm[hf * 128 + r] = m_ref;
+        xl[hf * 128 + r] = l;
+        named_bar_sync(1, 256);
+        const float m_o = xm[(hf ^ 1) * 128 + r], l_o = xl[(hf ^ 1) * 128 + r];
+        const float m = fmaxf(m_ref, m_o);
+        const float w_me = fast_exp2(m_ref - m), w_o = fast_exp2(m_o - m);
+        const float wa = hf == 0 ? w_me : w_o, wb = hf == 0 ? w_o : w_me;
+        const float lt = l * w_me + l_o * w_o;
+        const float inv_l = 1.0f / lt;
+        const int q = q0 + r;
+        {
+            const int c = hf;                                    // this thread stores 32 of the 64 output columns
+            uint32_t va[32], vb[32];
+            tmem_ld32(tOa + lane_off + c * 32, va);
+            tmem_ld32(tOb + lane_off + c * 32, vb);
+            tc_wait_ld();
+            if (q < P.Tq) {
+                __nv_bfloat16* dst = P.O + ((long long)b * P.Tq + q) * P.ldo + h * HD + c * 32;
+                const float sa = wa * inv_l, sb = wb * inv_l;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) f[t] = fmaf(__uint_as_float(va[e + t]), sa, __uint_as_float(vb[e + t]) * sb);
+                    uint4 o;
+                    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
+        }
+        if (hf == 0 && q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m + log2f(lt)) * LN2;
     }
     tc_fence_before();
     __syncthreads();
@@ -830,6 +1064,8 @@ using namespace aoz;
 
 extern "C" {
 
+static int g_fwd_split = 1;
+
 int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                  void* lse, int B, int H, int Tq, int Tk, float scale, void* stream) {
     AOZ_CHECK_ARG(q && k && v && o && lse, "aoz_attn_fwd: null pointer");
@@ -844,12 +1080,20 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
     P.O = (__nv_bfloat16*)o; P.ldo = ldo; P.lse = (float*)lse;
     static bool attr = false;
-    if (!attr) { cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL); attr = true; }
+    if (!attr) {
+        cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL);
+        attr = true;
+    }
     const int grid = B * H * ((Tq + TILE - 1) / TILE);
-    launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
+    if (g_fwd_split) launch_k(attn_fwd_split_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
+    else launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
     return AOZ_OK;
 }
+
+// experiment switch: 1 = split-statistics forward (separate running max / O tile per key half, default), 0 = shared-maximum forward
+int aoz_attn_set_fwd_split(int on) { g_fwd_split = on ? 1 : 0; return AOZ_OK; }
 
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
 

@@ -240,6 +240,31 @@ def test_attention_fwd_bwd(B, H, Tq, Tk):
     check(dv, vr.grad.permute(0, 2, 1, 3), rel=8e-3)
 
 
+@pytest.mark.parametrize("B,H,Tq,Tk", [(2, 10, 1024, 1024), (1, 3, 1008, 1008), (2, 10, 1024, 77), (1, 2, 64, 64), (1, 2, 300, 40)])
+def test_attention_forward_variants_agree(B, H, Tq, Tk):
+    """Split-statistics forward (separate running max / O tile per key half, merged at the end) against the shared-maximum
+    forward: same softmax, different rescale points -> equal within bf16 rounding; LSE equal to 1e-5."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(26)
+    q = (torch.randn(B, Tq, H, 64, device="cuda", generator=g) * 1.5).to(BF16)
+    k = (torch.randn(B, Tk, H, 64, device="cuda", generator=g) * 1.5).to(BF16)
+    v = torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(BF16)
+    res = {}
+    try:
+        for split in (1, 0):
+            _lib.call("aoz_attn_set_fwd_split", split)
+            o, lse = ops.attn_fwd(q, k, v, 0.125)
+            res[split] = (o.clone(), lse.clone())
+    finally:
+        _lib.call("aoz_attn_set_fwd_split", 1)
+    check(res[1][0], res[0][0], rel=4e-3)
+    assert (res[1][1] - res[0][1]).abs().max().item() < 2e-5
+    qr, kr, vr = [t.float().permute(0, 2, 1, 3) for t in (q, k, v)]
+    ref = torch.nn.functional.scaled_dot_product_attention(qr, kr, vr, scale=0.125).permute(0, 2, 1, 3)
+    check(res[1][0], ref, rel=6e-3)
+
+
 def test_cross_attention_backward_one_kernel_equals_two_kernels():
     """With one KV tile (77 text tokens) the dK/dV kernel also produces dQ; same dS tile, same MMA chain as the dQ kernel."""
     from aozora_sdxl_training_b200 import _lib
