@@ -99,9 +99,11 @@ struct FwdSmem {
     static constexpr int V = K + 2 * TILE_BYTES;        // 2 stages
     static constexpr int P = V + 2 * TILE_BYTES;        // 32 KB
     static constexpr int BAR = P + 2 * TILE_BYTES;      // 256 B of mbarriers
-    static constexpr int XCH = BAR + 256;               // 2 KB: row-max / row-sum exchange between the two column halves
-    static constexpr int TOTAL = XCH + 2048;            // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB
+    static constexpr int XCH = BAR + 256;               // 512 B: row-max / row-sum exchange between the two column halves
+    static constexpr int TOTAL = XCH + 512;             // 2 CTAs/SM: 2 * (TOTAL + 1 KB reserved) <= 228 KB  (512 B of slack: measured,
+                                                        // 1.5 KB more drops the kernel to one CTA per SM and 321 -> 470 us)
 };
+static_assert(2 * (FwdSmem::TOTAL + 1024) <= 228 * 1024, "attention forward must keep two CTAs per SM");
 
 constexpr int ATT_FWD_THREADS = 320;                    // 8 softmax warps + producer + issuer
 
@@ -437,8 +439,8 @@ attn_fwd_split_kernel(const __grid_constant__ AttnParams P) {
         const int r = qtr * 32 + lane;
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const uint32_t sP = smem_u32(smem + FwdSmem::P);
-        float* xm = (float*)(smem + FwdSmem::XCH);                       // [2][128] running max of each half, exchanged once at the end
-        float* xl = xm + 256;                                            // [2][128] row sums
+        float* xm = (float*)(smem + FwdSmem::P);                         // [2][128] running max of each half, exchanged once at the end
+        float* xl = xm + 256;                                            // [2][128] row sums  (the P tile is idle by then)
         const float sl2 = P.scale * LOG2E;
         float m_ref = -INFINITY, l = 0.f;
         // exp2(s * sl2 - m_ref) of this thread's 64 columns -> bf16 P tile in shared memory; returns the partial row sum and
