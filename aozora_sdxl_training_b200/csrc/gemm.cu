@@ -630,6 +630,11 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     }
                 }
             } else {
+                // dbg 32 (experiments): CTA 0, first epilogue warp logs clock64 at its phase boundaries into the tail scratch
+                const bool prof = (P.dbg & 32) && blockIdx.x == 0 && warp == 2 && lane == 0 && P.tail_ws != nullptr;
+                long long* plog = reinterpret_cast<long long*>(P.tail_ws);
+                int pslot = prof ? (int)plog[0] : 0;
+                if (prof && pslot < 200) plog[1 + pslot++] = -clock64();         // negative: tile start (after the accumulator wait)
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
                     if (col0 + c >= col_limit) break;          // warp-uniform
@@ -645,8 +650,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = 0u;
                     }
+                    if (prof && pslot < 200) plog[1 + pslot++] = clock64();          // after the TMEM read
                     stage_chunk(stg, lane, r);
                     __syncwarp();
+                    if (prof && pslot < 200) plog[1 + pslot++] = clock64();          // after staging
                     const int col = col0 + c + lcol;
 #pragma unroll
                     for (int st = 0; st < 4; ++st) {
@@ -657,7 +664,9 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                             epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, col, col_limit, f, pre_res, rcur[st]);
                     }
                     __syncwarp();
+                    if (prof && pslot < 200) plog[1 + pslot++] = clock64();          // after the four store steps
                 }
+                if (prof) plog[0] = pslot;
             }
             }
         epilogue_done:
@@ -818,6 +827,7 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     const int total_work = P.full_work + P.tail_tiles * P.tail_splits;
     if (total_work <= 0) return AOZ_OK;
     P.dbg = g_dbg;
+    if (g_dbg & 32) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
     const int stage_bytes = BM * BK * 2 + b_rows * BK * 2;
     P.stages = SMEM_TILE_BYTES / stage_bytes;

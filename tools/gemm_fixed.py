@@ -67,6 +67,7 @@ def main():
     print("K64_single_bn128_by_grid", row, flush=True)
     # what the epilogue of a tile is made of: K = 64 (main loop = one iteration), 320 tiles of 128 x 128 = 3 rounds per CTA.
     # flags: 1 = no epilogue at all, 8 = everything but the global stores, 16 = everything but the TMEM read, 24 = staging only
+    _lib.call("aoz_gemm_set_tail_mode", 0)
     x = torch.randn(4096, 64, device="cuda").to(BF)
     w = (torch.randn(1280, 64, device="cuda") * 0.02).to(BF)
     out = torch.empty(4096, 1280, device="cuda", dtype=BF)
@@ -76,6 +77,31 @@ def main():
         row[f"dbg{flags}"] = round(kernel_us(lambda: ops.gemm(x, w, out=out, splits=1)), 1)
     _lib.call("aoz_gemm_debug_flags", 0)
     print("K64_4096x1280_bn128_epilogue_parts", row, flush=True)
+    # clock64 log of CTA 0's first epilogue warp (dbg 32), K = 64 and K = 1280: cycles per phase of each 32-column chunk
+    scratch = ops._gemm_scratch[torch.cuda.current_device()]
+    for K in (64, 1280):
+        xk = torch.randn(4096, K, device="cuda").to(BF)
+        wk = (torch.randn(1280, K, device="cuda") * 0.02).to(BF)
+        ops.gemm(xk, wk, out=out, splits=1)
+        torch.cuda.synchronize()
+        scratch[:8 * 256].zero_()
+        _lib.call("aoz_gemm_debug_flags", 32)
+        ops.gemm(xk, wk, out=out, splits=1)
+        torch.cuda.synchronize()
+        _lib.call("aoz_gemm_debug_flags", 0)
+        log = scratch[:8 * 256].view(torch.int64).cpu().tolist()
+        n, ev = log[0], log[1:1 + log[0]]
+        t0 = None
+        parts = []
+        for v in ev:
+            if v < 0:
+                t0 = -v
+                parts.append("| tile:")
+                last = t0
+            else:
+                parts.append(str(v - last))
+                last = v
+        print(f"K{K}_epilogue_clock_deltas (tmem, stage, stores per chunk)", " ".join(parts), flush=True)
     _lib.call("aoz_gemm_set_pair_mode", 1); _lib.call("aoz_gemm_force_bn", 0); _lib.call("aoz_gemm_set_tail_mode", 1)
 
 
