@@ -133,8 +133,8 @@ def gemm_roofline(torch, peaks, iters=20):
     return dict(bound="tensor", kernel="gemm_bf16_kernel<256> (GEGLU epilogue) M=4096 K=1280 N=10240", achieved=round(ach, 1),
                 peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this exact launch from the committed `ncu --set full` capture
-                # (36.86 MB read + 77.51 MB written; algorithmic bytes: 36.7 MB operands + 125.8 MB outputs, part still in L2)
-                traffic=114366464, traffic_source="profiles/r01_gemm_geglu_ncu_v2.txt",
+                # (algorithmic bytes: 36.7 MB operands + 125.8 MB outputs, part of the output still in L2 when the kernel ends)
+                traffic=113691392, traffic_source="profiles/r01_gemm_geglu_ncu_v5.txt (dram__bytes_read 36.91 MB + dram__bytes_write 76.78 MB)",
                 peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
                 flops_per_launch=flops)
 
