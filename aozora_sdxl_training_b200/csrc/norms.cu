@@ -1030,6 +1030,8 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
                       const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
     AOZ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "aoz_layernorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
+    AOZ_CHECK_ARG(((((uintptr_t)dy) | ((uintptr_t)x) | ((uintptr_t)dres) | ((uintptr_t)dx)) & 15) == 0,
+                  "aoz_layernorm_bwd: dy / x / dres / dx must be 16-byte aligned (TMA bulk copies, 16-byte stores)");
     if (rows <= 0) return AOZ_OK;
     cudaStream_t s = (cudaStream_t)stream;
     const int cols_pad = ((C / 8 + 31) / 32) * 32;
