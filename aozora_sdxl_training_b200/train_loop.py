@@ -1,7 +1,7 @@
 """The reference's training loop (train.py:2558-2828 ``main``) over the B200 pieces: cached dataset -> bucketed batch
 schedule -> pinned-memory feeder -> ``SDXLTrainStep`` (noise, UNet, loss, reverse sweep, clip, Raven) -> periodic export.
 
-Only what the loop needs is here (no GUI reporter, no caching pass, no VAE): it exists so that a run can be started,
+Only what the loop needs is here (no GUI reporter; the caching pass is ``ensure_cache`` with the caller's encoders): it exists so that a run can be started,
 checkpointed and resumed with the reference's files -- same cache directory, same ``.safetensors`` / ``.pt`` outputs, same
 schedule and ticket positions after a resume (train.py:2566-2582, 2700-2712).
 """
@@ -11,7 +11,7 @@ from pathlib import Path
 
 import torch
 
-from . import checkpoint, data, host
+from . import cache_builder, checkpoint, data, host
 from .optimizers import RavenAdamW
 from .trainer import SDXLTrainStep
 
@@ -28,6 +28,23 @@ def build_optimizer(config, unet, dp=None):
         return dp.make_optimizer(lr=lr, **kw)
     params = [p for p in unet.parameters() if p.requires_grad]
     return RavenAdamW([{"params": params, "lr_scale": 1.0}], lr=lr, momentum_dtype=getattr(config, "MOMENTUM_DTYPE", torch.bfloat16), **kw)
+
+
+def ensure_cache(config, encoders, device="cuda", dp=None) -> bool:
+    """The caching pass in front of the loop (train.py:2575-2602): build / refresh the latent and text cache when it is missing or
+    stale.  ``encoders`` = (tokenizer_1, tokenizer_2, text_encoder_1, text_encoder_2, vae).  Under data parallel rank 0 builds
+    while the other ranks wait at a barrier.  Returns True if a build ran."""
+    if not hasattr(config, "is_rectified_flow"):
+        config.is_rectified_flow = getattr(config, "PREDICTION_TYPE", "epsilon") == "rectified_flow"
+    ran = False
+    if dp is None or dp.rank == 0:
+        if cache_builder.cache_needs_build(config):
+            cache_builder.build_cache(config, *encoders, device)
+            ran = True
+    if dp is not None:
+        import torch.distributed as dist
+        dist.barrier(group=dp.group)
+    return ran
 
 
 def run_training(config, unet, *, device="cuda", dp=None, optimizer=None, resume_state_path=None, base_checkpoint_path=None,

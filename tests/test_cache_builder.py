@@ -252,3 +252,7 @@ def test_build_reuse_and_incremental_update(tmp_path):
     assert not [n for n in os.listdir(cdir) if n.startswith("small")] and not cb.cache_needs_build(cfg)
     with pytest.raises(RuntimeError):
         cb.build_cache(cfg_for(root, VAE_NORMALIZATION_MODE="flux_bn32"), *models(), "cpu")
+    from aozora_sdxl_training_b200 import train_loop
+    assert train_loop.ensure_cache(cfg, models(), "cpu") is False              # current: the loop's caching hook does nothing
+    os.remove(os.path.join(cdir, "null_embeds.pt"))
+    assert train_loop.ensure_cache(cfg, models(), "cpu") is True and os.path.exists(os.path.join(cdir, "null_embeds.pt"))
