@@ -208,6 +208,22 @@ def test_cache_equals_the_reference_builders_file_for_file(case, tmp_path):
     assert len(ref_ds) == len(our_ds) > 0 and ref_ds.bucket_keys == our_ds.bucket_keys
 
 
+@pytest.mark.parametrize("case", list(CASES))
+def test_cache_equals_the_frozen_reference_output(case, tmp_path):
+    """The same comparison without the reference tree: digests of what its caching pass wrote (tests/golden/make_cache_golden.py)."""
+    sys.path.insert(0, os.path.join(HERE, "golden"))
+    from make_cache_golden import digest_cache
+    gold = json.load(open(os.path.join(HERE, "golden", "cache_golden.json")))[case]
+    root = str(tmp_path / "ds")
+    opts = CASES[case]
+    make_folder(root, json_mode=opts.get("CAPTION_SOURCE_TYPE") == "json")
+    cfg = cfg_for(root, **opts)
+    cb.build_cache(cfg, *models(0.1 if case == "txt_plain_shift" else None), "cpu")
+    got = digest_cache(os.path.join(root, cb.cache_folder_name(cfg)), root, data.stable_item_key)
+    assert sorted(got) == sorted(gold)
+    assert got == gold
+
+
 def test_token_chunks_and_text_batching():
     t1, t2, te1, te2, _ = models()
     rows = cb.chunked_tokens(t1, LONG, 3)
