@@ -422,15 +422,19 @@ def test_glue_kernels():
 
 @pytest.mark.parametrize("mode", ["epsilon", "v_prediction", "rectified_flow"])
 def test_noise_target_matches_scheduler_semantics(mode):
-    """aoz_noise_target vs the torch expression of train.py:2743-2758 / DDPMScheduler (identical rounding points)."""
+    """aoz_noise_target vs the ORACLE's restatement of train.py:2743-2758 (oracle.train_step_ref.make_targets over
+    oracle.scheduler_ref.RefDDPMScheduler, identical rounding points); the product's own scheduler class must agree too."""
     ops = _ops()
     from aozora_sdxl_training_b200.scheduler import DDPMScheduler
+    from oracle.scheduler_ref import RefDDPMScheduler
     g = gen(10)
     lat = (torch.randn(3, 4, 16, 16, device="cuda", generator=g) * 0.8).to(BF16)
     noise = torch.randn(3, 4, 16, 16, device="cuda", generator=g)
     tickets = torch.tensor([3, 500, 999], device="cuda")
     jitter = torch.rand(3, device="cuda", generator=g)
-    sch = DDPMScheduler()
+    sch = RefDDPMScheduler(prediction_type=mode)
+    assert torch.equal(DDPMScheduler(prediction_type=mode).alphas_cumprod, sch.alphas_cumprod)
+    assert torch.equal(DDPMScheduler().add_noise(lat, noise, tickets), sch.add_noise(lat, noise, tickets))
     acp = sch.alphas_cumprod.cuda()
     xt8, target, cond = ops.noise_target(lat, noise, tickets, None if mode == "rectified_flow" else acp,
                                          jitter if mode == "rectified_flow" else None, mode)
