@@ -301,11 +301,17 @@ def pack_sample_schedule(image_schedule, batch_size):
     return [[pack_sample_index(d, bi * batch_size + li) for li, d in enumerate(batch)] for bi, batch in enumerate(image_schedule)]
 
 
+def rank_rows(global_len, rank, world):
+    """[lo, hi) = the rows of a ``global_len``-row global batch that rank ``rank`` of ``world`` processes.  A short batch (the
+    bucket leftovers of train.py:493-496) gives the last ranks fewer, possibly zero, rows."""
+    per = math.ceil(global_len / world) if global_len else 0
+    return min(global_len, rank * per), min(global_len, (rank + 1) * per)
+
+
 def rank_slice(global_batch, rank, world):
-    """Data parallel: rank r's rows of a global batch (global-batch equivalence).  A short batch gives the last
-    ranks fewer (possibly zero) samples."""
-    per = math.ceil(len(global_batch) / world) if global_batch else 0
-    return global_batch[rank * per:(rank + 1) * per]
+    """Data parallel: rank r's rows of a global batch (global-batch equivalence)."""
+    lo, hi = rank_rows(len(global_batch), rank, world)
+    return global_batch[lo:hi]
 
 
 # ------------------------------------------------------------------------------------------------------------
@@ -340,6 +346,13 @@ class BatchFeeder:
                 for k, v in batch.items():
                     if isinstance(v, torch.Tensor):
                         batch[k] = v.pin_memory()
+        if self.world > 1:
+            # every rank must know the size of the GLOBAL batch and where its rows sit in it: tickets, noise rows and the loss
+            # normaliser are those of the single-process run (SDXLTrainStep reads these two keys); a rank whose slice is empty
+            # still gets a (metadata-only) batch, because it has to take part in the step's collectives
+            batch = dict(batch) if batch else {}
+            batch["global_batch_len"] = len(packed_batch)
+            batch["global_row_offset"] = rank_rows(len(packed_batch), self.rank, self.world)[0]
         return batch
 
     def _worker(self, q):

@@ -163,9 +163,15 @@ class TimestepSampler:
         return torch.tensor(picked, dtype=torch.long, device=self.device), picked[0]
 
     def sample_rank(self, local_batch, rank, world):
-        picked = self._pop(local_batch * world)
-        mine = picked[rank * local_batch:(rank + 1) * local_batch]
-        return torch.tensor(mine, dtype=torch.long, device=self.device), picked[0]
+        return self.sample_rows(local_batch * world, rank * local_batch, local_batch)
+
+    def sample_rows(self, global_len, row_offset, rows):
+        """Data parallel with short / unequal global batches (train.py:493-496 leftover batches, 2733): EVERY rank pops the
+        ``global_len`` tickets the single-process run would pop for this micro-step -- so the pool index stays identical on
+        all ranks -- and keeps those of its own rows ``[row_offset, row_offset + rows)`` (possibly none)."""
+        picked = self._pop(global_len)
+        mine = picked[row_offset:row_offset + rows]
+        return torch.tensor(mine, dtype=torch.long, device=self.device), (picked[0] if picked else None)
 
     def update(self, raw_grad_norm):
         pass

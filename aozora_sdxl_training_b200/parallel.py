@@ -255,7 +255,17 @@ class DataParallel:
     # ---- gradient path -----------------------------------------------------------------------------------
     def _reset_pending(self):
         self._pending = list(self.bucket_need)
+        self._arrived = bytearray(len(self.params))
         self._works = []
+
+    def no_gradients_this_step(self):
+        """This rank holds no sample of the micro-step (short global batch): its contribution to every bucket is zero."""
+        self._reset_pending()
+        self.flat_g.zero_()
+        self._arrived = bytearray(b"\x01" * len(self.params))
+        for k in range(len(self.layout.buckets)):
+            self._pending[k] = 0
+            self._reduce_bucket(k)
 
     def _reduce_bucket(self, k):
         s, e = self.layout.buckets[k]
@@ -285,6 +295,9 @@ class DataParallel:
         i = self.index.get(p)
         if i is None:
             return
+        if self._arrived[i]:
+            raise _lib.AozoraError("DataParallel: a parameter's gradient arrived twice in one sweep (its bucket may already be reduced)")
+        self._arrived[i] = 1
         off = self.layout.offsets[i]
         if g.data_ptr() != self.flat_g.data_ptr() + off * self.flat_g.element_size() or not g.is_contiguous():
             self.flat_g[off:off + p.numel()].copy_(g.reshape(-1))
@@ -323,7 +336,13 @@ class DataParallel:
         """Finish the reduce-scatter, clip by the GLOBAL norm, update this rank's slices, all-gather the parameters.
         CUDA-graph capturable: under capture the step counter / hyper table are left to ``advance_host_state``."""
         capturing = self.device.type == "cuda" and torch.cuda.is_current_stream_capturing()
-        if any(c != 0 for c in self._pending):       # gradients that never arrived (unused parameters): reduce what is there
+        if any(c != 0 for c in self._pending):
+            # parameters that produced no gradient in this sweep: their slots still hold an earlier step's values -- this
+            # rank's contribution is zero, so clear them before the buckets they sit in are reduced
+            for i, seen in enumerate(self._arrived):
+                if not seen:
+                    off = self.layout.offsets[i]
+                    self.flat_g[off:off + self.layout.numels[i]].zero_()
             for k, c in enumerate(self._pending):
                 if c != 0:
                     self._reduce_bucket(k)

@@ -89,28 +89,33 @@ class SDXLTrainStep:
             t = t.to(dtype)
         return t.contiguous()
 
-    def _noise(self, shape_local):
-        """Global-batch equivalence: draw the whole global tensor with the reference's reseed and keep
-        this rank's rows, so N ranks x b samples see exactly the noise of one process with BATCH_SIZE = N*b."""
-        gshape = (self.global_batch,) + tuple(shape_local[1:])
+    def _noise(self, shape_local, global_len, row_offset):
+        """train.py:2735-2742: ``randn(latents.shape)`` after the per-step reseed.  The draw has the shape of the batch the
+        single-process run would see -- (global_len, 4, h, w), which on one GPU is exactly ``latents.shape``, short leftover
+        batches included (CUDA Philox output depends on the element count, so a larger draw would not reproduce it) -- and a
+        data-parallel rank keeps its own rows: N ranks see the noise of one process with the same global batch."""
+        b = shape_local[0]
+        gshape = (global_len,) + tuple(shape_local[1:])
         noise = host.generate_noise(torch.empty(gshape, device="meta"), self.noise_gen, self.device, step=self.micro_step + 1,
                                     seed=self.seed)
-        if self.world == 1:
+        if global_len == b:
             return noise
-        return noise[self.rank * self.local_batch:(self.rank + 1) * self.local_batch].contiguous()
+        return noise[row_offset:row_offset + b].contiguous()
 
-    def _jitter(self):
+    def _jitter(self, b, global_len, row_offset):
         gen = host.seeded_torch_generator(self.device, self.seed, self.micro_step + 1, 0x5D1)
-        j = torch.rand((self.global_batch,), device=self.device, dtype=torch.float32, generator=gen)
-        return j[self.rank * self.local_batch:(self.rank + 1) * self.local_batch].contiguous()
+        j = torch.rand((global_len,), device=self.device, dtype=torch.float32, generator=gen)
+        return j if global_len == b else j[row_offset:row_offset + b].contiguous()
 
     # ---- the step ------------------------------------------------------------------------------------------
-    def _device_step(self, latents, embeds, pooled, time_ids, tickets, noise, jitter, b, taps=None):
-        """Everything that runs on the GPU for one micro-step (graph-capturable: no host reads, static shapes)."""
+    def _device_step(self, latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len, taps=None):
+        """Everything that runs on the GPU for one micro-step (graph-capturable: no host reads, static shapes).
+        ``global_len``: rows of the GLOBAL batch of this micro-step -- the loss is the mean over them (train.py:2408-2416), so
+        the sum of the ranks' gradients is the single-process gradient also when the ranks hold unequal row counts."""
         xt8, target, cond = ops.noise_target(latents, noise, tickets, None if self.is_rf else self.alphas_cumprod, jitter,
                                              self.prediction_type, cpad=8)
         pred, bwd = self.unet.forward_nhwc(xt8, cond, embeds, pooled, time_ids, taps=taps)
-        denom = float(b * self.world)
+        denom = float(global_len)
         loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
                                        grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
         if self.dp is None:
@@ -128,27 +133,60 @@ class SDXLTrainStep:
             tid = torch.tensor(tid, dtype=BF16)
         time_ids = self._to_device(tid, BF16)
         b = latents.shape[0]
+        global_len, row_offset = self._global_rows(batch, b)
         if self.world == 1:
             tickets, _ = self.sampler.sample(b)
         else:
-            tickets, _ = self.sampler.sample_rank(b, self.rank, self.world)
+            tickets, _ = self.sampler.sample_rows(global_len, row_offset, b)
         # ``noise`` / ``jitter`` overrides exist for parity tests (the CPU oracle cannot reproduce CUDA Philox draws)
-        noise = self._noise(latents.shape) if noise is None else self._to_device(noise, torch.float32)
+        if noise is None:
+            noise = self._noise(latents.shape, global_len, row_offset)
+        else:
+            noise = self._to_device(noise, torch.float32)
+            if tuple(noise.shape) != tuple(latents.shape):
+                raise ValueError(f"noise override has shape {tuple(noise.shape)}, latents {tuple(latents.shape)}")
         if self.is_rf:
-            jitter = self._jitter() if jitter is None else self._to_device(jitter, torch.float32)
+            jitter = self._jitter(b, global_len, row_offset) if jitter is None else self._to_device(jitter, torch.float32)
         else:
             jitter = None
-        return latents, embeds, pooled, time_ids, tickets, noise, jitter, b
+        return latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len
+
+    def _global_rows(self, batch, b):
+        """(rows of the global batch, offset of this rank's first row).  One process: the batch IS the global batch.  Data
+        parallel: ``BatchFeeder`` attaches both numbers; a caller that does not is taken to feed every rank ``b`` rows."""
+        if self.world == 1:
+            return b, 0
+        gl = batch.get("global_batch_len")
+        if gl is None:
+            return b * self.world, self.rank * b
+        return int(gl), int(batch.get("global_row_offset", self.rank * b))
+
+    def _rank_without_rows(self, batch):
+        """Data parallel, short global batch: this rank has no sample in the micro-step (train.py:493-496 leftovers cut over N
+        ranks).  It still advances every host-side stream exactly like the others (tickets, micro-step, LR curve) and joins the
+        collectives with an all-zero gradient, so the reduce-scatter / all-gather sequence stays aligned across ranks."""
+        global_len, row_offset = self._global_rows(batch, 0)
+        tickets, _ = self.sampler.sample_rows(global_len, row_offset, 0)
+        self.micro_step += 1
+        if self.lr_scheduler is not None:
+            self.lr_scheduler.step(self.micro_step)
+        self.dp.no_gradients_this_step()
+        norm = self._optimizer_phase(None)
+        self.optimizer_steps += 1
+        return StepResult(loss=torch.zeros(1, dtype=torch.float32, device=self.device), grad_norm=norm, timesteps=tickets,
+                          did_optimizer_step=True, lr=self.optimizer.param_groups[0]["lr"])
 
     @torch.no_grad()
     def step(self, batch, *, noise=None, jitter=None, taps=None) -> StepResult:
         """batch: dict with ``latents`` [b,4,h,w] (bf16, pinned host or device), ``embeds`` [b,L,2048], ``pooled`` [b,1280],
         ``time_ids`` [b,6] (list or tensor; converted to bf16 as train.py:2726-2731 does)."""
+        if self.dp is not None and batch.get("latents") is None:
+            return self._rank_without_rows(batch)
         inputs = self._host_inputs(batch, noise, jitter)
         if self.use_cuda_graph and self.grad_accum == 1 and taps is None:
             return self._graph_step(inputs)
-        latents, embeds, pooled, time_ids, tickets, noise, jitter, b = inputs
-        loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b, taps=taps)
+        latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len = inputs
+        loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len, taps=taps)
         self.micro_step += 1
         if self.grad_accum > 1:
             if self._accum is None:
@@ -175,8 +213,8 @@ class SDXLTrainStep:
 
     # ---- CUDA-graph path: the whole device side of the step is captured once and replayed ---------------------
     def _graph_step(self, inputs):
-        latents, embeds, pooled, time_ids, tickets, noise, jitter, b = inputs
-        key = (tuple(latents.shape), tuple(embeds.shape))
+        latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len = inputs
+        key = (tuple(latents.shape), tuple(embeds.shape), global_len)      # the loss normaliser is baked into the captured kernels
         self.micro_step += 1
         if self.lr_scheduler is not None:
             self.lr_scheduler.step(self.micro_step)
@@ -186,7 +224,7 @@ class SDXLTrainStep:
         st["calls"] += 1
         if st["graph"] is None and st["calls"] <= self.graph_warmup:
             # eager warm-up: sizes the workspaces, allocates optimizer state, loads every kernel
-            loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, b)
+            loss, grads = self._device_step(latents, embeds, pooled, time_ids, tickets, noise, jitter, global_len)
             norm = self._optimizer_phase(grads)
             self.optimizer_steps += 1
             return StepResult(loss=loss, grad_norm=norm, timesteps=tickets, did_optimizer_step=True,
@@ -198,7 +236,7 @@ class SDXLTrainStep:
             g = torch.cuda.CUDAGraph()
             with torch.cuda.graph(g):
                 sl, se, sp, sti, stk, sn, sj = st["static"]
-                loss, grads = self._device_step(sl, se, sp, sti, stk, sn, sj, b)
+                loss, grads = self._device_step(sl, se, sp, sti, stk, sn, sj, global_len)
                 norm = self._optimizer_phase(grads)
                 st["out"] = (loss, norm)
                 del grads

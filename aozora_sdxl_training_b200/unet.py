@@ -246,6 +246,10 @@ class GradSink:
             self.grads[p] = g
             if self.on_grad is not None:
                 self.on_grad(p, g)
+        elif self.on_grad is not None:
+            # under data parallel on_grad may already have launched the reduce-scatter of this parameter's bucket: a later
+            # contribution would be lost silently.  No SDXL parameter is used twice; anything else must fail loudly.
+            raise _lib.AozoraError("GradSink: second gradient contribution to a parameter whose gradient was already handed to on_grad")
         else:
             ops.add(cur, g, out=cur)
 
