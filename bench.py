@@ -207,13 +207,19 @@ def kernel_table(torch, peaks):
     return out
 
 
-def cpu_reference_step(res, batch, steps, warmup, mode):
-    """The reference's step semantics on the host cores via the CPU oracle (bounded sample)."""
+def cpu_config1_step(steps, warmup):
+    """BASELINE config 1 on the box's host cores, as BASELINE.md section 4 specifies: the reference's step semantics
+    (train.py:2719-2784) through the CPU oracle -- random-init full SDXL UNet, 512x512 (latent 4x64x64), batch 1, epsilon, cached-shape
+    conditioning, fp32 weights / fp32 Raven moments, autocast off -- timed with perf_counter and split into fwd+bwd / clip / Raven,
+    best of ``steps`` (>= 3) after ``warmup`` (>= 1).  All host threads: torchrun exports OMP_NUM_THREADS=1, which is overridden."""
     import torch
     from oracle import host_ref
     from oracle.scheduler_ref import RefDDPMScheduler
-    from oracle.train_step_ref import RefRaven, ref_train_step
+    from oracle.train_step_ref import RefRaven, ref_forward_loss
     from oracle.unet_ref import RefUNet2DConditionModel, sdxl_config
+    ncpu = os.cpu_count() or 1
+    torch.set_num_threads(ncpu)
+    res, batch, mode = 512, 1, "epsilon"
     torch.manual_seed(0)
     model = RefUNet2DConditionModel(sdxl_config())
     with torch.no_grad():
@@ -224,22 +230,44 @@ def cpu_reference_step(res, batch, steps, warmup, mode):
                 p.zero_()
             else:
                 p.normal_(0.0, 0.02)
-    opt = RefRaven(list(model.parameters()), lr=8e-7, momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
+    params = list(model.parameters())
+    opt = RefRaven(params, lr=8e-7, momentum_dtype=torch.float32, **Cfg.RAVEN)
     sch = RefDDPMScheduler(prediction_type=mode)
     sampler = host_ref.RefTimestepSampler(Cfg.MAX_TRAIN_STEPS, batch, Cfg.SEED, None, False)
     b = synth_batch(batch, res, 1)
     rb = dict(latents=b["latents"], embeds=b["embeds"].float(), pooled=b["pooled"].float(),
               time_ids_data=[[res, res, 0, 0, res, res]] * batch)
-    times = []
+    rows = []
     for i in range(warmup + steps):
         ts, _ = sampler.sample(batch)
         t0 = time.perf_counter()
-        ref_train_step(model, sch, opt, rb, prediction_type=mode, timesteps=ts, micro_step=i + 1, seed=Cfg.SEED,
-                       compute_dtype=torch.float32, autocast=False, clip_grad_norm=Cfg.CLIP_GRAD_NORM)
-        dt = time.perf_counter() - t0
+        loss, _, _, _ = ref_forward_loss(model, sch, rb, prediction_type=mode, timesteps=ts, micro_step=i + 1, seed=Cfg.SEED,
+                                         compute_dtype=torch.float32, autocast=False)
+        loss.backward()
+        t1 = time.perf_counter()
+        torch.nn.utils.clip_grad_norm_(params, Cfg.CLIP_GRAD_NORM)
+        t2 = time.perf_counter()
+        opt.step()
+        opt.zero_grad(set_to_none=True)
+        t3 = time.perf_counter()
         if i >= warmup:
-            times.append(dt)
-    return sum(times) / len(times), torch.get_num_threads()
+            rows.append((t3 - t0, t1 - t0, t2 - t1, t3 - t2))
+    best = min(rows)                                          # best whole step; its own split is reported
+    return dict(sec=best[0], fwd_bwd_s=best[1], clip_s=best[2], raven_s=best[3], threads=torch.get_num_threads(), cpus=ncpu,
+                steps_timed=len(rows), mean_sec=sum(r[0] for r in rows) / len(rows), loss=float(loss.detach()))
+
+
+CONFIG1 = ("BASELINE config 1: SDXL UNet random-init single train step, epsilon, 512x512 (64x64x4 latents), batch 1, cached 77x2048 "
+           "text embeds + 1280 pooled, Raven step, fp32 weights and moments, torch-CPU")
+
+
+def cpu_baseline_record(r):
+    return dict(value=round(1.0 / r["sec"], 6), unit="imgs/s", cores=r["threads"], kind="port",
+                sample=(f"{CONFIG1}; best of {r['steps_timed']} steps after warm-up, 1 image of 512x512 per step, no rescaling "
+                        f"(the GPU arm's images are 1024x1024: 4x the pixels, so the two imgs/s are not the same unit of work)"),
+                seconds_per_step=round(r["sec"], 3), fwd_bwd_s=round(r["fwd_bwd_s"], 3), clip_s=round(r["clip_s"], 3),
+                raven_s=round(r["raven_s"], 3), mean_seconds_per_step=round(r["mean_sec"], 3), os_cpu_count=r["cpus"],
+                torch_threads=r["threads"], same_config=False)
 
 
 def main():
