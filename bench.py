@@ -9,7 +9,9 @@ every step, nothing skipped.  ``value`` = imgs/s with inputs resident in HBM; ``
 HOST buffers (H2D of latents / text embeddings inside the timed region) with the loss read back to the host each step.
 ``roofline`` = the dominant kernel (the tcgen05 GEMM, at the GEGLU feed-forward shape) timed live with CUDA events.
 ``cpu_baseline`` / ``--impl reference`` = the reference's step semantics on the box's host cores through the CPU oracle
-(oracle/train_step_ref.py; the UNet arithmetic is diffusers', restated -- kind "port").
+(oracle/train_step_ref.py; the UNet arithmetic is diffusers', restated -- kind "port") at BASELINE config 1 (512x512, batch 1,
+epsilon, fp32), split into fwd+bwd / clip / Raven, best of >= 3 steps, no rescaling.  ``--workload 3 | 4`` select BASELINE
+configs 3 (rectified flow, logit-normal tickets, batch 8/GPU) and 4 (layer exclusion over three aspect-ratio buckets).
 """
 from __future__ import annotations
 
@@ -47,13 +49,14 @@ class Cfg:
 
 
 def synth_batch(b, res, seed, device="cpu", pin=False):
+    """``res``: side of a square image or a (width, height) bucket; latents [b, 4, height/8, width/8], time_ids as train.py:2726-2731."""
     import torch
     g = torch.Generator().manual_seed(seed)
-    h = res // 8
-    out = dict(latents=(torch.randn(b, 4, h, h, generator=g) * 0.8).to(torch.bfloat16),
+    wpx, hpx = (res, res) if isinstance(res, int) else res
+    out = dict(latents=(torch.randn(b, 4, hpx // 8, wpx // 8, generator=g) * 0.8).to(torch.bfloat16),
                embeds=torch.randn(b, 77, 2048, generator=g).to(torch.bfloat16),
                pooled=torch.randn(b, 1280, generator=g).to(torch.bfloat16),
-               time_ids=torch.tensor([[res, res, 0, 0, res, res]] * b, dtype=torch.bfloat16))
+               time_ids=torch.tensor([[hpx, wpx, 0, 0, hpx, wpx]] * b, dtype=torch.bfloat16))
     if device != "cpu":
         out = {k: v.to(device) for k, v in out.items()}
     elif pin:
@@ -139,7 +142,7 @@ def gemm_roofline(torch, peaks, iters=20):
                 flops_per_launch=flops)
 
 
-def kernel_table(torch, peaks):
+def kernel_table(torch, peaks, param_numels=None):
     """Side metrics BASELINE.json names: attention TFLOPS (4096 tok x 10 heads x 64) and Raven step HBM GB/s."""
     from aozora_sdxl_training_b200 import ops
     from aozora_sdxl_training_b200.optimizers import RavenAdamW
@@ -165,6 +168,31 @@ def kernel_table(torch, peaks):
     o, lse = ops.attn_fwd(q, k, v, 0.125)
     ms = timeit(lambda: ops.attn_bwd(q, k, v, o, do, lse, 0.125))
     out["attn_bwd_tflops"] = round(2.5 * f / ms / 1e9, 1)
+    # cross-attention (attn2): 4096 queries x 77 keys x 10 heads x 64 (BASELINE config 5); latency / occupancy bound, one KV tile
+    kc, vc = [torch.randn(B, 77, H, 64, device="cuda").to(torch.bfloat16) for _ in range(2)]
+    fc = 4.0 * B * H * T * 77 * 64
+    ms = timeit(lambda: ops.attn_fwd(q, kc, vc, 0.125), n=20)
+    out["cross_attn_fwd_tflops"] = round(fc / ms / 1e9, 1)
+    out["cross_attn_fwd_us"] = round(ms * 1e3, 1)
+    oc, lsec = ops.attn_fwd(q, kc, vc, 0.125)
+    ms = timeit(lambda: ops.attn_bwd(q, kc, vc, oc, do, lsec, 0.125), n=20)
+    out["cross_attn_bwd_tflops"] = round(2.5 * fc / ms / 1e9, 1)
+    out["cross_attn_bwd_us"] = round(ms * 1e3, 1)
+    del q, k, v, do, o, lse, kc, vc, oc, lsec
+    if param_numels:
+        # Raven over the REAL table: 1680 tensors / 2,567,463,684 parameters, bf16 p, g, m, v (14 B per parameter = 35.9 GB per step)
+        ps = [torch.nn.Parameter(torch.zeros(nn_, device="cuda", dtype=torch.bfloat16)) for nn_ in param_numels]
+        for p in ps:
+            p.grad = torch.full_like(p, 1e-3)
+        opt = RavenAdamW(ps, lr=8e-7, **Cfg.RAVEN)
+        ms = timeit(lambda: opt.step(), n=5)
+        tot = sum(param_numels)
+        out["raven_sdxl_table_gbs"] = round(14.0 * tot / ms / 1e6, 1)
+        out["raven_sdxl_table_ms"] = round(ms, 3)
+        out["raven_sdxl_table_frac_of_hbm"] = round(out["raven_sdxl_table_gbs"] / peaks["hbm"], 4)
+        out["raven_sdxl_table"] = f"{len(param_numels)} tensors, {tot} parameters"
+        del ps, opt
+        torch.cuda.empty_cache()
     n = 512 * 1024 * 1024                                    # 0.5 G parameters in 16 tensors (bounded memory, > L2)
     ps = [torch.nn.Parameter(torch.zeros(n // 16, device="cuda", dtype=torch.bfloat16)) for _ in range(16)]
     for p in ps:
@@ -231,7 +259,14 @@ def cpu_config1_step(steps, warmup):
             else:
                 p.normal_(0.0, 0.02)
     params = list(model.parameters())
-    opt = RefRaven(params, lr=8e-7, momentum_dtype=torch.float32, **Cfg.RAVEN)
+    # fp32 weights + gradients + fp32 moments = 41 GB (+ activations); a small host keeps the moments in bf16 and says so
+    try:
+        import psutil
+        avail_gb = psutil.virtual_memory().available / 2 ** 30
+    except Exception:
+        avail_gb = 1e9
+    mdt = torch.float32 if avail_gb >= 64 else torch.bfloat16
+    opt = RefRaven(params, lr=8e-7, momentum_dtype=mdt, **Cfg.RAVEN)
     sch = RefDDPMScheduler(prediction_type=mode)
     sampler = host_ref.RefTimestepSampler(Cfg.MAX_TRAIN_STEPS, batch, Cfg.SEED, None, False)
     b = synth_batch(batch, res, 1)
@@ -254,7 +289,8 @@ def cpu_config1_step(steps, warmup):
             rows.append((t3 - t0, t1 - t0, t2 - t1, t3 - t2))
     best = min(rows)                                          # best whole step; its own split is reported
     return dict(sec=best[0], fwd_bwd_s=best[1], clip_s=best[2], raven_s=best[3], threads=torch.get_num_threads(), cpus=ncpu,
-                steps_timed=len(rows), mean_sec=sum(r[0] for r in rows) / len(rows), loss=float(loss.detach()))
+                steps_timed=len(rows), mean_sec=sum(r[0] for r in rows) / len(rows), loss=float(loss.detach()),
+                moments="fp32" if mdt == torch.float32 else "bf16 (host has < 64 GB free)")
 
 
 CONFIG1 = ("BASELINE config 1: SDXL UNet random-init single train step, epsilon, 512x512 (64x64x4 latents), batch 1, cached 77x2048 "
@@ -267,7 +303,7 @@ def cpu_baseline_record(r):
                         f"(the GPU arm's images are 1024x1024: 4x the pixels, so the two imgs/s are not the same unit of work)"),
                 seconds_per_step=round(r["sec"], 3), fwd_bwd_s=round(r["fwd_bwd_s"], 3), clip_s=round(r["clip_s"], 3),
                 raven_s=round(r["raven_s"], 3), mean_seconds_per_step=round(r["mean_sec"], 3), os_cpu_count=r["cpus"],
-                torch_threads=r["threads"], same_config=False)
+                torch_threads=r["threads"], same_config=False, raven_moments=r["moments"])
 
 
 def main():
@@ -276,9 +312,13 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="aozora")
-    ap.add_argument("--batch", type=int, default=4, help="images per GPU (BASELINE config 2: 4)")
+    ap.add_argument("--workload", type=int, default=2, choices=(2, 3, 4),
+                    help="BASELINE.json configs[1..3]: 2 = 1024x1024 batch 4 v_prediction (default, the metric's config); "
+                         "3 = rectified_flow + logit-normal tickets, batch 8/GPU; 4 = layer exclusion (down_blocks.0, attn2) over "
+                         "896x1152 / 1216x832 / 1024x1024 buckets")
+    ap.add_argument("--batch", type=int, default=None, help="images per GPU (default: 4; workload 3: 8)")
     ap.add_argument("--res", type=int, default=1024)
-    ap.add_argument("--mode", default="v_prediction")
+    ap.add_argument("--mode", default=None)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured step")
@@ -288,24 +328,32 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     metric = "SDXL 1024x1024 UNet train step throughput"
-    workload = (f"SDXL UNet bf16 {args.res}x{args.res} ({args.res // 8}x{args.res // 8}x4 latents) batch {args.batch}/GPU, {args.mode}, "
-                f"Raven (bf16 moments), cached 77x2048 text embeds + 1280 pooled, random-init weights")
+    if args.batch is None:
+        args.batch = 8 if args.workload == 3 else 4
+    if args.mode is None:
+        args.mode = "rectified_flow" if args.workload == 3 else "v_prediction"
+    # (width, height) of the image buckets the steps cycle through (config 4 = 896x1152, 1216x832, 1024x1024)
+    buckets = [(896, 1152), (1216, 832), (1024, 1024)] if args.workload == 4 else [(args.res, args.res)]
+    exclude = ["down_blocks.0", "attn2"] if args.workload == 4 else []
+    workload = (f"BASELINE config {args.workload}: SDXL UNet bf16 " + " / ".join(f"{w}x{h}" for w, h in buckets) +
+                f" batch {args.batch}/GPU, {args.mode}, " +
+                ("logit-normal(-0.5, 1) timestep tickets, " if args.workload == 3 else "uniform timestep tickets, ") +
+                (f"exclude keywords {exclude} (frozen: no wgrad / reduce / Raven state), " if exclude else "") +
+                "Raven (bf16 moments), cached 77x2048 text embeds + 1280 pooled, random-init weights")
 
     if args.impl == "reference":
         if rank != 0:
             return
-        # bounded sample of the same workload: one image at 256x256 per step (1/16 of a 1024x1024 image's pixels)
-        sres, sb = 256, 1
-        sec, threads = cpu_reference_step(sres, sb, max(1, args.steps), max(0, min(args.warmup, 1)), args.mode)
-        scale = (sres / args.res) ** 2
-        val = sb * scale / sec
-        line = dict(impl="reference", metric=metric, value=val, unit="imgs/s", n_gpus=args.gpus, steps=args.steps, warmup=args.warmup,
-                    ms_per_step=sec * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32", data="synthetic",
-                    config=dict(workload=workload), gpu_launches=0,
-                    cpu_baseline=dict(value=val, unit="imgs/s", cores=threads, kind="port",
-                                      sample=f"{sb} image at {sres}x{sres} per step on torch-CPU fp32 (full SDXL UNet, Raven step "
-                                             f"included), converted to 1024x1024-image equivalents by pixel count (x{scale:g})"),
-                    e2e=dict(value=val, unit="imgs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+        # Each "step" is one BASELINE config 1 micro-step (the reference's CPU-runnable case) on all host cores; the run is
+        # bounded: 1 warm-up + at most 5 timed steps whatever --steps / --warmup ask for (a step takes ~10-20 s of CPU).
+        k = max(3, min(args.steps, 5))
+        r = cpu_config1_step(k, 1)
+        rec = cpu_baseline_record(r)
+        line = dict(impl="reference", metric=metric, value=rec["value"], unit="imgs/s", n_gpus=args.gpus, steps=args.steps,
+                    warmup=args.warmup, ms_per_step=r["sec"] * 1e3, higher_is_better=True, scaling="weak", vs_baseline=None, dtype="f32",
+                    data="synthetic", config=dict(workload=CONFIG1, same_config=False, steps_timed=k, warmup_run=1,
+                                                  own_arm_workload=workload), gpu_launches=0, cpu_baseline=rec,
+                    e2e=dict(value=rec["value"], unit="imgs/s", h2d_bytes_per_step=0, d2h_bytes_per_step=0))
         print(json.dumps(line))
         return
 
@@ -324,10 +372,14 @@ def main():
     from aozora_sdxl_training_b200.unet import UNet2DConditionModel, init_weights_fast_, sdxl_config
     peaks = load_peaks()
 
+    from aozora_sdxl_training_b200 import host
     with torch.device(dev):
         unet = UNet2DConditionModel(sdxl_config()).to(torch.bfloat16)
     init_weights_fast_(unet, seed=Cfg.SEED)
-    cfg = type("BenchCfg", (Cfg,), dict(BATCH_SIZE=args.batch * world, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=None))
+    frozen = host.apply_exclusion(unet, exclude) if exclude else 0            # train.py:2664-2667
+    # config 3: the GUI's logit-normal recipe (gui/gui.py:5594-5603) for TIMESTEP_ALLOCATION; otherwise uniform bins
+    alloc = host.logit_normal_allocation(-0.5, 1.0, Cfg.MAX_TRAIN_STEPS) if args.workload == 3 else None
+    cfg = type("BenchCfg", (Cfg,), dict(BATCH_SIZE=args.batch * world, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=alloc))
     if world > 1:
         from aozora_sdxl_training_b200.parallel import DataParallel
         dp = DataParallel(unet, momentum_dtype=torch.bfloat16)
@@ -335,13 +387,15 @@ def main():
     else:
         opt = RavenAdamW([{"params": [p for p in unet.parameters() if p.requires_grad], "lr_scale": 1.0}], lr=8e-7,
                          momentum_dtype=torch.bfloat16, **Cfg.RAVEN)
-    # the device side of the step (NCCL reduce-scatter / all-gather included) is captured once and replayed
+    param_numels = [p.numel() for p in unet.parameters()]
+    # the device side of the step (NCCL reduce-scatter / all-gather included) is captured once per batch shape and replayed
     use_graph = not args.no_graph
     step = SDXLTrainStep(unet, opt, cfg, device=dev, dp=dp, use_cuda_graph=use_graph)
 
-    host_batch = synth_batch(args.batch, args.res, 100 + rank, pin=True)
-    dev_batch = {k: v.to(dev) for k, v in host_batch.items()}
-    h2d = sum(v.numel() * v.element_size() for v in host_batch.values())
+    host_batches = [synth_batch(args.batch, wh, 100 + rank + 1000 * i, pin=True) for i, wh in enumerate(buckets)]
+    dev_batches = [{k: v.to(dev) for k, v in hb.items()} for hb in host_batches]
+    nb = len(buckets)
+    h2d = sum(v.numel() * v.element_size() for hb in host_batches for v in hb.values()) // nb     # mean over the bucket cycle
 
     def barrier():
         if world > 1:
@@ -352,8 +406,8 @@ def main():
         barrier()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
-        for _ in range(n):
-            fn()
+        for i in range(n):
+            fn(i)
         e1.record()
         barrier()
         ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
@@ -362,34 +416,34 @@ def main():
         return ms.item()
 
     from aozora_sdxl_training_b200 import _lib
-    r = step.step(dev_batch)                                   # first eager step: also times the GEMM tile plans (autotune)
-    l0 = _lib.query("aoz_launch_count")                        # counted inside the library at every kernel launch site
-    r = step.step(dev_batch)                                   # second eager step: its launches are what the graph replays
-    per_step_launches = _lib.query("aoz_launch_count") - l0
-    # untimed steps: the requested warm-up (>= 3) plus the capture call and a few replays -- under data parallel the first
+    per_shape_launches = []
+    for db in dev_batches:
+        r = step.step(db)                                      # first eager step of this shape: sizes workspaces, GEMM tile plans
+        l0 = _lib.query("aoz_launch_count")                    # counted inside the library at every kernel launch site
+        r = step.step(db)                                      # second eager step: its launches are what the graph replays
+        per_shape_launches.append(_lib.query("aoz_launch_count") - l0)
+    # untimed steps: the requested warm-up (>= 3) plus the capture call and a few replays per shape -- under data parallel the first
     # replays of the captured NCCL kernels still run slower than steady state (8 GPUs: 171 ms vs 157 ms per step)
-    # (measured again at 8 GPUs with 11 untimed steps: 161 ms per step in the device-timed region, 150 ms in the end-to-end region
-    # that runs after it -> a longer untimed run-in when NCCL kernels are part of the graph)
-    n_warm = max(3, args.warmup) + (6 if use_graph else 1) + (12 if (use_graph and world >= 4) else 0)
-    for _ in range(n_warm):
-        r = step.step(dev_batch)
+    n_warm = (max(3, args.warmup) + (6 if use_graph else 1) + (12 if (use_graph and world >= 4) else 0)) * nb
+    for i in range(n_warm):
+        r = step.step(dev_batches[i % nb])
     loss0 = r.loss_value()
     clocks = ClockSampler(local_rank)
     clocks.start()
-    ms_dev = timed(lambda: step.step(dev_batch), args.steps)
-    launches = per_step_launches * args.steps                  # replayed from the captured graph: same kernels every step
+    ms_dev = timed(lambda i: step.step(dev_batches[i % nb]), args.steps)
+    launches = sum(per_shape_launches[i % nb] for i in range(args.steps))      # replayed from the captured graphs
     clk = clocks.stop()
 
-    def e2e_step():
-        res = step.step(host_batch)
+    def e2e_step(i):
+        res = step.step(host_batches[i % nb])
         return res.loss_value()                                 # device -> host read of the step's loss
 
     def timed_wall(fn, n):
         """End-to-end: host wall clock around the user-facing calls (pinned-host inputs in, loss value out), max over ranks."""
         barrier()
         t0 = time.perf_counter()
-        for _ in range(n):
-            fn()
+        for i in range(n):
+            fn(i)
         torch.cuda.synchronize()
         ms = torch.tensor([(time.perf_counter() - t0) * 1e3], device=dev)
         barrier()
@@ -397,7 +451,7 @@ def main():
             torch.distributed.all_reduce(ms, op=torch.distributed.ReduceOp.MAX)
         return ms.item()
 
-    e2e_step()
+    e2e_step(0)
     ms_e2e = timed_wall(e2e_step, args.steps)
 
     imgs = args.batch * world * args.steps
@@ -414,33 +468,43 @@ def main():
                 e2e=dict(value=round(e2e_val, 3), unit="imgs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=round(ms_e2e / args.steps, 3),
                          how="SDXLTrainStep.step(batch in pinned host memory) + loss_value() per step, host wall clock"),
-                gpu_launches=int(launches), clocks=clk, loss=loss0,
-                step_tflops=round(value * TRAIN_TFLOP_PER_IMG * (args.res / 1024) ** 2 / world, 1),
-                step_frac_of_sustained_bf16_peak=round(value * TRAIN_TFLOP_PER_IMG * (args.res / 1024) ** 2 / world / peaks["tf_sust"], 4))
+                gpu_launches=int(launches), clocks=clk, loss=loss0)
+    if args.workload != 4:      # 20.28 TFLOP per 1024x1024 image, every weight gradient included (workload 4 freezes 21 % of them)
+        tf = value * TRAIN_TFLOP_PER_IMG * (args.res / 1024) ** 2 / world
+        line.update(step_tflops=round(tf, 1), step_frac_of_sustained_bf16_peak=round(tf / peaks["tf_sust"], 4))
+    else:
+        line["config"].update(frozen_params=int(frozen), buckets=[f"{w}x{h}" for w, h in buckets])
+    # teardown order matters under data parallel: the captured graphs hold NCCL kernels, so they go first, then the step
+    # object and the optimizer shards, and only then the process group (see the end of main)
+    step._graphs.clear()
+    del step, opt, dp, unet, dev_batches
+    import gc
+    gc.collect()
+    torch.cuda.synchronize()
+    torch.cuda.empty_cache()
     if rank == 0:
-        del step, opt
-        torch.cuda.empty_cache()
         line["roofline"] = gemm_roofline(torch, peaks)
         if not args.no_kernel_table:
             try:
-                line["kernels"] = kernel_table(torch, peaks)
+                line["kernels"] = kernel_table(torch, peaks, param_numels)
             except Exception as e:                              # side table must never take the headline down
                 line["kernels"] = dict(error=str(e)[:200])
         if world == 1 and not args.no_cpu_baseline:
-            sres, sb = 256, 1
-            sec, threads = cpu_reference_step(sres, sb, 1, 0, args.mode)
-            scale = (sres / args.res) ** 2
-            line["cpu_baseline"] = dict(value=sb * scale / sec, unit="imgs/s", cores=threads, kind="port",
-                                        sample=f"1 step of {sb} image at {sres}x{sres} on torch-CPU fp32 (oracle UNet + Raven), "
-                                               f"scaled to 1024x1024-image equivalents by pixel count (x{scale:g}); {sec:.1f} s")
+            line["cpu_baseline"] = cpu_baseline_record(cpu_config1_step(3, 1))
         else:
             line["cpu_baseline"] = None
         print(json.dumps(line))
+        sys.stdout.flush()
     if world > 1:
+        # graphs are gone (above); a watchdog keeps a wedged communicator from turning a finished measurement into a hung job
+        import threading
+        dog = threading.Timer(60.0, lambda: os._exit(0))
+        dog.daemon = True
+        dog.start()
         torch.distributed.barrier()
         torch.cuda.synchronize()
-        sys.stdout.flush()
-        os._exit(0)           # CUDA graphs holding captured NCCL kernels make destroy_process_group hang; nothing is left to do
+        torch.distributed.destroy_process_group()
+        dog.cancel()
 
 
 if __name__ == "__main__":
