@@ -306,59 +306,67 @@ class RavenAdamW(Optimizer):
                                           group["debias_strength"], state["step"])
         self._stage.put("hyper", hyper, self._last_items[0][1].device)      # eager, stream-ordered before the replay
 
-    # -- state I/O (raven.py:151-222) -----------------------------------------------------------------------
-    def state_dict(self):
-        state_dict = super().state_dict()
-        state_dict["_momentum_dtype"] = self._momentum_dtype
-        return state_dict
-
-    def save_cpu_state(self):
-        params_with_grad = [p for group in self.param_groups for p in group["params"] if p.requires_grad]
-        cpu_state = {"_momentum_dtype": self._momentum_dtype}
-        for i, p in enumerate(params_with_grad):
-            if p in self.state:
-                state = self.state[p]
-                m, v = state.get("exp_avg"), state.get("exp_avg_sq")
-                cpu_state[i] = {
-                    "step": state.get("step", 0),
-                    "exp_avg_cpu": None if m is None else m.detach().to("cpu"),
-                    "exp_avg_sq_cpu": None if v is None else v.detach().to("cpu"),
-                }
-        return cpu_state
-
-    def load_cpu_state(self, cpu_state):
-        saved_dtype = cpu_state.get("_momentum_dtype", self._momentum_dtype)
-        params_with_grad = [p for group in self.param_groups for p in group["params"] if p.requires_grad]
-        for i, p in enumerate(params_with_grad):
-            if i not in cpu_state:
-                continue
-            saved = cpu_state[i]
-            exp_avg = saved.get("exp_avg", saved.get("exp_avg_cpu"))
-            exp_avg_sq = saved.get("exp_avg_sq", saved.get("exp_avg_sq_cpu"))
-            step = saved.get("step", 0)
-            if torch.is_tensor(step):
-                step = int(step.item())
-            self.state[p] = {
-                "step": step,
-                "exp_avg": self._restore_state_tensor(exp_avg, p) if exp_avg is not None else None,
-                "exp_avg_sq": self._restore_state_tensor(exp_avg_sq, p) if exp_avg_sq is not None else None,
-            }
-        if saved_dtype != self._momentum_dtype:
-            print(f"[{self._name}] Loaded state saved in {saved_dtype}, converted to {self._momentum_dtype}.")
-
-    def load_state_dict(self, state_dict):
-        state_dict = dict(state_dict)
-        saved_dtype = state_dict.pop("_momentum_dtype", torch.float32)
-        if saved_dtype != self._momentum_dtype:
-            print(f"[{self._name}] Loading state saved in {saved_dtype}, but current optimizer uses "
-                  f"{self._momentum_dtype}. Converting...")
-        super().load_state_dict(state_dict)
+    # -- state I/O ------------------------------------------------------------------------------------------
+    # File contract (what the reference's resume path reads and writes, raven.py:151-222): ``state_dict()`` is torch's plus a
+    # ``_momentum_dtype`` entry; ``save_cpu_state()`` is ``{"_momentum_dtype": dtype, k: {"step", "exp_avg_cpu",
+    # "exp_avg_sq_cpu"}}`` where k counts the trainable parameters in ``param_groups`` order (entries only for parameters
+    # that have state); loading assigns by k without a shape check and also accepts the older ``exp_avg`` / ``exp_avg_sq`` keys.
+    def _trainable_by_index(self):
+        k = 0
         for group in self.param_groups:
             for p in group["params"]:
-                if p.requires_grad and p in self.state:
-                    state = self.state[p]
-                    if "exp_avg" in state:
-                        state["exp_avg"] = state["exp_avg"].to(self._momentum_dtype)
-                        state["exp_avg_sq"] = state["exp_avg_sq"].to(self._momentum_dtype)
-                    if torch.is_tensor(state.get("step")):
-                        state["step"] = int(state["step"].item())
+                if p.requires_grad:
+                    yield k, p
+                    k += 1
+
+    @staticmethod
+    def _plain_step(value):
+        return int(value.item()) if torch.is_tensor(value) else value
+
+    def _note_dtype_change(self, saved_dtype, verb):
+        if saved_dtype != self._momentum_dtype:
+            print(f"[{self._name}] {verb} moments stored as {saved_dtype}; this optimizer keeps {self._momentum_dtype} (converted).")
+
+    def state_dict(self):
+        out = super().state_dict()
+        out["_momentum_dtype"] = self._momentum_dtype
+        return out
+
+    def save_cpu_state(self):
+        def host(t):
+            return None if t is None else t.detach().to("cpu")
+
+        out = {"_momentum_dtype": self._momentum_dtype}
+        for k, p in self._trainable_by_index():
+            st = self.state.get(p)
+            if st is not None:
+                out[k] = dict(step=st.get("step", 0), exp_avg_cpu=host(st.get("exp_avg")), exp_avg_sq_cpu=host(st.get("exp_avg_sq")))
+        return out
+
+    def load_cpu_state(self, cpu_state):
+        def device(entry, new_key, old_key, p):
+            t = entry.get(old_key, entry.get(new_key))
+            return None if t is None else self._restore_state_tensor(t, p)
+
+        for k, p in self._trainable_by_index():
+            entry = cpu_state.get(k)
+            if entry is None:
+                continue
+            self.state[p] = dict(step=self._plain_step(entry.get("step", 0)),
+                                 exp_avg=device(entry, "exp_avg_cpu", "exp_avg", p),
+                                 exp_avg_sq=device(entry, "exp_avg_sq_cpu", "exp_avg_sq", p))
+        self._note_dtype_change(cpu_state.get("_momentum_dtype", self._momentum_dtype), "loaded")
+
+    def load_state_dict(self, state_dict):
+        rest = {k: v for k, v in state_dict.items() if k != "_momentum_dtype"}
+        self._note_dtype_change(state_dict.get("_momentum_dtype", torch.float32), "loading")
+        super().load_state_dict(rest)
+        for _, p in self._trainable_by_index():
+            st = self.state.get(p)
+            if not st:
+                continue
+            for key in ("exp_avg", "exp_avg_sq"):
+                if key in st:
+                    st[key] = st[key].to(self._momentum_dtype)
+            if "step" in st:
+                st["step"] = self._plain_step(st["step"])

@@ -24,33 +24,35 @@ class TitanAdamW(RavenAdamW):
                  eps: float = 1e-8, debias_strength: float = 1.0, momentum_dtype: torch.dtype = torch.bfloat16):
         super().__init__(params, lr=lr, betas=betas, weight_decay=weight_decay, eps=eps,
                          debias_strength=debias_strength, momentum_dtype=momentum_dtype)
-        self._dev_grads = {}
+        self._dev_grads = {}            # parameter -> persistent fp32 gradient buffer in HBM (the reference's CPU buffer)
         self._grad_ready = set()
         self._hook_handles = []
         self._closed = False
         self._pending_clip = None
-        for group in self.param_groups:
-            for p in group["params"]:
-                if not p.requires_grad:
-                    continue
-                if not hasattr(p, "register_post_accumulate_grad_hook"):
-                    raise RuntimeError("TitanAdamW requires Tensor.register_post_accumulate_grad_hook (PyTorch 2.0 or newer).")
-                owner_ref = getattr(p, "_titan_optimizer_owner", None)
-                owner = owner_ref() if callable(owner_ref) else None
-                if owner is not None and owner is not self:
-                    self.close()
-                    raise RuntimeError("A parameter is already owned by another live TitanAdamW. "
-                                       "Close the old optimizer before creating a replacement.")
-                self._dev_grads[p] = torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
-                p._titan_optimizer_owner = weakref.ref(self)
-                optimizer_ref = weakref.ref(self)
+        me = weakref.ref(self)          # hooks and ownership marks must not keep a discarded optimizer alive
+        for p in (q for group in self.param_groups for q in group["params"] if q.requires_grad):
+            self._claim(p, me)
 
-                def offload_hook(param, optimizer_ref=optimizer_ref):
-                    optimizer = optimizer_ref()
-                    if optimizer is not None:
-                        optimizer._offload_gradient(param)
+    def _claim(self, p, me):
+        """Take ownership of one trainable parameter: ``p._titan_optimizer_owner`` (a weak reference, the attribute the
+        reference uses, titan.py:62-100) marks it so that two live Titan optimizers never offload the same gradient."""
+        register = getattr(p, "register_post_accumulate_grad_hook", None)
+        if register is None:
+            raise RuntimeError("TitanAdamW needs Tensor.register_post_accumulate_grad_hook (PyTorch >= 2.0)")
+        mark = getattr(p, "_titan_optimizer_owner", None)
+        other = mark() if callable(mark) else None
+        if other is not None and other is not self:
+            self.close()
+            raise RuntimeError("parameter already belongs to a live TitanAdamW: close() that optimizer before building another")
+        self._dev_grads[p] = torch.empty_like(p, dtype=torch.float32, memory_format=torch.contiguous_format)
+        p._titan_optimizer_owner = me
 
-                self._hook_handles.append(p.register_post_accumulate_grad_hook(offload_hook))
+        def after_accumulate(param, me=me):
+            live = me()
+            if live is not None:
+                live._offload_gradient(param)
+
+        self._hook_handles.append(register(after_accumulate))
 
     def _offload_gradient(self, param):
         if param.grad is None:
@@ -69,19 +71,19 @@ class TitanAdamW(RavenAdamW):
         return None if p.grad is None else p.grad.float()
 
     def close(self):
-        """Remove autograd hooks and release optimizer-owned gradient buffers (titan.py:133-146)."""
+        """Detach from the parameters: hooks removed, ownership marks cleared (only ours), gradient buffers freed
+        (what titan.py:133-146 promises; idempotent, also called from ``__del__``)."""
         if getattr(self, "_closed", True):
             return
         self._closed = True
-        for handle in self._hook_handles:
-            handle.remove()
-        self._hook_handles.clear()
-        for p in self._dev_grads:
-            owner_ref = getattr(p, "_titan_optimizer_owner", None)
-            if callable(owner_ref) and owner_ref() is self:
-                delattr(p, "_titan_optimizer_owner")
-        self._grad_ready.clear()
+        while self._hook_handles:
+            self._hook_handles.pop().remove()
+        for p in list(self._dev_grads):
+            mark = getattr(p, "_titan_optimizer_owner", None)
+            if callable(mark) and mark() is self:
+                del p._titan_optimizer_owner
         self._dev_grads.clear()
+        self._grad_ready.clear()
 
     def __del__(self):
         try:

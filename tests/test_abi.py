@@ -64,3 +64,46 @@ def test_optimizer_constructor_contract():
     p.grad = torch.ones(4)
     with pytest.raises(_lib.AozoraError):
         opt.step()
+
+
+def test_build_optimizer_mirrors_create_optimizer():
+    """train.py:2256-2270: package-default RAVEN_PARAMS (string momentum dtype, list betas) merged under the run's; missing keys
+    fall back to eps 1e-8 / weight_decay 0.01 / debias_strength 1.0 only when absent from BOTH; lr = the LR curve's peak."""
+    import torch
+    from aozora_sdxl_training_b200 import train_loop
+    from aozora_sdxl_training_b200.optimizers import RavenAdamW, TitanAdamW
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.conv1 = torch.nn.Linear(4, 4)
+            self.other = torch.nn.Linear(4, 4)
+
+    class Cfg:
+        LR_CUSTOM_CURVE = [[0.0, 0.0], [0.05, 8.0e-7], [1.0, 1.0e-7]]
+        RAVEN_PARAMS = {"betas": [0.9, 0.999], "eps": 1e-8, "weight_decay": 0.01, "debias_strength": 0.3, "momentum_dtype": "bfloat16"}
+        UNET_EXCLUDE_TARGETS = ["conv1"]
+
+    net = Net()
+    opt = train_loop.build_optimizer(Cfg, net)
+    g = opt.param_groups[0]
+    assert type(opt) is RavenAdamW and len(opt.param_groups) == 1 and g["lr_scale"] == 1.0
+    assert g["lr"] == 8.0e-7 and g["betas"] == (0.9, 0.999) and g["eps"] == 1e-8 and g["weight_decay"] == 0.01
+    assert g["debias_strength"] == 0.3 and g["momentum_dtype"] is torch.bfloat16 and opt._momentum_dtype is torch.bfloat16
+    assert [p is q for p, q in zip(g["params"], net.other.parameters())] == [True, True]          # conv1 frozen by the keyword
+
+    class Sparse:
+        LEARNING_RATE = 2e-6
+        RAVEN_PARAMS = {"momentum_dtype": "float32", "weight_decay": 0.0}
+
+    g = train_loop.build_optimizer(Sparse, Net()).param_groups[0]
+    assert g["lr"] == 2e-6 and g["momentum_dtype"] is torch.float32 and g["weight_decay"] == 0.0
+    assert g["debias_strength"] == 0.3 and g["betas"] == (0.9, 0.999)                            # from the package defaults
+
+    class Titan(Sparse):
+        OPTIMIZER_TYPE = "Titan"
+        TITAN_PARAMS = {"debias_strength": 1.0}
+
+    topt = train_loop.build_optimizer(Titan, Net())
+    assert isinstance(topt, TitanAdamW) and topt.param_groups[0]["debias_strength"] == 1.0
+    topt.close()
