@@ -389,7 +389,7 @@ def test_raven_and_clip_over_the_sdxl_parameter_table():
         coef = min(1.0, max_norm / (total + 1e-6))
         assert coef < 1.0 and abs(got_coef - coef) <= 1e-5 * coef, (got_coef, coef)
         coefs.append(norms[st][1].cpu())                         # the oracle update uses the coefficient just verified
-    worst = 0.0
+    misses = 0
     for i, p in enumerate(ps):
         rp = p0[i].cpu()
         rm, rv = torch.zeros_like(rp), torch.zeros_like(rp)
@@ -400,8 +400,9 @@ def test_raven_and_clip_over_the_sdxl_parameter_table():
         got = p.detach().cpu()
         assert_close_1e6(got, rp, update_terms(before, gc, m_prev, rv, 2), (i, shapes[i], "p"))
         assert_close_1e6(opt.state[p]["exp_avg"].cpu(), rm, gc, (i, shapes[i], "exp_avg"))
-        worst = max(worst, (~torch.isclose(got, rp, rtol=1e-6, atol=1e-9)).float().mean().item())
-    assert worst < 1e-3                                           # per tensor: plain allclose(1e-6) holds for > 99.9 % of the elements
+        misses += int((~torch.isclose(got, rp, rtol=1e-6, atol=1e-9)).sum())
+    # and in the plain sense, isclose(rtol 1e-6) holds for all but the cancelling elements (~1e-4 of them, see update_terms)
+    assert misses < 3e-4 * 2_567_463_684, misses
 
 
 # ------------------------------------------------------------------------------------------------------------------
