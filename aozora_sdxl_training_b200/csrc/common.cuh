@@ -211,6 +211,17 @@ __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 __device__ __forceinline__ void tc_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 
+// One lane of a CONVERGED warp (the same lane every time: the lowest active one).  The MMA-issuing warp must stay converged and
+// elect around the single instruction: inside an `if (lane == 0)` region the operands of tcgen05.mma / commit (uniform-datapath
+// instructions) live in vector registers and ptxas wraps every issue in an ELECT / R2UR / BRA.U.ANY loop -- ~15 dependent
+// instructions per MMA, which made the issuing thread, not a pipe, the bottleneck of the attention kernels (ncu r02: the issuer
+// warp busy 93 % of the time, the softmax warps 21 % of theirs waiting for S).
+__device__ __forceinline__ bool elect_one_sync() {
+    uint32_t pred;
+    asm volatile("{\n\t.reg .pred P1;\n\telect.sync _|P1, 0xffffffff;\n\tselp.u32 %0, 1, 0, P1;\n\t}" : "=r"(pred));
+    return pred != 0;
+}
+
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate; issued by ONE thread.
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                           uint32_t accumulate) {

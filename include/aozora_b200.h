@@ -85,8 +85,9 @@ int aoz_pack_conv_weight(const void* w, int Cout, int Cin, int ks, int CinPad, i
  * lse: [B, H, Tq] fp32 (log-sum-exp of the scaled scores, natural log). */
 int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                  void* lse, int B, int H, int Tq, int Tk, float scale, void* stream);
-/* experiment switch: 1 = split-statistics forward kernel (default), 0 = shared-maximum forward kernel */
-int aoz_attn_set_fwd_split(int on);
+/* experiment switch: 2 = P-in-TMEM forward kernel (64-key tiles, double-buffered scores, P V with A read from tensor memory;
+ * default), 1 = split-statistics forward kernel (P through shared memory), 0 = shared-maximum forward kernel */
+int aoz_attn_set_fwd_split(int mode);
 /* experiment switch: 1 = with a single KV tile (cross-attention, Tk <= 128) the dK/dV kernel also produces dQ and the dQ
  * launch is skipped, 0 = always two kernels (default: the fused form measured slower inside the training step) */
 int aoz_attn_set_fused_cross_bwd(int on);
