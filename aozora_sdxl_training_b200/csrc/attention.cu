@@ -581,33 +581,37 @@ attn_fwd_split_kernel(const __grid_constant__ AttnParams P) {
 // forward, P-in-TMEM form (default)
 // ================================================================================================
 // Measured on B200 (tools/tmem_probe.cu, profiles/r02_tmem_probe.txt): tcgen05.ld sustains ~930 B/clk/SM and ex2 exactly 16 /clk/SM,
-// so a 128 x 128 score tile costs 1024 MUFU cycles against 512 MMA cycles and ~70 cycles of TMEM reads -- the split-statistics kernel
-// above (1966 cycles per tile, ncu r01) was bound by its own serialisation, not by a pipe: P went through shared memory and the
-// single P tile made softmax(j) wait for P V(j-1), which the issuer had queued BEHIND S(j+1).  This form removes both:
-//   * key tiles are 64 wide and the score accumulator is DOUBLE-BUFFERED in tensor memory (S0 | S1 | O_a | O_b = 4 x 64 columns, still
-//     two CTAs per SM); S(j+2) is issued as soon as P V(j) is queued, so the softmax warps find their next tile already computed;
-//   * P never leaves tensor memory: each thread overwrites the front of ITS OWN 32 score columns with 16 packed bf16x2 words
-//     (tcgen05.st) and P V is a tcgen05.mma whose A operand is read from TMEM (layout verified by tools/tmem_probe.cu);
-//   * the exponentials are split between the MUFU pipe (ex2.approx) and the FMA pipe (Cody-Waite reduction + degree-3 polynomial,
-//     relative error 9e-5 << bf16's 2^-9) -- POLY_MASK selects which elements of every 16 take the polynomial.
-// The two threads of a row own 32 of the 64 keys each, with separate running maxima / row sums / O accumulators (merged once at
-// the end), exactly as in the split-statistics kernel.
+// so a 128 x 128 score tile costs 1024 MUFU cycles against 512 MMA cycles and ~70 cycles of TMEM reads: the exponentials are the
+// bound.  The split-statistics kernel above ran at 1966 cycles per tile (ncu r01) for two reasons that ncu's source view showed in
+// round 2: its single issuing THREAD was the critical path (see elect_one_sync), and with ~9 instructions per score element the
+// softmax warps were issue-bound.  This form is built to keep the MUFU pipe fed:
+//   * one thread per query row and 64-key tiles; per score element 1 FFMA + 1 MUFU + 1 FADD + 0.5 F2FP + 0.17 integer max;
+//   * P never leaves tensor memory: a thread overwrites the front of ITS OWN score row with 32 packed bf16x2 words (tcgen05.st) and
+//     P V is a tcgen05.mma whose A operand is read from TMEM (layout verified by tools/tmem_probe.cu) -- no shared-memory P tile,
+//     no proxy fence, 48 KB of shared memory and 128 TMEM columns (S | O) per CTA, so FOUR CTAs are resident per SM and the
+//     hardware interleaves their softmax / MMA phases (16 softmax warps per SM; measured 3 CTAs: 697, 4 CTAs: 724 TFLOP/s);
+//   * the running maximum is only a REFERENCE (any value that keeps 2^(s - ref) finite works: LSE = ref + log2 l exactly), so the
+//     common path does not track the maximum of S at all -- it takes an integer max over the packed bf16 P words and falls back
+//     to an exact max + rescale of O and l only when some P exceeded 2^8;
+//   * optionally part of the exponentials go to the FMA pipe (Cody-Waite reduction + degree-3 polynomial, relative error 9e-5 <<
+//     bf16's 2^-9), POLY_MASK selecting which elements of every 16.
 constexpr int KT = 64;                         // keys per score tile
 constexpr int KT_BYTES = KT * HD * 2;          // 8 KB: one [64, 64] bf16 tile
-constexpr int TM_STAGES = 4;                   // K / V ring: K(j+2) is fetched while V(j) is still being read
+constexpr int TM_STAGES = 2;                   // K / V ring
+constexpr int ATT_TM_THREADS = 192;            // 4 softmax warps + producer + issuer
+constexpr int TM_CTAS = 4;                     // resident CTAs per SM (TMEM: 4 x 128 columns; 80 registers per thread)
 
 struct TmSmem {
     static constexpr int Q = 0;
     static constexpr int K = Q + TILE_BYTES;
     static constexpr int V = K + TM_STAGES * KT_BYTES;
     static constexpr int BAR = V + TM_STAGES * KT_BYTES;    // 256 B of mbarriers
-    static constexpr int XCH = BAR + 256;                   // [2][128] max + [2][128] sum, fp32: merge of the two key halves
-    static constexpr int TOTAL = XCH + 2048;
+    static constexpr int TOTAL = BAR + 256;
 };
-static_assert(2 * (TmSmem::TOTAL + 1024) <= 228 * 1024, "attention forward must keep two CTAs per SM");
+static_assert(TM_CTAS * (TmSmem::TOTAL + 1024) <= 228 * 1024, "attention forward must keep TM_CTAS CTAs per SM");
 
-// 2^x for x <= ~8 on the FMA pipe: n = round(x), r = x - n in [-0.5, 0.5], 2^r by a degree-3 minimax polynomial, exponent added
-// through the integer view.  Max relative error 8.8e-5 (the result is rounded to bf16, 3.9e-3).  x below -126 flushes to 0.
+// 2^x for x <= ~100 on the FMA pipe: n = round(x), r = x - n in [-0.5, 0.5], 2^r by a degree-3 minimax polynomial, exponent added
+// through the integer view.  Max relative error 8.8e-5 (the result is rounded to bf16, 3.9e-3).  x below -126 flushes to ~0.
 __device__ __forceinline__ float poly_exp2(float x) {
     x = fmaxf(x, -126.0f);
     const float t = x + 12582912.0f;                        // 1.5 * 2^23: low mantissa bits now hold round(x) (two's complement)
@@ -617,10 +621,7 @@ __device__ __forceinline__ float poly_exp2(float x) {
     p = fmaf(p, r, 1.0f);
     return __int_as_float(__float_as_int(p) + (__float_as_int(t) << 23));
 }
-
-#ifndef AOZ_ATTN_POLY_MASK
-#define AOZ_ATTN_POLY_MASK 0x8888u             // elements 3, 7, 11, 15 of every 16 (one in four) take the polynomial
-#endif
+// which elements of every 16 take the polynomial: 0x8888 = one in four, 0x8080 = one in eight, 0 = none, 0xAAAA = every other
 
 __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -629,25 +630,23 @@ __device__ __forceinline__ void umma_bf16_ts(uint32_t tmem_d, uint32_t tmem_a, u
         "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t}"
         :: "r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
-__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r) {
-    asm volatile(
-        "tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
-        :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
-           "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15])
-        : "memory");
+__device__ __forceinline__ uint32_t max_u16x2(uint32_t a, uint32_t b) {
+    uint32_t d;
+    asm("max.u16x2 %0, %1, %2;" : "=r"(d) : "r"(a), "r"(b));
+    return d;
 }
 
-__global__ void __launch_bounds__(ATT_FWD_THREADS, 2)
+template <uint32_t POLY_MASK>
+__global__ void __launch_bounds__(ATT_TM_THREADS, TM_CTAS)
 attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
     extern __shared__ __align__(1024) uint8_t smem[];
     uint64_t* bars = (uint64_t*)(smem + TmSmem::BAR);
     uint64_t* q_full = bars;                    // 1
     uint64_t* kv_full = bars + 1;               // TM_STAGES
     uint64_t* kv_empty = bars + 1 + TM_STAGES;  // TM_STAGES
-    uint64_t* s_ready = bars + 1 + 2 * TM_STAGES;      // 2: S(j) has landed in buffer j & 1
-    uint64_t* p_ready = s_ready + 2;                   // 2: P(j) is in tensor memory (256 arrivals)
-    uint64_t* pv_done = p_ready + 2;                   // 1: P V(j) has retired (O may be rescaled until P(j+1) is published)
-    uint64_t* o_ready = pv_done + 1;
+    uint64_t* s_ready = bars + 1 + 2 * TM_STAGES;      // S(j) has landed (and with it every earlier MMA of the issuer: P V(j-1) has retired)
+    uint64_t* p_ready = s_ready + 1;                   // P(j) is in tensor memory (128 arrivals)
+    uint64_t* o_ready = p_ready + 1;
     uint32_t* tmem_slot = (uint32_t*)(o_ready + 1);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -661,32 +660,31 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TM_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        for (int i = 0; i < 2; ++i) { mbar_init(&s_ready[i], 1); mbar_init(&p_ready[i], 256); }
-        mbar_init(pv_done, 1); mbar_init(o_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(o_ready, 1);
         fence_mbar_init();
     }
-    if (warp == 9) tmem_alloc(tmem_slot, 256);
+    if (warp == 5) tmem_alloc(tmem_slot, 128);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t tOa = tmem + 128, tOb = tmem + 192;          // S buffers: tmem + 0, tmem + 64
+    const uint32_t tS = tmem, tO = tmem + 64;
     pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
 
-    if (warp == 8) {
+    if (warp == 4) {
         if (lane == 0) {
             tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV);
             mbar_arrive_expect_tx(q_full, TILE_BYTES);
             tma_load_4d(smem + TmSmem::Q, &P.tmQ, q_full, 0, h, q0, b);
             for (int j = 0; j < nkv; ++j) {
                 const int s = j % TM_STAGES;
-                mbar_wait(&kv_empty[s], ((j / TM_STAGES) & 1) ^ 1);
+                mbar_wait_relaxed(&kv_empty[s], ((j / TM_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[s], 2 * KT_BYTES);
                 tma_load_4d(smem + TmSmem::K + s * KT_BYTES, &P.tmK, &kv_full[s], 0, h, j * KT, b);
                 tma_load_4d(smem + TmSmem::V + s * KT_BYTES, &P.tmV, &kv_full[s], 0, h, j * KT, b);
             }
         }
-    } else if (warp == 9) {
+    } else if (warp == 5) {
         // MMA issuer: the WHOLE warp runs this loop converged (waits included) and one elected lane issues -- see elect_one_sync().
         // Every descriptor is the stage-0 descriptor plus an integer offset on its low word (address field, 16-byte units).
         const uint32_t idesc_qk = make_idesc_bf16(128, KT, 0, 0);
@@ -699,179 +697,171 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
             mbar_wait(&kv_full[s], (j / TM_STAGES) & 1);
             tc_fence_after();
             if (elect_one_sync()) {
-                const uint32_t tS = tmem + (j & 1) * KT;
                 const uint64_t dk = dK + (uint64_t)(s * (KT_BYTES >> 4));
                 umma_bf16(tS, dQ, dk, idesc_qk, 0u);
 #pragma unroll
                 for (int k = 1; k < 4; ++k) umma_bf16(tS, dQ + 2 * k, dk + 2 * k, idesc_qk, 1u);
-                umma_commit(&s_ready[j & 1]);
+                umma_commit(s_ready);
             }
             __syncwarp();
         };
         mbar_wait(q_full, 0);
         issue_s(0);
-        if (nkv > 1) issue_s(1);
         for (int j = 0; j < nkv; ++j) {
             const int s = j % TM_STAGES;
-            mbar_wait(&p_ready[j & 1], (j >> 1) & 1);
+            mbar_wait(p_ready, j & 1);
             tc_fence_after();
             if (elect_one_sync()) {
-                const uint32_t tP = tmem + (j & 1) * KT;           // P(j): words [0,16) = keys 0..31 of the tile, words [32,48) = keys 32..63
-                const uint64_t dv = dV + (uint64_t)(s * (KT_BYTES >> 4));
-                const uint32_t acc = j > 0 ? 1u : 0u;
-                umma_bf16_ts(tOa, tP, dv, idesc_pv, acc);
-                umma_bf16_ts(tOa, tP + 8, dv + 128, idesc_pv, 1u);
-                umma_bf16_ts(tOb, tP + 32, dv + 256, idesc_pv, acc);
-                umma_bf16_ts(tOb, tP + 40, dv + 384, idesc_pv, 1u);
+                const uint64_t dv = dV + (uint64_t)(s * (KT_BYTES >> 4));       // P(j): 32 packed words over the front of the score tile
+                umma_bf16_ts(tO, tS, dv, idesc_pv, j > 0 ? 1u : 0u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16_ts(tO, tS + 8 * k, dv + 128 * k, idesc_pv, 1u);
                 umma_commit(&kv_empty[s]);
-                umma_commit(pv_done);
                 if (j + 1 == nkv) umma_commit(o_ready);
             }
             __syncwarp();
-            if (j + 2 < nkv) issue_s(j + 2);                       // overwrites S / P(j): ordered behind P V(j) inside the tensor pipe
+            if (j + 1 < nkv) issue_s(j + 1);                       // overwrites S / P(j): ordered behind P V(j) inside the tensor pipe
         }
     } else {
-        // ---- softmax warps 0..7: two threads per query row, each owns 32 of the 64 key columns of a tile ----
-        const int qtr = warp & 3, hf = warp >> 2;
-        const int r = qtr * 32 + lane;
-        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
-        float* xm = (float*)(smem + TmSmem::XCH);                        // [2][128] running max of each half, exchanged once at the end
-        float* xl = xm + 256;                                            // [2][128] row sums
+        // ---- softmax warps 0..3: one thread per query row, all 64 key columns of a tile ----
+        const int r = warp * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(warp * 32) << 16;
         const float sl2 = P.scale * LOG2E;
         float m_ref = -INFINITY, l = 0.f;
-        const uint32_t tOx = hf == 0 ? tOa : tOb;
-        // exp2(s * sl2 - m_ref) of this thread's 32 columns of score buffer `tS` -> 16 packed words in `w`; returns the partial row sum
-        // and (through mx) the raw maximum.  Two 16-column chunks: the tcgen05.ld of chunk 1 is in flight during chunk 0's math.
-        auto softmax_pass = [&](uint32_t tS, int kvalid, bool full, float& mx, uint32_t* w) -> float {
-            float lsum0 = 0.f, lsum1 = 0.f;
+        // P(j) = 2^(s * sl2 - m_ref) for the 64 score columns -> 32 packed words in w; adds the row sum to lsum and returns the u16x2 max
+        // over the words (bf16 bit patterns of non-negative numbers order like the numbers).  Four 16-column chunks, the tcgen05.ld of
+        // chunk c + 1 in flight during the math of chunk c.
+        auto exp_pass = [&](uint32_t* w, float& lsum) -> uint32_t {
             uint32_t v[2][16];
-            const int col0 = hf * 32;
-            tmem_ld16(tS + lane_off + col0, v[0]);
+            uint32_t mw = 0;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            tmem_ld16(tS + lane_off, v[0]);
 #pragma unroll
-            for (int c = 0; c < 2; ++c) {
+            for (int c = 0; c < 4; ++c) {
                 tc_wait_ld();
-                if (c == 0) tmem_ld16(tS + lane_off + col0 + 16, v[1]);
-                const uint32_t* cv = v[c];
-                if (full) {
+                if (c + 1 < 4) tmem_ld16(tS + lane_off + (c + 1) * 16, v[(c + 1) & 1]);
+                const uint32_t* cv = v[c & 1];
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
-                        mx = fmaxf(mx, fmaxf(s0, s1));
-                        const float x0 = fmaf(s0, sl2, -m_ref), x1 = fmaf(s1, sl2, -m_ref);
-                        const float p0 = ((AOZ_ATTN_POLY_MASK >> e) & 1u) ? poly_exp2(x0) : fast_exp2(x0);
-                        const float p1 = ((AOZ_ATTN_POLY_MASK >> (e + 1)) & 1u) ? poly_exp2(x1) : fast_exp2(x1);
-                        lsum0 += p0; lsum1 += p1;
-                        w[c * 8 + (e >> 1)] = pack_bf16(p0, p1);
-                    }
-                } else {
+                for (int e = 0; e < 16; e += 4) {
+                    float p[4];
 #pragma unroll
-                    for (int e = 0; e < 16; e += 2) {
-                        const int ka = col0 + c * 16 + e;
-                        const bool ok0 = ka < kvalid, ok1 = ka + 1 < kvalid;
-                        const float s0 = __uint_as_float(cv[e]), s1 = __uint_as_float(cv[e + 1]);
-                        if (ok0) mx = fmaxf(mx, s0);
-                        if (ok1) mx = fmaxf(mx, s1);
-                        const float p0 = ok0 ? fast_exp2(fmaf(s0, sl2, -m_ref)) : 0.f;
-                        const float p1 = ok1 ? fast_exp2(fmaf(s1, sl2, -m_ref)) : 0.f;
-                        lsum0 += p0; lsum1 += p1;
-                        w[c * 8 + (e >> 1)] = pack_bf16(p0, p1);
+                    for (int t = 0; t < 4; ++t) {
+                        const float x = fmaf(__uint_as_float(cv[e + t]), sl2, -m_ref);
+                        p[t] = ((POLY_MASK >> (e + t)) & 1u) ? poly_exp2(x) : fast_exp2(x);
                     }
+                    a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+                    const uint32_t w0 = pack_bf16(p[0], p[1]), w1 = pack_bf16(p[2], p[3]);
+                    w[c * 8 + (e >> 1)] = w0; w[c * 8 + (e >> 1) + 1] = w1;
+                    mw = max_u16x2(mw, max_u16x2(w0, w1));
                 }
             }
-            return lsum0 + lsum1;
+            lsum = (a0 + a1) + (a2 + a3);
+            return mw;
         };
-        for (int j = 0; j < nkv; ++j) {
-            const uint32_t tS = tmem + (j & 1) * KT;
-            mbar_wait(&s_ready[j & 1], (j >> 1) & 1);
-            tc_fence_after();
-            const int kvalid = P.Tk - j * KT;                // keys >= kvalid are padding
-            const bool full = kvalid >= KT;                  // warp-uniform: full tiles skip every per-element predicate
-            uint32_t w[16];
-            if (j == 0) {
-                // first tile: a max-only pass over this thread's 32 columns seeds ITS reference (no exchange with the other half)
-                float mx = -3.0e38f;
+        // exact maximum of the valid columns of S (first tile, and the rare rescale)
+        auto max_pass = [&](int kvalid) -> float {
+            float mx = -3.0e38f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
                 uint32_t v[32];
-                tmem_ld32(tS + lane_off + hf * 32, v);
+                tmem_ld32(tS + lane_off + c * 32, v);
                 tc_wait_ld();
 #pragma unroll
                 for (int e = 0; e < 32; ++e)
-                    if (full || hf * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
-                m_ref = mx * sl2;
-                float dummy = -3.0e38f;
-                l = softmax_pass(tS, kvalid, full, dummy, w);
+                    if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+            }
+            return mx;
+        };
+        // masked variant of exp_pass for the last, partial tile (keys >= kvalid are padding: P = 0)
+        auto exp_pass_masked = [&](int kvalid, uint32_t* w, float& lsum) {
+            float acc = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tS + lane_off + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int ka = c * 32 + e;
+                    const float p0 = ka < kvalid ? fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref)) : 0.f;
+                    const float p1 = ka + 1 < kvalid ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref)) : 0.f;
+                    acc += p0 + p1;
+                    const uint32_t pk = pack_bf16(p0, p1);
+                    if (c == 0) w[e >> 1] = pk; else w[16 + (e >> 1)] = pk;
+                }
+            }
+            lsum = acc;
+        };
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_ready, j & 1);                       // also: P V(j-1) has retired, O may be rescaled
+            tc_fence_after();
+            const int kvalid = P.Tk - j * KT;                // keys >= kvalid are padding
+            uint32_t w[32];
+            float lsum = 0.f;
+            if (j == 0) {
+                m_ref = max_pass(kvalid) * sl2;              // the first tile seeds the reference with its exact maximum
+                if (kvalid >= KT) exp_pass(w, lsum); else exp_pass_masked(kvalid, w, lsum);
             } else {
-                // optimistic single pass against the running reference; redo only if the row maximum jumped by > 2^8
-                float mx = -3.0e38f;
-                float lsum = softmax_pass(tS, kvalid, full, mx, w);
-                const float m_new = fmaxf(m_ref, mx * sl2);
-                const bool need = (m_new - m_ref) > 8.0f;
-                // P V(j-1) accumulates into O until pv_done; it was queued one whole softmax pass ago, so this wait is already satisfied
-                // (waited every tile: an mbarrier phase that nobody observes could not be told from the one two tiles later)
-                mbar_wait(pv_done, (j - 1) & 1);
+                bool need;
+                if (kvalid >= KT) {
+                    const uint32_t mw = exp_pass(w, lsum);   // optimistic pass against the running reference
+                    need = (mw & 0xffffu) > 0x4380u || (mw >> 16) > 0x4380u;          // some P above 2^8 (bf16 256.0 = 0x4380)
+                } else {
+                    need = max_pass(kvalid) * sl2 - m_ref > 8.0f;
+                    if (!__any_sync(0xffffffffu, need)) exp_pass_masked(kvalid, w, lsum);
+                }
                 if (__any_sync(0xffffffffu, need)) {
-                    tc_fence_after();
+                    const float m_new = fmaxf(m_ref, max_pass(kvalid) * sl2);
                     const float alpha = fast_exp2(m_ref - m_new);
 #pragma unroll 1
                     for (int c = 0; c < 2; ++c) {
                         uint32_t v[32];
-                        tmem_ld32(tOx + lane_off + c * 32, v);
+                        tmem_ld32(tO + lane_off + c * 32, v);
                         tc_wait_ld();
 #pragma unroll
                         for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
-                        tmem_st32(tOx + lane_off + c * 32, v);
+                        tmem_st32(tO + lane_off + c * 32, v);
                         tc_wait_st();
                     }
                     l *= alpha;
                     m_ref = m_new;
-                    float dummy = -3.0e38f;
-                    lsum = softmax_pass(tS, kvalid, full, dummy, w);    // P of this tile again, against the new reference (S is still intact)
+                    if (kvalid >= KT) exp_pass(w, lsum); else exp_pass_masked(kvalid, w, lsum);     // S is still intact: P again, new reference
                 }
-                l += lsum;
             }
-            // P(j) over the front of this thread's own score columns: words [hf * 32, hf * 32 + 16) of buffer j & 1
-            tmem_st16(tS + lane_off + hf * 32, w);
+            l += lsum;
+            // P(j) over the front of this thread's own score row: words [0, 32)
+            tmem_st32(tS + lane_off, w);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(&p_ready[j & 1]);
+            mbar_arrive(p_ready);
         }
         mbar_wait(o_ready, 0);
         tc_fence_after();
-        // combine the two halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
-        xm[hf * 128 + r] = m_ref;
-        xl[hf * 128 + r] = l;
-        named_bar_sync(1, 256);
-        const float m_o = xm[(hf ^ 1) * 128 + r], l_o = xl[(hf ^ 1) * 128 + r];
-        const float m = fmaxf(m_ref, m_o);
-        const float w_me = fast_exp2(m_ref - m), w_o = fast_exp2(m_o - m);
-        const float wa = hf == 0 ? w_me : w_o, wb = hf == 0 ? w_o : w_me;
-        const float lt = l * w_me + l_o * w_o;
-        const float inv_l = 1.0f / lt;
         const int q = q0 + r;
-        {
-            const int c = hf;                                    // this thread stores 32 of the 64 output columns
-            uint32_t va[32], vb[32];
-            tmem_ld32(tOa + lane_off + c * 32, va);
-            tmem_ld32(tOb + lane_off + c * 32, vb);
+        const float inv_l = 1.0f / l;
+#pragma unroll 1
+        for (int c = 0; c < 2; ++c) {
+            uint32_t v[32];
+            tmem_ld32(tO + lane_off + c * 32, v);
             tc_wait_ld();
             if (q < P.Tq) {
                 __nv_bfloat16* dst = P.O + ((long long)b * P.Tq + q) * P.ldo + h * HD + c * 32;
-                const float sa = wa * inv_l, sb = wb * inv_l;
 #pragma unroll
                 for (int e = 0; e < 32; e += 8) {
-                    float f[8];
-#pragma unroll
-                    for (int t = 0; t < 8; ++t) f[t] = fmaf(__uint_as_float(va[e + t]), sa, __uint_as_float(vb[e + t]) * sb);
                     uint4 o;
-                    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                    o.x = pack_bf16(__uint_as_float(v[e]) * inv_l, __uint_as_float(v[e + 1]) * inv_l);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * inv_l, __uint_as_float(v[e + 3]) * inv_l);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * inv_l, __uint_as_float(v[e + 5]) * inv_l);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * inv_l, __uint_as_float(v[e + 7]) * inv_l);
                     *reinterpret_cast<uint4*>(dst + e) = o;
                 }
             }
         }
-        if (hf == 0 && q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m + log2f(lt)) * LN2;
+        if (q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 256); }
+    if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 128); }
 }
 
 // ================================================================================================
@@ -1374,7 +1364,7 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     memset(&P, 0, sizeof(P));
     int rc;
     if ((rc = make_qkv_map(&P.tmQ, q, ldq, B, H, Tq)) != AOZ_OK) return rc;
-    const int kv_rows = g_fwd_split == 2 ? KT : TILE;          // the P-in-TMEM kernel streams 64-key tiles
+    const int kv_rows = g_fwd_split >= 2 ? KT : TILE;          // the P-in-TMEM kernel streams 64-key tiles
     if ((rc = make_qkv_map(&P.tmK, k, ldk, B, H, Tk, kv_rows)) != AOZ_OK) return rc;
     if ((rc = make_qkv_map(&P.tmV, v, ldv, B, H, Tk, kv_rows)) != AOZ_OK) return rc;
     P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
@@ -1383,11 +1373,17 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     if (!attr) {
         cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL);
         cudaFuncSetAttribute(attn_fwd_split_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FwdSmem::TOTAL);
-        cudaFuncSetAttribute(attn_fwd_tm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_tm_kernel<0x8888u>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_tm_kernel<0x8080u>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_tm_kernel<0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_tm_kernel<0xAAAAu>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
         attr = true;
     }
     const int grid = B * H * ((Tq + TILE - 1) / TILE);
-    if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    if (g_fwd_split == 3) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel<0x8080u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 4) launch_k(attn_fwd_tm_kernel<0u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 5) launch_k(attn_fwd_tm_kernel<0xAAAAu>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split) launch_k(attn_fwd_split_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     else launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
@@ -1395,7 +1391,8 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
 }
 
 // experiment switch: 2 = P-in-TMEM forward (default), 1 = split-statistics forward (P through shared memory), 0 = shared-maximum forward
-int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 2 ? 2 : mode); return AOZ_OK; }
+// (2: 1/8 of the exponentials on the FMA pipe; 3 / 4 / 5: the same kernel with 1/4, none, 1/2 -- measurement variants)
+int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 5 ? 2 : mode); return AOZ_OK; }
 
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
 
