@@ -982,51 +982,65 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
     } else if (warp == BWD_CW + 1) {
         // Software pipeline: S / dP of Q tile i+1 are issued as soon as the compute warps have pulled tile i's S / dP into
         // registers, so the tensor pipe works on tile i+1 while they do the exp / dS math of tile i.
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);           // A = P / dS read MN-major, B = dO / Q read MN-major
-            const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);            // A = dS read K-major (over keys), B = K read MN-major
-            const uint32_t sK = smem_u32(smem + KvSmem::K), sV = smem_u32(smem + KvSmem::V);
-            const uint32_t sQ = smem_u32(smem + KvSmem::Q), sDO = smem_u32(smem + KvSmem::DO);
-            const uint32_t sP = smem_u32(smem + KvSmem::PT), sDS = smem_u32(smem + KvSmem::DST);
-            auto issue_scores = [&](int i) {
-                const int s = i % BWD_STAGES;
-                mbar_wait(&q_full[s], (i / BWD_STAGES) & 1);
-                tc_fence_after();
+        // The whole warp runs the loop converged and one elected lane issues (see elect_one_sync in common.cuh); descriptors are the
+        // stage-0 descriptors plus integer offsets on the address field (16-byte units).
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 1, 1);           // A = P / dS read MN-major, B = dO / Q read MN-major
+        const uint32_t idesc_dq = make_idesc_bf16(128, 64, 0, 1);            // A = dS read K-major (over keys), B = K read MN-major
+        const uint64_t dK_k = desc_kmajor(smem_u32(smem + KvSmem::K), 0), dV_k = desc_kmajor(smem_u32(smem + KvSmem::V), 0);
+        const uint64_t dQ_k = desc_kmajor(smem_u32(smem + KvSmem::Q), 0), dDO_k = desc_kmajor(smem_u32(smem + KvSmem::DO), 0);
+        const uint64_t dQ_r = desc_rows_as_k(smem_u32(smem + KvSmem::Q), 0), dDO_r = desc_rows_as_k(smem_u32(smem + KvSmem::DO), 0);
+        const uint64_t dK_r = desc_rows_as_k(smem_u32(smem + KvSmem::K), 0);
+        const uint64_t dP_r = desc_ptile_rows_as_k(smem_u32(smem + KvSmem::PT), 0), dDS_r = desc_ptile_rows_as_k(smem_u32(smem + KvSmem::DST), 0);
+        const uint32_t sDS = smem_u32(smem + KvSmem::DST);
+        constexpr uint64_t STG = TILE_BYTES >> 4;
+        auto issue_scores = [&](int i) {
+            const int s = i % BWD_STAGES;
+            mbar_wait(&q_full[s], (i / BWD_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t q = dQ_k + s * STG, d = dDO_k + s * STG;
+                umma_bf16(tS, q, dK_k, idesc_s, 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ + s * TILE_BYTES, k), desc_kmajor(sK, k), idesc_s, k > 0);
+                for (int k = 1; k < 4; ++k) umma_bf16(tS, q + 2 * k, dK_k + 2 * k, idesc_s, 1u);
+                umma_bf16(tdP, d, dV_k, idesc_s, 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tdP, desc_kmajor(sDO + s * TILE_BYTES, k), desc_kmajor(sV, k), idesc_s, k > 0);
+                for (int k = 1; k < 4; ++k) umma_bf16(tdP, d + 2 * k, dV_k + 2 * k, idesc_s, 1u);
                 umma_commit(s_ready);
-            };
-            mbar_wait(kv_once, 0);
-            issue_scores(0);
-            for (int i = 0; i < nq; ++i) {
-                const int s = i % BWD_STAGES;
-                if (i + 1 < nq) {
-                    mbar_wait(st_free, i & 1);
-                    tc_fence_after();
-                    issue_scores(i + 1);
-                }
-                mbar_wait(pds_ready, i & 1);
+            }
+            __syncwarp();
+        };
+        mbar_wait(kv_once, 0);
+        issue_scores(0);
+        for (int i = 0; i < nq; ++i) {
+            const int s = i % BWD_STAGES;
+            if (i + 1 < nq) {
+                mbar_wait(st_free, i & 1);
                 tc_fence_after();
+                issue_scores(i + 1);
+            }
+            mbar_wait(pds_ready, i & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t q = dQ_r + s * STG, d = dDO_r + s * STG;
+                const uint32_t acc = i > 0 ? 1u : 0u;
+                umma_bf16(tdV, dP_r, d, idesc_acc, acc);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tdV, desc_ptile_rows_as_k(sP, k), desc_rows_as_k(sDO + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                for (int k = 1; k < 8; ++k) umma_bf16(tdV, dP_r + 128 * k, d + 128 * k, idesc_acc, 1u);
+                umma_bf16(tdK, dDS_r, q, idesc_acc, acc);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tdK, desc_ptile_rows_as_k(sDS, k), desc_rows_as_k(sQ + s * TILE_BYTES, k), idesc_acc, (i > 0 || k > 0) ? 1u : 0u);
+                for (int k = 1; k < 8; ++k) umma_bf16(tdK, dDS_r + 128 * k, q + 128 * k, idesc_acc, 1u);
                 if (P.fuse_dq) {
                     // the only KV tile: dQ(i) = dS(i) K is complete after this tile (the compute warps drain it during tile i+1)
 #pragma unroll
-                    for (int k = 0; k < 8; ++k) umma_bf16(tdQ, desc_ptile(sDS, k), desc_rows_as_k(sK, k), idesc_dq, k > 0 ? 1u : 0u);
+                    for (int k = 0; k < 8; ++k) umma_bf16(tdQ, desc_ptile(sDS, k), dK_r + 128 * k, idesc_dq, k > 0 ? 1u : 0u);
                 }
                 umma_commit(&q_empty[s]);
                 umma_commit(pd_free);
                 if (i == nq - 1) umma_commit(acc_ready);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         // compute warps: quarter = warp & 3 (TMEM lanes = query rows), hf = warp >> 2 selects 32 of the tile's 128 key columns
         const int qtr = warp & 3, hf = warp >> 2;
@@ -1221,42 +1235,52 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
             }
         }
     } else if (warp == BWD_CW + 1) {
-        if (lane == 0) {
-            const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
-            const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
-            const uint32_t sQ = smem_u32(smem + DqSmem::Q), sDO = smem_u32(smem + DqSmem::DO);
-            const uint32_t sK = smem_u32(smem + DqSmem::K), sV = smem_u32(smem + DqSmem::V);
-            const uint32_t sDS = smem_u32(smem + DqSmem::DS);
-            auto issue_scores = [&](int j) {
-                const int s = j % BWD_STAGES;
-                mbar_wait(&kv_full[s], (j / BWD_STAGES) & 1);
-                tc_fence_after();
+        // converged warp, one elected lane issues (see elect_one_sync in common.cuh)
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_acc = make_idesc_bf16(128, 64, 0, 1);
+        const uint64_t dQ_k = desc_kmajor(smem_u32(smem + DqSmem::Q), 0), dDO_k = desc_kmajor(smem_u32(smem + DqSmem::DO), 0);
+        const uint64_t dK_k = desc_kmajor(smem_u32(smem + DqSmem::K), 0), dV_k = desc_kmajor(smem_u32(smem + DqSmem::V), 0);
+        const uint64_t dK_r = desc_rows_as_k(smem_u32(smem + DqSmem::K), 0);
+        const uint32_t sDS = smem_u32(smem + DqSmem::DS);
+        constexpr uint64_t STG = TILE_BYTES >> 4;
+        auto issue_scores = [&](int j) {
+            const int s = j % BWD_STAGES;
+            mbar_wait(&kv_full[s], (j / BWD_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t kk = dK_k + s * STG, vv = dV_k + s * STG;
+                umma_bf16(tS, dQ_k, kk, idesc_s, 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tS, desc_kmajor(sQ, k), desc_kmajor(sK + s * TILE_BYTES, k), idesc_s, k > 0);
+                for (int k = 1; k < 4; ++k) umma_bf16(tS, dQ_k + 2 * k, kk + 2 * k, idesc_s, 1u);
+                umma_bf16(tdP, dDO_k, vv, idesc_s, 0u);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) umma_bf16(tdP, desc_kmajor(sDO, k), desc_kmajor(sV + s * TILE_BYTES, k), idesc_s, k > 0);
+                for (int k = 1; k < 4; ++k) umma_bf16(tdP, dDO_k + 2 * k, vv + 2 * k, idesc_s, 1u);
                 umma_commit(s_ready);
-            };
-            mbar_wait(q_once, 0);
-            issue_scores(0);
-            for (int j = 0; j < nkv; ++j) {
-                const int s = j % BWD_STAGES;
-                if (j + 1 < nkv) {
-                    mbar_wait(st_free, j & 1);
-                    tc_fence_after();
-                    issue_scores(j + 1);
-                }
-                mbar_wait(ds_ready, j & 1);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_once, 0);
+        issue_scores(0);
+        for (int j = 0; j < nkv; ++j) {
+            const int s = j % BWD_STAGES;
+            if (j + 1 < nkv) {
+                mbar_wait(st_free, j & 1);
                 tc_fence_after();
+                issue_scores(j + 1);
+            }
+            mbar_wait(ds_ready, j & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t kr = dK_r + s * STG;
+                umma_bf16(tdQ, desc_ptile(sDS, 0), kr, idesc_acc, j > 0 ? 1u : 0u);
 #pragma unroll
-                for (int k = 0; k < 8; ++k)
-                    umma_bf16(tdQ, desc_ptile(sDS, k), desc_rows_as_k(sK + s * TILE_BYTES, k), idesc_acc, (j > 0 || k > 0) ? 1u : 0u);
+                for (int k = 1; k < 8; ++k) umma_bf16(tdQ, desc_ptile(sDS, k), kr + 128 * k, idesc_acc, 1u);
                 umma_commit(&kv_empty[s]);
                 umma_commit(ds_free);
                 if (j == nkv - 1) umma_commit(acc_ready);
             }
+            __syncwarp();
         }
-        __syncwarp();
     } else {
         const int qtr = warp & 3, hf = warp >> 2;            // four warps per TMEM lane quarter, each owns 32 key columns
         const int r = qtr * 32 + lane;
@@ -1380,10 +1404,10 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
         attr = true;
     }
     const int grid = B * H * ((Tq + TILE - 1) / TILE);
-    if (g_fwd_split == 3) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
-    else if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel<0x8080u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
-    else if (g_fwd_split == 4) launch_k(attn_fwd_tm_kernel<0u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
-    else if (g_fwd_split == 5) launch_k(attn_fwd_tm_kernel<0xAAAAu>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    if (g_fwd_split == 6) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 3) launch_k(attn_fwd_tm_kernel<0x8080u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel<0u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 4) launch_k(attn_fwd_tm_kernel<0xAAAAu>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split) launch_k(attn_fwd_split_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     else launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
@@ -1391,8 +1415,9 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
 }
 
 // experiment switch: 2 = P-in-TMEM forward (default), 1 = split-statistics forward (P through shared memory), 0 = shared-maximum forward
-// (2: 1/8 of the exponentials on the FMA pipe; 3 / 4 / 5: the same kernel with 1/4, none, 1/2 -- measurement variants)
-int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 5 ? 2 : mode); return AOZ_OK; }
+// (2: every exponential on the MUFU pipe -- measured as fast as any split, and LSE keeps ex2.approx accuracy; 3 / 6 / 4: the same
+// kernel with 1/8, 1/4, 1/2 of them on the FMA pipe -- measurement variants: 724 / 697 / 584 TFLOP/s against 718 for none)
+int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 6 ? 2 : mode); return AOZ_OK; }
 
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
 

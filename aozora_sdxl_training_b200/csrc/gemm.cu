@@ -433,10 +433,14 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             }
         }
     } else if (warp == 1) {
-        // ================================ MMA issuer (one thread; leader CTA only in pair mode) ================================
-        // Descriptors are advanced by integer adds on their low word: the issue loop must stay far below the
-        // 2*bn-cycle execution time of one K iteration or the tensor pipe starves.
-        if (leader && lane == 0) {
+        // ================================ MMA issuer (leader CTA only in pair mode) ================================
+        // The WHOLE warp runs this loop converged (barrier waits included) and one elected lane issues the tcgen05 instructions: with
+        // `if (lane == 0)` around the loop ptxas kept the descriptors in vector registers and wrapped every tcgen05.mma / commit in an
+        // ELECT + R2UR + BRA.U.ANY sequence (~15 dependent instructions per MMA), so the issuing THREAD paced the tensor pipe (found
+        // with ncu's source view on the attention kernels in round 2; see elect_one_sync in common.cuh).  Converged, the descriptors
+        // live in uniform registers and a K iteration is four back-to-back UTCHMMA.
+        // Descriptors are advanced by integer adds on their low word.
+        if (leader) {
             const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : BM, BN, P.a_mn, P.b_mn);
             const uint64_t hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);   // SBO, version, SW128
             const uint32_t smem_lo = (smem_u32(smem) & 0x3ffffu) >> 4;
@@ -456,20 +460,26 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 for (int kit = k_begin; kit < k_end; ++kit) {
                     if (!(P.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
-                    const uint32_t alo = a_lo0 + stage * stage_step, blo = b_lo0 + stage * stage_step;
+                    if (elect_one_sync()) {
+                        const uint32_t alo = a_lo0 + stage * stage_step, blo = b_lo0 + stage * stage_step;
 #pragma unroll
-                    for (int k = 0; k < BK / 16; ++k) {
-                        const uint64_t da = hi | (uint64_t)(alo + k * a_kstep);
-                        const uint64_t db = hi | (uint64_t)(blo + k * b_kstep);
-                        if (CTA2) umma2_bf16(tmem_d, da, db, idesc, accum); else umma_bf16(tmem_d, da, db, idesc, accum);
-                        accum = 1;
+                        for (int k = 0; k < BK / 16; ++k) {
+                            const uint64_t da = hi | (uint64_t)(alo + k * a_kstep);
+                            const uint64_t db = hi | (uint64_t)(blo + k * b_kstep);
+                            if (CTA2) umma2_bf16(tmem_d, da, db, idesc, k == 0 ? accum : 1u); else umma_bf16(tmem_d, da, db, idesc, k == 0 ? accum : 1u);
+                        }
+                        // frees the smem slot (in both CTAs) when the MMAs retire
+                        if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
                     }
-                    // frees the smem slot (in both CTAs) when the MMAs retire
-                    if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
+                    __syncwarp();
+                    accum = 1;
                     if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
                 }
                 // accumulator complete (an empty split still signals the epilogue)
-                if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+                if (elect_one_sync()) {
+                    if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
+                }
+                __syncwarp();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
