@@ -43,8 +43,14 @@ struct AttnParams {
     __nv_bfloat16* dQ; long long lddq;
     __nv_bfloat16* dK; long long lddk;
     __nv_bfloat16* dV; long long lddv;
-    int fuse_dq;                // dK/dV kernel, one KV tile (cross-attention): dQ = dS K of every Q tile is computed there too
+    int fuse_dq;                // dK/dV kernel also computes dQ = dS K of every Q tile: 1 = one KV tile (cross-attention), stored as
+                                // bf16; 2 = many KV tiles, partial tiles summed into dQacc with red.global.add (fp32)
+    float* dQacc;               // [B, H, Tq, 64] fp32, zeroed by the host (fuse_dq == 2)
 };
+
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" :: "l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
 
 __device__ __forceinline__ float fast_exp2(float x) {
     float y;
@@ -871,7 +877,8 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
 // the row; a warp covers 4 rows = 512 contiguous bytes per tensor when the heads are adjacent
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
-                     long long lddo, int B, int H, int Tq, float* __restrict__ D) {
+                     long long lddo, int B, int H, int Tq, float* __restrict__ D, const float* __restrict__ lse = nullptr,
+                     float* __restrict__ lse2 = nullptr) {
     pdl_enter();
     const long long total = (long long)B * Tq * H * 8;                    // one work item = 8 elements of one row
     const long long bound = (total + 31) & ~31LL;                         // whole warps stay in the loop (full-mask shuffles)
@@ -893,7 +900,11 @@ attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const _
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
-        if (part == 0 && w < (long long)B * Tq * H) D[((long long)b * H + h) * Tq + t] = s;
+        if (part == 0 && w < (long long)B * Tq * H) {
+            const long long idx = ((long long)b * H + h) * Tq + t;
+            D[idx] = s;
+            if (lse2 != nullptr) lse2[idx] = lse[idx] * LOG2E;              // the one-kernel backward works in the log2 domain
+        }
     }
 }
 
@@ -1063,7 +1074,13 @@ attn_bwd_dkv_kernel(const __grid_constant__ AttnParams P) {
             tmem_ld16(tdQ + lane_off + hf * 16, v);
             tc_wait_ld();
             const int q = i * TILE + r;
-            if (q < P.Tq) {
+            if (q < P.Tq && P.fuse_dq == 2) {
+                // this KV tile's share of dQ(i): summed in fp32 across the KV-tile CTAs (unscaled; the convert kernel applies `scale`)
+                float* dst = P.dQacc + (((long long)b * P.H + h) * P.Tq + q) * HD + hf * 16;
+#pragma unroll
+                for (int e = 0; e < 16; e += 4)
+                    red_add_v4(dst + e, __uint_as_float(v[e]), __uint_as_float(v[e + 1]), __uint_as_float(v[e + 2]), __uint_as_float(v[e + 3]));
+            } else if (q < P.Tq) {
                 __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD + hf * 16;
                 const float mul = P.scale;
 #pragma unroll
@@ -1364,6 +1381,374 @@ attn_bwd_dq_kernel(const __grid_constant__ AttnParams P) {
     if (warp == BWD_CW + 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
 }
 
+// ================================================================================================
+// backward, ONE kernel: dK, dV and dQ  (CTA = one KV tile of 128 keys; loop over Q tiles)
+// ================================================================================================
+// Five MMAs and ONE exponential pass per (Q tile, KV tile) pair instead of the seven MMAs and two passes of the dK/dV + dQ pair.
+// Scores are computed KEY-major (S^T = K Q^T, dP^T = V dO^T: a thread owns one key row), so that P^T and dS^T -- written back over
+// the front of the thread's own S^T / dP^T columns as packed bf16 (tcgen05.st) -- are the K-major A operands of dV += P^T dO and
+// dK += dS^T Q straight from TENSOR MEMORY: no shared-memory P tile, no proxy fence for it.  dS^T additionally goes to shared
+// memory once, as the MN-major A operand of dQ(i) = dS(i) K.  dQ(i) is only this KV tile's share: it is double-buffered in TMEM,
+// drained by four dedicated warps into a shared-memory staging tile and added into an fp32 buffer by ONE bulk reduction per tile
+// (cp.reduce.async.bulk .add.f32, 32 KB, issued by the TMA engine: no per-thread atomics on the load/store path -- the per-thread
+// red.global form measured SLOWER than two kernels, profiles/r02_attn_bwd_notes.txt).  attn_dq_tiles_convert_kernel then scales and
+// rounds.  The sum over KV tiles is not bit-reproducible (aoz_attn_set_bwd_mode(0) selects the two-kernel form).
+//
+// Tensor memory (512 columns): S^T | dP^T | dV | dK | dQ0 | dQ1.  The tensor pipe runs half a tile ahead of the compute warps:
+//   issuer:  ... dV(i) S^T(i+1) | dK(i) dQ(i) dP^T(i+1) | dV(i+1) S^T(i+2) | ...
+//   compute: ... exp phase (i)  ->  dS phase (i)        ->  exp phase (i+1) ...
+// S^T(i+1) overwrites P^T(i) and dP^T(i+1) overwrites dS^T(i): both are queued behind the MMAs that read them (in-order pipe).
+constexpr int FB_CW = 16;                                   // compute warps
+constexpr int FB_THREADS = (FB_CW + 2 + 4) * 32;            // + producer + issuer + 4 drain warps (one per TMEM lane quarter)
+constexpr int FB_STAGES = 3;                                // Q / dO / lse2 / D ring
+
+struct FbSmem {
+    static constexpr int K = 0;
+    static constexpr int V = K + TILE_BYTES;
+    static constexpr int Q = V + TILE_BYTES;                      // FB_STAGES
+    static constexpr int DO = Q + FB_STAGES * TILE_BYTES;         // FB_STAGES
+    static constexpr int DST = DO + FB_STAGES * TILE_BYTES;       // 32 KB: dS^T [128 keys][128 queries] bf16, two 64-query blocks
+    static constexpr int DQS = DST + 2 * TILE_BYTES;              // 32 KB: dQ staging tile [128 queries][64] fp32, 16-byte chunks XOR-swizzled
+    static constexpr int VEC = DQS + 2 * TILE_BYTES;              // FB_STAGES x (lse2[128], D[128]) fp32
+    static constexpr int BAR = VEC + FB_STAGES * 1024;
+    static constexpr int TOTAL = BAR + 256 + 1024;
+};
+static_assert(FbSmem::TOTAL <= 227 * 1024, "one-kernel attention backward: shared memory");
+
+__device__ __forceinline__ void tmem_st8(uint32_t taddr, const uint32_t* r) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void bulk_reduce_add_f32(float* gdst, const void* ssrc, uint32_t bytes) {
+    asm volatile("cp.reduce.async.bulk.global.shared::cta.bulk_group.add.f32 [%0], [%1], %2;"
+                 :: "l"(gdst), "r"(smem_u32(ssrc)), "r"(bytes) : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+
+__global__ void __launch_bounds__(FB_THREADS, 1)
+attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t* bars = (uint64_t*)(smem + FbSmem::BAR);
+    uint64_t* kv_once = bars;                 // 1
+    uint64_t* q_full = bars + 1;              // FB_STAGES
+    uint64_t* q_empty = bars + 4;             // FB_STAGES
+    uint64_t* s_ready = bars + 7;             // S^T(i) landed
+    uint64_t* dp_ready = bars + 8;            // dP^T(i) landed
+    uint64_t* p_ready = bars + 9;             // P^T(i) in tensor memory (512 arrivals)
+    uint64_t* ds_ready = bars + 10;           // dS^T(i) in tensor memory and shared memory (512 arrivals)
+    uint64_t* ds_free = bars + 11;            // dQ(i) has retired: the shared dS^T tile may be overwritten
+    uint64_t* dq_ready = bars + 12;           // 2: dQ(i) landed in buffer i & 1
+    uint64_t* dq_free = bars + 14;            // 2: the drain warps have read buffer i & 1 (128 arrivals)
+    uint64_t* acc_ready = bars + 16;
+    uint32_t* tmem_slot = (uint32_t*)(bars + 17);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int kv_tiles = (P.Tk + TILE - 1) / TILE;
+    const int kt = blockIdx.x % kv_tiles;
+    const int bh = blockIdx.x / kv_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int k0 = kt * TILE;
+    const int nq = (P.Tq + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(kv_once, 1);
+        for (int i = 0; i < FB_STAGES; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(dp_ready, 1); mbar_init(p_ready, FB_CW * 32); mbar_init(ds_ready, FB_CW * 32);
+        mbar_init(ds_free, 1);
+        for (int i = 0; i < 2; ++i) { mbar_init(&dq_ready[i], 1); mbar_init(&dq_free[i], 128); }
+        mbar_init(acc_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == FB_CW + 1) tmem_alloc(tmem_slot, 512);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tdP = tmem + 128, tdV = tmem + 256, tdK = tmem + 320, tdQ = tmem + 384;     // dQ buffers: +384, +448
+    pdl_enter();          // prologue done: wait for the previous kernel's results before the first global access
+    const long long vec0 = ((long long)b * P.H + h) * P.Tq;          // first element of this (b, h) in lse2 / D
+
+    if (warp == FB_CW) {
+        // ---------------- TMA producer ----------------
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV); tma_prefetch_desc(&P.tmDO);
+            mbar_arrive_expect_tx(kv_once, 2 * TILE_BYTES);
+            tma_load_4d(smem + FbSmem::K, &P.tmK, kv_once, 0, h, k0, b);
+            tma_load_4d(smem + FbSmem::V, &P.tmV, kv_once, 0, h, k0, b);
+            for (int i = 0; i < nq; ++i) {
+                const int s = i % FB_STAGES;
+                mbar_wait_relaxed(&q_empty[s], ((i / FB_STAGES) & 1) ^ 1);
+                const int rows = min(TILE, P.Tq - i * TILE);                   // Tq is a multiple of 4 here: 16-byte granules
+                mbar_arrive_expect_tx(&q_full[s], 2 * TILE_BYTES + 2 * rows * 4);
+                tma_load_4d(smem + FbSmem::Q + s * TILE_BYTES, &P.tmQ, &q_full[s], 0, h, i * TILE, b);
+                tma_load_4d(smem + FbSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
+                bulk_load_1d(smem + FbSmem::VEC + s * 1024, P.lse + vec0 + i * TILE, rows * 4, &q_full[s]);          // lse * log2(e)
+                bulk_load_1d(smem + FbSmem::VEC + s * 1024 + 512, P.Dvec + vec0 + i * TILE, rows * 4, &q_full[s]);
+            }
+        }
+    } else if (warp == FB_CW + 1) {
+        // ---------------- MMA issuer: converged warp, one elected lane issues (see elect_one_sync) ----------------
+        const uint32_t idesc_s = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_ts = make_idesc_bf16(128, 64, 0, 1);            // A = P^T / dS^T from tensor memory, B = dO / Q rows as K
+        const uint32_t idesc_dq = make_idesc_bf16(128, 64, 1, 1);            // A = dS^T tile in smem read MN-major, B = K rows as K
+        const uint64_t dK_k = desc_kmajor(smem_u32(smem + FbSmem::K), 0), dV_k = desc_kmajor(smem_u32(smem + FbSmem::V), 0);
+        const uint64_t dQ_k = desc_kmajor(smem_u32(smem + FbSmem::Q), 0), dDO_k = desc_kmajor(smem_u32(smem + FbSmem::DO), 0);
+        const uint64_t dQ_r = desc_rows_as_k(smem_u32(smem + FbSmem::Q), 0), dDO_r = desc_rows_as_k(smem_u32(smem + FbSmem::DO), 0);
+        const uint64_t dK_r = desc_rows_as_k(smem_u32(smem + FbSmem::K), 0);
+        const uint64_t dDS_r = desc_ptile_rows_as_k(smem_u32(smem + FbSmem::DST), 0);
+        constexpr uint64_t STG = TILE_BYTES >> 4;
+        auto issue_st = [&](int i) {                                            // S^T(i) = K Q(i)^T
+            const int s = i % FB_STAGES;
+            mbar_wait(&q_full[s], (i / FB_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t q = dQ_k + s * STG;
+                umma_bf16(tS, dK_k, q, idesc_s, 0u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16(tS, dK_k + 2 * k, q + 2 * k, idesc_s, 1u);
+                umma_commit(s_ready);
+            }
+            __syncwarp();
+        };
+        auto issue_dpt = [&](int i) {                                           // dP^T(i) = V dO(i)^T  (its stage was awaited by issue_st)
+            const int s = i % FB_STAGES;
+            if (elect_one_sync()) {
+                const uint64_t d = dDO_k + s * STG;
+                umma_bf16(tdP, dV_k, d, idesc_s, 0u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16(tdP, dV_k + 2 * k, d + 2 * k, idesc_s, 1u);
+                umma_commit(dp_ready);
+            }
+            __syncwarp();
+        };
+        mbar_wait(kv_once, 0);
+        issue_st(0);
+        issue_dpt(0);
+        for (int i = 0; i < nq; ++i) {
+            const int s = i % FB_STAGES;
+            const uint32_t acc = i > 0 ? 1u : 0u;
+            mbar_wait(p_ready, i & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {                                             // dV += P^T(i) dO(i)
+                const uint64_t d = dDO_r + s * STG;
+                umma_bf16_ts(tdV, tS, d, idesc_ts, acc);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) umma_bf16_ts(tdV, tS + 32 * (k >> 1) + 8 * (k & 1), d + 128 * k, idesc_ts, 1u);
+            }
+            __syncwarp();
+            if (i + 1 < nq) issue_st(i + 1);                                    // overwrites P^T(i): queued behind dV(i)
+            mbar_wait(ds_ready, i & 1);
+            tc_fence_after();
+            if (i >= 2) { mbar_wait(&dq_free[i & 1], ((i >> 1) - 1) & 1); tc_fence_after(); }
+            if (elect_one_sync()) {
+                const uint64_t q = dQ_r + s * STG;                              // dK += dS^T(i) Q(i)
+                umma_bf16_ts(tdK, tdP, q, idesc_ts, acc);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) umma_bf16_ts(tdK, tdP + 32 * (k >> 1) + 8 * (k & 1), q + 128 * k, idesc_ts, 1u);
+                const uint32_t tq = tdQ + (i & 1) * 64;                         // dQ(i) = dS(i) K   (this KV tile's share)
+                umma_bf16(tq, dDS_r, dK_r, idesc_dq, 0u);
+#pragma unroll
+                for (int k = 1; k < 8; ++k) umma_bf16(tq, dDS_r + 128 * k, dK_r + 128 * k, idesc_dq, 1u);
+                umma_commit(&dq_ready[i & 1]);
+                umma_commit(ds_free);
+                umma_commit(&q_empty[s]);
+                if (i == nq - 1) umma_commit(acc_ready);
+            }
+            __syncwarp();
+            if (i + 1 < nq) issue_dpt(i + 1);                                   // overwrites dS^T(i): queued behind dK(i)
+        }
+    } else if (warp >= FB_CW + 2) {
+        // ---------------- dQ drain warps: TMEM -> swizzled staging tile -> one bulk reduce-add per Q tile ----------------
+        const int qtr = warp & 3;                                               // warps 18..21 -> lane quarters 2, 3, 0, 1
+        const int r = qtr * 32 + lane;                                          // query row inside the tile
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+        const bool leader = warp == FB_CW + 2 && lane == 0;
+        uint8_t* stage = smem + FbSmem::DQS;
+        const int q_tiles = nq;
+        float* gtile = P.dQacc + ((long long)bh * q_tiles) * (TILE * HD);
+        for (int i = 0; i < nq; ++i) {
+            mbar_wait(&dq_ready[i & 1], (i >> 1) & 1);
+            tc_fence_after();
+            uint32_t v[64];
+            tmem_ld32(tdQ + (i & 1) * 64 + lane_off, v);
+            tmem_ld32(tdQ + (i & 1) * 64 + lane_off + 32, v + 32);
+            tc_wait_ld();
+            tc_fence_before();
+            mbar_arrive(&dq_free[i & 1]);
+            if (leader) bulk_wait_read0();                                      // the previous tile's reduction has read the staging tile
+            named_bar_sync(2, 128);
+#pragma unroll
+            for (int c = 0; c < 16; ++c)                                        // 16-byte chunk c of row r lives at chunk c ^ (r & 15)
+                st_shared_v4(smem_u32(stage) + r * 256 + ((c ^ (r & 15)) << 4), v[4 * c], v[4 * c + 1], v[4 * c + 2], v[4 * c + 3]);
+            fence_proxy_async_smem();
+            named_bar_sync(2, 128);
+            if (leader) bulk_reduce_add_f32(gtile + (long long)i * (TILE * HD), stage, TILE * HD * 4);
+        }
+        if (leader) bulk_wait0();
+    } else {
+        // ---------------- compute warps: qtr = TMEM lane quarter (key rows), hf = which 32 of the tile's 128 query columns ----------------
+        const int qtr = warp & 3, hf = warp >> 2;
+        const int r = qtr * 32 + lane;                                          // key row inside the tile
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+        const uint32_t sDS = smem_u32(smem + FbSmem::DST);
+        const float sl2 = P.scale * LOG2E;
+        const bool key_ok = k0 + r < P.Tk;                                      // padded key rows contribute nothing
+        for (int i = 0; i < nq; ++i) {
+            const int s = i % FB_STAGES;
+            const uint32_t vec = smem_u32(smem + FbSmem::VEC + s * 1024) + hf * 128;         // lse2[hf * 32 ..], D at + 512
+            const int qvalid = P.Tq - i * TILE - hf * 32;                        // this thread's columns >= qvalid are padded queries
+            mbar_wait(&q_full[s], (i / FB_STAGES) & 1);                          // lse2 / D of this Q tile are in shared memory
+            // ---- exp phase: P^T = 2^(S^T sl2 - lse2[q]) ----
+            mbar_wait(s_ready, i & 1);
+            tc_fence_after();
+            float p[32];
+            {
+                uint32_t vs[2][16];
+                tmem_ld16(tS + lane_off + hf * 32, vs[0]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tc_wait_ld();
+                    if (c == 0) tmem_ld16(tS + lane_off + hf * 32 + 16, vs[1]);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 l4 = ld_shared_f4(vec + (c * 16 + e) * 4);
+                        p[c * 16 + e] = fast_exp2(fmaf(__uint_as_float(vs[c][e]), sl2, -l4.x));
+                        p[c * 16 + e + 1] = fast_exp2(fmaf(__uint_as_float(vs[c][e + 1]), sl2, -l4.y));
+                        p[c * 16 + e + 2] = fast_exp2(fmaf(__uint_as_float(vs[c][e + 2]), sl2, -l4.z));
+                        p[c * 16 + e + 3] = fast_exp2(fmaf(__uint_as_float(vs[c][e + 3]), sl2, -l4.w));
+                    }
+                }
+            }
+            if (!key_ok || qvalid < 32) {
+#pragma unroll
+                for (int e = 0; e < 32; ++e) if (!key_ok || e >= qvalid) p[e] = 0.f;
+            }
+            {
+                uint32_t pw[16];
+#pragma unroll
+                for (int e = 0; e < 16; ++e) pw[e] = pack_bf16(p[2 * e], p[2 * e + 1]);
+                tmem_st16(tS + lane_off + hf * 32, pw);                          // over the front of this thread's own S^T columns
+            }
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+            // ---- dS phase: dS^T = P^T (dP^T - D[q]) ----
+            mbar_wait(dp_ready, i & 1);
+            tc_fence_after();
+            uint32_t dsw[16];
+            {
+                uint32_t vp[2][16];
+                tmem_ld16(tdP + lane_off + hf * 32, vp[0]);
+#pragma unroll
+                for (int c = 0; c < 2; ++c) {
+                    tc_wait_ld();
+                    if (c == 0) tmem_ld16(tdP + lane_off + hf * 32 + 16, vp[1]);
+#pragma unroll
+                    for (int e = 0; e < 16; e += 4) {
+                        const float4 d4 = ld_shared_f4(vec + 512 + (c * 16 + e) * 4);
+                        const float a0 = p[c * 16 + e] * (__uint_as_float(vp[c][e]) - d4.x);
+                        const float a1 = p[c * 16 + e + 1] * (__uint_as_float(vp[c][e + 1]) - d4.y);
+                        const float a2 = p[c * 16 + e + 2] * (__uint_as_float(vp[c][e + 2]) - d4.z);
+                        const float a3 = p[c * 16 + e + 3] * (__uint_as_float(vp[c][e + 3]) - d4.w);
+                        dsw[c * 8 + (e >> 1)] = pack_bf16(a0, a1);
+                        dsw[c * 8 + (e >> 1) + 1] = pack_bf16(a2, a3);
+                    }
+                }
+            }
+            if (!key_ok || qvalid < 32) {                                        // padded rows / columns: exact zeros (their lse2 / D slots hold
+#pragma unroll                                                                   // whatever the ring slot held before: 0 x garbage could be NaN)
+                for (int e = 0; e < 16; ++e) if (!key_ok || 2 * e >= qvalid) dsw[e] = 0u;
+            }
+            tmem_st16(tdP + lane_off + hf * 32, dsw);                            // A operand of dK += dS^T Q
+            if (i > 0) mbar_wait(ds_free, (i - 1) & 1);                          // dQ(i-1) has finished reading the shared dS^T tile
+            store_p_16(sDS, r, hf * 32, dsw);                                    // A operand (MN-major) of dQ(i) = dS(i) K
+            store_p_16(sDS, r, hf * 32 + 16, dsw + 8);
+            fence_proxy_async_smem();
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(ds_ready);
+        }
+        mbar_wait(acc_ready, 0);
+        tc_fence_after();
+        const int key = k0 + r;
+        {
+            const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
+            const uint32_t tacc = which == 0 ? tdV : tdK;
+            const float mul = which == 0 ? 1.0f : P.scale;
+            __nv_bfloat16* base = which == 0 ? P.dV : P.dK;
+            const long long ld = which == 0 ? P.lddv : P.lddk;
+            uint32_t v[32];
+            tmem_ld32(tacc + lane_off + c * 32, v);
+            tc_wait_ld();
+            if (key < P.Tk) {
+                __nv_bfloat16* dst = base + ((long long)b * P.Tk + key) * ld + h * HD + c * 32;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    uint4 o;
+                    o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                    o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                    o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                    o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == FB_CW + 1) { tc_fence_after(); tmem_dealloc(tmem, 512); }
+}
+
+// dQ = scale * (sum of the KV tiles' shares): fp32 tiles [B * H][q_tiles][128][64] with XOR-swizzled 16-byte chunks (the staging
+// layout of attn_bwd_fused_kernel) -> bf16 [B, Tq, H, 64] with a row stride
+__global__ void __launch_bounds__(256)
+attn_dq_tiles_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long lddq, int B, int H, int Tq, float scale) {
+    pdl_enter();
+    const int q_tiles = (Tq + TILE - 1) / TILE;
+    const long long total = (long long)B * H * q_tiles * TILE * 8;         // one work item = 8 elements (two 16-byte fp32 chunks)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int part = (int)(i & 7);
+        const long long row = i >> 3;                                     // (bh, tile, r)
+        const int r = (int)(row % TILE);
+        const long long bt = row / TILE;
+        const int tile = (int)(bt % q_tiles);
+        const long long bh = bt / q_tiles;
+        const int q = tile * TILE + r;
+        if (q >= Tq) continue;
+        const int h = (int)(bh % H), b = (int)(bh / H);
+        const float* src = acc + row * HD;
+        const float4 a0 = *reinterpret_cast<const float4*>(src + (((2 * part) ^ (r & 15)) << 2));
+        const float4 a1 = *reinterpret_cast<const float4*>(src + (((2 * part + 1) ^ (r & 15)) << 2));
+        uint4 o;
+        o.x = pack_bf16(a0.x * scale, a0.y * scale); o.y = pack_bf16(a0.z * scale, a0.w * scale);
+        o.z = pack_bf16(a1.x * scale, a1.y * scale); o.w = pack_bf16(a1.z * scale, a1.w * scale);
+        *reinterpret_cast<uint4*>(dq + ((long long)b * Tq + q) * lddq + h * HD + part * 8) = o;
+    }
+}
+
+// dQ = scale * dQacc: fp32 [B, H, Tq, 64] (head-major accumulation buffer) -> bf16 [B, Tq, H, 64] with a row stride
+__global__ void __launch_bounds__(256)
+attn_dq_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long lddq, int B, int H, int Tq, float scale) {
+    pdl_enter();
+    const long long total = (long long)B * H * Tq * 8;                    // one work item = 8 elements
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int part = (int)(i & 7);
+        const long long row = i >> 3;                                     // (b, h, q)
+        const int q = (int)(row % Tq);
+        const long long bh = row / Tq;
+        const int h = (int)(bh % H), b = (int)(bh / H);
+        const float4 a0 = *reinterpret_cast<const float4*>(acc + row * HD + part * 8);
+        const float4 a1 = *reinterpret_cast<const float4*>(acc + row * HD + part * 8 + 4);
+        uint4 o;
+        o.x = pack_bf16(a0.x * scale, a0.y * scale); o.y = pack_bf16(a0.z * scale, a0.w * scale);
+        o.z = pack_bf16(a1.x * scale, a1.y * scale); o.w = pack_bf16(a1.z * scale, a1.w * scale);
+        *reinterpret_cast<uint4*>(dq + ((long long)b * Tq + q) * lddq + h * HD + part * 8) = o;
+    }
+}
+
 static int make_qkv_map(CUtensorMap* m, const void* base, long long ld, int B, int H, int T, int rows = TILE) {
     uint64_t dims[4] = {(uint64_t)HD, (uint64_t)H, (uint64_t)T, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)HD * 2, (uint64_t)ld * 2, (uint64_t)T * (uint64_t)ld * 2};
@@ -1419,12 +1804,23 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
 // kernel with 1/8, 1/4, 1/2 of them on the FMA pipe -- measurement variants: 724 / 697 / 584 TFLOP/s against 718 for none)
 int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 6 ? 2 : mode); return AOZ_OK; }
 
-long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) { return (long long)B * H * Tq; }
+// D vector [B, H, Tq] + the fp32 dQ accumulation buffer [B, H, Tq, 64] of the one-kernel backward
+static long long bwd_vec_floats(int B, int H, int Tq) { return (((long long)B * H * Tq + 31) / 32) * 32; }      // 128-byte granules
+long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) {
+    return 2 * bwd_vec_floats(B, H, Tq) + (long long)B * H * ((Tq + TILE - 1) / TILE) * TILE * HD;
+}
 
 // Measured (profiles/r01_cross_bwd_ab.txt): alone the fused kernel wins (1024 queries x 77 keys x 20 heads: 48.1 -> 30.6 us) and the
 // per-kernel times inside the step drop by 1.2 ms, but the event-timed training step is 1.5 ms SLOWER (139.3 vs 137.8 ms, two
 // runs each): one 80-CTA kernel per layer leaves 68 SMs idle for 25 us where the 640-CTA dQ kernel filled them.  Off by default.
 static int g_fuse_cross_dq = 0;
+// Self-attention (more than one KV tile): 1 = ONE kernel -- the dK/dV kernel also forms dQ(i) = dS(i) K for every Q tile and adds it
+// into an fp32 buffer with red.global.add (5 MMAs and one exponential pass per tile pair instead of 7 and two; the sum over KV tiles
+// is not bit-reproducible), 0 = dK/dV kernel + dQ kernel (bit-reproducible).
+// 2 = attn_bwd_fused_kernel (key-major scores, P^T / dS^T in tensor memory, bulk-reduced dQ; default), 1 = the dK/dV kernel with a
+// per-thread red.global drain (measured slower than two kernels; kept for the record), 0 = two kernels.
+static int g_bwd_fused = 2;
+int aoz_attn_set_bwd_mode(int fused) { g_bwd_fused = fused < 0 ? 0 : (fused > 2 ? 2 : fused); return AOZ_OK; }
 // experiment switch: 1 = cross-attention (Tk <= 128) backward runs as ONE kernel, 0 = dK/dV + dQ kernels (default)
 int aoz_attn_set_fused_cross_bwd(int on) { g_fuse_cross_dq = on ? 1 : 0; return AOZ_OK; }
 
@@ -1451,8 +1847,28 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         const long long items = (long long)B * Tq * H * 8;
         long long blocks = (items + 255) / 256;
         if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-        launch_k(attn_bwd_prep_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace);
+        launch_k(attn_bwd_prep_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace,
+                 (const float*)lse, (float*)workspace + bwd_vec_floats(B, H, Tq));
         AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");
+    }
+    float* const acc_ws = (float*)workspace + 2 * bwd_vec_floats(B, H, Tq);
+    if (Tk > TILE && g_bwd_fused == 2 && (Tq % 4) == 0) {
+        // one kernel: dK, dV and this KV tile's share of dQ; lse is read in the log2 domain from the workspace
+        static bool attr_f = false;
+        if (!attr_f) { cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::TOTAL); attr_f = true; }
+        const int q_tiles = (Tq + TILE - 1) / TILE;
+        cudaError_t e = cudaMemsetAsync(acc_ws, 0, sizeof(float) * (size_t)B * H * q_tiles * TILE * HD, s);
+        if (e != cudaSuccess) { set_error("aoz_attn_bwd: memset: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
+        P.lse = (float*)workspace + bwd_vec_floats(B, H, Tq);
+        P.dQacc = acc_ws;
+        launch_k(attn_bwd_fused_kernel, dim3(B * H * ((Tk + TILE - 1) / TILE)), dim3(FB_THREADS), (size_t)(FbSmem::TOTAL), s, P);
+        AOZ_CHECK_LAUNCH("attn_bwd_fused_kernel");
+        const long long items = (long long)B * H * q_tiles * TILE * 8;
+        long long blocks = (items + 255) / 256;
+        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+        launch_k(attn_dq_tiles_convert_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const float*)acc_ws, (__nv_bfloat16*)dq, lddq, B, H, Tq, scale);
+        AOZ_CHECK_LAUNCH("attn_dq_tiles_convert_kernel");
+        return AOZ_OK;
     }
     static bool attr = false;
     if (!attr) {
@@ -1462,10 +1878,23 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
     }
     // one KV tile (cross-attention, 77 text tokens): the dK/dV kernel's dS tile is all dQ needs, so it computes dQ as well and
     // the dQ launch (one prologue-bound CTA per Q tile: 24..44 us for a few GFLOP) disappears
-    P.fuse_dq = (Tk <= TILE && g_fuse_cross_dq) ? 1 : 0;
+    P.fuse_dq = (Tk <= TILE && g_fuse_cross_dq) ? 1 : ((Tk > TILE && g_bwd_fused == 1) ? 2 : 0);
+    if (P.fuse_dq == 2) {
+        P.dQacc = acc_ws;
+        cudaError_t e = cudaMemsetAsync(P.dQacc, 0, sizeof(float) * (size_t)B * H * Tq * HD, s);
+        if (e != cudaSuccess) { set_error("aoz_attn_bwd: memset: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
+    }
     launch_k(attn_bwd_dkv_kernel, dim3(B * H * ((Tk + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(KvSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dkv_kernel");
-    if (P.fuse_dq) return AOZ_OK;
+    if (P.fuse_dq == 1) return AOZ_OK;
+    if (P.fuse_dq == 2) {
+        const long long items = (long long)B * H * Tq * 8;
+        long long blocks = (items + 255) / 256;
+        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
+        launch_k(attn_dq_convert_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const float*)P.dQacc, (__nv_bfloat16*)dq, lddq, B, H, Tq, scale);
+        AOZ_CHECK_LAUNCH("attn_dq_convert_kernel");
+        return AOZ_OK;
+    }
     launch_k(attn_bwd_dq_kernel, dim3(B * H * ((Tq + TILE - 1) / TILE)), dim3(ATT_BWD_THREADS), (size_t)(DqSmem::TOTAL), s, P);
     AOZ_CHECK_LAUNCH("attn_bwd_dq_kernel");
     return AOZ_OK;

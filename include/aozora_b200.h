@@ -91,6 +91,9 @@ int aoz_attn_set_fwd_split(int mode);
 /* experiment switch: 1 = with a single KV tile (cross-attention, Tk <= 128) the dK/dV kernel also produces dQ and the dQ
  * launch is skipped, 0 = always two kernels (default: the fused form measured slower inside the training step) */
 int aoz_attn_set_fused_cross_bwd(int on);
+/* experiment switch, self-attention backward (Tk > 128): 1 = one kernel, dQ summed over the KV tiles in fp32 with red.global.add
+ * (default; not bit-reproducible), 0 = dK/dV kernel + dQ kernel (bit-reproducible) */
+int aoz_attn_set_bwd_mode(int fused);
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq);
 int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, const void* o,
                  long long ldo, const void* d_o, long long lddo, const void* lse, void* dq, long long lddq, void* dk,
