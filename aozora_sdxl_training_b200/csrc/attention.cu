@@ -1548,6 +1548,12 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
                 umma_bf16_ts(tdK, tdP, q, idesc_ts, acc);
 #pragma unroll
                 for (int k = 1; k < 8; ++k) umma_bf16_ts(tdK, tdP + 32 * (k >> 1) + 8 * (k & 1), q + 128 * k, idesc_ts, 1u);
+            }
+            __syncwarp();
+            if (i + 1 < nq) issue_dpt(i + 1);                                   // overwrites dS^T(i) in TMEM: queued behind dK(i); ahead of
+                                                                                // dQ(i), which reads dS from shared memory (dP^T is on the
+                                                                                // compute warps' critical path, dQ is not)
+            if (elect_one_sync()) {
                 const uint32_t tq = tdQ + (i & 1) * 64;                         // dQ(i) = dS(i) K   (this KV tile's share)
                 umma_bf16(tq, dDS_r, dK_r, idesc_dq, 0u);
 #pragma unroll
@@ -1558,7 +1564,6 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
                 if (i == nq - 1) umma_commit(acc_ready);
             }
             __syncwarp();
-            if (i + 1 < nq) issue_dpt(i + 1);                                   // overwrites dS^T(i): queued behind dK(i)
         }
     } else if (warp >= FB_CW + 2) {
         // ---------------- dQ drain warps: TMEM -> swizzled staging tile -> one bulk reduce-add per Q tile ----------------
@@ -1600,8 +1605,8 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             const int s = i % FB_STAGES;
             const uint32_t vec = smem_u32(smem + FbSmem::VEC + s * 1024) + hf * 128;         // lse2[hf * 32 ..], D at + 512
             const int qvalid = P.Tq - i * TILE - hf * 32;                        // this thread's columns >= qvalid are padded queries
-            mbar_wait(&q_full[s], (i / FB_STAGES) & 1);                          // lse2 / D of this Q tile are in shared memory
             // ---- exp phase: P^T = 2^(S^T sl2 - lse2[q]) ----
+            // (lse2 / D of this Q tile arrived with Q: the issuer waited for q_full before the MMAs that s_ready reports)
             mbar_wait(s_ready, i & 1);
             tc_fence_after();
             float p[32];
