@@ -45,7 +45,10 @@ struct AttnParams {
     __nv_bfloat16* dV; long long lddv;
     int fuse_dq;                // dK/dV kernel also computes dQ = dS K of every Q tile: 1 = one KV tile (cross-attention), stored as
                                 // bf16; 2 = many KV tiles, partial tiles summed into dQacc with red.global.add (fp32)
-    float* dQacc;               // [B, H, Tq, 64] fp32, zeroed by the host (fuse_dq == 2)
+    float* dQacc;               // [B, H, Tq, 64] fp32, zeroed by the host (fuse_dq == 2); one-kernel backward: swizzled fp32 tiles
+    int q_split;                // one-kernel backward: the Q tiles of a KV tile are cut over q_split CTAs (cross-attention: one KV tile,
+    float* dKacc;               //   B * H CTAs would leave most SMs idle); with q_split > 1 the CTAs' dK / dV shares are summed into
+    float* dVacc;               //   these fp32 tile buffers by bulk reduce-add, like dQ
 };
 
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
@@ -1447,11 +1450,15 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int kv_tiles = (P.Tk + TILE - 1) / TILE;
-    const int kt = blockIdx.x % kv_tiles;
-    const int bh = blockIdx.x / kv_tiles;
+    const int qs = blockIdx.x % P.q_split;                  // which share of the Q tiles
+    const int kt = (blockIdx.x / P.q_split) % kv_tiles;
+    const int bh = blockIdx.x / (P.q_split * kv_tiles);
     const int h = bh % P.H, b = bh / P.H;
     const int k0 = kt * TILE;
-    const int nq = (P.Tq + TILE - 1) / TILE;
+    const int q_tiles = (P.Tq + TILE - 1) / TILE;
+    const int per = (q_tiles + P.q_split - 1) / P.q_split;
+    const int i0 = qs * per;                                // this CTA's Q tiles: i0 .. i0 + nq - 1 (loop index i is LOCAL below)
+    const int nq = max(0, min(per, q_tiles - i0));
 
     if (threadIdx.x == 0) {
         mbar_init(kv_once, 1);
@@ -1481,12 +1488,13 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             for (int i = 0; i < nq; ++i) {
                 const int s = i % FB_STAGES;
                 mbar_wait_relaxed(&q_empty[s], ((i / FB_STAGES) & 1) ^ 1);
-                const int rows = min(TILE, P.Tq - i * TILE);                   // Tq is a multiple of 4 here: 16-byte granules
+                const int qrow = (i0 + i) * TILE;
+                const int rows = min(TILE, P.Tq - qrow);                       // Tq is a multiple of 4 here: 16-byte granules
                 mbar_arrive_expect_tx(&q_full[s], 2 * TILE_BYTES + 2 * rows * 4);
-                tma_load_4d(smem + FbSmem::Q + s * TILE_BYTES, &P.tmQ, &q_full[s], 0, h, i * TILE, b);
-                tma_load_4d(smem + FbSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, i * TILE, b);
-                bulk_load_1d(smem + FbSmem::VEC + s * 1024, P.lse + vec0 + i * TILE, rows * 4, &q_full[s]);          // lse * log2(e)
-                bulk_load_1d(smem + FbSmem::VEC + s * 1024 + 512, P.Dvec + vec0 + i * TILE, rows * 4, &q_full[s]);
+                tma_load_4d(smem + FbSmem::Q + s * TILE_BYTES, &P.tmQ, &q_full[s], 0, h, qrow, b);
+                tma_load_4d(smem + FbSmem::DO + s * TILE_BYTES, &P.tmDO, &q_full[s], 0, h, qrow, b);
+                bulk_load_1d(smem + FbSmem::VEC + s * 1024, P.lse + vec0 + qrow, rows * 4, &q_full[s]);          // lse * log2(e)
+                bulk_load_1d(smem + FbSmem::VEC + s * 1024 + 512, P.Dvec + vec0 + qrow, rows * 4, &q_full[s]);
             }
         }
     } else if (warp == FB_CW + 1) {
@@ -1525,8 +1533,7 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             __syncwarp();
         };
         mbar_wait(kv_once, 0);
-        issue_st(0);
-        issue_dpt(0);
+        if (nq > 0) { issue_st(0); issue_dpt(0); }
         for (int i = 0; i < nq; ++i) {
             const int s = i % FB_STAGES;
             const uint32_t acc = i > 0 ? 1u : 0u;
@@ -1572,8 +1579,7 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
         const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
         const bool leader = warp == FB_CW + 2 && lane == 0;
         uint8_t* stage = smem + FbSmem::DQS;
-        const int q_tiles = nq;
-        float* gtile = P.dQacc + ((long long)bh * q_tiles) * (TILE * HD);
+        float* gtile = P.dQacc + ((long long)bh * q_tiles + i0) * (TILE * HD);
         for (int i = 0; i < nq; ++i) {
             mbar_wait(&dq_ready[i & 1], (i >> 1) & 1);
             tc_fence_after();
@@ -1583,6 +1589,24 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             tc_wait_ld();
             tc_fence_before();
             mbar_arrive(&dq_free[i & 1]);
+            if (kv_tiles == 1) {
+                // one KV tile: this IS dQ(i) -- scaled, rounded and stored directly (no accumulation buffer, no convert pass)
+                const int q = (i0 + i) * TILE + r;
+                if (q < P.Tq) {
+                    __nv_bfloat16* dst = P.dQ + ((long long)b * P.Tq + q) * P.lddq + h * HD;
+                    const float mul = P.scale;
+#pragma unroll
+                    for (int e = 0; e < 64; e += 8) {
+                        uint4 o;
+                        o.x = pack_bf16(__uint_as_float(v[e]) * mul, __uint_as_float(v[e + 1]) * mul);
+                        o.y = pack_bf16(__uint_as_float(v[e + 2]) * mul, __uint_as_float(v[e + 3]) * mul);
+                        o.z = pack_bf16(__uint_as_float(v[e + 4]) * mul, __uint_as_float(v[e + 5]) * mul);
+                        o.w = pack_bf16(__uint_as_float(v[e + 6]) * mul, __uint_as_float(v[e + 7]) * mul);
+                        *reinterpret_cast<uint4*>(dst + e) = o;
+                    }
+                }
+                continue;
+            }
             if (leader) bulk_wait_read0();                                      // the previous tile's reduction has read the staging tile
             named_bar_sync(2, 128);
 #pragma unroll
@@ -1604,7 +1628,7 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
         for (int i = 0; i < nq; ++i) {
             const int s = i % FB_STAGES;
             const uint32_t vec = smem_u32(smem + FbSmem::VEC + s * 1024) + hf * 128;         // lse2[hf * 32 ..], D at + 512
-            const int qvalid = P.Tq - i * TILE - hf * 32;                        // this thread's columns >= qvalid are padded queries
+            const int qvalid = P.Tq - (i0 + i) * TILE - hf * 32;                 // this thread's columns >= qvalid are padded queries
             // ---- exp phase: P^T = 2^(S^T sl2 - lse2[q]) ----
             // (lse2 / D of this Q tile arrived with Q: the issuer waited for q_full before the MMAs that s_ready reports)
             mbar_wait(s_ready, i & 1);
@@ -1676,10 +1700,30 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             tc_fence_before();
             mbar_arrive(ds_ready);
         }
-        mbar_wait(acc_ready, 0);
-        tc_fence_after();
+        if (nq > 0) { mbar_wait(acc_ready, 0); tc_fence_after(); }
         const int key = k0 + r;
-        {
+        if (P.q_split > 1) {
+            // this CTA saw only a share of the Q tiles: dV / dK shares (unscaled fp32) go through swizzled staging tiles in the idle
+            // Q / dO ring and two bulk reduce-adds; attn_dq_tiles_convert_kernel rounds (and scales dK) afterwards
+            if (nq > 0) {
+                const int which = hf >> 1, c = hf & 1;
+                uint32_t v[32];
+                tmem_ld32((which == 0 ? tdV : tdK) + lane_off + c * 32, v);
+                tc_wait_ld();
+                const uint32_t st = smem_u32(smem + (which == 0 ? FbSmem::Q : FbSmem::DO)) + r * 256;
+#pragma unroll
+                for (int e = 0; e < 8; ++e)
+                    st_shared_v4(st + (((c * 8 + e) ^ (r & 15)) << 4), v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+                fence_proxy_async_smem();
+            }
+            named_bar_sync(3, FB_CW * 32);
+            if (threadIdx.x == 0 && nq > 0) {
+                const long long tile = ((long long)bh * kv_tiles + kt) * (TILE * HD);
+                bulk_reduce_add_f32(P.dVacc + tile, smem + FbSmem::Q, TILE * HD * 4);
+                bulk_reduce_add_f32(P.dKacc + tile, smem + FbSmem::DO, TILE * HD * 4);
+                bulk_wait0();
+            }
+        } else {
             const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
             const uint32_t tacc = which == 0 ? tdV : tdK;
             const float mul = which == 0 ? 1.0f : P.scale;
@@ -1710,11 +1754,16 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
 // dQ = scale * (sum of the KV tiles' shares): fp32 tiles [B * H][q_tiles][128][64] with XOR-swizzled 16-byte chunks (the staging
 // layout of attn_bwd_fused_kernel) -> bf16 [B, Tq, H, 64] with a row stride
 __global__ void __launch_bounds__(256)
-attn_dq_tiles_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long lddq, int B, int H, int Tq, float scale) {
+attn_dq_tiles_convert_kernel(const float* __restrict__ acc, __nv_bfloat16* __restrict__ dq, long long lddq, int B, int H, int Tq, float scale,
+                             const float* __restrict__ acc2 = nullptr, __nv_bfloat16* __restrict__ out2 = nullptr, long long ld2 = 0,
+                             float scale2 = 1.0f) {
     pdl_enter();
     const int q_tiles = (Tq + TILE - 1) / TILE;
-    const long long total = (long long)B * H * q_tiles * TILE * 8;         // one work item = 8 elements (two 16-byte fp32 chunks)
-    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+    const long long per_tensor = (long long)B * H * q_tiles * TILE * 8;    // one work item = 8 elements (two 16-byte fp32 chunks)
+    const long long total = acc2 != nullptr ? 2 * per_tensor : per_tensor; // second tensor of the same shape (dK and dV in one launch)
+    for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += (long long)gridDim.x * blockDim.x) {
+        long long i = i0;
+        if (i >= per_tensor) { i -= per_tensor; acc = acc2; dq = out2; lddq = ld2; scale = scale2; }
         const int part = (int)(i & 7);
         const long long row = i >> 3;                                     // (bh, tile, r)
         const int r = (int)(row % TILE);
@@ -1812,7 +1861,8 @@ int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 6 ? 
 // D vector [B, H, Tq] + the fp32 dQ accumulation buffer [B, H, Tq, 64] of the one-kernel backward
 static long long bwd_vec_floats(int B, int H, int Tq) { return (((long long)B * H * Tq + 31) / 32) * 32; }      // 128-byte granules
 long long aoz_attn_bwd_workspace_floats(int B, int H, int Tq) {
-    return 2 * bwd_vec_floats(B, H, Tq) + (long long)B * H * ((Tq + TILE - 1) / TILE) * TILE * HD;
+    // D and lse2 vectors, the dQ tile buffer, and (one KV tile, Q tiles cut over several CTAs) one dK and one dV tile per (b, h)
+    return 2 * bwd_vec_floats(B, H, Tq) + (long long)B * H * ((Tq + TILE - 1) / TILE + 2) * TILE * HD;
 }
 
 // Measured (profiles/r01_cross_bwd_ab.txt): alone the fused kernel wins (1024 queries x 77 keys x 20 heads: 48.1 -> 30.6 us) and the
@@ -1857,22 +1907,50 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
         AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");
     }
     float* const acc_ws = (float*)workspace + 2 * bwd_vec_floats(B, H, Tq);
-    if (Tk > TILE && g_bwd_fused == 2 && (Tq % 4) == 0) {
+    if (g_bwd_fused == 2 && (Tq % 4) == 0) {
         // one kernel: dK, dV and this KV tile's share of dQ; lse is read in the log2 domain from the workspace
         static bool attr_f = false;
         if (!attr_f) { cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::TOTAL); attr_f = true; }
-        const int q_tiles = (Tq + TILE - 1) / TILE;
-        cudaError_t e = cudaMemsetAsync(acc_ws, 0, sizeof(float) * (size_t)B * H * q_tiles * TILE * HD, s);
-        if (e != cudaSuccess) { set_error("aoz_attn_bwd: memset: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
+        const int q_tiles = (Tq + TILE - 1) / TILE, kv_tiles = (Tk + TILE - 1) / TILE;
+        // One KV tile (cross-attention): B * H CTAs would leave most of the 148 SMs idle, so the Q tiles are cut over q_split CTAs
+        // (about two waves of CTAs, at least two Q tiles each) whose dK / dV shares are summed like dQ.
+        int q_split = 1;
+        if (kv_tiles == 1) {
+            q_split = (2 * sm_count() + B * H - 1) / (B * H);
+            if (q_split > (q_tiles + 1) / 2) q_split = (q_tiles + 1) / 2;
+            if (q_split < 1) q_split = 1;
+            const int per = (q_tiles + q_split - 1) / q_split;
+            q_split = (q_tiles + per - 1) / per;                    // no CTA without a Q tile
+        }
+        const long long dq_floats = (long long)B * H * q_tiles * TILE * HD, kv_floats = (long long)B * H * kv_tiles * TILE * HD;
+        // zeroed: the dQ tile buffer when several KV tiles add into it; the dK / dV tile buffers when several CTAs share a KV tile
+        float* const z0 = kv_tiles > 1 ? acc_ws : acc_ws + dq_floats;
+        const long long zn = (kv_tiles > 1 ? dq_floats : 0) + (q_split > 1 ? 2 * kv_floats : 0);
+        if (zn > 0) {
+            cudaError_t e = cudaMemsetAsync(z0, 0, sizeof(float) * (size_t)zn, s);
+            if (e != cudaSuccess) { set_error("aoz_attn_bwd: memset: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
+        }
         P.lse = (float*)workspace + bwd_vec_floats(B, H, Tq);
         P.dQacc = acc_ws;
-        launch_k(attn_bwd_fused_kernel, dim3(B * H * ((Tk + TILE - 1) / TILE)), dim3(FB_THREADS), (size_t)(FbSmem::TOTAL), s, P);
+        P.dKacc = acc_ws + dq_floats;
+        P.dVacc = acc_ws + dq_floats + kv_floats;
+        P.q_split = q_split;
+        launch_k(attn_bwd_fused_kernel, dim3(B * H * kv_tiles * q_split), dim3(FB_THREADS), (size_t)(FbSmem::TOTAL), s, P);
         AOZ_CHECK_LAUNCH("attn_bwd_fused_kernel");
-        const long long items = (long long)B * H * q_tiles * TILE * 8;
-        long long blocks = (items + 255) / 256;
-        if (blocks > sm_count() * 16) blocks = sm_count() * 16;
-        launch_k(attn_dq_tiles_convert_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const float*)acc_ws, (__nv_bfloat16*)dq, lddq, B, H, Tq, scale);
-        AOZ_CHECK_LAUNCH("attn_dq_tiles_convert_kernel");
+        auto blocks_for = [&](long long items) {
+            long long blocks = (items + 255) / 256;
+            return (int)(blocks > sm_count() * 16 ? sm_count() * 16 : blocks);
+        };
+        if (kv_tiles > 1) {                                         // (one KV tile: the drain warps stored dQ directly)
+            launch_k(attn_dq_tiles_convert_kernel, dim3(blocks_for((long long)B * H * q_tiles * TILE * 8)), dim3(256), (size_t)(0), s,
+                     (const float*)P.dQacc, (__nv_bfloat16*)dq, lddq, B, H, Tq, scale, (const float*)nullptr, (__nv_bfloat16*)nullptr, 0LL, 1.0f);
+            AOZ_CHECK_LAUNCH("attn_dq_tiles_convert_kernel");
+        }
+        if (q_split > 1) {                                          // dK (scaled) and dV in one launch
+            launch_k(attn_dq_tiles_convert_kernel, dim3(blocks_for(2LL * B * H * kv_tiles * TILE * 8)), dim3(256), (size_t)(0), s,
+                     (const float*)P.dKacc, (__nv_bfloat16*)dk, lddk, B, H, Tk, scale, (const float*)P.dVacc, (__nv_bfloat16*)dv, lddv, 1.0f);
+            AOZ_CHECK_LAUNCH("attn_dq_tiles_convert_kernel");
+        }
         return AOZ_OK;
     }
     static bool attr = false;

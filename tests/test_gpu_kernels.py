@@ -269,7 +269,8 @@ def test_attention_forward_variants_agree(B, H, Tq, Tk):
 
 
 def test_cross_attention_backward_one_kernel_equals_two_kernels():
-    """With one KV tile (77 text tokens) the dK/dV kernel also produces dQ; same dS tile, same MMA chain as the dQ kernel."""
+    """The bit-reproducible two-kernel backward (aoz_attn_set_bwd_mode(0)): with one KV tile (77 text tokens) its dK/dV kernel can
+    also produce dQ; same dS tile, same MMA chain as the dQ kernel -> identical bits."""
     from aozora_sdxl_training_b200 import _lib
     ops = _ops()
     g = gen(16)
@@ -279,13 +280,43 @@ def test_cross_attention_backward_one_kernel_equals_two_kernels():
     o, lse = ops.attn_fwd(q, k, v, 0.125)
     res = {}
     try:
+        _lib.call("aoz_attn_set_bwd_mode", 0)
         for fused in (1, 0):
             _lib.call("aoz_attn_set_fused_cross_bwd", fused)
             res[fused] = [t.clone() for t in ops.attn_bwd(q, k, v, o, do, lse, 0.125)]
     finally:
         _lib.call("aoz_attn_set_fused_cross_bwd", 0)
+        _lib.call("aoz_attn_set_bwd_mode", 2)
     for a, b in zip(res[1], res[0]):
         assert torch.equal(a, b)
+
+
+@pytest.mark.parametrize("B,H,Tq,Tk", [(2, 10, 1024, 1024), (1, 3, 1008, 1008), (2, 10, 1024, 77), (1, 10, 4096, 77), (1, 2, 64, 64),
+                                        (1, 2, 300, 40), (1, 5, 988, 154), (1, 2, 300, 128), (2, 3, 200, 77)])
+def test_attention_backward_variants_agree(B, H, Tq, Tk):
+    """The one-kernel backward (key-major scores, P^T / dS^T in tensor memory, dQ -- and with a single KV tile dK / dV -- summed over
+    CTAs by bulk reduce-add in fp32; default) against the bit-reproducible dK/dV + dQ kernel pair: the same five products with
+    different rounding points (dS is formed from the unrounded P in both) -> equal within bf16 rounding of the results; both against
+    fp32 autograd."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(36)
+    q, do = [torch.randn(B, Tq, H, 64, device="cuda", generator=g).to(BF16) for _ in range(2)]
+    k, v = [torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(BF16) for _ in range(2)]
+    o, lse = ops.attn_fwd(q, k, v, 0.125)
+    res = {}
+    try:
+        for mode in (2, 0):
+            _lib.call("aoz_attn_set_bwd_mode", mode)
+            res[mode] = [t.clone() for t in ops.attn_bwd(q, k, v, o, do, lse, 0.125)]
+    finally:
+        _lib.call("aoz_attn_set_bwd_mode", 2)
+    qr, kr, vr = [t.float().permute(0, 2, 1, 3).requires_grad_(True) for t in (q, k, v)]
+    torch.nn.functional.scaled_dot_product_attention(qr, kr, vr, scale=0.125).backward(do.float().permute(0, 2, 1, 3))
+    for a, b, ref in zip(res[2], res[0], (qr.grad, kr.grad, vr.grad)):
+        check(a, b, rel=6e-3)
+        check(a, ref.permute(0, 2, 1, 3), rel=8e-3)
+        check(b, ref.permute(0, 2, 1, 3), rel=8e-3)
 
 
 @pytest.mark.parametrize("NB,HW,C,silu", [(2, 64, 320, True), (2, 256, 1280, False), (1, 100, 960, True), (4, 4096, 320, True),
