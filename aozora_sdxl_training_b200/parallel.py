@@ -12,6 +12,13 @@ ways, replacing the reference's CPU offload, raven.py:64-69/114-117).  After the
 owned slices -> all-reduce of one fp32 scalar -> clip coefficient on device -> ONE multi-tensor Raven launch over the
 owned segments -> per-bucket **all-gather** of the updated bf16 parameters.  No host synchronisation anywhere.
 
+``defer_all_gather=True`` moves that all-gather off the tail of the step: it is issued at the START of the next step, bucket by
+bucket in the order the forward pass first touches the parameters (embeddings, conv_in, down blocks, mid block, up blocks, output
+convolution -- not the flat / registration order, in which ``mid_block`` comes last), asynchronously on NCCL's stream, and every
+UNet block waits only for the buckets that hold its own weights (``gate``): the transfer hides behind the down path instead of
+being 4.5 GB of serial tail at 8 GPUs.  Between steps the non-owned slices of ``flat_p`` are then stale: anything that reads the
+parameters outside a step (checkpoint export, evaluation, comparing weights) calls ``gather_params()`` first.
+
 Deviation stated: the data-parallel gradient norm is the fp32 norm of the summed gradient (torch's bf16 per-tensor
 rounding, SURVEY.md a7, cannot be reproduced on slices); the single-GPU path emulates it exactly.
 """
@@ -180,8 +187,13 @@ class ShardedRavenAdamW(RavenAdamW):
 
 class DataParallel:
     def __init__(self, unet, momentum_dtype=torch.bfloat16, bucket_mb=64, group=None, backend=None, flat_dtype=None,
-                 bucket_elems=None):
+                 bucket_elems=None, defer_all_gather=False):
         self.group = group
+        self.defer_all_gather = bool(defer_all_gather)
+        self._params_stale = False           # deferred mode: the last update's slices have not been gathered yet
+        self._ag_works = None                # deferred mode, inside a step: (bucket, work) in issue order, not yet waited for
+        self._gate_rank = {}                 # module -> how many all-gathers (in issue order) must have completed before it runs
+        self._ag_order = None
         self.world = dist.get_world_size(group)
         self.rank = dist.get_rank(group)
         self.backend = backend or _KernelBackend
@@ -226,6 +238,75 @@ class DataParallel:
         self._coef = torch.zeros(2, dtype=torch.float32, device=self.device)
         self.optimizer = None
         self._reset_pending()
+        if self.defer_all_gather:
+            self._plan_gather_order(unet)
+
+    # ---- deferred all-gather -------------------------------------------------------------------------------
+    def _plan_gather_order(self, unet):
+        """Order the buckets by first use in the forward pass and note, per gated module, how many of them it needs.  Gated modules
+        are the units ``UNet2DConditionModel.forward_nhwc`` announces (``_forward_units``); a model without that method gets one
+        gate over everything."""
+        units = list(unet._forward_units()) if hasattr(unet, "_forward_units") else [unet]
+        order, seen = [], set()
+        self._gate_rank = {}
+        for mod in units:
+            need = 0
+            for p in mod.parameters(recurse=True):
+                i = self.index.get(p)
+                if i is None:
+                    continue
+                for k in self.param_buckets[i]:
+                    if k not in seen:
+                        seen.add(k)
+                        order.append(k)
+                    need = max(need, order.index(k) + 1)
+            self._gate_rank[mod] = need
+        for k in range(len(self.layout.buckets)):               # buckets no announced module touches (padding only): last
+            if k not in seen:
+                order.append(k)
+        self._ag_order = order
+
+    def _all_gather_bucket(self, k, async_op):
+        s, e = self.layout.buckets[k]
+        n = (e - s) // self.world
+        mine = self.flat_p[s + self.rank * n:s + (self.rank + 1) * n]
+        if dist.get_backend(self.group) == "nccl":
+            return dist.all_gather_into_tensor(self.flat_p[s:e], mine, group=self.group, async_op=async_op)
+        outs = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(outs, mine.clone(), group=self.group)
+        self.flat_p[s:e].copy_(torch.cat(outs))
+        return None
+
+    def begin_forward(self):
+        """Deferred mode, first thing in a step: issue the all-gather of the previous update, every bucket asynchronously, in
+        forward-use order.  Always issued (the first step gathers identical data): a captured step must not depend on host state."""
+        if not self.defer_all_gather:
+            return
+        self._ag_works = [(k, self._all_gather_bucket(k, async_op=True)) for k in self._ag_order]
+        self._ag_done = 0
+        # NCCL writes flat_p behind autograd's back: caches keyed on the version counters (the UNet's packed conv weights) must be
+        # rebuilt by this forward pass -- each after its module's gate, i.e. from gathered data
+        torch.autograd.graph.increment_version(self.params)
+
+    def gate(self, mod=None):
+        """Make the current stream wait for the buckets ``mod`` reads (``None``: all of them)."""
+        if self._ag_works is None:
+            return
+        need = len(self._ag_works) if mod is None else self._gate_rank.get(mod, len(self._ag_works))
+        while self._ag_done < need:
+            w = self._ag_works[self._ag_done][1]
+            if w is not None:
+                w.wait()
+            self._ag_done += 1
+        if self._ag_done == len(self._ag_works):
+            self._ag_works = None
+            self._params_stale = False
+
+    def gather_params(self):
+        """Deferred mode, outside a step: bring every rank's ``flat_p`` up to date (no-op when it already is)."""
+        if self.defer_all_gather and self._params_stale:
+            self.begin_forward()
+            self.gate(None)
 
     def make_optimizer(self, **raven_kwargs):
         opt = ShardedRavenAdamW([{"params": self.params, "lr_scale": 1.0}], momentum_dtype=self.momentum_dtype, **raven_kwargs)
@@ -365,16 +446,12 @@ class DataParallel:
         be.clip_coef(sumsq, max_norm if clip else 3.0e38, self._coef)
         be.raven(seg_p, seg_g, seg_m, seg_v, self._plan, hyper, self._coef[1:2] if clip else None, self.dtype, self.dtype,
                  opt._momentum_dtype, **kw)
-        # all-gather the updated parameter slices (in place inside flat_p)
-        for k, (s, e) in enumerate(self.layout.buckets):
-            n = (e - s) // self.world
-            mine = self.flat_p[s + self.rank * n:s + (self.rank + 1) * n]
-            if dist.get_backend(self.group) == "nccl":
-                dist.all_gather_into_tensor(self.flat_p[s:e], mine, group=self.group)
-            else:
-                outs = [torch.empty_like(mine) for _ in range(self.world)]
-                dist.all_gather(outs, mine.clone(), group=self.group)
-                self.flat_p[s:e].copy_(torch.cat(outs))
+        # all-gather the updated parameter slices (in place inside flat_p) -- or leave it to the start of the next step
+        if self.defer_all_gather:
+            self._params_stale = True
+        else:
+            for k in range(len(self.layout.buckets)):
+                self._all_gather_bucket(k, async_op=False)
         # the parameters changed behind autograd's back (kernels / NCCL wrote flat_p): bump their version counters so caches
         # keyed on them -- the packed conv weights of the UNet -- are rebuilt (RavenAdamW.step does the same)
         torch.autograd.graph.increment_version(self.params)

@@ -121,6 +121,8 @@ def run_training(config, unet, *, device="cuda", dp=None, optimizer=None, resume
             on_step(step.micro_step, res)
         if save_every and res.did_optimizer_step and step.optimizer_steps % save_every == 0:
             gs = step.optimizer_steps
+            if dp is not None:
+                dp.gather_params()                 # deferred all-gather: the export below reads every rank's full parameters
             state_path = out_dir / f"{stem}_training_state_step_{gs}.pt"
             # under data parallel every rank takes part in the gather inside save_cpu_state; rank 0 writes
             st = checkpoint.save_training_state(state_path if rank == 0 else out_dir / f".rank{rank}_{stem}_state.pt", global_step=gs,
@@ -132,5 +134,7 @@ def run_training(config, unet, *, device="cuda", dp=None, optimizer=None, resume
                     checkpoint.save_model(out_dir / f"{stem}_step_{gs}.safetensors", unet, base_checkpoint_path,
                                           getattr(config, "compute_dtype", torch.bfloat16))
                 saved.append(state_path)
+    if dp is not None:
+        dp.gather_params()
     loss_values = torch.cat([l.reshape(1).float() for l in losses]).cpu().tolist() if losses else []
     return dict(losses=loss_values, micro_step=step.micro_step, saved=saved, step=step)

@@ -112,9 +112,16 @@ class SDXLTrainStep:
         """Everything that runs on the GPU for one micro-step (graph-capturable: no host reads, static shapes).
         ``global_len``: rows of the GLOBAL batch of this micro-step -- the loss is the mean over them (train.py:2408-2416), so
         the sum of the ranks' gradients is the single-process gradient also when the ranks hold unequal row counts."""
+        if self.dp is not None and self.dp.defer_all_gather:
+            # the all-gather of the PREVIOUS update starts now and hides behind the down path: every UNet block waits only for the
+            # buckets that hold its own weights
+            self.dp.begin_forward()
+            self.unet.param_gate = self.dp.gate
         xt8, target, cond = ops.noise_target(latents, noise, tickets, None if self.is_rf else self.alphas_cumprod, jitter,
                                              self.prediction_type, cpad=8)
         pred, bwd = self.unet.forward_nhwc(xt8, cond, embeds, pooled, time_ids, taps=taps)
+        if self.dp is not None and self.dp.defer_all_gather:
+            self.dp.gate(None)
         denom = float(global_len)
         loss, _, dpred8 = ops.mse_loss(pred, target, tickets, self.loss_table, denom=denom,
                                        grad_scale=1.0 / (denom * self.grad_accum), pred_nhwc=True, dpred_ld=8)
@@ -167,6 +174,9 @@ class SDXLTrainStep:
         collectives with an all-zero gradient, so the reduce-scatter / all-gather sequence stays aligned across ranks."""
         global_len, row_offset = self._global_rows(batch, 0)
         tickets, _ = self.sampler.sample_rows(global_len, row_offset, 0)
+        if self.dp.defer_all_gather:                   # the other ranks open their step with the all-gather of the previous update
+            self.dp.begin_forward()
+            self.dp.gate(None)
         self.micro_step += 1
         if self.lr_scheduler is not None:
             self.lr_scheduler.step(self.micro_step)

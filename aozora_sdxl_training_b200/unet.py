@@ -645,6 +645,32 @@ class UNet2DConditionModel(nn.Module):
         pass
 
     # ---- core: forward over channels-last tensors, returning the reverse-sweep closure -------------------
+    def _forward_units(self):
+        """The modules ``forward_nhwc`` announces to ``param_gate`` before it first reads their parameters, in execution order
+        (data parallel with a deferred all-gather orders its buckets by this and lets every unit wait only for its own)."""
+        yield self.time_embedding
+        yield self.add_embedding
+        yield self.conv_in
+        for blk in self.down_blocks:
+            for i, res in enumerate(blk.resnets):
+                yield res
+                if blk.attentions is not None:
+                    yield blk.attentions[i]
+            if blk.downsamplers is not None:
+                yield blk.downsamplers[0]
+        yield self.mid_block.resnets[0]
+        yield self.mid_block.attentions[0]
+        yield self.mid_block.resnets[1]
+        for blk in self.up_blocks:
+            for i, res in enumerate(blk.resnets):
+                yield res
+                if blk.attentions is not None:
+                    yield blk.attentions[i]
+            if blk.upsamplers is not None:
+                yield blk.upsamplers[0]
+        yield self.conv_norm_out
+        yield self.conv_out
+
     def forward_nhwc(self, x8, cond, ctx, text_embeds, time_ids, taps=None):
         """x8: [B,H,W,8] bf16 (latent channels zero-padded to 8); cond: fp32 [B] timesteps; ctx: [B,Tc,ctx_dim] bf16;
         text_embeds [B,pooled] bf16; time_ids [B,6] (bf16 values).  Returns (pred [B,H,W,out_channels] bf16, bwd) where
@@ -657,9 +683,11 @@ class UNet2DConditionModel(nn.Module):
         B = x8.shape[0]
         Tc = ctx.shape[1]
         ctx2 = ctx.reshape(B * Tc, ctx.shape[2]).contiguous()
+        gate = getattr(self, "param_gate", None) or (lambda mod: None)       # see _forward_units
 
         # --- embeddings (Timesteps -> MLP; text_time addition embedding) ---
         t_emb = ops.timestep_embedding(cond.float().contiguous(), cfg.block_out_channels[0])
+        gate(self.time_embedding)
         e1, b_te1 = _linear(t_emb, self.time_embedding.linear_1.weight, self.time_embedding.linear_1.bias, G, need_dx=False)
         e1s = ops.silu_fwd(e1)
         e2, b_te2 = _linear(e1s, self.time_embedding.linear_2.weight, self.time_embedding.linear_2.bias, G)
@@ -667,6 +695,7 @@ class UNet2DConditionModel(nn.Module):
         add_in = torch.empty((B, cfg.add_in_dim), dtype=BF16, device=x8.device)
         ops.copy_channels(text_embeds.contiguous(), 0, add_in, 0, cfg.pooled_dim)
         ops.copy_channels(tid.view(B, 6 * cfg.addition_time_embed_dim), 0, add_in, cfg.pooled_dim, 6 * cfg.addition_time_embed_dim)
+        gate(self.add_embedding)
         a1, b_ae1 = _linear(add_in, self.add_embedding.linear_1.weight, self.add_embedding.linear_1.bias, G, need_dx=False)
         a1s = ops.silu_fwd(a1)
         emb, b_ae2 = _linear(a1s, self.add_embedding.linear_2.weight, self.add_embedding.linear_2.bias, G, residual=e2)
@@ -675,19 +704,23 @@ class UNet2DConditionModel(nn.Module):
         tape = []          # closures in forward order: (kind, fn)
 
         # --- down path ---
+        gate(self.conv_in)
         x, b_cin = _conv(x8, self.conv_in, G, packs, need_dx=False, cin_real=cfg.in_channels)
         skips = [x]
         tape.append(("conv_in", b_cin))
         for bi, blk in enumerate(self.down_blocks):
             for i, res in enumerate(blk.resnets):
+                gate(res)
                 x, b_r = _resnet(res, x, semb, G, packs)
                 tape.append(("res", b_r))
                 if blk.attentions is not None:
+                    gate(blk.attentions[i])
                     x, b_a = _transformer(blk.attentions[i], x, ctx2, Tc, G)
                     tape.append(("attn", b_a))
                 skips.append(x)
                 tape.append(("skip_out", None))
             if blk.downsamplers is not None:
+                gate(blk.downsamplers[0])
                 x, b_d = _conv(x, blk.downsamplers[0].conv, G, packs, stride=2)
                 tape.append(("conv", b_d))
                 skips.append(x)
@@ -695,10 +728,13 @@ class UNet2DConditionModel(nn.Module):
             if taps is not None:
                 taps[f"down_blocks.{bi}"] = x
         # --- mid ---
+        gate(self.mid_block.resnets[0])
         x, b_r = _resnet(self.mid_block.resnets[0], x, semb, G, packs)
         tape.append(("res", b_r))
+        gate(self.mid_block.attentions[0])
         x, b_a = _transformer(self.mid_block.attentions[0], x, ctx2, Tc, G)
         tape.append(("attn", b_a))
+        gate(self.mid_block.resnets[1])
         x, b_r = _resnet(self.mid_block.resnets[1], x, semb, G, packs)
         tape.append(("res", b_r))
         if taps is not None:
@@ -709,20 +745,25 @@ class UNet2DConditionModel(nn.Module):
                 skip = skips.pop()
                 cat = ops.concat_channels(x, skip)
                 tape.append(("cat", (x.shape[-1], skip.shape[-1])))
+                gate(res)
                 x, b_r = _resnet(res, cat, semb, G, packs)
                 del cat
                 tape.append(("res", b_r))
                 if blk.attentions is not None:
+                    gate(blk.attentions[i])
                     x, b_a = _transformer(blk.attentions[i], x, ctx2, Tc, G)
                     tape.append(("attn", b_a))
             if blk.upsamplers is not None:
+                gate(blk.upsamplers[0])
                 xu = ops.upsample2x_fwd(x)
                 x, b_u = _conv(xu, blk.upsamplers[0].conv, G, packs)
                 del xu
                 tape.append(("up", b_u))
             if taps is not None:
                 taps[f"up_blocks.{bi}"] = x
+        gate(self.conv_norm_out)
         hn, b_gno = _groupnorm(x, self.conv_norm_out, G, silu=True)
+        gate(self.conv_out)
         pred, b_cout = _conv(hn, self.conv_out, G, packs)
         del hn, x
         n_skips = 3 * len(self.up_blocks)

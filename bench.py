@@ -322,6 +322,8 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured step")
+    ap.add_argument("--no-defer-all-gather", action="store_true",
+                    help="data parallel: all-gather the updated parameters at the end of the step instead of behind the next forward pass")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))
@@ -382,7 +384,7 @@ def main():
     cfg = type("BenchCfg", (Cfg,), dict(BATCH_SIZE=args.batch * world, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=alloc))
     if world > 1:
         from aozora_sdxl_training_b200.parallel import DataParallel
-        dp = DataParallel(unet, momentum_dtype=torch.bfloat16)
+        dp = DataParallel(unet, momentum_dtype=torch.bfloat16, defer_all_gather=not args.no_defer_all_gather)
         opt = dp.make_optimizer(lr=8e-7, **Cfg.RAVEN)
     else:
         opt = RavenAdamW([{"params": [p for p in unet.parameters() if p.requires_grad], "lr_scale": 1.0}], lr=8e-7,
@@ -460,7 +462,9 @@ def main():
     line = dict(metric=metric, value=round(value, 3), unit="imgs/s", n_gpus=world, steps=args.steps, warmup=max(3, args.warmup),
                 ms_per_step=round(ms_dev / args.steps, 3), higher_is_better=True, scaling="weak", vs_baseline=None, dtype="bf16",
                 data="synthetic",
-                config=dict(workload=workload, global_batch=args.batch * world, parallelism=f"dp{world}",
+                config=dict(workload=workload, global_batch=args.batch * world,
+                            parallelism=f"dp{world}" + ("" if world == 1 else (" (sharded Raven; parameter all-gather behind the next forward pass)"
+                                                                               if not args.no_defer_all_gather else " (sharded Raven)")),
                             l2="per-step working set (5.1 GB weights + activations) far exceeds the 126 MB L2; no explicit flush",
                             recompute="none (all activations kept in HBM)",
                             launch="CUDA graph replay of the captured step" if use_graph else "eager",

@@ -117,10 +117,85 @@ def _worker(rank, world, port, q):
         dist.destroy_process_group()
 
 
+def _worker_deferred(rank, world, port, q):
+    """Deferred all-gather: after an update only the owned slices of flat_p are current; begin_forward + gates (in forward-use
+    order, here: reverse registration order) restore every rank's copy to what the immediate all-gather produces."""
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from aozora_sdxl_training_b200.parallel import DataParallel
+        shapes = [(5,), (40, 25), (17,), (3, 3, 8, 8), (3,), (701,)]
+
+        class Net(torch.nn.Module):
+            def __init__(self):
+                super().__init__()
+                torch.manual_seed(0)
+                self.units = torch.nn.ModuleList([torch.nn.ParameterList([torch.nn.Parameter(torch.randn(s))]) for s in shapes])
+
+            def _forward_units(self):                # "forward" touches the units in reverse registration order
+                return reversed(list(self.units))
+
+        results = {}
+        for defer in (False, True):
+            net = Net()
+            dp = DataParallel(net, momentum_dtype=torch.float32, backend=_OracleBackend, flat_dtype=torch.float32, bucket_elems=256,
+                              defer_all_gather=defer)
+            opt = dp.make_optimizer(**HP)
+            _OracleBackend.hp = HP
+            if defer:
+                nb = len(dp.layout.buckets)
+                assert sorted(dp._ag_order) == list(range(nb)) and dp._ag_order[0] == dp.param_buckets[-1][0]     # the last parameter's buckets go first
+                for u in net.units:                                                              # a unit's gate covers its own buckets
+                    own = {k for p in u.parameters() for k in dp.param_buckets[dp.index[p]]}
+                    assert own <= set(dp._ag_order[:dp._gate_rank[u]])
+            for step in (1, 2):
+                _OracleBackend.step = step
+                if defer:
+                    dp.begin_forward()
+                    for u in net._forward_units():
+                        dp.gate(u)
+                    dp.gate(None)
+                    assert not dp._params_stale
+                for i in reversed(range(len(shapes))):
+                    g = torch.randn(shapes[i], generator=torch.Generator().manual_seed(1000 * step + 10 * rank + i))
+                    dp.grad_ready(dp.params[i], g)
+                dp.reduce_clip_step(opt, 0.5)
+            if defer:
+                assert dp._params_stale
+                stale = dp.flat_p.clone()
+                dp.gather_params()
+                assert not dp._params_stale and not torch.equal(stale, dp.flat_p)
+                dp.gather_params()                                                                  # idempotent
+            results[defer] = dp.flat_p.clone()
+        assert torch.equal(results[True], results[False])
+        q.put((rank, "ok"))
+    except Exception:
+        import traceback
+        q.put((rank, traceback.format_exc()))
+    finally:
+        dist.destroy_process_group()
+
+
 def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+@pytest.mark.timeout(180)
+def test_deferred_all_gather_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_deferred, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=150) for _ in procs]
+    for p in procs:
+        p.join(timeout=30)
+    for rank, msg in results:
+        assert msg == "ok", f"rank {rank}: {msg}"
 
 
 @pytest.mark.timeout(180)

@@ -47,7 +47,8 @@ def main():
     cfg = type("C", (Cfg,), dict(BATCH_SIZE=B))
     # data-parallel run
     m_dp = init_weights_(UNet2DConditionModel(tiny_config()), seed=7, std=0.05).to(BF16).to(dev)
-    dp = DataParallel(m_dp, momentum_dtype=torch.float32)
+    defer = "--defer" in sys.argv            # all-gather of the updated parameters deferred into the next step's forward pass
+    dp = DataParallel(m_dp, momentum_dtype=torch.float32, defer_all_gather=defer)
     opt_dp = dp.make_optimizer(**hp)
     use_graph = "--graph" in sys.argv
     step_dp = SDXLTrainStep(m_dp, opt_dp, cfg, device=dev, dp=dp, use_cuda_graph=use_graph, graph_warmup=2)
@@ -68,6 +69,7 @@ def main():
         if rank == 0:
             print(f"step {i}: loss dp {l_dp.item():.6f} single {r_1.loss.item():.6f} rel {rel:.2e} | grad norm rel {gn_rel:.2e}", flush=True)
         ok = ok and rel < 3e-3 and gn_rel < 3e-2
+    dp.gather_params()                        # deferred mode: the last update's slices are gathered on demand
     num = sum(float((a.detach().float() - c.detach().float()).abs().sum()) for a, c in zip(m_dp.parameters(), m_1.parameters()))
     den = sum(float(c.detach().float().abs().sum()) for c in m_1.parameters())
     moved = sum(float((c.detach().float() - init_weights_(UNet2DConditionModel(tiny_config()), seed=7, std=0.05).to(BF16).state_dict()[n].to(dev).float()).abs().sum())
@@ -78,7 +80,7 @@ def main():
     t = torch.tensor([1.0 if ok else 0.0], device=dev)
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
     if rank == 0:
-        print("DP PARITY", "OK" if t.item() == 1.0 else "FAILED", flush=True)
+        print("DP PARITY", "(deferred all-gather)" if defer else "", "(graph)" if use_graph else "(eager)", "OK" if t.item() == 1.0 else "FAILED", flush=True)
     dist.barrier()
     torch.cuda.synchronize()
     code = 0 if t.item() == 1.0 else 1
