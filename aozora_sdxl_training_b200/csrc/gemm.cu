@@ -812,6 +812,15 @@ wgrad_permute_reduce_kernel(const float* __restrict__ partial, int splits, long 
 static int g_dbg = 0;
 static int g_force_bn = 0;        // > 0: experiments only (aoz_gemm_force_bn)
 static int g_pair_mode = 1;       // 0 = single-CTA tiles only, 1 = the cost model may use CTA pairs (default), 2 = force pairs
+// SMs the persistent GEMM / conv launches may occupy (0 = all).  Under data parallel NCCL's reduce-scatter / all-gather kernels run
+// beside the reverse sweep: a persistent launch sized to all 148 SMs then has CTAs that cannot start until an NCCL CTA leaves their
+// SM (231 KB of shared memory per GEMM CTA), and with static work assignment every such CTA holds the whole launch back.  Leaving
+// NCCL its SMs (NCCL_MAX_CTAS of them) costs their share of the tensor throughput and removes the stall.
+static int g_gemm_sm_budget = 0;
+static inline int gemm_sms() {
+    const int n = sm_count();
+    return (g_gemm_sm_budget > 0 && g_gemm_sm_budget < n) ? g_gemm_sm_budget : n;
+}
 static int g_tail_mode = 1;       // 0 = never cut the last wave along K, 1 = the cost model may (default), 2 = whenever possible
 static float* g_tail_ws = nullptr;        // caller-owned scratch for the tail slices (aoz_gemm_set_scratch)
 static long long g_tail_bytes = 0;
@@ -843,10 +852,10 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     P.stages = SMEM_TILE_BYTES / stage_bytes;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     if (!CTA2) {
-        const int grid = total_work < sm_count() ? total_work : sm_count();
+        const int grid = total_work < gemm_sms() ? total_work : gemm_sms();
         launch_k(gemm_bf16_kernel<false>, dim3(grid), dim3(GEMM_THREADS), (size_t)(GEMM_SMEM_TOTAL), stream, P);
     } else {
-        const int pairs = sm_count() / 2;
+        const int pairs = gemm_sms() / 2;
         const int grid = 2 * (total_work < pairs ? total_work : pairs);
         cudaLaunchConfig_t cfg;
         memset(&cfg, 0, sizeof(cfg));
@@ -881,7 +890,7 @@ struct TilePlan { int bn; bool pair; int n_tiles; double cycles; int tail_tiles,
 template <class UnitsFn>
 static TilePlan plan_tiles_core(UnitsFn units_of, bool can_pair, int k_iters_per_unit, int splits, bool b_mn, bool geglu, bool allow_tail) {
     TilePlan best{128, false, 0, 1e300, 0, 1}, best_tail{128, false, 0, 1e300, 0, 1};
-    const int sms = sm_count();
+    const int sms = gemm_sms();
     const int step = b_mn ? 64 : 32;
     for (int pair = 0; pair <= 1; ++pair) {
         if (pair && (g_pair_mode == 0 || !can_pair)) continue;
@@ -947,7 +956,7 @@ static std::unordered_map<std::string, TilePlan> g_tuned;
 template <class UnitsFn>
 static std::vector<TilePlan> enumerate_plans(UnitsFn units_of, bool can_pair, int k_iters_per_unit, bool b_mn, bool geglu, bool allow_tail) {
     std::vector<TilePlan> out;
-    const int sms = sm_count();
+    const int sms = gemm_sms();
     const int step = b_mn ? 64 : 32;
     for (int pair = 0; pair <= 1; ++pair) {
         if (pair && !can_pair) continue;
@@ -1039,6 +1048,7 @@ extern "C" {
 
 // 0 = single-CTA tiles only, 1 = cost model may choose CTA-pair (cta_group::2) tiles (default), 2 = force pairs
 int aoz_gemm_set_pair_mode(int mode) { g_pair_mode = mode; return AOZ_OK; }
+int aoz_gemm_set_sm_budget(int sms) { g_gemm_sm_budget = sms > 0 ? (sms & ~1) : 0; return AOZ_OK; }      // even: CTA pairs
 
 // 0 = never split the last wave along K, 1 = cost model decides (default), 2 = split whenever the shape allows it
 int aoz_gemm_set_tail_mode(int mode) { g_tail_mode = mode; return AOZ_OK; }

@@ -25,6 +25,7 @@ import time
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+NCCL_CTAS_DEFAULT = 0                # data parallel: CTAs (and SMs) reserved for NCCL; see --nccl-ctas
 TRAIN_TFLOP_PER_IMG = 20.28          # fwd + dgrad + wgrad at 1024x1024, SURVEY.md 8d (recompute not counted)
 
 
@@ -322,6 +323,9 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kernel-table", action="store_true")
     ap.add_argument("--no-graph", action="store_true", help="issue every kernel from Python instead of replaying the captured step")
+    ap.add_argument("--nccl-ctas", type=int, default=-1,
+                    help="data parallel: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and leave them their own SMs (persistent GEMMs are "
+                         "sized to the rest); 0 = NCCL defaults, all SMs to the GEMMs; default: the measured best")
     ap.add_argument("--no-defer-all-gather", action="store_true",
                     help="data parallel: all-gather the updated parameters at the end of the step instead of behind the next forward pass")
     args = ap.parse_args()
@@ -365,14 +369,21 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     dp = None
+    nccl_ctas = args.nccl_ctas if args.nccl_ctas >= 0 else NCCL_CTAS_DEFAULT
     if world > 1:
         import torch.distributed as dist
+        if nccl_ctas > 0:                                  # read by NCCL when the communicator is created
+            os.environ["NCCL_MAX_CTAS"] = str(nccl_ctas)
+            os.environ["NCCL_MIN_CTAS"] = str(min(nccl_ctas, int(os.environ.get("NCCL_MIN_CTAS", nccl_ctas))))
         dist.init_process_group("nccl", device_id=dev)
     from aozora_sdxl_training_b200 import ops
     from aozora_sdxl_training_b200.optimizers import RavenAdamW
     from aozora_sdxl_training_b200.trainer import SDXLTrainStep
     from aozora_sdxl_training_b200.unet import UNet2DConditionModel, init_weights_fast_, sdxl_config
     peaks = load_peaks()
+    if world > 1 and nccl_ctas > 0:
+        from aozora_sdxl_training_b200 import _lib as _l
+        _l.call("aoz_gemm_set_sm_budget", _l.query("aoz_sm_count") - nccl_ctas)
 
     from aozora_sdxl_training_b200 import host
     with torch.device(dev):
@@ -468,7 +479,7 @@ def main():
                             l2="per-step working set (5.1 GB weights + activations) far exceeds the 126 MB L2; no explicit flush",
                             recompute="none (all activations kept in HBM)",
                             launch="CUDA graph replay of the captured step" if use_graph else "eager",
-                            untimed_steps=n_warm + 2),
+                            untimed_steps=n_warm + 2, **({"nccl_ctas": nccl_ctas} if world > 1 else {})),
                 e2e=dict(value=round(e2e_val, 3), unit="imgs/s", h2d_bytes_per_step=h2d, d2h_bytes_per_step=4,
                          ms_per_step=round(ms_e2e / args.steps, 3),
                          how="SDXLTrainStep.step(batch in pinned host memory) + loss_value() per step, host wall clock"),

@@ -48,6 +48,10 @@ int aoz_clip_coef_from_sumsq(const void* sumsq, float max_norm, int emulate_bf16
 /* ---- dense contractions [3P]: nn.Linear (to_q/k/v, to_out.0, proj_in/out, ff.net.0.proj + GEGLU, ff.net.2,
  *      time/add embedding MLPs) forward, dgrad, wgrad; nn.Conv2d 3x3/1x1 as implicit GEMM -------------------- */
 int aoz_gemm_set_pair_mode(int mode);
+/* SMs the persistent GEMM / conv launches may occupy (0 = all, rounded down to even): data-parallel runs leave NCCL's CTAs their own
+ * SMs (set NCCL_MAX_CTAS to the difference) so that no persistent CTA waits behind a collective kernel.  Set before the first GEMM:
+ * tile plans are cached per shape. */
+int aoz_gemm_set_sm_budget(int sms);
 int aoz_gemm_force_bn(int bn);
 /* tail split: tiles of the last, partly filled wave are cut along K across the idle SMs (fp32 slices in the caller-owned
  * scratch, finished by a fix-up kernel).  mode 0 = off, 1 = cost model decides (default), 2 = whenever possible.
