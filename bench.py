@@ -138,9 +138,12 @@ def gemm_roofline(torch, peaks, iters=20):
                 peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this exact launch from the committed `ncu --set full` capture
                 # (algorithmic bytes: 36.7 MB operands + 125.8 MB outputs, part of the output still in L2 when the kernel ends)
-                traffic=113691392, traffic_source="profiles/r01_gemm_geglu_ncu_v5.txt (dram__bytes_read 36.91 MB + dram__bytes_write 76.78 MB)",
+                traffic=113007616, traffic_source="profiles/r02_gemm_geglu_ncu_v1.txt (dram__bytes_read 36.91 MB + dram__bytes_write 76.10 MB)",
                 peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
-                flops_per_launch=flops)
+                flops_per_launch=flops,
+                # the whole GEMM / conv family inside the step (1211 launches, FLOP-weighted): tools/gemm_in_step.py, recorded once per round
+                family_in_step=dict(tflops=878.3, frac_of_burst=round(878.3 / peaks["tf_burst"], 4), ms=81.64, launches=1211,
+                                    source="profiles/r02_gemm_in_step_v1.txt (71.70 TFLOP of GEMM / conv work per step in 81.64 ms)"))
 
 
 def kernel_table(torch, peaks, param_numels=None):
