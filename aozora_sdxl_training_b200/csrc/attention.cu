@@ -46,6 +46,8 @@ struct AttnParams {
     int fuse_dq;                // dK/dV kernel also computes dQ = dS K of every Q tile: 1 = one KV tile (cross-attention), stored as
                                 // bf16; 2 = many KV tiles, partial tiles summed into dQacc with red.global.add (fp32)
     float* dQacc;               // [B, H, Tq, 64] fp32, zeroed by the host (fuse_dq == 2); one-kernel backward: swizzled fp32 tiles
+    int fwd_full, fwd_split;    // forward: CTAs that take a whole (b, h, Q tile) unit; CTAs per unit of the cut tail wave
+    float* fwd_ws;              // forward: [tail units][fwd_split][128][64 + 4] fp32 shares (O, reference, row sum, pad)
     int q_split;                // one-kernel backward: the Q tiles of a KV tile are cut over q_split CTAs (cross-attention: one KV tile,
     float* dKacc;               //   B * H CTAs would leave most SMs idle); with q_split > 1 the CTAs' dK / dV shares are summed into
     float* dVacc;               //   these fp32 tile buffers by bulk reduce-add, like dQ
@@ -660,11 +662,23 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int q_tiles = (P.Tq + TILE - 1) / TILE;
-    const int qt = blockIdx.x % q_tiles;
-    const int bh = blockIdx.x / q_tiles;
+    // Work units are (b, h, Q tile).  The first P.fwd_full CTAs take one whole unit each; the units of the last, partly filled wave
+    // are cut along the keys over P.fwd_split CTAs each (their unnormalised O, reference and row sum go to P.fwd_ws and
+    // attn_fwd_combine_kernel merges them): 1280 equal CTAs on 592 slots would otherwise cost three waves for 2.16 waves of work.
+    const int kv_all = (P.Tk + KT - 1) / KT;
+    int unit = blockIdx.x, j0 = 0, nkv = kv_all, part = -1;
+    if ((int)blockIdx.x >= P.fwd_full) {
+        const int idx = blockIdx.x - P.fwd_full;
+        unit = P.fwd_full + idx / P.fwd_split;
+        part = idx % P.fwd_split;
+        const int per = (kv_all + P.fwd_split - 1) / P.fwd_split;
+        j0 = part * per;
+        nkv = max(0, min(per, kv_all - j0));                 // key tiles j0 .. j0 + nkv - 1 (the loop index j below is LOCAL)
+    }
+    const int qt = unit % q_tiles;
+    const int bh = unit / q_tiles;
     const int h = bh % P.H, b = bh / P.H;
     const int q0 = qt * TILE;
-    const int nkv = (P.Tk + KT - 1) / KT;
 
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
@@ -689,8 +703,8 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
                 const int s = j % TM_STAGES;
                 mbar_wait_relaxed(&kv_empty[s], ((j / TM_STAGES) & 1) ^ 1);
                 mbar_arrive_expect_tx(&kv_full[s], 2 * KT_BYTES);
-                tma_load_4d(smem + TmSmem::K + s * KT_BYTES, &P.tmK, &kv_full[s], 0, h, j * KT, b);
-                tma_load_4d(smem + TmSmem::V + s * KT_BYTES, &P.tmV, &kv_full[s], 0, h, j * KT, b);
+                tma_load_4d(smem + TmSmem::K + s * KT_BYTES, &P.tmK, &kv_full[s], 0, h, (j0 + j) * KT, b);
+                tma_load_4d(smem + TmSmem::V + s * KT_BYTES, &P.tmV, &kv_full[s], 0, h, (j0 + j) * KT, b);
             }
         }
     } else if (warp == 5) {
@@ -715,7 +729,7 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
             __syncwarp();
         };
         mbar_wait(q_full, 0);
-        issue_s(0);
+        if (nkv > 0) issue_s(0);
         for (int j = 0; j < nkv; ++j) {
             const int s = j % TM_STAGES;
             mbar_wait(p_ready, j & 1);
@@ -804,7 +818,7 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
         for (int j = 0; j < nkv; ++j) {
             mbar_wait(s_ready, j & 1);                       // also: P V(j-1) has retired, O may be rescaled
             tc_fence_after();
-            const int kvalid = P.Tk - j * KT;                // keys >= kvalid are padding
+            const int kvalid = P.Tk - (j0 + j) * KT;         // keys >= kvalid are padding
             uint32_t w[32];
             float lsum = 0.f;
             if (j == 0) {
@@ -844,9 +858,22 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
             tc_fence_before();
             mbar_arrive(p_ready);
         }
-        mbar_wait(o_ready, 0);
-        tc_fence_after();
+        if (nkv > 0) { mbar_wait(o_ready, 0); tc_fence_after(); }
         const int q = q0 + r;
+        if (part >= 0) {
+            // a share of the keys: unnormalised accumulator, reference and row sum (an empty share: l = 0, reference -inf)
+            const long long slot = (long long)(unit - P.fwd_full) * P.fwd_split + part;
+            float* wo = P.fwd_ws + (slot * TILE + r) * (HD + 4);
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                if (nkv > 0) { tmem_ld32(tO + lane_off + c * 32, v); tc_wait_ld(); }
+#pragma unroll
+                for (int e = 0; e < 32; e += 2)
+                    *reinterpret_cast<float2*>(wo + c * 32 + e) = nkv > 0 ? make_float2(__uint_as_float(v[e]), __uint_as_float(v[e + 1])) : make_float2(0.f, 0.f);
+            }
+            *reinterpret_cast<float2*>(wo + HD) = make_float2(m_ref, l);
+        } else {
         const float inv_l = 1.0f / l;
 #pragma unroll 1
         for (int c = 0; c < 2; ++c) {
@@ -867,10 +894,53 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
             }
         }
         if (q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m_ref + log2f(l)) * LN2;
+        }
     }
     tc_fence_before();
     __syncthreads();
     if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+// Merge the key shares of the units that attn_fwd_tm_kernel cut (see there): one thread per (unit, row, 8 output columns).
+//   m = max_i m_i,  L = sum_i l_i 2^(m_i - m),  O = sum_i O_i 2^(m_i - m) / L,  LSE = (m + log2 L) ln 2
+__global__ void __launch_bounds__(256)
+attn_fwd_combine_kernel(const float* __restrict__ ws, int n_units, int unit0, int split, int B, int H, int Tq, __nv_bfloat16* __restrict__ O,
+                        long long ldo, float* __restrict__ lse) {
+    pdl_enter();
+    const int q_tiles = (Tq + TILE - 1) / TILE;
+    const long long total = (long long)n_units * TILE * 8;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long long)gridDim.x * blockDim.x) {
+        const int c8 = (int)(i & 7);
+        const long long ur = i >> 3;
+        const int r = (int)(ur % TILE);
+        const int u = (int)(ur / TILE);
+        const int unit = unit0 + u;
+        const int qt = unit % q_tiles, bh = unit / q_tiles;
+        const int h = bh % H, b = bh / H;
+        const int q = qt * TILE + r;
+        if (q >= Tq) continue;
+        const float* base = ws + ((long long)u * split * TILE + r) * (HD + 4);
+        const long long pstride = (long long)TILE * (HD + 4);
+        float m = -INFINITY;
+        for (int p = 0; p < split; ++p) m = fmaxf(m, base[p * pstride + HD]);
+        float L = 0.f, acc[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int p = 0; p < split; ++p) {
+            const float* wp = base + p * pstride;
+            const float lp = wp[HD + 1];
+            if (lp <= 0.f) continue;                                     // empty share
+            const float w = fast_exp2(wp[HD] - m);
+            L = fmaf(lp, w, L);
+            const float4 a = *reinterpret_cast<const float4*>(wp + c8 * 8), c = *reinterpret_cast<const float4*>(wp + c8 * 8 + 4);
+            acc[0] = fmaf(a.x, w, acc[0]); acc[1] = fmaf(a.y, w, acc[1]); acc[2] = fmaf(a.z, w, acc[2]); acc[3] = fmaf(a.w, w, acc[3]);
+            acc[4] = fmaf(c.x, w, acc[4]); acc[5] = fmaf(c.y, w, acc[5]); acc[6] = fmaf(c.z, w, acc[6]); acc[7] = fmaf(c.w, w, acc[7]);
+        }
+        const float inv = 1.0f / L;
+        uint4 o;
+        o.x = pack_bf16(acc[0] * inv, acc[1] * inv); o.y = pack_bf16(acc[2] * inv, acc[3] * inv);
+        o.z = pack_bf16(acc[4] * inv, acc[5] * inv); o.w = pack_bf16(acc[6] * inv, acc[7] * inv);
+        *reinterpret_cast<uint4*>(O + ((long long)b * Tq + q) * ldo + h * HD + c8 * 8) = o;
+        if (c8 == 0) lse[((long long)b * H + h) * Tq + q] = (m + log2f(L)) * LN2;
+    }
 }
 
 // ================================================================================================
@@ -1818,8 +1888,42 @@ extern "C" {
 
 static int g_fwd_split = 2;       // 2 = P-in-TMEM kernel (default), 1 = split-statistics kernel (P through smem), 0 = shared-maximum kernel
 
+// Tail-wave plan of the P-in-TMEM forward: how many CTAs take whole units, and into how many key shares each remaining unit is cut.
+static void fwd_tail_plan(int units, int kv_tiles, int* full, int* split) {
+    const int slots = TM_CTAS * sm_count();
+    const int rem = units % slots;
+    *full = units; *split = 1;
+    if (units < slots || rem == 0 || 4 * rem > 3 * slots || kv_tiles < 4) return;     // one wave, or a tail that is nearly full anyway
+    int s = slots / rem;                                                               // shares that fit beside each other
+    if (s > kv_tiles / 2) s = kv_tiles / 2;                                            // at least two key tiles per share
+    if (s < 2) return;
+    *full = units - rem; *split = s;
+}
+// Measured (profiles/r02_attn_bench_tail_split.json): 4096 tokens x 10 heads 729 against 718 TFLOP/s, 1024 tokens x 20 heads 410 against
+// 467 -- co-resident CTAs share the MUFU pipe, so a thinly filled last "wave" simply runs faster per CTA; the cut only adds
+// prologues and a merge launch.  Off by default.
+static int g_fwd_tail_split = 0;
+// experiment switch: 1 = cut the units of the last, partly filled wave along the keys, 0 = every CTA takes a whole unit (default)
+int aoz_attn_set_fwd_tail_split(int on) { g_fwd_tail_split = on ? 1 : 0; return AOZ_OK; }
+
+long long aoz_attn_fwd_workspace_floats(int B, int H, int Tq, int Tk) {
+    int full, split;
+    fwd_tail_plan(B * H * ((Tq + TILE - 1) / TILE), (Tk + KT - 1) / KT, &full, &split);
+    const int units = B * H * ((Tq + TILE - 1) / TILE);
+    return split > 1 ? (long long)(units - full) * split * TILE * (HD + 4) : 0;
+}
+
+int aoz_attn_fwd_ws(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                    void* lse, int B, int H, int Tq, int Tk, float scale, void* workspace, void* stream);
+
 int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
                  void* lse, int B, int H, int Tq, int Tk, float scale, void* stream) {
+    return aoz_attn_fwd_ws(q, ldq, k, ldk, v, ldv, o, ldo, lse, B, H, Tq, Tk, scale, nullptr, stream);
+}
+
+// `workspace`: aoz_attn_fwd_workspace_floats(B, H, Tq, Tk) floats, or null (then every CTA takes a whole unit)
+int aoz_attn_fwd_ws(const void* q, long long ldq, const void* k, long long ldk, const void* v, long long ldv, void* o, long long ldo,
+                    void* lse, int B, int H, int Tq, int Tk, float scale, void* workspace, void* stream) {
     AOZ_CHECK_ARG(q && k && v && o && lse, "aoz_attn_fwd: null pointer");
     AOZ_CHECK_ARG(B > 0 && H > 0 && Tq > 0 && Tk > 0, "aoz_attn_fwd: empty problem");
     AOZ_CHECK_ARG((ldq % 8) == 0 && (ldk % 8) == 0 && (ldv % 8) == 0 && (ldo % 8) == 0, "aoz_attn_fwd: strides must be multiples of 8");
@@ -1842,7 +1946,13 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
         cudaFuncSetAttribute(attn_fwd_tm_kernel<0xAAAAu>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
         attr = true;
     }
-    const int grid = B * H * ((Tq + TILE - 1) / TILE);
+    int grid = B * H * ((Tq + TILE - 1) / TILE);
+    P.fwd_full = grid; P.fwd_split = 1; P.fwd_ws = nullptr;
+    const int units = grid;
+    if (g_fwd_split >= 2 && workspace != nullptr && g_fwd_tail_split) {
+        fwd_tail_plan(units, (Tk + KT - 1) / KT, &P.fwd_full, &P.fwd_split);
+        if (P.fwd_split > 1) { P.fwd_ws = (float*)workspace; grid = P.fwd_full + (units - P.fwd_full) * P.fwd_split; }
+    }
     if (g_fwd_split == 6) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split == 3) launch_k(attn_fwd_tm_kernel<0x8080u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel<0u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
@@ -1850,6 +1960,13 @@ int aoz_attn_fwd(const void* q, long long ldq, const void* k, long long ldk, con
     else if (g_fwd_split) launch_k(attn_fwd_split_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     else launch_k(attn_fwd_kernel, dim3(grid), dim3(ATT_FWD_THREADS), (size_t)(FwdSmem::TOTAL), (cudaStream_t)stream, P);
     AOZ_CHECK_LAUNCH("attn_fwd_kernel");
+    if (P.fwd_split > 1) {
+        const int n_tail = units - P.fwd_full;
+        long long blocks = ((long long)n_tail * TILE * 8 + 255) / 256;
+        launch_k(attn_fwd_combine_kernel, dim3((int)blocks), dim3(256), (size_t)(0), (cudaStream_t)stream, (const float*)P.fwd_ws, n_tail, P.fwd_full,
+                 P.fwd_split, B, H, Tq, (__nv_bfloat16*)o, ldo, (float*)lse);
+        AOZ_CHECK_LAUNCH("attn_fwd_combine_kernel");
+    }
     return AOZ_OK;
 }
 

@@ -268,6 +268,28 @@ def test_attention_forward_variants_agree(B, H, Tq, Tk):
     check(res[2][0], ref, rel=6e-3)
 
 
+def test_attention_forward_tail_wave_key_split():
+    """Switchable path (off by default): the units of the last, partly filled wave of forward CTAs are cut along the keys and merged
+    by attn_fwd_combine_kernel -- same softmax, one more merge: equal within bf16 rounding, LSE to 2e-5."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(46)
+    B, H, Tq, Tk = 4, 10, 4096, 1024                    # 1280 units on 592 slots: 96 tail units, cut six ways
+    q = torch.randn(B, Tq, H, 64, device="cuda", generator=g).to(BF16)
+    k, v = [torch.randn(B, Tk, H, 64, device="cuda", generator=g).to(BF16) for _ in range(2)]
+    o0, lse0 = ops.attn_fwd(q, k, v, 0.125)
+    try:
+        _lib.call("aoz_attn_set_fwd_tail_split", 1)
+        ops._ATTN_FWD_TAIL_SPLIT = True
+        assert _lib.query("aoz_attn_fwd_workspace_floats", B, H, Tq, Tk) > 0
+        o1, lse1 = ops.attn_fwd(q, k, v, 0.125)
+    finally:
+        _lib.call("aoz_attn_set_fwd_tail_split", 0)
+        ops._ATTN_FWD_TAIL_SPLIT = False
+    check(o1, o0, rel=4e-3)
+    assert (lse1 - lse0).abs().max().item() < 2e-5
+
+
 def test_cross_attention_backward_one_kernel_equals_two_kernels():
     """The bit-reproducible two-kernel backward (aoz_attn_set_bwd_mode(0)): with one KV tile (77 text tokens) its dK/dV kernel can
     also produce dQ; same dS tile, same MMA chain as the dQ kernel -> identical bits."""
