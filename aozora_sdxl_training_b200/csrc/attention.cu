@@ -683,7 +683,7 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(q_full, 1);
         for (int i = 0; i < TM_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(p_ready, 128); mbar_init(o_ready, 1);
+        mbar_init(s_ready, 1); mbar_init(p_ready, 4); mbar_init(o_ready, 1);      // p_ready: ONE arrival per softmax warp
         fence_mbar_init();
     }
     if (warp == 5) tmem_alloc(tmem_slot, 128);
@@ -856,7 +856,8 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
             tmem_st32(tS + lane_off, w);
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(p_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);             // one arrival per warp: 32 same-address arrivals serialise in the MIO pipe
         }
         if (nkv > 0) { mbar_wait(o_ready, 0); tc_fence_after(); }
         const int q = q0 + r;
@@ -899,6 +900,260 @@ attn_fwd_tm_kernel(const __grid_constant__ AttnParams P) {
     tc_fence_before();
     __syncthreads();
     if (warp == 5) { tc_fence_after(); tmem_dealloc(tmem, 128); }
+}
+
+// ================================================================================================
+// forward, P-in-TMEM form with 128-key tiles and two threads per query row (measurement variant, aoz_attn_set_fwd_split(7))
+// ================================================================================================
+// Same ingredients as attn_fwd_tm_kernel, other balance: one S -> P -> P V round trip (~900 cycles through two mbarriers and the tensor
+// pipe) per 128 keys instead of per 64; two threads per row with SEPARATE references, row sums and O accumulators (S | O_a | O_b =
+// 256 TMEM columns, two CTAs of 8 softmax warps per SM), merged once at the end like the round-1 split-statistics kernel.
+constexpr int ATT_TM2_THREADS = 320;           // 8 softmax warps + producer + issuer
+constexpr int TM2_STAGES = 2;
+
+struct Tm2Smem {
+    static constexpr int Q = 0;
+    static constexpr int K = Q + TILE_BYTES;
+    static constexpr int V = K + TM2_STAGES * TILE_BYTES;
+    static constexpr int BAR = V + TM2_STAGES * TILE_BYTES;
+    static constexpr int XCH = BAR + 256;                   // [2][128] reference + [2][128] row sum, fp32: merge of the two key halves
+    static constexpr int TOTAL = XCH + 2048;
+};
+static_assert(2 * (Tm2Smem::TOTAL + 1024) <= 228 * 1024, "attention forward (128-key variant) must keep two CTAs per SM");
+
+__global__ void __launch_bounds__(ATT_TM2_THREADS, 2)
+attn_fwd_tm2_kernel(const __grid_constant__ AttnParams P) {
+    extern __shared__ __align__(1024) uint8_t smem[];
+    uint64_t* bars = (uint64_t*)(smem + Tm2Smem::BAR);
+    uint64_t* q_full = bars;
+    uint64_t* kv_full = bars + 1;               // TM2_STAGES
+    uint64_t* kv_empty = bars + 1 + TM2_STAGES; // TM2_STAGES
+    uint64_t* s_ready = bars + 1 + 2 * TM2_STAGES;
+    uint64_t* p_ready = s_ready + 1;            // 256 arrivals
+    uint64_t* o_ready = p_ready + 1;
+    uint32_t* tmem_slot = (uint32_t*)(o_ready + 1);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int q_tiles = (P.Tq + TILE - 1) / TILE;
+    const int qt = blockIdx.x % q_tiles;
+    const int bh = blockIdx.x / q_tiles;
+    const int h = bh % P.H, b = bh / P.H;
+    const int q0 = qt * TILE;
+    const int nkv = (P.Tk + TILE - 1) / TILE;
+
+    if (threadIdx.x == 0) {
+        mbar_init(q_full, 1);
+        for (int i = 0; i < TM2_STAGES; ++i) { mbar_init(&kv_full[i], 1); mbar_init(&kv_empty[i], 1); }
+        mbar_init(s_ready, 1); mbar_init(p_ready, 256); mbar_init(o_ready, 1);
+        fence_mbar_init();
+    }
+    if (warp == 9) tmem_alloc(tmem_slot, 256);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t tS = tmem, tOa = tmem + 128, tOb = tmem + 192;
+    pdl_enter();
+
+    if (warp == 8) {
+        if (lane == 0) {
+            tma_prefetch_desc(&P.tmQ); tma_prefetch_desc(&P.tmK); tma_prefetch_desc(&P.tmV);
+            mbar_arrive_expect_tx(q_full, TILE_BYTES);
+            tma_load_4d(smem + Tm2Smem::Q, &P.tmQ, q_full, 0, h, q0, b);
+            for (int j = 0; j < nkv; ++j) {
+                const int s = j % TM2_STAGES;
+                mbar_wait_relaxed(&kv_empty[s], ((j / TM2_STAGES) & 1) ^ 1);
+                mbar_arrive_expect_tx(&kv_full[s], 2 * TILE_BYTES);
+                tma_load_4d(smem + Tm2Smem::K + s * TILE_BYTES, &P.tmK, &kv_full[s], 0, h, j * TILE, b);
+                tma_load_4d(smem + Tm2Smem::V + s * TILE_BYTES, &P.tmV, &kv_full[s], 0, h, j * TILE, b);
+            }
+        }
+    } else if (warp == 9) {
+        const uint32_t idesc_qk = make_idesc_bf16(128, 128, 0, 0);
+        const uint32_t idesc_pv = make_idesc_bf16(128, 64, 0, 1);
+        const uint64_t dQ = desc_kmajor(smem_u32(smem + Tm2Smem::Q), 0);
+        const uint64_t dK = desc_kmajor(smem_u32(smem + Tm2Smem::K), 0);
+        const uint64_t dV = desc_rows_as_k(smem_u32(smem + Tm2Smem::V), 0);
+        auto issue_s = [&](int j) {
+            const int s = j % TM2_STAGES;
+            mbar_wait(&kv_full[s], (j / TM2_STAGES) & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t dk = dK + (uint64_t)(s * (TILE_BYTES >> 4));
+                umma_bf16(tS, dQ, dk, idesc_qk, 0u);
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16(tS, dQ + 2 * k, dk + 2 * k, idesc_qk, 1u);
+                umma_commit(s_ready);
+            }
+            __syncwarp();
+        };
+        mbar_wait(q_full, 0);
+        issue_s(0);
+        for (int j = 0; j < nkv; ++j) {
+            const int s = j % TM2_STAGES;
+            mbar_wait(p_ready, j & 1);
+            tc_fence_after();
+            if (elect_one_sync()) {
+                const uint64_t dv = dV + (uint64_t)(s * (TILE_BYTES >> 4));
+                const uint32_t acc = j > 0 ? 1u : 0u;
+                umma_bf16_ts(tOa, tS, dv, idesc_pv, acc);                           // keys 0..63: P words at columns [0, 32)
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16_ts(tOa, tS + 8 * k, dv + 128 * k, idesc_pv, 1u);
+                umma_bf16_ts(tOb, tS + 64, dv + 128 * 4, idesc_pv, acc);            // keys 64..127: P words at columns [64, 96)
+#pragma unroll
+                for (int k = 1; k < 4; ++k) umma_bf16_ts(tOb, tS + 64 + 8 * k, dv + 128 * (4 + k), idesc_pv, 1u);
+                umma_commit(&kv_empty[s]);
+                if (j + 1 == nkv) umma_commit(o_ready);
+            }
+            __syncwarp();
+            if (j + 1 < nkv) issue_s(j + 1);
+        }
+    } else {
+        const int qtr = warp & 3, hf = warp >> 2;
+        const int r = qtr * 32 + lane;
+        const uint32_t lane_off = (uint32_t)(qtr * 32) << 16;
+        const uint32_t tSh = tS + hf * 64;                     // this thread's 64 score columns; its P words go over their front
+        const uint32_t tOx = hf == 0 ? tOa : tOb;
+        float* xm = (float*)(smem + Tm2Smem::XCH);
+        float* xl = xm + 256;
+        const float sl2 = P.scale * LOG2E;
+        float m_ref = -INFINITY, l = 0.f;
+        auto exp_pass = [&](uint32_t* w, float& lsum) -> uint32_t {
+            uint32_t v[2][16];
+            uint32_t mw = 0;
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            tmem_ld16(tSh + lane_off, v[0]);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                tc_wait_ld();
+                if (c + 1 < 4) tmem_ld16(tSh + lane_off + (c + 1) * 16, v[(c + 1) & 1]);
+                const uint32_t* cv = v[c & 1];
+#pragma unroll
+                for (int e = 0; e < 16; e += 4) {
+                    float p[4];
+#pragma unroll
+                    for (int t = 0; t < 4; ++t) p[t] = fast_exp2(fmaf(__uint_as_float(cv[e + t]), sl2, -m_ref));
+                    a0 += p[0]; a1 += p[1]; a2 += p[2]; a3 += p[3];
+                    const uint32_t w0 = pack_bf16(p[0], p[1]), w1 = pack_bf16(p[2], p[3]);
+                    w[c * 8 + (e >> 1)] = w0; w[c * 8 + (e >> 1) + 1] = w1;
+                    mw = max_u16x2(mw, max_u16x2(w0, w1));
+                }
+            }
+            lsum = (a0 + a1) + (a2 + a3);
+            return mw;
+        };
+        auto max_pass = [&](int kvalid) -> float {             // kvalid: valid columns of THIS half
+            float mx = -3.0e38f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tSh + lane_off + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; ++e)
+                    if (c * 32 + e < kvalid) mx = fmaxf(mx, __uint_as_float(v[e]));
+            }
+            return mx;
+        };
+        auto exp_pass_masked = [&](int kvalid, uint32_t* w, float& lsum) {
+            float acc = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 2; ++c) {
+                uint32_t v[32];
+                tmem_ld32(tSh + lane_off + c * 32, v);
+                tc_wait_ld();
+#pragma unroll
+                for (int e = 0; e < 32; e += 2) {
+                    const int ka = c * 32 + e;
+                    const float p0 = ka < kvalid ? fast_exp2(fmaf(__uint_as_float(v[e]), sl2, -m_ref)) : 0.f;
+                    const float p1 = ka + 1 < kvalid ? fast_exp2(fmaf(__uint_as_float(v[e + 1]), sl2, -m_ref)) : 0.f;
+                    acc += p0 + p1;
+                    const uint32_t pk = pack_bf16(p0, p1);
+                    if (c == 0) w[e >> 1] = pk; else w[16 + (e >> 1)] = pk;
+                }
+            }
+            lsum = acc;
+        };
+        for (int j = 0; j < nkv; ++j) {
+            mbar_wait(s_ready, j & 1);
+            tc_fence_after();
+            const int kvalid = P.Tk - j * TILE - hf * 64;        // valid keys among this thread's 64 columns (may be <= 0)
+            uint32_t w[32];
+            float lsum = 0.f;
+            if (j == 0) {
+                m_ref = max_pass(kvalid) * sl2;                  // (-3e38 * sl2 when this half has no valid key: every P is masked to 0)
+                if (kvalid >= 64) exp_pass(w, lsum); else exp_pass_masked(kvalid, w, lsum);
+            } else {
+                bool need;
+                if (kvalid >= 64) {
+                    const uint32_t mw = exp_pass(w, lsum);
+                    need = (mw & 0xffffu) > 0x4380u || (mw >> 16) > 0x4380u;
+                } else {
+                    need = max_pass(kvalid) * sl2 - m_ref > 8.0f;
+                    if (!__any_sync(0xffffffffu, need)) exp_pass_masked(kvalid, w, lsum);
+                }
+                if (__any_sync(0xffffffffu, need)) {
+                    const float m_new = fmaxf(m_ref, max_pass(kvalid) * sl2);
+                    const float alpha = fast_exp2(m_ref - m_new);
+#pragma unroll 1
+                    for (int c = 0; c < 2; ++c) {
+                        uint32_t v[32];
+                        tmem_ld32(tOx + lane_off + c * 32, v);
+                        tc_wait_ld();
+#pragma unroll
+                        for (int e = 0; e < 32; ++e) v[e] = __float_as_uint(__uint_as_float(v[e]) * alpha);
+                        tmem_st32(tOx + lane_off + c * 32, v);
+                        tc_wait_st();
+                    }
+                    l *= alpha;
+                    m_ref = m_new;
+                    if (kvalid >= 64) exp_pass(w, lsum); else exp_pass_masked(kvalid, w, lsum);
+                }
+            }
+            l += lsum;
+            tmem_st32(tSh + lane_off, w);
+            tc_wait_st();
+            tc_fence_before();
+            mbar_arrive(p_ready);
+        }
+        mbar_wait(o_ready, 0);
+        tc_fence_after();
+        // combine the two halves: O = (O_a 2^(m_a - m) + O_b 2^(m_b - m)) / (l_a 2^(m_a - m) + l_b 2^(m_b - m))
+        xm[hf * 128 + r] = m_ref;
+        xl[hf * 128 + r] = l;
+        named_bar_sync(1, 256);
+        const float m_o = xm[(hf ^ 1) * 128 + r], l_o = xl[(hf ^ 1) * 128 + r];
+        const float m = fmaxf(m_ref, m_o);
+        const float w_me = fast_exp2(m_ref - m), w_o = fast_exp2(m_o - m);
+        const float wa = hf == 0 ? w_me : w_o, wb = hf == 0 ? w_o : w_me;
+        const float lt = l * w_me + l_o * w_o;
+        const float inv_l = 1.0f / lt;
+        const int q = q0 + r;
+        {
+            const int c = hf;
+            uint32_t va[32], vb[32];
+            tmem_ld32(tOa + lane_off + c * 32, va);
+            tmem_ld32(tOb + lane_off + c * 32, vb);
+            tc_wait_ld();
+            if (q < P.Tq) {
+                __nv_bfloat16* dst = P.O + ((long long)b * P.Tq + q) * P.ldo + h * HD + c * 32;
+                const float sa = wa * inv_l, sb = wb * inv_l;
+#pragma unroll
+                for (int e = 0; e < 32; e += 8) {
+                    float f[8];
+#pragma unroll
+                    for (int t = 0; t < 8; ++t) f[t] = fmaf(__uint_as_float(va[e + t]), sa, __uint_as_float(vb[e + t]) * sb);
+                    uint4 o;
+                    o.x = pack_bf16(f[0], f[1]); o.y = pack_bf16(f[2], f[3]); o.z = pack_bf16(f[4], f[5]); o.w = pack_bf16(f[6], f[7]);
+                    *reinterpret_cast<uint4*>(dst + e) = o;
+                }
+            }
+        }
+        if (hf == 0 && q < P.Tq) P.lse[((long long)b * P.H + h) * P.Tq + q] = (m + log2f(lt)) * LN2;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 9) { tc_fence_after(); tmem_dealloc(tmem, 256); }
 }
 
 // Merge the key shares of the units that attn_fwd_tm_kernel cut (see there): one thread per (unit, row, 8 output columns).
@@ -951,8 +1206,11 @@ attn_fwd_combine_kernel(const float* __restrict__ ws, int n_units, int unit0, in
 __global__ void __launch_bounds__(256)
 attn_bwd_prep_kernel(const __nv_bfloat16* __restrict__ O, long long ldo, const __nv_bfloat16* __restrict__ dO,
                      long long lddo, int B, int H, int Tq, float* __restrict__ D, const float* __restrict__ lse = nullptr,
-                     float* __restrict__ lse2 = nullptr) {
+                     float* __restrict__ lse2 = nullptr, float4* __restrict__ zero = nullptr, long long zero_n4 = 0) {
     pdl_enter();
+    // the one-kernel backward's fp32 accumulation tiles are cleared here (saves a memset node per attention layer)
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < zero_n4; i += (long long)gridDim.x * blockDim.x)
+        zero[i] = make_float4(0.f, 0.f, 0.f, 0.f);
     const long long total = (long long)B * Tq * H * 8;                    // one work item = 8 elements of one row
     const long long bound = (total + 31) & ~31LL;                         // whole warps stay in the loop (full-mask shuffles)
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < bound; i += (long long)gridDim.x * blockDim.x) {
@@ -1533,9 +1791,9 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
     if (threadIdx.x == 0) {
         mbar_init(kv_once, 1);
         for (int i = 0; i < FB_STAGES; ++i) { mbar_init(&q_full[i], 1); mbar_init(&q_empty[i], 1); }
-        mbar_init(s_ready, 1); mbar_init(dp_ready, 1); mbar_init(p_ready, FB_CW * 32); mbar_init(ds_ready, FB_CW * 32);
+        mbar_init(s_ready, 1); mbar_init(dp_ready, 1); mbar_init(p_ready, FB_CW); mbar_init(ds_ready, FB_CW);          // one arrival per compute warp
         mbar_init(ds_free, 1);
-        for (int i = 0; i < 2; ++i) { mbar_init(&dq_ready[i], 1); mbar_init(&dq_free[i], 128); }
+        for (int i = 0; i < 2; ++i) { mbar_init(&dq_ready[i], 1); mbar_init(&dq_free[i], 4); }
         mbar_init(acc_ready, 1);
         fence_mbar_init();
     }
@@ -1658,7 +1916,8 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             tmem_ld32(tdQ + (i & 1) * 64 + lane_off + 32, v + 32);
             tc_wait_ld();
             tc_fence_before();
-            mbar_arrive(&dq_free[i & 1]);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&dq_free[i & 1]);
             if (kv_tiles == 1) {
                 // one KV tile: this IS dQ(i) -- scaled, rounded and stored directly (no accumulation buffer, no convert pass)
                 const int q = (i0 + i) * TILE + r;
@@ -1733,7 +1992,8 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             }
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(p_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(p_ready);                                 // one arrival per warp (32 same-address arrivals serialise)
             // ---- dS phase: dS^T = P^T (dP^T - D[q]) ----
             mbar_wait(dp_ready, i & 1);
             tc_fence_after();
@@ -1768,7 +2028,8 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             fence_proxy_async_smem();
             tc_wait_st();
             tc_fence_before();
-            mbar_arrive(ds_ready);
+            __syncwarp();
+            if (lane == 0) mbar_arrive(ds_ready);
         }
         if (nq > 0) { mbar_wait(acc_ready, 0); tc_fence_after(); }
         const int key = k0 + r;
@@ -1931,7 +2192,7 @@ int aoz_attn_fwd_ws(const void* q, long long ldq, const void* k, long long ldk, 
     memset(&P, 0, sizeof(P));
     int rc;
     if ((rc = make_qkv_map(&P.tmQ, q, ldq, B, H, Tq)) != AOZ_OK) return rc;
-    const int kv_rows = g_fwd_split >= 2 ? KT : TILE;          // the P-in-TMEM kernel streams 64-key tiles
+    const int kv_rows = (g_fwd_split >= 2 && g_fwd_split != 7) ? KT : TILE;          // the P-in-TMEM kernel streams 64-key tiles
     if ((rc = make_qkv_map(&P.tmK, k, ldk, B, H, Tk, kv_rows)) != AOZ_OK) return rc;
     if ((rc = make_qkv_map(&P.tmV, v, ldv, B, H, Tk, kv_rows)) != AOZ_OK) return rc;
     P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
@@ -1944,16 +2205,18 @@ int aoz_attn_fwd_ws(const void* q, long long ldq, const void* k, long long ldk, 
         cudaFuncSetAttribute(attn_fwd_tm_kernel<0x8080u>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
         cudaFuncSetAttribute(attn_fwd_tm_kernel<0u>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
         cudaFuncSetAttribute(attn_fwd_tm_kernel<0xAAAAu>, cudaFuncAttributeMaxDynamicSharedMemorySize, TmSmem::TOTAL);
+        cudaFuncSetAttribute(attn_fwd_tm2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, Tm2Smem::TOTAL);
         attr = true;
     }
     int grid = B * H * ((Tq + TILE - 1) / TILE);
     P.fwd_full = grid; P.fwd_split = 1; P.fwd_ws = nullptr;
     const int units = grid;
-    if (g_fwd_split >= 2 && workspace != nullptr && g_fwd_tail_split) {
+    if (g_fwd_split >= 2 && g_fwd_split != 7 && workspace != nullptr && g_fwd_tail_split) {
         fwd_tail_plan(units, (Tk + KT - 1) / KT, &P.fwd_full, &P.fwd_split);
         if (P.fwd_split > 1) { P.fwd_ws = (float*)workspace; grid = P.fwd_full + (units - P.fwd_full) * P.fwd_split; }
     }
-    if (g_fwd_split == 6) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
+    if (g_fwd_split == 7) launch_k(attn_fwd_tm2_kernel, dim3(units), dim3(ATT_TM2_THREADS), (size_t)(Tm2Smem::TOTAL), (cudaStream_t)stream, P);
+    else if (g_fwd_split == 6) launch_k(attn_fwd_tm_kernel<0x8888u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split == 3) launch_k(attn_fwd_tm_kernel<0x8080u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split == 2) launch_k(attn_fwd_tm_kernel<0u>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
     else if (g_fwd_split == 4) launch_k(attn_fwd_tm_kernel<0xAAAAu>, dim3(grid), dim3(ATT_TM_THREADS), (size_t)(TmSmem::TOTAL), (cudaStream_t)stream, P);
@@ -1973,7 +2236,7 @@ int aoz_attn_fwd_ws(const void* q, long long ldq, const void* k, long long ldk, 
 // experiment switch: 2 = P-in-TMEM forward (default), 1 = split-statistics forward (P through shared memory), 0 = shared-maximum forward
 // (2: every exponential on the MUFU pipe -- measured as fast as any split, and LSE keeps ex2.approx accuracy; 3 / 6 / 4: the same
 // kernel with 1/8, 1/4, 1/2 of them on the FMA pipe -- measurement variants: 724 / 697 / 584 TFLOP/s against 718 for none)
-int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 6 ? 2 : mode); return AOZ_OK; }
+int aoz_attn_set_fwd_split(int mode) { g_fwd_split = mode < 0 ? 0 : (mode > 7 ? 2 : mode); return AOZ_OK; }
 
 // D vector [B, H, Tq] + the fp32 dQ accumulation buffer [B, H, Tq, 64] of the one-kernel backward
 static long long bwd_vec_floats(int B, int H, int Tq) { return (((long long)B * H * Tq + 31) / 32) * 32; }      // 128-byte granules
@@ -2015,38 +2278,36 @@ int aoz_attn_bwd(const void* q, long long ldq, const void* k, long long ldk, con
     P.B = B; P.H = H; P.Tq = Tq; P.Tk = Tk; P.scale = scale;
     P.lse = (float*)const_cast<void*>(lse); P.Dvec = (const float*)workspace;
     P.dQ = (__nv_bfloat16*)dq; P.lddq = lddq; P.dK = (__nv_bfloat16*)dk; P.lddk = lddk; P.dV = (__nv_bfloat16*)dv; P.lddv = lddv;
+    float* const acc_ws = (float*)workspace + 2 * bwd_vec_floats(B, H, Tq);
+    const bool one_kernel = g_bwd_fused == 2 && (Tq % 4) == 0;
+    const int q_tiles = (Tq + TILE - 1) / TILE, kv_tiles = (Tk + TILE - 1) / TILE;
+    // One KV tile (cross-attention): B * H CTAs would leave most of the 148 SMs idle, so the Q tiles are cut over q_split CTAs
+    // (about two waves of CTAs, at least two Q tiles each) whose dK / dV shares are summed like dQ.
+    int q_split = 1;
+    if (one_kernel && kv_tiles == 1) {
+        q_split = (2 * sm_count() + B * H - 1) / (B * H);
+        if (q_split > (q_tiles + 1) / 2) q_split = (q_tiles + 1) / 2;
+        if (q_split < 1) q_split = 1;
+        const int per = (q_tiles + q_split - 1) / q_split;
+        q_split = (q_tiles + per - 1) / per;                    // no CTA without a Q tile
+    }
+    const long long dq_floats = (long long)B * H * q_tiles * TILE * HD, kv_floats = (long long)B * H * kv_tiles * TILE * HD;
+    // cleared by the prep kernel: the dQ tile buffer when several KV tiles add into it; the dK / dV tile buffers when several CTAs
+    // share a KV tile
+    float* const z0 = kv_tiles > 1 ? acc_ws : acc_ws + dq_floats;
+    const long long zn = one_kernel ? (kv_tiles > 1 ? dq_floats : 0) + (q_split > 1 ? 2 * kv_floats : 0) : 0;
     {
         const long long items = (long long)B * Tq * H * 8;
         long long blocks = (items + 255) / 256;
         if (blocks > sm_count() * 16) blocks = sm_count() * 16;
         launch_k(attn_bwd_prep_kernel, dim3((int)blocks), dim3(256), (size_t)(0), s, (const __nv_bfloat16*)o, ldo, (const __nv_bfloat16*)d_o, lddo, B, H, Tq, (float*)workspace,
-                 (const float*)lse, (float*)workspace + bwd_vec_floats(B, H, Tq));
+                 (const float*)lse, (float*)workspace + bwd_vec_floats(B, H, Tq), (float4*)z0, zn / 4);
         AOZ_CHECK_LAUNCH("attn_bwd_prep_kernel");
     }
-    float* const acc_ws = (float*)workspace + 2 * bwd_vec_floats(B, H, Tq);
-    if (g_bwd_fused == 2 && (Tq % 4) == 0) {
+    if (one_kernel) {
         // one kernel: dK, dV and this KV tile's share of dQ; lse is read in the log2 domain from the workspace
         static bool attr_f = false;
         if (!attr_f) { cudaFuncSetAttribute(attn_bwd_fused_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FbSmem::TOTAL); attr_f = true; }
-        const int q_tiles = (Tq + TILE - 1) / TILE, kv_tiles = (Tk + TILE - 1) / TILE;
-        // One KV tile (cross-attention): B * H CTAs would leave most of the 148 SMs idle, so the Q tiles are cut over q_split CTAs
-        // (about two waves of CTAs, at least two Q tiles each) whose dK / dV shares are summed like dQ.
-        int q_split = 1;
-        if (kv_tiles == 1) {
-            q_split = (2 * sm_count() + B * H - 1) / (B * H);
-            if (q_split > (q_tiles + 1) / 2) q_split = (q_tiles + 1) / 2;
-            if (q_split < 1) q_split = 1;
-            const int per = (q_tiles + q_split - 1) / q_split;
-            q_split = (q_tiles + per - 1) / per;                    // no CTA without a Q tile
-        }
-        const long long dq_floats = (long long)B * H * q_tiles * TILE * HD, kv_floats = (long long)B * H * kv_tiles * TILE * HD;
-        // zeroed: the dQ tile buffer when several KV tiles add into it; the dK / dV tile buffers when several CTAs share a KV tile
-        float* const z0 = kv_tiles > 1 ? acc_ws : acc_ws + dq_floats;
-        const long long zn = (kv_tiles > 1 ? dq_floats : 0) + (q_split > 1 ? 2 * kv_floats : 0);
-        if (zn > 0) {
-            cudaError_t e = cudaMemsetAsync(z0, 0, sizeof(float) * (size_t)zn, s);
-            if (e != cudaSuccess) { set_error("aoz_attn_bwd: memset: %s", cudaGetErrorString(e)); return AOZ_ERR_CUDA; }
-        }
         P.lse = (float*)workspace + bwd_vec_floats(B, H, Tq);
         P.dQacc = acc_ws;
         P.dKacc = acc_ws + dq_floats;
