@@ -342,6 +342,92 @@ __device__ __forceinline__ void colsum_body(const __nv_bfloat16* __restrict__ x,
     }
 }
 
+// GEGLU backward WITH the bias gradient of the projection: daux = [dh | dg] is written as in geglu_bwd_kernel and its column sums
+// (db of ff.net.0.proj, 2 * half = 10240 columns at C = 1280) are formed from the rounded values on the way out -- the separate
+// column-sum launch re-read the 84 MB it had just written.  Same grid / partial / ticket scheme as colsum_body: a thread owns 8
+// columns of the value half AND the same 8 of the gate half, 8 row lanes per block, four rows in flight.
+__global__ void __launch_bounds__(256)
+geglu_bwd_colsum_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ aux, long long M, int half,
+                        __nv_bfloat16* __restrict__ daux, float* __restrict__ partial, __nv_bfloat16* __restrict__ db, int accumulate) {
+    pdl_enter();
+    __shared__ float smh[8][256], smg[8][256];
+    __shared__ unsigned int s_last;
+    const int vcol = blockIdx.x * 32 + (threadIdx.x & 31);
+    const int rl = threadIdx.x >> 5;
+    const int chunks = gridDim.y;
+    const int N = 2 * half;
+    const long long rows_per_chunk = (M + chunks - 1) / chunks;
+    const long long r0 = blockIdx.y * rows_per_chunk, r1 = min(M, r0 + rows_per_chunk);
+    float acch[8] = {0, 0, 0, 0, 0, 0, 0, 0}, accg[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (vcol * 8 < half) {
+        auto one_row = [&](long long r, const uint4& qd, const uint4& qh, const uint4& qg) {
+            float d[8], h[8], g[8], dh[8], dg[8];
+            unpack8e(qd, d); unpack8e(qh, h); unpack8e(qg, g);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                float ex;
+                const float cdf = gelu_cdf(g[e], ex);
+                const float pdf = 0.39894228040143267794f * ex;
+                const float gelu = round_bf16(g[e] * cdf);
+                dh[e] = round_bf16(d[e] * gelu);
+                dg[e] = round_bf16(round_bf16(d[e] * h[e]) * (cdf + g[e] * pdf));
+                acch[e] += dh[e]; accg[e] += dg[e];
+            }
+            st_stream(daux + r * N + vcol * 8, pack8e(dh));
+            st_stream(daux + r * N + half + vcol * 8, pack8e(dg));
+        };
+        long long r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {
+            uint4 qd[4], qh[4], qg[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+                qd[u] = ld_stream(dy + (r + 8 * u) * half + vcol * 8);
+                qh[u] = ld_stream(aux + (r + 8 * u) * N + vcol * 8);
+                qg[u] = ld_stream(aux + (r + 8 * u) * N + half + vcol * 8);
+            }
+#pragma unroll
+            for (int u = 0; u < 4; ++u) one_row(r + 8 * u, qd[u], qh[u], qg[u]);
+        }
+        for (; r < r1; r += 8)
+            one_row(r, ld_stream(dy + r * half + vcol * 8), ld_stream(aux + r * N + vcol * 8), ld_stream(aux + r * N + half + vcol * 8));
+    }
+#pragma unroll
+    for (int e = 0; e < 8; ++e) { smh[rl][(threadIdx.x & 31) * 8 + e] = acch[e]; smg[rl][(threadIdx.x & 31) * 8 + e] = accg[e]; }
+    __syncthreads();
+    const int c = threadIdx.x;
+    float sh = 0.f, sg = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { sh += smh[k][c]; sg += smg[k][c]; }
+    const int col = blockIdx.x * 256 + c;
+    if (col < half) {
+        partial[(long long)blockIdx.y * N + col] = sh;
+        partial[(long long)blockIdx.y * N + half + col] = sg;
+    }
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicInc(&g_colsum_tickets[blockIdx.x & 4095], (unsigned int)chunks - 1);
+        s_last = (t == (unsigned int)chunks - 1);
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    if (col < half) {
+#pragma unroll 1
+        for (int part = 0; part < 2; ++part) {
+            const int oc = part * half + col;
+            float v[64];
+#pragma unroll
+            for (int k = 0; k < 64; ++k) v[k] = k < chunks ? __ldcg(partial + (long long)k * N + oc) : 0.f;
+            float t = 0.f;
+#pragma unroll
+            for (int k = 0; k < 64; ++k) t += v[k];
+            if (accumulate) t = round_bf16(t) + __bfloat162float(db[oc]);
+            db[oc] = __float2bfloat16_rn(t);
+        }
+    }
+}
+
 __global__ void __launch_bounds__(256)
 colsum_kernel(const __nv_bfloat16* __restrict__ x0, long long M, int N, long long ld, long long group_stride,
               float* __restrict__ partial0, __nv_bfloat16* __restrict__ out0, int accumulate) {
@@ -519,6 +605,27 @@ int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* 
     launch_k(geglu_bwd_kernel, dim3(grid_for(M * (half / 8), 256)), dim3(256), (size_t)(0), (cudaStream_t)stream, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, M, half,
                                                                                       (__nv_bfloat16*)daux);
     AOZ_CHECK_LAUNCH("geglu_bwd_kernel");
+    return AOZ_OK;
+}
+
+static int geglu_colsum_chunks(long long M, int half) {
+    const int colblocks = (half + 255) / 256;
+    int chunks = (sm_count() * 4 + colblocks - 1) / colblocks;
+    if (chunks > 64) chunks = 64;
+    if ((long long)chunks * 8 > M) chunks = (int)((M + 7) / 8);
+    return chunks < 1 ? 1 : chunks;
+}
+long long aoz_geglu_bwd_colsum_workspace_floats(long long M, int half) { return (long long)geglu_colsum_chunks(M, half) * 2 * half; }
+// geglu_bwd + db = column sums of daux (the bias gradient of ff.net.0.proj) in one pass; workspace: the function above
+int aoz_geglu_bwd_colsum(const void* dy, const void* aux, long long M, int half, void* daux, void* db, int accumulate, void* workspace,
+                         void* stream) {
+    AOZ_CHECK_ARG(dy && aux && daux && db && workspace && half % 8 == 0, "aoz_geglu_bwd_colsum: bad arguments");
+    if (M <= 0) return AOZ_OK;
+    const int colblocks = (half + 255) / 256;
+    AOZ_CHECK_ARG(colblocks <= 4096, "aoz_geglu_bwd_colsum: too many columns");
+    launch_k(geglu_bwd_colsum_kernel, dim3(colblocks, geglu_colsum_chunks(M, half)), dim3(256), (size_t)(0), (cudaStream_t)stream,
+             (const __nv_bfloat16*)dy, (const __nv_bfloat16*)aux, M, half, (__nv_bfloat16*)daux, (float*)workspace, (__nv_bfloat16*)db, accumulate);
+    AOZ_CHECK_LAUNCH("geglu_bwd_colsum_kernel");
     return AOZ_OK;
 }
 

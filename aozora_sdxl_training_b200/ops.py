@@ -394,13 +394,21 @@ def mse_loss(pred, target_nchw, tickets, table, denom, grad_scale=1.0, *, pred_n
     return loss, per, dpred
 
 
-def geglu_bwd(dy, aux):
+def geglu_bwd(dy, aux, bias_grad=None):
+    """-> daux.  ``bias_grad``: a bf16 [2 * half] destination: the column sums of daux (the projection's bias gradient) are formed
+    in the same pass (saves the column-sum launch's re-read of daux)."""
     _chk(dy, "geglu_bwd dy")
     _chk(aux, "geglu_bwd aux")
     half = dy.shape[-1]
     M = dy.numel() // half
     daux = torch.empty_like(aux)
-    _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _stream())
+    if bias_grad is not None:
+        _chk(bias_grad, "geglu_bwd bias_grad")
+        ws = workspace(_lib.query("aoz_geglu_bwd_colsum_workspace_floats", M, half), dy.device)
+        _lib.call("aoz_geglu_bwd_colsum", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), bias_grad.data_ptr(), 0,
+                  ws.data_ptr(), _stream())
+    else:
+        _lib.call("aoz_geglu_bwd", dy.data_ptr(), aux.data_ptr(), M, half, daux.data_ptr(), _stream())
     _count()
     return daux
 

@@ -297,11 +297,16 @@ def _geglu(x, w, b, G, defer=False):
     y = ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
 
     def bwd(dy):
-        daux = ops.geglu_bwd(dy, aux)
+        if b.requires_grad:             # the bias gradient (column sums of daux) rides the same pass
+            db = G.out_for(b)
+            if db is None:
+                db = torch.empty_like(b)
+            daux = ops.geglu_bwd(dy, aux, bias_grad=db)
+            G.add(b, db)
+        else:
+            daux = ops.geglu_bwd(dy, aux)
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
-        if b.requires_grad:
-            G.bias_grad(b, daux)
         return ops.gemm(daux, w, b_mn=True)
 
     return y, bwd

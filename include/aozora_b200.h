@@ -39,6 +39,8 @@ int aoz_mt_chunk_elems(void);
 int aoz_raven_step_mt(int n_tensors, int n_chunks, const void* p_ptrs, const void* g_ptrs, const void* m_ptrs,
                       const void* v_ptrs, const void* numel, const void* chunk_start, const void* chunk_tensor,
                       const void* hyper, const void* clip_coef, int p_dtype, int g_dtype, int m_dtype, void* stream);
+/* experiment switch: 1 = the update streams through shared memory with cp.async.bulk copies (default), 0 = register-streaming kernel */
+int aoz_raven_set_bulk(int on);
 /* out3 = {total_norm, clip_coef = min(1, max_norm/(norm+1e-6)), sum_of_squares}; partial: n_chunks floats */
 int aoz_gradnorm_mt(int n_tensors, int n_chunks, const void* g_ptrs, const void* numel, const void* chunk_start,
                     const void* chunk_tensor, void* partial, float max_norm, int emulate_bf16, void* out3,
@@ -139,6 +141,11 @@ int aoz_mse_loss(const void* pred, long long p_sn, long long p_sc, long long p_s
                  void* per_sample, void* weights, void* loss_out, void* dpred, long long d_sn, long long d_sc, long long d_shw,
                  void* stream);
 int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* daux, void* stream);
+/* The same pass also forming db = column sums of daux (the bias gradient of ff.net.0.proj, from the rounded values: equal to
+ * aoz_colsum over daux); workspace: aoz_geglu_bwd_colsum_workspace_floats(M, half) floats */
+int aoz_geglu_bwd_colsum(const void* dy, const void* aux, long long M, int half, void* daux, void* db, int accumulate, void* workspace,
+                         void* stream);
+long long aoz_geglu_bwd_colsum_workspace_floats(long long M, int half);
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream);
 int aoz_silu_bwd(const void* dy, const void* x, long long n, void* dx, void* stream);
 int aoz_add(const void* a, const void* b, long long n, void* y, void* stream);

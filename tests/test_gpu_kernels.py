@@ -178,6 +178,26 @@ def test_geglu_fused_epilogue_and_backward(M, C):
     check(ops.geglu_bwd(dy, aux), pr.grad, rel=8e-3)
 
 
+def test_geglu_backward_with_fused_bias_gradient():
+    """geglu_bwd_colsum_kernel: daux identical to geglu_bwd_kernel's, and the bias gradient equal to the column sums of that daux
+    (formed from the rounded values; same partial / ticket scheme as colsum, other chunking -> fp32 summation order differs)."""
+    ops = _ops()
+    g = gen(56)
+    for M, C in ((4096, 1280), (1000, 640), (16, 320)):
+        half = 4 * C
+        dy = torch.randn(M, half, device="cuda", generator=g).to(BF16)
+        aux = torch.randn(M, 2 * half, device="cuda", generator=g).to(BF16)
+        ref = ops.geglu_bwd(dy, aux)
+        db = torch.empty(2 * half, device="cuda", dtype=BF16)
+        got = ops.geglu_bwd(dy, aux, bias_grad=db)
+        assert torch.equal(got, ref)
+        want = ref.float().sum(0)
+        err = (db.float() - want).abs()
+        assert bool((err <= 2 ** -7 * want.abs() + 2e-2).all()), float(err.max())
+        check(db, ops.colsum(ref), rel=3e-3)
+
+
+
 @pytest.mark.parametrize("NB,H,W,Cin,Cout,ks,stride", [
     (2, 16, 16, 64, 128, 3, 1), (1, 18, 14, 320, 192, 3, 1), (2, 16, 16, 64, 64, 3, 2), (1, 13, 19, 128, 64, 3, 2),
     (2, 16, 16, 128, 64, 1, 1), (2, 16, 16, 8, 320, 3, 1), (2, 16, 16, 320, 8, 3, 1), (1, 32, 32, 640, 320, 3, 1),
