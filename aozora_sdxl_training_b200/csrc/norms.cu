@@ -676,9 +676,13 @@ __global__ void __launch_bounds__(LNB_MAX_THREADS, 1)
 ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ x,
               const __nv_bfloat16* __restrict__ gamma, const float* __restrict__ mean, const float* __restrict__ rstd,
               long long rows, int C, const __nv_bfloat16* __restrict__ dres, __nv_bfloat16* __restrict__ dx,
-              float* __restrict__ partial, int cols_pad, int RL, long long rows_per_block) {
+              float* __restrict__ partial, int cols_pad, int RL, long long rows_per_block, int want_col) {
+    // want_col: also the column sums of dx (as stored, bf16-rounded) -> third row of the partials.  dx of a pre-LN transformer
+    // sublayer is the gradient of the PREVIOUS Linear's output (to_out / ff.net.2 / proj_in), so this is that layer's bias
+    // gradient, free of the separate column-sum launch that re-read dx (210 launches per step).
     pdl_enter();
     extern __shared__ __align__(128) uint8_t lnb_smem[];
+    const int ncomp = want_col ? 3 : 2;
     const int tc = threadIdx.x % cols_pad, rl = threadIdx.x / cols_pad;
     const int lane = threadIdx.x & 31, wcol = tc >> 5, W = cols_pad >> 5;
     const int nv = C / 8;
@@ -689,12 +693,12 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     uint8_t* ring = lnb_smem;                                                  // [2 slots][x | dy | dres][tensor_bytes]
     float* red = reinterpret_cast<float*>(lnb_smem + 6 * (size_t)tensor_bytes);   // [tile_rows][W][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + (size_t)tile_rows * W * 2);
-    float gm[8], ag[8], ab[8];
+    float gm[8], ag[8], ab[8], ac[8];
     {
         const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + tc * 8) : make_uint4(0, 0, 0, 0);
         unpack8(g4, gm);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; }
+        for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; ac[e] = 0.f; }
     }
     const long long rb0 = (long long)blockIdx.x * rows_per_block;
     const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
@@ -792,51 +796,57 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
 #pragma unroll
                 for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
             }
+            if (want_col) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) { o[e] = round_bf16(o[e]); ac[e] += o[e]; }
+            }
             const long long row = base + (long long)t * RL + rl;
             st_stream(dx + row * C + tc * 8, pack8(o));
         }
         __syncthreads();               // slot and table are free: refill the slot with the tile after next
         if (threadIdx.x == 0 && i + 2 < ntiles) issue(i + 2);
     }
-    // accumulators -> [RL][2][C] (over the idle ring) -> fixed-order sum over the row lanes -> this block's partial row
+    // accumulators -> [RL][ncomp][C] (over the idle ring) -> fixed-order sum over the row lanes -> this block's partial row
     float* fin = reinterpret_cast<float*>(lnb_smem);
     if (active) {
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            fin[(size_t)(rl * 2 + 0) * C + tc * 8 + e] = ag[e];
-            fin[(size_t)(rl * 2 + 1) * C + tc * 8 + e] = ab[e];
+            fin[(size_t)(rl * ncomp + 0) * C + tc * 8 + e] = ag[e];
+            fin[(size_t)(rl * ncomp + 1) * C + tc * 8 + e] = ab[e];
+            if (want_col) fin[(size_t)(rl * ncomp + 2) * C + tc * 8 + e] = ac[e];
         }
     }
     __syncthreads();
-    float* out = partial + (size_t)blockIdx.x * 2 * C;
-    for (int i = threadIdx.x; i < 2 * C; i += blockDim.x) {
+    float* out = partial + (size_t)blockIdx.x * ncomp * C;
+    for (int i = threadIdx.x; i < ncomp * C; i += blockDim.x) {
         float a = 0.f;
-        for (int l = 0; l < RL; ++l) a += fin[(size_t)l * 2 * C + i];
+        for (int l = 0; l < RL; ++l) a += fin[(size_t)l * ncomp * C + i];
         out[i] = a;
     }
 }
 
-// reduce [blocks][2][C] -> dgamma (first C), dbeta (second C)
+// reduce [blocks][ncomp][C] -> dgamma (first C), dbeta (second C) and, with ncomp == 3, the column sums of dx (third C)
 // block = 32 columns x 32 row lanes: lane (cx, ry) sums partial rows ry, ry+32, ... of its column (a warp reads 128
 // contiguous bytes per row), then the 32 row lanes are combined through shared memory in fixed order
 __global__ void __launch_bounds__(1024)
 ln_bwd_finalize_kernel(const float* __restrict__ partial, int blocks, int C, __nv_bfloat16* __restrict__ dgamma,
-                       __nv_bfloat16* __restrict__ dbeta, int accumulate) {
+                       __nv_bfloat16* __restrict__ dbeta, int accumulate, __nv_bfloat16* __restrict__ dcol, int ncomp, int skip_params) {
     pdl_enter();
     __shared__ float sm[32][33];
     const int cx = threadIdx.x & 31, ry = threadIdx.x >> 5;
     const int i = blockIdx.x * 32 + cx;
     float s = 0.f;
-    if (i < 2 * C)
-        for (int b = ry; b < blocks; b += 32) s += partial[(size_t)b * 2 * C + i];
+    if (i < ncomp * C)
+        for (int b = ry; b < blocks; b += 32) s += partial[(size_t)b * ncomp * C + i];
     sm[ry][cx] = s;
     __syncthreads();
-    if (ry == 0 && i < 2 * C) {
+    if (ry == 0 && i < ncomp * C) {
+        if (skip_params && i < 2 * C) return;                 // frozen LayerNorm: only the column sums are wanted
         float t = 0.f;
 #pragma unroll
         for (int k = 0; k < 32; ++k) t += sm[k][cx];
-        __nv_bfloat16* dst = i < C ? dgamma + i : dbeta + (i - C);
-        if (accumulate) t = round_bf16(t) + __bfloat162float(*dst);
+        __nv_bfloat16* dst = i < C ? dgamma + i : (i < 2 * C ? dbeta + (i - C) : dcol + (i - 2 * C));
+        if (accumulate && i < 2 * C) t = round_bf16(t) + __bfloat162float(*dst);
         *dst = __float2bfloat16_rn(t);
     }
 }
@@ -1026,8 +1036,20 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
 
 long long aoz_layernorm_bwd_workspace_floats(int C) { return (long long)sm_count() * 2 * 2 * C; }
 
+int aoz_layernorm_bwd_colsum(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
+                             const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* dcolsum, void* workspace,
+                             void* stream);
+
 int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
                       const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream) {
+    return aoz_layernorm_bwd_colsum(dy, x, gamma, mean, rstd, rows, C, dres, dx, dgamma, dbeta, accumulate, nullptr, workspace, stream);
+}
+
+// The same with dcolsum != null: additionally dcolsum[c] = sum over rows of dx[r, c] (the stored, bf16-rounded dx), i.e. the bias
+// gradient of the Linear whose output this LayerNorm's input is (to_out / ff.net.2 / proj_in of a pre-LN transformer block).
+int aoz_layernorm_bwd_colsum(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
+                             const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* dcolsum, void* workspace,
+                             void* stream) {
     AOZ_CHECK_ARG(dy && x && gamma && mean && rstd && dx && dgamma && dbeta && workspace, "aoz_layernorm_bwd: null pointer");
     AOZ_CHECK_ARG(C % 8 == 0 && C <= LN_MAXV * 256, "aoz_layernorm_bwd: C=%d unsupported", C);
     AOZ_CHECK_ARG(((((uintptr_t)dy) | ((uintptr_t)x) | ((uintptr_t)dres) | ((uintptr_t)dx)) & 15) == 0,
@@ -1052,10 +1074,11 @@ int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const vo
     }
     launch_k(ln_bwd_kernel, dim3((int)blocks), dim3(cols_pad * RL), smem, s, (const __nv_bfloat16*)dy, (const __nv_bfloat16*)x,
              (const __nv_bfloat16*)gamma, (const float*)mean, (const float*)rstd, rows, C, (const __nv_bfloat16*)dres,
-             (__nv_bfloat16*)dx, (float*)workspace, cols_pad, RL, rows_per_block);
+             (__nv_bfloat16*)dx, (float*)workspace, cols_pad, RL, rows_per_block, dcolsum != nullptr ? 1 : 0);
     AOZ_CHECK_LAUNCH("ln_bwd_kernel");
-    launch_k(ln_bwd_finalize_kernel, dim3((2 * C + 31) / 32), dim3(1024), (size_t)(0), s, (const float*)workspace, (int)blocks, C,
-             (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate);
+    const int ncomp = dcolsum != nullptr ? 3 : 2;
+    launch_k(ln_bwd_finalize_kernel, dim3((ncomp * C + 31) / 32), dim3(1024), (size_t)(0), s, (const float*)workspace, (int)blocks, C,
+             (__nv_bfloat16*)dgamma, (__nv_bfloat16*)dbeta, accumulate, (__nv_bfloat16*)dcolsum, ncomp, 0);
     AOZ_CHECK_LAUNCH("ln_bwd_finalize_kernel");
     return AOZ_OK;
 }

@@ -295,8 +295,9 @@ def layernorm_fwd(x, gamma, beta, eps=1e-5):
     return y, mean, rstd
 
 
-def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
-    """``dgamma`` / ``dbeta``: optional destinations (e.g. slices of a flat gradient buffer)."""
+def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None, dx_colsum=None):
+    """``dgamma`` / ``dbeta``: optional destinations (e.g. slices of a flat gradient buffer).  ``dx_colsum``: a bf16 [C] destination
+    for the column sums of dx (the bias gradient of the Linear that produced this LayerNorm's input), formed in the same pass."""
     _chk(dy, "layernorm dy")
     C = x.shape[-1]
     rows = x.numel() // C
@@ -304,8 +305,8 @@ def layernorm_bwd(dy, x, gamma, mean, rstd, dres=None, dgamma=None, dbeta=None):
     dgamma = torch.empty_like(gamma) if dgamma is None else dgamma
     dbeta = torch.empty_like(gamma) if dbeta is None else dbeta
     ws = workspace(_lib.query("aoz_layernorm_bwd_workspace_floats", C), x.device)
-    _lib.call("aoz_layernorm_bwd", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
-              _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0, ws.data_ptr(), _stream())
+    _lib.call("aoz_layernorm_bwd_colsum", dy.data_ptr(), x.data_ptr(), gamma.data_ptr(), mean.data_ptr(), rstd.data_ptr(), rows, C,
+              _p(dres), dx.data_ptr(), dgamma.data_ptr(), dbeta.data_ptr(), 0, _p(dx_colsum), ws.data_ptr(), _stream())
     _count(2)
     return dx, dgamma, dbeta
 

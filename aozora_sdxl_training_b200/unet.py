@@ -16,6 +16,8 @@ always-on gradient checkpointing, train.py:2660, is unnecessary).  The ``nn.Conv
 """
 from __future__ import annotations
 
+import os
+
 from types import SimpleNamespace
 
 import torch
@@ -29,6 +31,11 @@ BF16 = torch.bfloat16
 # ------------------------------------------------------------------------------------------------------------
 # parameter containers (names and registration order follow diffusers)
 # ------------------------------------------------------------------------------------------------------------
+# A/B switch (AOZ_LN_COLSUM=0): bias gradients of to_out / ff.net.2 / proj_in as separate column-sum launches instead of riding the
+# LayerNorm backward that produces their dy
+LN_COLSUM = os.environ.get("AOZ_LN_COLSUM", "1") != "0"
+
+
 class TimestepEmbedding(nn.Module):
     def __init__(self, in_dim, dim):
         super().__init__()
@@ -277,13 +284,14 @@ def _linear(x, w, b, G, *, residual=None, need_dx=True, w_param=None, defer=Fals
     y = ops.gemm(x, w, bias=b, residual=residual)
     wp = w if w_param is None else w_param
 
-    def bwd(dy, out=None, accumulate=False):
+    def bwd(dy, out=None, accumulate=False, bias_done=False):
+        """``bias_done``: the producer of ``dy`` (a LayerNorm backward, see ``_layernorm``) already formed this layer's bias gradient."""
         if wp.requires_grad:
             if w_param is None:
                 G.wgrad((wp,), dy, x, defer=defer)
             else:
                 G.add(wp, ops.gemm(dy, x, a_mn=True, b_mn=True))
-        if b is not None and b.requires_grad:
+        if b is not None and b.requires_grad and not (bias_done and LN_COLSUM):
             G.bias_grad(b, dy)          # right away: dy is still L2-resident (deferring it to the block's flush measured slower)
         if not need_dx:
             return None
@@ -359,14 +367,24 @@ def _groupnorm(x, mod, G, silu):
 def _layernorm(x, mod, G):
     y, mean, rstd = ops.layernorm_fwd(x, mod.weight, mod.bias, mod.eps)
 
-    def bwd(dy, dres=None):
+    def bwd(dy, dres=None, bias_of_dx=None):
+        """``bias_of_dx``: the bias of the Linear whose output is this LayerNorm's input (the previous sublayer's to_out / ff.net.2,
+        or proj_in): its gradient is the column sum of the dx computed here, formed in the same pass (the consumer of dx is then
+        called with ``bias_done=True``)."""
         both = mod.weight.requires_grad and mod.bias.requires_grad
+        dcol = None
+        if LN_COLSUM and bias_of_dx is not None and bias_of_dx.requires_grad:
+            dcol = G.out_for(bias_of_dx)
+            if dcol is None:
+                dcol = torch.empty_like(bias_of_dx)
         dx, dg, db = ops.layernorm_bwd(dy, x, mod.weight, mean, rstd, dres=dres, dgamma=G.out_for(mod.weight) if both else None,
-                                       dbeta=G.out_for(mod.bias) if both else None)
+                                       dbeta=G.out_for(mod.bias) if both else None, dx_colsum=dcol)
         if mod.weight.requires_grad:
             G.add(mod.weight, dg)
         if mod.bias.requires_grad:
             G.add(mod.bias, db)
+        if dcol is not None:
+            G.add(bias_of_dx, dcol)
         return dx
 
     return y, bwd
@@ -479,11 +497,13 @@ def _basic_block(blk, x, ctx, B, T, Tc, G, kv_pre=None):
     M, Mc = x.shape[0], ctx.shape[0]
     del n1, q, k, v, o1, n2, q2, k2, v2, o2, n3, g
 
-    def bwd(dy):
-        dg = b_f2(dy)
+    def bwd(dy, dy_bias_done=False, prev_bias=None):
+        """``dy_bias_done``: ff.net.2's bias gradient (column sums of dy) came with dy from the LayerNorm backward that produced it;
+        ``prev_bias``: the bias whose gradient is the column sum of the dx returned here (the previous block's ff.net.2, or proj_in)."""
+        dg = b_f2(dy, bias_done=dy_bias_done)
         dn3 = b_g(dg)
-        dx2 = b_n3(dn3, dres=dy)
-        do2 = b_o2(dx2)
+        dx2 = b_n3(dn3, dres=dy, bias_of_dx=a2.to_out[0].bias)
+        do2 = b_o2(dx2, bias_done=True)
         if w_kv is not None:
             dkv2 = torch.empty((Mc, 2 * C), dtype=BF16, device=dy.device)
             dq2 = torch.empty((M, C), dtype=BF16, device=dy.device)
@@ -494,8 +514,8 @@ def _basic_block(blk, x, ctx, B, T, Tc, G, kv_pre=None):
             b_k2(dk2)
             b_v2(dv2)
         dn2 = b_q2(dq2)
-        dx1 = b_n2(dn2, dres=dx2)
-        do1 = b_o1(dx1)
+        dx1 = b_n2(dn2, dres=dx2, bias_of_dx=a1.to_out[0].bias)
+        do1 = b_o1(dx1, bias_done=True)
         if w_qkv is not None:
             dqkv = torch.empty((M, 3 * C), dtype=BF16, device=dy.device)
             b_at1(do1, out=(dqkv[:, :C], dqkv[:, C:2 * C], dqkv[:, 2 * C:]))
@@ -506,7 +526,7 @@ def _basic_block(blk, x, ctx, B, T, Tc, G, kv_pre=None):
             b_k(dk, out=dn1, accumulate=True)
             b_v(dv, out=dn1, accumulate=True)
         G.flush()                      # this block's queued weight gradients: one grouped launch
-        return b_n1(dn1, dres=dx1)
+        return b_n1(dn1, dres=dx1, bias_of_dx=prev_bias)
 
     return x3, bwd
 
@@ -530,10 +550,16 @@ def _transformer(tr, x, ctx, Tc, G):
     def bwd(dy):
         dy2 = dy.view(B * T, C)
         dh = b_po(dy2)
-        while blocks:
-            dh = blocks.pop()(dh)
+        # the dx a block returns is the gradient of the PREVIOUS Linear's output -- the block before it's ff.net.2, or proj_in --
+        # so that layer's bias gradient (column sums of dx) is formed by the block's first LayerNorm backward
+        n = len(blocks)
+        for i in range(n - 1, -1, -1):
+            prev_bias = tr.transformer_blocks[i - 1].ff.net[2].bias if i > 0 else tr.proj_in.bias
+            dh = blocks[i](dh, dy_bias_done=(i < n - 1), prev_bias=prev_bias)
+            blocks[i] = None
+        blocks.clear()
         G.flush(late=True)             # cross-attention k/v weight gradients of all blocks: one grouped launch
-        dhn = b_pi(dh)
+        dhn = b_pi(dh, bias_done=True)
         return b_gn(dhn.view(B, H, W, C), dres=dy)
 
     return y.view(B, H, W, C), bwd

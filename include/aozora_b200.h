@@ -129,6 +129,11 @@ int aoz_layernorm_fwd(const void* x, const void* gamma, const void* beta, long l
 long long aoz_layernorm_bwd_workspace_floats(int C);
 int aoz_layernorm_bwd(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
                       const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* workspace, void* stream);
+/* The same, additionally dcolsum[c] = sum_r dx[r, c] (of the stored bf16 dx; null: not wanted): dx of a pre-LN transformer sublayer
+ * is the gradient of the previous Linear's output, so this is that layer's bias gradient without the column-sum launch */
+int aoz_layernorm_bwd_colsum(const void* dy, const void* x, const void* gamma, const void* mean, const void* rstd, long long rows, int C,
+                             const void* dres, void* dx, void* dgamma, void* dbeta, int accumulate, void* dcolsum, void* workspace,
+                             void* stream);
 
 /* ---- step glue: noising + target (train.py:2743-2758; DDPMScheduler.add_noise/get_velocity [3P]),
  *      weighted_sdxl_mse_loss + dL/dpred (train.py:2408-2416, 2765), layout and elementwise pieces [3P] ------- */

@@ -178,6 +178,27 @@ def test_geglu_fused_epilogue_and_backward(M, C):
     check(ops.geglu_bwd(dy, aux), pr.grad, rel=8e-3)
 
 
+def test_layernorm_backward_with_column_sums_of_dx():
+    """ln_bwd_kernel's third accumulator: the column sums of the dx it stores (bf16-rounded) = the bias gradient of the Linear that
+    produced the LayerNorm's input.  dx / dgamma / dbeta must not change; the sums must equal colsum(dx) up to fp32 summation order."""
+    ops = _ops()
+    g = gen(57)
+    for rows, C, with_res in ((4096, 1280, True), (16384, 640, True), (1000, 320, False), (7, 64, True)):
+        x = torch.randn(rows, C, device="cuda", generator=g).to(BF16)
+        dy = torch.randn(rows, C, device="cuda", generator=g).to(BF16)
+        dres = torch.randn(rows, C, device="cuda", generator=g).to(BF16) if with_res else None
+        ga = (1 + 0.1 * torch.randn(C, device="cuda", generator=g)).to(BF16)
+        be = torch.zeros(C, device="cuda", dtype=BF16)
+        _, mean, rstd = ops.layernorm_fwd(x, ga, be)
+        dx0, dg0, db0 = ops.layernorm_bwd(dy, x, ga, mean, rstd, dres=dres)
+        col = torch.empty(C, device="cuda", dtype=BF16)
+        dx1, dg1, db1 = ops.layernorm_bwd(dy, x, ga, mean, rstd, dres=dres, dx_colsum=col)
+        assert torch.equal(dx0, dx1) and torch.equal(dg0, dg1) and torch.equal(db0, db1)
+        want = dx1.float().sum(0)
+        err = (col.float() - want).abs()
+        assert bool((err <= 2 ** -7 * want.abs() + 2e-2).all()), float(err.max())
+
+
 def test_geglu_backward_with_fused_bias_gradient():
     """geglu_bwd_colsum_kernel: daux identical to geglu_bwd_kernel's, and the bias gradient equal to the column sums of that daux
     (formed from the rounded values; same partial / ticket scheme as colsum, other chunking -> fp32 summation order differs)."""
