@@ -329,6 +329,7 @@ def main():
     ap.add_argument("--nccl-ctas", type=int, default=-1,
                     help="data parallel: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and leave them their own SMs (persistent GEMMs are "
                          "sized to the rest); 0 = NCCL defaults, all SMs to the GEMMs; default: the measured best")
+    ap.add_argument("--bucket-mb", type=int, default=256, help="data parallel: gradient reduce-scatter bucket size")
     ap.add_argument("--no-defer-all-gather", action="store_true",
                     help="data parallel: all-gather the updated parameters at the end of the step instead of behind the next forward pass")
     args = ap.parse_args()
@@ -398,7 +399,7 @@ def main():
     cfg = type("BenchCfg", (Cfg,), dict(BATCH_SIZE=args.batch * world, PREDICTION_TYPE=args.mode, TIMESTEP_ALLOCATION=alloc))
     if world > 1:
         from aozora_sdxl_training_b200.parallel import DataParallel
-        dp = DataParallel(unet, momentum_dtype=torch.bfloat16, defer_all_gather=not args.no_defer_all_gather)
+        dp = DataParallel(unet, momentum_dtype=torch.bfloat16, defer_all_gather=not args.no_defer_all_gather, bucket_mb=args.bucket_mb)
         opt = dp.make_optimizer(lr=8e-7, **Cfg.RAVEN)
     else:
         opt = RavenAdamW([{"params": [p for p in unet.parameters() if p.requires_grad], "lr_scale": 1.0}], lr=8e-7,
