@@ -186,11 +186,12 @@ class ShardedRavenAdamW(RavenAdamW):
 
 
 class DataParallel:
-    def __init__(self, unet, momentum_dtype=torch.bfloat16, bucket_mb=256, group=None, backend=None, flat_dtype=None,
+    def __init__(self, unet, momentum_dtype=torch.bfloat16, bucket_mb=512, group=None, backend=None, flat_dtype=None,
                  bucket_elems=None, defer_all_gather=False):
         # bucket_mb: measured at 2 B200 (profiles/r02_bench_dp2_mb*.json, ms per step): 16 MB 148.0, 64 MB 139.8, 256 MB 138.5 on one
         # box; 256 / 512 / 1024 MB 136.6 / 136.6 / 136.1 on another -- every collective launch disturbs the persistent GEMM waves, so
-        # fewer, larger buckets win until the last bucket's un-overlapped reduce-scatter starts to show
+        # fewer, larger buckets win until the last bucket's un-overlapped reduce-scatter starts to show; at 8 B200: 64 MB 145.9,
+        # 256 MB 140.5, 512 MB 139.5 ms per step
         self.group = group
         self.defer_all_gather = bool(defer_all_gather)
         self._params_stale = False           # deferred mode: the last update's slices have not been gathered yet

@@ -329,7 +329,7 @@ def main():
     ap.add_argument("--nccl-ctas", type=int, default=-1,
                     help="data parallel: cap NCCL at this many CTAs (NCCL_MAX_CTAS) and leave them their own SMs (persistent GEMMs are "
                          "sized to the rest); 0 = NCCL defaults, all SMs to the GEMMs; default: the measured best")
-    ap.add_argument("--bucket-mb", type=int, default=256, help="data parallel: gradient reduce-scatter bucket size")
+    ap.add_argument("--bucket-mb", type=int, default=512, help="data parallel: gradient reduce-scatter bucket size")
     ap.add_argument("--no-defer-all-gather", action="store_true",
                     help="data parallel: all-gather the updated parameters at the end of the step instead of behind the next forward pass")
     args = ap.parse_args()
