@@ -355,10 +355,12 @@ def test_cross_attention_backward_one_kernel_equals_two_kernels():
 
 
 @pytest.mark.parametrize("B,H,Tq,Tk", [(2, 10, 1024, 1024), (1, 3, 1008, 1008), (2, 10, 1024, 77), (1, 10, 4096, 77), (1, 2, 64, 64),
-                                        (1, 2, 300, 40), (1, 5, 988, 154), (1, 2, 300, 128), (2, 3, 200, 77)])
+                                        (1, 2, 300, 40), (1, 5, 988, 154), (1, 2, 300, 128), (2, 3, 200, 77), (1, 2, 333, 200),
+                                        (2, 2, 130, 129), (1, 1, 4, 300)])
 def test_attention_backward_variants_agree(B, H, Tq, Tk):
     """The one-kernel backward (key-major scores, P^T / dS^T in tensor memory, dQ -- and with a single KV tile dK / dV -- summed over
-    CTAs by bulk reduce-add in fp32; default) against the bit-reproducible dK/dV + dQ kernel pair: the same five products with
+    CTAs by bulk reduce-add in fp32; default; Tq = 333 is not a multiple of 4 and takes the two-kernel path in both modes, 130 x 129
+    has one-row / one-key partial tiles) against the bit-reproducible dK/dV + dQ kernel pair: the same five products with
     different rounding points (dS is formed from the unrounded P in both) -> equal within bf16 rounding of the results; both against
     fp32 autograd."""
     from aozora_sdxl_training_b200 import _lib
