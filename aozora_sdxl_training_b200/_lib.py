@@ -73,6 +73,8 @@ def load():
         lib.aoz_attn_set_fused_cross_bwd(int(os.environ["AOZ_FUSED_CROSS_BWD"]))
     if os.environ.get("AOZ_ATTN_FWD_SPLIT") is not None:
         lib.aoz_attn_set_fwd_split(int(os.environ["AOZ_ATTN_FWD_SPLIT"]))
+    if os.environ.get("AOZ_TAIL_INKERNEL") is not None:
+        lib.aoz_gemm_set_tail_inkernel(int(os.environ["AOZ_TAIL_INKERNEL"]))
     if os.environ.get("AOZ_ATTN_BWD_MODE") is not None:
         lib.aoz_attn_set_bwd_mode(int(os.environ["AOZ_ATTN_BWD_MODE"]))
     if os.environ.get("AOZ_GN_SLAB") is not None:

@@ -60,6 +60,7 @@ struct GemmParams {
     // `tail_ws` ([slice][128 rows][bn]) and finished (sum + fused epilogue) by tail_fixup_kernel.
     int full_work, tail_tiles, tail_splits;
     float* tail_ws;
+    int tail_inkernel;              // 1: the slices' own CTAs sum the partials and run the fused epilogue (no tail_fixup_kernel launch)
     int vec_ok;                     // EPI_STORE: every output / bias / residual row segment is 16-byte aligned
     // conv geometry (NHWC).  H, W = OUTPUT spatial size (CONV_FWD) / dy spatial size (CONV_WGRAD)
     int NB, H, W, TH, TW, tiles_h, tiles_w;
@@ -156,6 +157,19 @@ __device__ __forceinline__ void unstage8(uint32_t stg, int lane, int step, float
     ld_shared_v4f(stg + rr * 128 + ((j0 ^ (rr & 7)) << 4), f);
     ld_shared_v4f(stg + rr * 128 + (((j0 + 1) ^ (rr & 7)) << 4), f + 4);
 }
+
+// In-kernel tail fix-up: per (tail tile, CTA rank) an arrival counter and a done counter.  Every K slice of a tail tile runs on its
+// own CTA (pair) in the last round (the planner keeps tail_tiles * tail_splits <= work units), so its epilogue warps may wait for
+// the sibling slices: after writing its fp32 partial a CTA arrives, waits until all tail_splits slices have arrived, and then sums
+// and stores ITS share of the tile's 32-column chunks (chunk c belongs to slice c % tail_splits).  The last CTA to finish
+// resets both counters for the next launch (launches that use the scratch are stream-ordered).
+__device__ unsigned int g_tail_arrive[1024], g_tail_done[1024];
+__device__ __forceinline__ unsigned int ld_acquire_u32(const unsigned int* p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 3, 256;" ::: "memory"); }      // the 8 epilogue warps
 
 struct WorkItem { int tile, split, k_begin, k_end, tail_slot; };      // tail_slot < 0: not a tail slice
 
@@ -614,6 +628,52 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) *reinterpret_cast<uint4*>(dstp + c + j) = make_uint4(r[j], r[j + 1], r[j + 2], r[j + 3]);
                 }
+                if (P.tail_inkernel) {
+                    const int t = wi.tail_slot / P.tail_splits;
+                    const int cidx = t * m_sub + (int)rank;
+                    __threadfence();
+                    epi_bar_sync();
+                    if (warp == 2 && lane == 0) atomicAdd(&g_tail_arrive[cidx], 1u);
+                    if (lane == 0) {
+                        unsigned int spins = 0;
+                        while (ld_acquire_u32(&g_tail_arrive[cidx]) < (unsigned int)P.tail_splits) {
+                            __nanosleep(64);
+                            if (++spins > (1u << 24)) __trap();
+                        }
+                    }
+                    __syncwarp();
+                    // this slice's share of the chunks; its two warps per lane quarter alternate over them
+                    const int n_chunks = BN / 32;
+                    const long long slice_stride = (long long)m_sub * BM * BN;
+                    const float* base = P.tail_ws + ((long long)(t * P.tail_splits * m_sub + (int)rank) * BM) * BN;
+                    int pos = 0;
+                    for (int ci = split; ci < n_chunks; ci += P.tail_splits, ++pos) {
+                        if ((pos & 1) != half) continue;
+                        const int colg = col0 + ci * 32 + lcol;
+#pragma unroll
+                        for (int st = 0; st < 4; ++st) {
+                            if (!rmap[st].ok || colg >= col_limit) continue;
+                            const int rit = q * 32 + st * 8 + (lane >> 2);
+                            const float* src = base + (long long)rit * BN + ci * 32 + lcol;
+                            float f[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+#pragma unroll 4
+                            for (int sp = 0; sp < P.tail_splits; ++sp) {
+                                const float4 v0 = __ldcg(reinterpret_cast<const float4*>(src + sp * slice_stride));
+                                const float4 v1 = __ldcg(reinterpret_cast<const float4*>(src + sp * slice_stride + 4));
+                                f[0] += v0.x; f[1] += v0.y; f[2] += v0.z; f[3] += v0.w;
+                                f[4] += v1.x; f[5] += v1.y; f[6] += v1.z; f[7] += v1.w;
+                            }
+                            epi_store8(P, pr.C, pr.ldc, rmap[st].row, rmap[st].group, colg, col_limit, f);
+                        }
+                    }
+                    epi_bar_sync();
+                    if (warp == 2 && lane == 0) {
+                        if (atomicAdd(&g_tail_done[cidx], 1u) == (unsigned int)P.tail_splits - 1u) {
+                            g_tail_arrive[cidx] = 0u; g_tail_done[cidx] = 0u;
+                            __threadfence();
+                        }
+                    }
+                }
             } else if (P.epi == EPI_PARTIAL) {
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
@@ -821,6 +881,10 @@ static inline int gemm_sms() {
     const int n = sm_count();
     return (g_gemm_sm_budget > 0 && g_gemm_sm_budget < n) ? g_gemm_sm_budget : n;
 }
+// Measured inside the step (B200, two runs each, same box): in-kernel 136.9 / 136.4 ms, separate launch 134.1 / 133.9 ms -- the slices
+// of a tile wait for the slowest sibling (which may still be finishing a full tile) and then few CTAs do the reduction that
+// tail_fixup_kernel spreads over thousands of threads.  Off by default.
+static int g_tail_inkernel = 0;   // 1 = tail slices are summed and stored by their own CTAs, 0 = separate tail_fixup_kernel launch (default)
 static int g_tail_mode = 1;       // 0 = never cut the last wave along K, 1 = the cost model may (default), 2 = whenever possible
 static float* g_tail_ws = nullptr;        // caller-owned scratch for the tail slices (aoz_gemm_set_scratch)
 static long long g_tail_bytes = 0;
@@ -839,6 +903,7 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     if (P.tail_tiles > 0) {
         P.full_work = tiles - P.tail_tiles;
         P.tail_ws = g_tail_ws;
+        P.tail_inkernel = (g_tail_inkernel && P.tail_tiles * (CTA2 ? 2 : 1) <= 1024) ? 1 : 0;
     } else {
         P.full_work = tiles * P.splits;
         P.tail_tiles = 0; P.tail_splits = 1;
@@ -1052,6 +1117,8 @@ int aoz_gemm_set_sm_budget(int sms) { g_gemm_sm_budget = sms > 0 ? (sms & ~1) : 
 
 // 0 = never split the last wave along K, 1 = cost model decides (default), 2 = split whenever the shape allows it
 int aoz_gemm_set_tail_mode(int mode) { g_tail_mode = mode; return AOZ_OK; }
+// experiment switch: 1 = in-kernel tail fix-up, 0 = tail_fixup_kernel launch (default: measured 2.5 ms per step faster)
+int aoz_gemm_set_tail_inkernel(int on) { g_tail_inkernel = on ? 1 : 0; return AOZ_OK; }
 
 // Caller-owned fp32 scratch for the K slices of tail tiles (stream-ordered: every GEMM that uses it must run on the
 // same stream).  Without it the tail split is off.  20 MB covers every shape (148 slices x 128 x 256 floats).

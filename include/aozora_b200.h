@@ -59,6 +59,9 @@ int aoz_gemm_force_bn(int bn);
  * scratch, finished by a fix-up kernel).  mode 0 = off, 1 = cost model decides (default), 2 = whenever possible.
  * The scratch (>= 20 MB covers every shape) is used stream-ordered: all GEMM / conv calls must share one stream. */
 int aoz_gemm_set_tail_mode(int mode);
+/* experiment switch: 1 = the K slices of tail tiles are summed and stored by their own CTAs, 0 = tail_fixup_kernel launch (default:
+ * the in-kernel form measured 2.5 ms per step slower) */
+int aoz_gemm_set_tail_inkernel(int on);
 /* measured plan selection: the first EAGER call of every distinct GEMM / conv problem times the candidate tile plans on the
  * caller's operands and caches the fastest (never during CUDA-graph capture, never for accumulate epilogues).  Off by
  * default: on B200 the L2-warm timings mis-ranked the plans for the in-step (cold-weight) launches (profiles/r01 notes). */

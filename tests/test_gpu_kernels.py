@@ -178,6 +178,27 @@ def test_geglu_fused_epilogue_and_backward(M, C):
     check(ops.geglu_bwd(dy, aux), pr.grad, rel=8e-3)
 
 
+def test_gemm_tail_fixup_in_kernel_equals_separate_launch():
+    """Switchable path (off by default): the K slices of the tail tiles summed and stored by their own CTAs instead of by
+    tail_fixup_kernel -- same partials, same summation order, same fused epilogue: identical bits."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(58)
+    for M, N, K in ((4096, 1280, 1280), (4096, 1280, 5120), (16384, 640, 640)):
+        x = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+        w = (torch.randn(N, K, device="cuda", generator=g) * 0.05).to(BF16)
+        b = torch.randn(N, device="cuda", generator=g).to(BF16)
+        res = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+        ref = ops.gemm(x, w, bias=b, residual=res)
+        try:
+            _lib.call("aoz_gemm_set_tail_inkernel", 1)
+            for _ in range(3):                                  # the counters must come back to zero after every launch
+                got = ops.gemm(x, w, bias=b, residual=res)
+        finally:
+            _lib.call("aoz_gemm_set_tail_inkernel", 0)
+        assert torch.equal(got, ref)
+
+
 def test_layernorm_backward_with_column_sums_of_dx():
     """ln_bwd_kernel's third accumulator: the column sums of the dx it stores (bf16-rounded) = the bias gradient of the Linear that
     produced the LayerNorm's input.  dx / dgamma / dbeta must not change; the sums must equal colsum(dx) up to fp32 summation order."""
