@@ -608,9 +608,11 @@ int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* 
     return AOZ_OK;
 }
 
+static int g_geglu_chunk_mul = 4;         // row chunks ~ this many blocks per SM (experiment knob: aoz_geglu_colsum_set_blocks_per_sm)
+int aoz_geglu_colsum_set_blocks_per_sm(int n) { g_geglu_chunk_mul = n < 1 ? 1 : n; return AOZ_OK; }
 static int geglu_colsum_chunks(long long M, int half) {
     const int colblocks = (half + 255) / 256;
-    int chunks = (sm_count() * 4 + colblocks - 1) / colblocks;
+    int chunks = (sm_count() * g_geglu_chunk_mul + colblocks - 1) / colblocks;
     if (chunks > 64) chunks = 64;
     if ((long long)chunks * 8 > M) chunks = (int)((M + 7) / 8);
     return chunks < 1 ? 1 : chunks;

@@ -34,6 +34,10 @@ BF16 = torch.bfloat16
 # A/B switch (AOZ_LN_COLSUM=0): bias gradients of to_out / ff.net.2 / proj_in as separate column-sum launches instead of riding the
 # LayerNorm backward that produces their dy
 LN_COLSUM = os.environ.get("AOZ_LN_COLSUM", "1") != "0"
+# A/B switch (AOZ_GEGLU_COLSUM=1): ff.net.0.proj's bias gradient formed inside the GEGLU backward kernel.  Off: the column-owner
+# thread mapping that the fused sums need streams worse than the elementwise kernel (tools/geglu_bwd_bench.py, 4096 x 10240:
+# 61-66 us fused against 50.8 us for geglu_bwd + colsum)
+GEGLU_COLSUM = os.environ.get("AOZ_GEGLU_COLSUM", "0") == "1"
 
 
 class TimestepEmbedding(nn.Module):
@@ -305,7 +309,7 @@ def _geglu(x, w, b, G, defer=False):
     y = ops.gemm(x, w, bias=b, epi=ops.EPI_GEGLU, aux=aux)
 
     def bwd(dy):
-        if b.requires_grad:             # the bias gradient (column sums of daux) rides the same pass
+        if b.requires_grad and GEGLU_COLSUM:        # the bias gradient (column sums of daux) in the same pass -- measured slower
             db = G.out_for(b)
             if db is None:
                 db = torch.empty_like(b)
@@ -313,6 +317,8 @@ def _geglu(x, w, b, G, defer=False):
             G.add(b, db)
         else:
             daux = ops.geglu_bwd(dy, aux)
+            if b.requires_grad:
+                G.bias_grad(b, daux)
         if w.requires_grad:
             G.wgrad((w,), daux, x, defer=defer)
         return ops.gemm(daux, w, b_mn=True)

@@ -154,6 +154,8 @@ int aoz_geglu_bwd(const void* dy, const void* aux, long long M, int half, void* 
 int aoz_geglu_bwd_colsum(const void* dy, const void* aux, long long M, int half, void* daux, void* db, int accumulate, void* workspace,
                          void* stream);
 long long aoz_geglu_bwd_colsum_workspace_floats(long long M, int half);
+/* experiment knob: row chunks of the fused kernel ~ this many blocks per SM (capped at 64 chunks) */
+int aoz_geglu_colsum_set_blocks_per_sm(int n);
 int aoz_silu_fwd(const void* x, long long n, void* y, void* stream);
 int aoz_silu_bwd(const void* dy, const void* x, long long n, void* dx, void* stream);
 int aoz_add(const void* a, const void* b, long long n, void* y, void* stream);
