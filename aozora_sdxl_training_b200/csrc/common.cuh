@@ -166,6 +166,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     }
 }
 
+// (Measured, round 2: letting ONE lane poll and parking the other 31 at __syncwarp -- "32 lanes polling the same mbarrier are wasted
+// transactions" -- HALVES the attention kernels' throughput (forward 690 -> 374, backward 825 -> 347 TFLOP/s): the warp-wide
+// try_wait suspends the whole warp in hardware, the divergent single-lane loop does not.  Every lane waits.)
+
 // Wait that is NOT on a latency-critical path (a producer waiting for a free ring slot): try_wait with a suspend-time hint, so the
 // thread sleeps in hardware until the phase completes instead of polling -- a polling producer warp took 6 % of the attention
 // kernel's issue slots away from the softmax warps on its scheduler (ncu r02).
