@@ -23,7 +23,9 @@ def _line(name):
 
 
 @pytest.mark.parametrize("name,n", [("r01_bench_v7.json", 1), ("r01_bench_dp2_v2.json", 2), ("r01_bench_dp4_v1.json", 4),
-                                    ("r01_bench_dp8_v2.json", 8)])
+                                    ("r01_bench_dp8_v2.json", 8), ("r02_bench_v3.json", 1), ("r02_bench_dp2_final.json", 2),
+                                    ("r02_bench_dp8_mb512.json", 8), ("r02_bench_w3.json", 1), ("r02_bench_w4.json", 1),
+                                    ("r02_bench_dp8_w3.json", 8)])
 def test_recorded_bench_lines_follow_the_contract(name, n):
     d = _line(name)
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
@@ -41,8 +43,19 @@ def test_recorded_bench_lines_follow_the_contract(name, n):
     # whole-job value = images of all ranks / max-over-ranks step time
     imgs_per_step = d["config"]["global_batch"]
     assert abs(d["value"] - imgs_per_step / (d["ms_per_step"] * 1e-3)) / d["value"] < 5e-3
-    if n == 1:
+    if n == 1 and d.get("cpu_baseline") is not None:      # (recorded with --no-cpu-baseline: absent)
         assert CPU_KEYS <= set(d["cpu_baseline"]) and d["cpu_baseline"]["kind"] in ("reference", "port")
+
+
+def test_recorded_reference_arm_line():
+    """`bench.py --impl reference` as recorded on the GPU box's host: BASELINE config 1 on all host cores, split timings."""
+    d = _line("r02_bench_reference_arm.json")
+    assert d["impl"] == "reference" and d["unit"] == "imgs/s" and d["higher_is_better"] is True and d["gpu_launches"] == 0
+    cb = d["cpu_baseline"]
+    assert CPU_KEYS <= set(cb) and cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"]
+    assert abs(cb["seconds_per_step"] - (cb["fwd_bwd_s"] + cb["clip_s"] + cb["raven_s"])) < 0.05
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and d["e2e"]["d2h_bytes_per_step"] == 0
+    assert "config 1" in d["config"]["workload"] and d["config"]["same_config"] is False
 
 
 def test_bench_cli_defaults_and_reference_arm_flag():
