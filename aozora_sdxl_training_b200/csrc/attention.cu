@@ -1945,7 +1945,7 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
             named_bar_sync(2, 128);
             if (leader) bulk_reduce_add_f32(gtile + (long long)i * (TILE * HD), stage, TILE * HD * 4);
         }
-        if (leader) bulk_wait0();
+        if (leader) bulk_wait_read0();         // shared memory must outlive the reads; the global writes complete with the kernel
     } else {
         // ---------------- compute warps: qtr = TMEM lane quarter (key rows), hf = which 32 of the tile's 128 query columns ----------------
         const int qtr = warp & 3, hf = warp >> 2;
@@ -2052,7 +2052,7 @@ attn_bwd_fused_kernel(const __grid_constant__ AttnParams P) {
                 const long long tile = ((long long)bh * kv_tiles + kt) * (TILE * HD);
                 bulk_reduce_add_f32(P.dVacc + tile, smem + FbSmem::Q, TILE * HD * 4);
                 bulk_reduce_add_f32(P.dKacc + tile, smem + FbSmem::DO, TILE * HD * 4);
-                bulk_wait0();
+                bulk_wait_read0();
             }
         } else {
             const int which = hf >> 1, c = hf & 1;               // warps hf 0,1 store dV chunks 0,1; hf 2,3 store dK chunks 0,1
