@@ -75,6 +75,8 @@ def load():
         lib.aoz_attn_set_fwd_split(int(os.environ["AOZ_ATTN_FWD_SPLIT"]))
     if os.environ.get("AOZ_TAIL_INKERNEL") is not None:
         lib.aoz_gemm_set_tail_inkernel(int(os.environ["AOZ_TAIL_INKERNEL"]))
+    if os.environ.get("AOZ_GEMM_WIDE") is not None:
+        lib.aoz_gemm_set_wide_mode(int(os.environ["AOZ_GEMM_WIDE"]), int(os.environ.get("AOZ_GEMM_WIDE_N2", "0")))
     if os.environ.get("AOZ_ATTN_BWD_MODE") is not None:
         lib.aoz_attn_set_bwd_mode(int(os.environ["AOZ_ATTN_BWD_MODE"]))
     if os.environ.get("AOZ_GN_SLAB") is not None:

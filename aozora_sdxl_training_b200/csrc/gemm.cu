@@ -50,7 +50,8 @@ struct GemmParams {
     CUtensorMap tmA, tmB;
     int mode, epi;
     int dbg;                        // experiment flags: 1 = epilogue does not load/store, 2 = MMA ignores full barriers, 4 = producer ignores empty barriers
-    int bn, stages;                 // N extent of the accumulator tile (multiple of 32, <= 256); smem pipeline depth
+    int bn, stages;                 // N extent of the accumulator tile (multiple of 32, <= 256; 320 = the wide one-wave plan); smem pipeline depth
+    int wide_n2;                    // bn == 320 (CTA pairs only): N of the second MMA of a K step (64; 128 = whole third B chunk, MN-major fallback)
     int a_mn, b_mn;                 // 1 = MN-major operand
     int M, N, K;                    // logical extents (CONV_FWD: M = NB*H*W output pixels, K = taps*cin_chunks*64)
     int m_tiles, n_tiles, k_iters;  // tile counts; k_iters = total K iterations (before split)
@@ -308,10 +309,19 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     const int BN = P.bn;                                      // accumulator tile width (runtime: picked by the host cost model)
     const int B_ROWS = CTA2 ? BN / 2 : BN;                    // B rows this CTA stages (a pair splits the B tile)
     const int A_BYTES = BM * BK * 2;
-    const int STAGE_BYTES = A_BYTES + B_ROWS * BK * 2;
+    // MN-major B arrives in whole 64-wide chunks (the wide plan's 160 rows = 2.5 chunks: the third is half used)
+    const int B_BYTES = P.b_mn ? ((B_ROWS + 63) / 64) * 8192 : B_ROWS * BK * 2;
+    const int STAGE_BYTES = A_BYTES + B_BYTES;
+    // Wide one-wave plan (CTA pairs, BN = 320): ONE 256 x 320 tile per pair, a single accumulator of 320 TMEM columns written by
+    // two MMAs per K step (N = 256 over B rows [0, 128) of each CTA, N = 64 over rows [128, 160)).  4096 x 1280 outputs are
+    // 16 x 4 = 64 tiles on 74 SM pairs instead of 80 tiles of 256 x 256 = two rounds with the second one 8 % full.
+    const bool WIDE = CTA2 && BN == 320;
     const int STAGES = P.stages;
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    // dbg 64 (experiments): CTA 0 stamps clock64 at its phase boundaries into the scratch buffer (tools/gemm_timeline.py)
+    long long* tl = ((P.dbg & 64) && blockIdx.x == 0 && P.tail_ws != nullptr) ? reinterpret_cast<long long*>(P.tail_ws) : nullptr;
+    if (tl && threadIdx.x == 0) tl[0] = clock64();
     const uint32_t rank = CTA2 ? cluster_ctarank() : 0u;
     const bool leader = rank == 0;
     const int unit = CTA2 ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;          // persistent work unit (CTA or CTA pair)
@@ -324,11 +334,22 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         fence_mbar_init();
     }
     if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
+    if (warp >= 2 && lane == 0) {
+        // Touch the kernel parameters' constant-bank lines (64 B apart) while warps 0 / 1 set up barriers and TMEM: the roles' first
+        // reads of P otherwise miss one after another (tools/gemm_timeline.py: ~2300 cycles from the prologue to the first TMA issue).
+        constexpr int kWords = (int)(offsetof(GemmParams, grp) / 4);
+        const int* pw = reinterpret_cast<const int*>(&P);
+        int v = 0;
+        for (int i = (warp - 2) * 16; i < kWords; i += 8 * 16) v ^= pw[i];
+        if (v == 0x5bd1e995 && P.dbg == -1) tmem_slot[1] = (uint32_t)v;          // never true: keeps the loads
+    }
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    pdl_enter();          // prologue done (barriers, TMEM, descriptors): only now wait for the previous kernel's results
+    if (tl && threadIdx.x == 0) tl[1] = clock64();
+    pdl_enter();
+    if (tl && threadIdx.x == 0) tl[2] = clock64();          // prologue done (barriers, TMEM, descriptors): only now wait for the previous kernel's results
 
     const int total_work = P.full_work + P.tail_tiles * P.tail_splits;      // (m_tiles counts 256-row pair tiles when CTA2)
     const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
@@ -342,7 +363,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             long long issued = 0;
             const uint32_t fb0_cluster = CTA2 ? mapa_rank(smem_u32(&full_bar[0]), 0) : 0u;   // leader's full barriers
             const bool a_mn = P.a_mn != 0, b_mn = P.b_mn != 0;
-            const int b_chunks = B_ROWS / 64;
+            const int b_chunks = (B_ROWS + 63) / 64;
             for (int work = unit; work < total_work; work += n_units) {
                 const WorkItem wi = decode_work(P, work, k_per_split);
                 const Prob pr = select_prob(P, wi.tile);
@@ -432,6 +453,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         if (++p_tw == P.tiles_w) { p_tw = 0; if (++p_th == P.tiles_h) { p_th = 0; ++p_im; } }
                     }
                     if (++stage == (uint32_t)STAGES) { stage = 0; phase ^= 1; }
+                    if (tl && issued == 0) tl[3] = clock64();
                     ++issued;
                 }
             }
@@ -455,7 +477,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         // live in uniform registers and a K iteration is four back-to-back UTCHMMA.
         // Descriptors are advanced by integer adds on their low word.
         if (leader) {
-            const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : BM, BN, P.a_mn, P.b_mn);
+            const uint32_t idesc = make_idesc_bf16(CTA2 ? 256 : BM, WIDE ? 256 : BN, P.a_mn, P.b_mn);
+            const uint32_t idesc2 = make_idesc_bf16(256, P.wide_n2, P.a_mn, P.b_mn);          // wide plan: accumulator columns [256, 256 + wide_n2)
             const uint64_t hi = ((uint64_t)(1024 >> 4) << 32) | ((uint64_t)1 << 46) | ((uint64_t)2 << 61);   // SBO, version, SW128
             const uint32_t smem_lo = (smem_u32(smem) & 0x3ffffu) >> 4;
             const uint32_t a_lo0 = smem_lo | ((P.a_mn ? (8192u >> 4) : 1u) << 16);
@@ -469,11 +492,12 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 const int k_begin = wi.k_begin, k_end = wi.k_end;
                 mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * 256;
+                const uint32_t tmem_d = tmem_base + (WIDE ? 0u : acc * 256);
                 uint32_t accum = 0;
                 for (int kit = k_begin; kit < k_end; ++kit) {
                     if (!(P.dbg & 2)) mbar_wait(&full_bar[stage], phase);
                     tc_fence_after();
+                    if (tl && lane == 0 && kit == k_begin) tl[4] = clock64();
                     if (elect_one_sync()) {
                         const uint32_t alo = a_lo0 + stage * stage_step, blo = b_lo0 + stage * stage_step;
 #pragma unroll
@@ -481,6 +505,8 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                             const uint64_t da = hi | (uint64_t)(alo + k * a_kstep);
                             const uint64_t db = hi | (uint64_t)(blo + k * b_kstep);
                             if (CTA2) umma2_bf16(tmem_d, da, db, idesc, k == 0 ? accum : 1u); else umma_bf16(tmem_d, da, db, idesc, k == 0 ? accum : 1u);
+                            // B rows [128, 160) of each CTA start 16 KB into its B stage in either operand major
+                            if (CTA2 && WIDE) umma2_bf16(tmem_d + 256, da, db + (16384u >> 4), idesc2, k == 0 ? accum : 1u);
                         }
                         // frees the smem slot (in both CTAs) when the MMAs retire
                         if (CTA2) umma2_commit_both(&empty_bar[stage]); else umma_commit(&empty_bar[stage]);
@@ -494,6 +520,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     if (CTA2) umma2_commit_both(&tfull_bar[acc]); else umma_commit(&tfull_bar[acc]);
                 }
                 __syncwarp();
+                if (tl && lane == 0) tl[5] = clock64();
                 if (++acc == 2) { acc = 0; acc_phase ^= 1; }
             }
         }
@@ -545,8 +572,13 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 rmap[st] = map_row(P, pr.M, m_blk, q * 32 + st * 8 + (lane >> 2));
                 rnext[st] = make_uint4(0u, 0u, 0u, 0u);
             }
+            // wide plan: accumulator chunk -> (TMEM column, output column).  CTA r holds B rows [160 r, 160 r + 160) of the tile, the
+            // first MMA covers rows [0, 128) of both CTAs and the second rows [128, 160): accumulator columns [0, 128) = n [0, 128),
+            // [128, 256) = n [160, 288), [256, 288) = n [128, 160), [256 + wide_n2 / 2, +32) = n [288, 320)
+            auto out_c = [&](int c) { return !WIDE ? c : c < 128 ? c : c < 256 ? c + 32 : c == 256 ? 128 : 288; };
+            auto tmem_c = [&](int c) { return (WIDE && c == 288) ? 256 + P.wide_n2 / 2 : c; };
             auto fetch_res = [&](int c) {
-                const int col = col0 + c + lcol;
+                const int col = col0 + out_c(c) + lcol;
 #pragma unroll
                 for (int st = 0; st < 4; ++st)
                     if (rmap[st].ok && col + 7 < col_limit)
@@ -556,9 +588,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 
             mbar_wait(&tfull_bar[acc], acc_phase);
             tc_fence_after();
+            if (tl && warp == 2 && lane == 0) tl[6] = clock64();
             if (P.dbg & 1) goto epilogue_done;
             {
-            const uint32_t taddr = tmem_base + acc * 256 + ((uint32_t)(q * 32) << 16);
+            const uint32_t taddr = tmem_base + (WIDE ? 0u : acc * 256) + ((uint32_t)(q * 32) << 16);
 
             if (P.epi == EPI_GEGLU) {
                 // columns [0, BN/2) = value, [BN/2, BN) = gate (same output columns)
@@ -699,6 +732,70 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         }
                     }
                 }
+            } else if (P.vec_ok && !P.accumulate && P.rowgroup_bias == nullptr && P.mode != GM_CONV_WGRAD && col0 + BN <= col_limit &&
+                       !empty_split && !(P.dbg & (8 | 16 | 32))) {
+                // Fast store path (every Linear / conv-forward tile that lies inside the output: bias and / or residual, 16-byte
+                // aligned rows).  The general loop below spends ~150 issued instructions per 8-column segment on per-segment address
+                // arithmetic (64-bit row x stride products for C, the residual and the time-embedding rows), parameter re-loads and
+                // the branches of epi_store8 -- with 8 epilogue warps on 4 schedulers that, not the store path, set the ~2500 cycles
+                // per 32 x 32 chunk measured in round 1 (tools/gemm_timeline.py: 12.6 k cycles for a 320-wide tile).  Here the four
+                // row pointers are formed once per tile, the bias vector travels with the residual prefetch and a segment is
+                // 2 LDS + 8 FADD (+ 8 round + 8 FADD) + 4 pack + 1 STG.  Same operations in the same order: identical bits.
+                const __nv_bfloat16* biasp = P.bias;
+                const bool has_res = P.residual != nullptr;
+                __nv_bfloat16* crow[4];
+                const __nv_bfloat16* rrow[4];
+#pragma unroll
+                for (int st = 0; st < 4; ++st) {
+                    crow[st] = pr.C + rmap[st].row * pr.ldc + col0 + lcol;
+                    rrow[st] = has_res ? P.residual + rmap[st].row * P.ldr + col0 + lcol : nullptr;
+                }
+                uint4 bnext = make_uint4(0u, 0u, 0u, 0u);
+                if (biasp) bnext = __ldg(reinterpret_cast<const uint4*>(biasp + col0 + out_c(half * 32) + lcol));
+#pragma unroll 1
+                for (int c = half * 32; c < BN; c += 64) {
+                    uint4 rcur[4];
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) rcur[st] = rnext[st];
+                    const uint4 bcur = bnext;
+                    if (c + 64 < BN) {
+                        const int ocn = out_c(c + 64);
+                        if (has_res) {
+#pragma unroll
+                            for (int st = 0; st < 4; ++st)
+                                if (rmap[st].ok) rnext[st] = *reinterpret_cast<const uint4*>(rrow[st] + ocn);
+                        }
+                        if (biasp) bnext = __ldg(reinterpret_cast<const uint4*>(biasp + col0 + ocn + lcol));
+                    }
+                    uint32_t r[32];
+                    tmem_ld32(taddr + tmem_c(c), r);
+                    tc_wait_ld();
+                    stage_chunk(stg, lane, r);
+                    __syncwarp();
+                    const int oc = out_c(c);
+                    const uint32_t bw[4] = {bcur.x, bcur.y, bcur.z, bcur.w};
+#pragma unroll
+                    for (int st = 0; st < 4; ++st) {
+                        float f[8];
+                        unstage8(stg, lane, st, f);
+                        if (biasp) {
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) { f[2 * e] += bf16lo(bw[e]); f[2 * e + 1] += bf16hi(bw[e]); }
+                        }
+                        if (has_res) {
+                            const uint32_t rw[4] = {rcur[st].x, rcur[st].y, rcur[st].z, rcur[st].w};
+#pragma unroll
+                            for (int e = 0; e < 4; ++e) {
+                                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
+                                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
+                            }
+                        }
+                        if (rmap[st].ok)
+                            *reinterpret_cast<uint4*>(crow[st] + oc) =
+                                make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+                    }
+                    __syncwarp();
+                }
             } else {
                 // dbg 32 (experiments): CTA 0, first epilogue warp logs clock64 at its phase boundaries into the tail scratch
                 const bool prof = (P.dbg & 32) && blockIdx.x == 0 && warp == 2 && lane == 0 && P.tail_ws != nullptr;
@@ -714,7 +811,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     if (pre_res && c + 64 < OUT_COLS && col0 + c + 64 < col_limit) fetch_res(c + 64);
                     uint32_t r[32];
                     if (!empty_split && !(P.dbg & 16)) {          // dbg 16 (experiments): epilogue without the TMEM read
-                        tmem_ld32(taddr + c, r);
+                        tmem_ld32(taddr + tmem_c(c), r);
                         tc_wait_ld();
                     } else {
 #pragma unroll
@@ -724,7 +821,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                     stage_chunk(stg, lane, r);
                     __syncwarp();
                     if (prof && pslot < 200) plog[1 + pslot++] = clock64();          // after staging
-                    const int col = col0 + c + lcol;
+                    const int col = col0 + out_c(c) + lcol;
 #pragma unroll
                     for (int st = 0; st < 4; ++st) {
                         float f[8];
@@ -743,6 +840,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             // release the accumulator buffer
             tc_fence_before();
             __syncwarp();
+            if (tl && lane == 0) tl[8 + warp] = clock64();
             if (lane == 0) {
                 if (CTA2 && !leader) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
                 else mbar_arrive(&tempty_bar[acc]);
@@ -753,6 +851,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
 
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();
+    if (tl && threadIdx.x == 0) tl[7] = clock64();
     if (warp == 1) {
         tc_fence_after();
         if (CTA2) tmem_dealloc2(tmem_base, 512); else tmem_dealloc(tmem_base, 512);
@@ -885,6 +984,10 @@ static inline int gemm_sms() {
 // of a tile wait for the slowest sibling (which may still be finishing a full tile) and then few CTAs do the reduction that
 // tail_fixup_kernel spreads over thousands of threads.  Off by default.
 static int g_tail_inkernel = 0;   // 1 = tail slices are summed and stored by their own CTAs, 0 = separate tail_fixup_kernel launch (default)
+// Wide one-wave plan for outputs that are a little more than one wave of 256 x 256 pair tiles (4096 x 1280: 80 tiles on 74 pairs):
+// 0 = off, 1 = the cost model may pick it (default), 2 = whenever the shape allows it.  g_wide_mn_n2: N of the second MMA for MN-major B.
+static int g_wide_mode = 1;
+static int g_wide_mn_n2 = 64;
 static int g_tail_mode = 1;       // 0 = never cut the last wave along K, 1 = the cost model may (default), 2 = whenever possible
 static float* g_tail_ws = nullptr;        // caller-owned scratch for the tail slices (aoz_gemm_set_scratch)
 static long long g_tail_bytes = 0;
@@ -911,9 +1014,13 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     const int total_work = P.full_work + P.tail_tiles * P.tail_splits;
     if (total_work <= 0) return AOZ_OK;
     P.dbg = g_dbg;
-    if (g_dbg & 32) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
+    if (g_dbg & (32 | 64)) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
-    const int stage_bytes = BM * BK * 2 + b_rows * BK * 2;
+    const int stage_bytes = BM * BK * 2 + (P.b_mn ? ((b_rows + 63) / 64) * 8192 : b_rows * BK * 2);
+    if (P.bn == 320 && (!CTA2 || total_work > gemm_sms() / 2 || P.mode != GM_LINEAR || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
+        set_error("gemm: the 320-wide plan is one 256 x 320 tile per CTA pair (GM_LINEAR, EPI_STORE, no tail split)");
+        return AOZ_ERR_ARG;
+    }
     P.stages = SMEM_TILE_BYTES / stage_bytes;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
     if (!CTA2) {
@@ -1080,6 +1187,16 @@ static TilePlan tune_plan(const std::string& key, const std::vector<TilePlan>& c
     return best;
 }
 
+// Wide one-wave plan (see the kernel's WIDE note): cycles by the model above, or 1e300 where the shape does not allow it.  One round:
+// main loop (MMA-bound: 640 cycles per K iteration at full clock, calibrated like plan_tiles_core) + the exposed epilogue of a
+// 320-wide tile + fill / drain.
+static double wide_plan_cycles(int m_tiles128, int N, int k_iters) {
+    if (g_wide_mode == 0 || g_pair_mode == 0 || g_force_bn != 0 || (N % 320) != 0 || m_tiles128 < 2) return 1e300;
+    if (g_tail_mode == 2 && g_wide_mode != 2) return 1e300;             // a forced tail split (tests / experiments) keeps its plan
+    if ((long long)ceil_div(m_tiles128, 2) * (N / 320) > gemm_sms() / 2) return 1e300;
+    return (double)k_iters * 775.0 + 2.0 * (6.0 * 320 + 400.0) + 3000.0;
+}
+
 // split-K factor for un-fused GEMMs: trades wave quantisation against fp32 partial traffic.  `store_direct`: with one split
 // the result is stored straight from the epilogue (Linear layers), so the tail split is available as an alternative to
 // split-K; conv weight gradients always go through fp32 partials + the permuting reduce.
@@ -1090,6 +1207,7 @@ static int plan_splits(int m_tiles128, int n_extent, int k_iters, long long out_
         const int kit = ceil_div(k_iters, s);
         TilePlan tp = plan_tiles(m_tiles128, n_extent, kit, s, b_mn, false, n_groups, /*allow_tail=*/store_direct && s == 1);
         double c = tp.cycles;
+        if (s == 1 && store_direct && n_groups == 1) c = fmin(c, wide_plan_cycles(m_tiles128, n_extent, k_iters));
         // partial write + reduce read, measured ~1.6 B/cycle/SM-equivalent on B200 (tools/kernel_times.py), + a launch
         if (s > 1 || !store_direct) c += (double)(2 * s + 1) * out_elems * 4.0 / 2400.0 / 2.0 + 4000.0;
         if (c < best_c) { best_c = c; best_s = s; }
@@ -1117,6 +1235,13 @@ int aoz_gemm_set_sm_budget(int sms) { g_gemm_sm_budget = sms > 0 ? (sms & ~1) : 
 
 // 0 = never split the last wave along K, 1 = cost model decides (default), 2 = split whenever the shape allows it
 int aoz_gemm_set_tail_mode(int mode) { g_tail_mode = mode; return AOZ_OK; }
+// 0 = never use the 320-wide one-wave plan, 1 = cost model decides (default), 2 = whenever the shape allows it;
+// mn_n2 (64 | 128, <= 0 keeps the current value): N of the second MMA of a K step when B is MN-major
+int aoz_gemm_set_wide_mode(int mode, int mn_n2) {
+    g_wide_mode = mode;
+    if (mn_n2 == 64 || mn_n2 == 128) g_wide_mn_n2 = mn_n2;
+    return AOZ_OK;
+}
 // experiment switch: 1 = in-kernel tail fix-up, 0 = tail_fixup_kernel launch (default: measured 2.5 ms per step faster)
 int aoz_gemm_set_tail_inkernel(int on) { g_tail_inkernel = on ? 1 : 0; return AOZ_OK; }
 
@@ -1140,7 +1265,11 @@ int aoz_gemm_debug_flags(int flags) { g_dbg = flags; return AOZ_OK; }
 long long aoz_gemm_describe_plan(int M, int N, int K, int b_mn, int splits) {
     const int mt = ceil_div(M, BM), kit = ceil_div(K, BK);
     if (splits <= 0) splits = plan_splits(mt, N, kit, (long long)M * N, b_mn != 0, 1, true);
-    const TilePlan tp = plan_tiles(mt, N, ceil_div(kit, splits), splits, b_mn != 0, false, 1, splits == 1);
+    TilePlan tp = plan_tiles(mt, N, ceil_div(kit, splits), splits, b_mn != 0, false, 1, splits == 1);
+    if (splits == 1) {
+        const double cyc = wide_plan_cycles(mt, N, kit);
+        if (cyc < 1e299 && (g_wide_mode == 2 || cyc < tp.cycles)) tp = TilePlan{320, true, N / 320, cyc, 0, 1};
+    }
     return tp.bn + 1000LL * tp.pair + 10000LL * (tp.tail_tiles ? tp.tail_splits : 0) + 1000000LL * tp.tail_tiles + 100000000LL * splits;
 }
 
@@ -1195,6 +1324,7 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         const int bn = tp.bn;
         const bool pair = tp.pair;
         Q.bn = bn;
+        Q.wide_n2 = (bn == 320 && b_mn) ? g_wide_mn_n2 : 64;
         Q.n_tiles = tp.n_tiles;
         Q.splits = splits;
         Q.tail_tiles = tp.tail_tiles; Q.tail_splits = tp.tail_splits;
@@ -1242,6 +1372,10 @@ int aoz_gemm_bf16(const void* A, long long lda, int a_mn, const void* B, long lo
         return (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * (*n_tiles) * splits;
     };
     TilePlan tp = plan_tiles(m_tiles128, geglu ? N / 2 : N, kit, splits, b_mn != 0, geglu, 1, allow_tail);
+    if (!geglu && splits == 1) {
+        const double cyc = wide_plan_cycles(m_tiles128, N, kit);
+        if (cyc < 1e299 && (g_wide_mode == 2 || cyc < tp.cycles)) tp = TilePlan{320, true, N / 320, cyc, 0, 1};
+    }
     if (!accumulate && tuning_allowed((cudaStream_t)stream)) {
         char key[160];
         snprintf(key, sizeof(key), "L %d %d %d %d %d e%d s%d f%d%d%d a%d", M, N, K, a_mn, b_mn, epi, splits, bias != nullptr, residual != nullptr,

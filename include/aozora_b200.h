@@ -62,6 +62,11 @@ int aoz_gemm_set_tail_mode(int mode);
 /* experiment switch: 1 = the K slices of tail tiles are summed and stored by their own CTAs, 0 = tail_fixup_kernel launch (default:
  * the in-kernel form measured 2.5 ms per step slower) */
 int aoz_gemm_set_tail_inkernel(int on);
+/* wide one-wave plan: outputs that are slightly more than one wave of 256 x 256 pair tiles (4096 x 1280 = 80 tiles on 74 SM pairs)
+ * run as ONE round of 256 x 320 tiles (a single 320-column accumulator, two MMAs per K step).  mode 0 = off, 1 = cost model
+ * decides (default), 2 = whenever the shape allows it (N % 320 == 0, tiles <= SM pairs, store epilogue, no split-K);
+ * mn_n2 = 64 | 128 selects the second MMA's N for MN-major B (<= 0: keep). */
+int aoz_gemm_set_wide_mode(int mode, int mn_n2);
 /* measured plan selection: the first EAGER call of every distinct GEMM / conv problem times the candidate tile plans on the
  * caller's operands and caches the fastest (never during CUDA-graph capture, never for accumulate epilogues).  Off by
  * default: on B200 the L2-warm timings mis-ranked the plans for the in-step (cold-weight) launches (profiles/r01 notes). */

@@ -199,6 +199,40 @@ def test_gemm_tail_fixup_in_kernel_equals_separate_launch():
         assert torch.equal(got, ref)
 
 
+def test_gemm_wide_one_wave_plan_equals_two_round_plan():
+    """The 320-wide one-wave plan (one 256 x 320 tile per CTA pair, two MMAs per K step into a single accumulator, permuted column
+    chunks in the epilogue) against the ordinary plans: every output element is the same K-ordered fp32 sum, so the bits agree; both
+    operand majors of B, with and without the fused bias / residual, accumulate, and a shape with fewer tiles than SM pairs."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(59)
+    for M, N, K, b_mn in ((4096, 1280, 1280, False), (4096, 1280, 1280, True), (4096, 1280, 5120, False), (4096, 1280, 3840, True),
+                          (512, 640, 320, False), (300, 320, 72, True), (4096, 1280, 10240, True)):
+        x = torch.randn(M, K, device="cuda", generator=g).to(BF16)
+        w = ((torch.randn(K, N, device="cuda", generator=g) if b_mn else torch.randn(N, K, device="cuda", generator=g)) * 0.05).to(BF16)
+        b = torch.randn(N, device="cuda", generator=g).to(BF16)
+        res = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+        acc0 = torch.randn(M, N, device="cuda", generator=g).to(BF16)
+        runs = {}
+        for mode in (0, 2):
+            try:
+                _lib.call("aoz_gemm_set_wide_mode", mode, 0)
+                _lib.call("aoz_gemm_set_tail_mode", 0)              # a tail split sums K slices in another order: not the reference here
+                plain = ops.gemm(x, w, b_mn=b_mn, splits=1)
+                fused = ops.gemm(x, w, b_mn=b_mn, bias=b, residual=res)
+                acc = acc0.clone()
+                ops.gemm(x, w, b_mn=b_mn, out=acc, accumulate=True, splits=1)
+            finally:
+                _lib.call("aoz_gemm_set_wide_mode", 1, 0)
+                _lib.call("aoz_gemm_set_tail_mode", 1)
+            runs[mode] = (plain, fused, acc)
+        wf = w.float() if b_mn else w.float().t()
+        check(runs[2][0], x.float() @ wf)
+        check(runs[2][1], x.float() @ wf + b.float() + res.float())
+        for got, ref in zip(runs[2], runs[0]):
+            assert torch.equal(got, ref), (M, N, K, b_mn, (got.float() - ref.float()).abs().max().item())
+
+
 def test_layernorm_backward_with_column_sums_of_dx():
     """ln_bwd_kernel's third accumulator: the column sums of the dx it stores (bf16-rounded) = the bias gradient of the Linear that
     produced the LayerNorm's input.  dx / dgamma / dbeta must not change; the sums must equal colsum(dx) up to fp32 summation order."""
