@@ -177,7 +177,8 @@ struct WorkItem { int tile, split, k_begin, k_end, tail_slot; };      // tail_sl
 __device__ __forceinline__ WorkItem decode_work(const GemmParams& P, int work, int k_per_split) {
     WorkItem w;
     if (work < P.full_work) {
-        w.tile = work / P.splits;
+        // (an integer division is ~200 cycles of dependent instructions for the single producer thread before its first TMA issue)
+        w.tile = P.splits == 1 ? work : work / P.splits;
         w.split = work - w.tile * P.splits;
         w.k_begin = w.split * k_per_split;
         w.k_end = min(P.k_iters, w.k_begin + k_per_split);
@@ -186,7 +187,7 @@ __device__ __forceinline__ WorkItem decode_work(const GemmParams& P, int work, i
         const int j = work - P.full_work;
         const int t = j / P.tail_splits;
         const int kps = (P.k_iters + P.tail_splits - 1) / P.tail_splits;
-        w.tile = P.full_work / P.splits + t;
+        w.tile = (P.splits == 1 ? P.full_work : P.full_work / P.splits) + t;
         w.split = j - t * P.tail_splits;
         w.k_begin = w.split * kps;
         w.k_end = min(P.k_iters, w.k_begin + kps);
@@ -254,8 +255,9 @@ __device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C
             const uint32_t gw[4] = {gg.x, gg.y, gg.z, gg.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(gw[e]);
-                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(gw[e]);
+                const uint32_t pk = pack_bf16(f[2 * e], f[2 * e + 1]);          // both roundings in one packed conversion
+                f[2 * e] = bf16lo(pk) + bf16lo(gw[e]);
+                f[2 * e + 1] = bf16hi(pk) + bf16hi(gw[e]);
             }
         }
         if (res) {
@@ -263,8 +265,9 @@ __device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C
             const uint32_t rw[4] = {rr.x, rr.y, rr.z, rr.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
-                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
+                const uint32_t pk = pack_bf16(f[2 * e], f[2 * e + 1]);          // both roundings in one packed conversion
+                f[2 * e] = bf16lo(pk) + bf16lo(rw[e]);
+                f[2 * e + 1] = bf16hi(pk) + bf16hi(rw[e]);
             }
         }
         if (P.accumulate) {
@@ -272,8 +275,9 @@ __device__ __forceinline__ void epi_store8(const GemmParams& P, __nv_bfloat16* C
             const uint32_t ow[4] = {oo.x, oo.y, oo.z, oo.w};
 #pragma unroll
             for (int e = 0; e < 4; ++e) {
-                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(ow[e]);
-                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(ow[e]);
+                const uint32_t pk = pack_bf16(f[2 * e], f[2 * e + 1]);          // both roundings in one packed conversion
+                f[2 * e] = bf16lo(pk) + bf16lo(ow[e]);
+                f[2 * e + 1] = bf16hi(pk) + bf16hi(ow[e]);
             }
         }
         *reinterpret_cast<uint4*>(dst) = make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
@@ -352,7 +356,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
     if (tl && threadIdx.x == 0) tl[2] = clock64();          // prologue done (barriers, TMEM, descriptors): only now wait for the previous kernel's results
 
     const int total_work = P.full_work + P.tail_tiles * P.tail_splits;      // (m_tiles counts 256-row pair tiles when CTA2)
-    const int k_per_split = (P.k_iters + P.splits - 1) / P.splits;
+    const int k_per_split = P.splits == 1 ? P.k_iters : (P.k_iters + P.splits - 1) / P.splits;
     const int m_sub = CTA2 ? 2 : 1;
 
     if (warp == 0) {
@@ -521,7 +525,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 }
                 __syncwarp();
                 if (tl && lane == 0) tl[5] = clock64();
-                if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+                if (++acc == (WIDE ? 1u : 2u)) { acc = 0; acc_phase ^= 1; }      // the wide plan has ONE accumulator: tiles of a CTA pair do not overlap
             }
         }
         __syncwarp();
@@ -752,6 +756,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 }
                 uint4 bnext = make_uint4(0u, 0u, 0u, 0u);
                 if (biasp) bnext = __ldg(reinterpret_cast<const uint4*>(biasp + col0 + out_c(half * 32) + lcol));
+                // the accumulator chunk of the NEXT iteration is requested as soon as this one's registers are staged, so the
+                // TMEM read (~300 cycles) runs under the four store steps
+                uint32_t r[32];
+                tmem_ld32(taddr + tmem_c(half * 32), r);
 #pragma unroll 1
                 for (int c = half * 32; c < BN; c += 64) {
                     uint4 rcur[4];
@@ -767,11 +775,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                         }
                         if (biasp) bnext = __ldg(reinterpret_cast<const uint4*>(biasp + col0 + ocn + lcol));
                     }
-                    uint32_t r[32];
-                    tmem_ld32(taddr + tmem_c(c), r);
                     tc_wait_ld();
                     stage_chunk(stg, lane, r);
                     __syncwarp();
+                    if (c + 64 < BN) tmem_ld32(taddr + tmem_c(c + 64), r);
                     const int oc = out_c(c);
                     const uint32_t bw[4] = {bcur.x, bcur.y, bcur.z, bcur.w};
 #pragma unroll
@@ -786,8 +793,10 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                             const uint32_t rw[4] = {rcur[st].x, rcur[st].y, rcur[st].z, rcur[st].w};
 #pragma unroll
                             for (int e = 0; e < 4; ++e) {
-                                f[2 * e] = round_bf16(f[2 * e]) + bf16lo(rw[e]);
-                                f[2 * e + 1] = round_bf16(f[2 * e + 1]) + bf16hi(rw[e]);
+                                // round_bf16 of both values in one packed conversion (F2FP) instead of two F2F on the quarter-rate pipe
+                                const uint32_t pk = pack_bf16(f[2 * e], f[2 * e + 1]);
+                                f[2 * e] = bf16lo(pk) + bf16lo(rw[e]);
+                                f[2 * e + 1] = bf16hi(pk) + bf16hi(rw[e]);
                             }
                         }
                         if (rmap[st].ok)
@@ -845,7 +854,7 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
                 if (CTA2 && !leader) mbar_arrive_cluster(mapa_rank(smem_u32(&tempty_bar[acc]), 0));
                 else mbar_arrive(&tempty_bar[acc]);
             }
-            if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+            if (++acc == (WIDE ? 1u : 2u)) { acc = 0; acc_phase ^= 1; }      // the wide plan has ONE accumulator: tiles of a CTA pair do not overlap
         }
     }
 
@@ -988,6 +997,7 @@ static int g_tail_inkernel = 0;   // 1 = tail slices are summed and stored by th
 // 0 = off, 1 = the cost model may pick it (default), 2 = whenever the shape allows it.  g_wide_mn_n2: N of the second MMA for MN-major B.
 static int g_wide_mode = 1;
 static int g_wide_mn_n2 = 64;
+static int g_wide_max_rounds = 2;       // rounds of 320-wide tiles the planner may consider (aoz_gemm_set_wide_max_rounds)
 static int g_tail_mode = 1;       // 0 = never cut the last wave along K, 1 = the cost model may (default), 2 = whenever possible
 static float* g_tail_ws = nullptr;        // caller-owned scratch for the tail slices (aoz_gemm_set_scratch)
 static long long g_tail_bytes = 0;
@@ -1017,8 +1027,8 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     if (g_dbg & (32 | 64)) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
     const int stage_bytes = BM * BK * 2 + (P.b_mn ? ((b_rows + 63) / 64) * 8192 : b_rows * BK * 2);
-    if (P.bn == 320 && (!CTA2 || total_work > gemm_sms() / 2 || P.mode != GM_LINEAR || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
-        set_error("gemm: the 320-wide plan is one 256 x 320 tile per CTA pair (GM_LINEAR, EPI_STORE, no tail split)");
+    if (P.bn == 320 && (!CTA2 || P.mode != GM_LINEAR || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
+        set_error("gemm: the 320-wide plan needs CTA pairs, GM_LINEAR, EPI_STORE and no tail split");
         return AOZ_ERR_ARG;
     }
     P.stages = SMEM_TILE_BYTES / stage_bytes;
@@ -1193,8 +1203,12 @@ static TilePlan tune_plan(const std::string& key, const std::vector<TilePlan>& c
 static double wide_plan_cycles(int m_tiles128, int N, int k_iters) {
     if (g_wide_mode == 0 || g_pair_mode == 0 || g_force_bn != 0 || (N % 320) != 0 || m_tiles128 < 2) return 1e300;
     if (g_tail_mode == 2 && g_wide_mode != 2) return 1e300;             // a forced tail split (tests / experiments) keeps its plan
-    if ((long long)ceil_div(m_tiles128, 2) * (N / 320) > gemm_sms() / 2) return 1e300;
-    return (double)k_iters * 775.0 + 2.0 * (6.0 * 320 + 400.0) + 3000.0;
+    const long long units = (long long)ceil_div(m_tiles128, 2) * (N / 320);
+    const int slots = gemm_sms() / 2;
+    const long long rounds = (units + slots - 1) / slots;
+    if (rounds > g_wide_max_rounds) return 1e300;
+    // one accumulator: main loop and epilogue of a pair's tiles run back to back
+    return (double)rounds * ((double)k_iters * 775.0 + 2.0 * (6.0 * 320 + 400.0)) + 3000.0;
 }
 
 // split-K factor for un-fused GEMMs: trades wave quantisation against fp32 partial traffic.  `store_direct`: with one split
@@ -1242,6 +1256,8 @@ int aoz_gemm_set_wide_mode(int mode, int mn_n2) {
     if (mn_n2 == 64 || mn_n2 == 128) g_wide_mn_n2 = mn_n2;
     return AOZ_OK;
 }
+// rounds of 320-wide tiles the planner may consider (default 2; 1 = only one-wave launches)
+int aoz_gemm_set_wide_max_rounds(int rounds) { g_wide_max_rounds = rounds < 1 ? 1 : rounds; return AOZ_OK; }
 // experiment switch: 1 = in-kernel tail fix-up, 0 = tail_fixup_kernel launch (default: measured 2.5 ms per step faster)
 int aoz_gemm_set_tail_inkernel(int on) { g_tail_inkernel = on ? 1 : 0; return AOZ_OK; }
 

@@ -67,6 +67,8 @@ int aoz_gemm_set_tail_inkernel(int on);
  * decides (default), 2 = whenever the shape allows it (N % 320 == 0, tiles <= SM pairs, store epilogue, no split-K);
  * mn_n2 = 64 | 128 selects the second MMA's N for MN-major B (<= 0: keep). */
 int aoz_gemm_set_wide_mode(int mode, int mn_n2);
+/* rounds of 320-wide tiles per SM pair the planner may consider (default 2; the single accumulator serialises a pair's tiles) */
+int aoz_gemm_set_wide_max_rounds(int rounds);
 /* measured plan selection: the first EAGER call of every distinct GEMM / conv problem times the candidate tile plans on the
  * caller's operands and caches the fastest (never during CUDA-graph capture, never for accumulate epilogues).  Off by
  * default: on B200 the L2-warm timings mis-ranked the plans for the in-step (cold-weight) launches (profiles/r01 notes). */

@@ -207,7 +207,8 @@ def test_gemm_wide_one_wave_plan_equals_two_round_plan():
     ops = _ops()
     g = gen(59)
     for M, N, K, b_mn in ((4096, 1280, 1280, False), (4096, 1280, 1280, True), (4096, 1280, 5120, False), (4096, 1280, 3840, True),
-                          (512, 640, 320, False), (300, 320, 72, True), (4096, 1280, 10240, True)):
+                          (512, 640, 320, False), (300, 320, 72, True), (4096, 1280, 10240, True),
+                          (16384, 640, 640, False), (16384, 640, 640, True)):          # two and three tiles per CTA pair
         x = torch.randn(M, K, device="cuda", generator=g).to(BF16)
         w = ((torch.randn(K, N, device="cuda", generator=g) if b_mn else torch.randn(N, K, device="cuda", generator=g)) * 0.05).to(BF16)
         b = torch.randn(N, device="cuda", generator=g).to(BF16)
@@ -217,6 +218,7 @@ def test_gemm_wide_one_wave_plan_equals_two_round_plan():
         for mode in (0, 2):
             try:
                 _lib.call("aoz_gemm_set_wide_mode", mode, 0)
+                _lib.call("aoz_gemm_set_wide_max_rounds", 3)
                 _lib.call("aoz_gemm_set_tail_mode", 0)              # a tail split sums K slices in another order: not the reference here
                 plain = ops.gemm(x, w, b_mn=b_mn, splits=1)
                 fused = ops.gemm(x, w, b_mn=b_mn, bias=b, residual=res)
@@ -224,6 +226,7 @@ def test_gemm_wide_one_wave_plan_equals_two_round_plan():
                 ops.gemm(x, w, b_mn=b_mn, out=acc, accumulate=True, splits=1)
             finally:
                 _lib.call("aoz_gemm_set_wide_mode", 1, 0)
+                _lib.call("aoz_gemm_set_wide_max_rounds", 2)
                 _lib.call("aoz_gemm_set_tail_mode", 1)
             runs[mode] = (plain, fused, acc)
         wf = w.float() if b_mn else w.float().t()

@@ -38,8 +38,13 @@ def main():
     big = torch.empty(64 << 20, device="cuda", dtype=torch.float32)
     flush = lambda: big.zero_()
     rows = []
+    _lib.call("aoz_gemm_set_wide_max_rounds", 2)
     for M, N, K, b_mn, fused in ((4096, 1280, 1280, False, True), (4096, 1280, 1280, True, False), (4096, 1280, 5120, False, True),
-                                 (4096, 1280, 3840, True, False), (4096, 1280, 10240, True, False), (4096, 1280, 320, False, True)):
+                                 (4096, 1280, 3840, True, False), (4096, 1280, 10240, True, False), (4096, 1280, 320, False, True),
+                                 # two rounds of wide tiles (aoz_gemm_set_wide_max_rounds(2)): the 640-channel level and batch 8
+                                 (16384, 640, 640, False, True), (16384, 640, 640, True, False), (16384, 640, 2560, False, True),
+                                 (16384, 640, 5120, True, False), (16384, 640, 1920, True, False), (8192, 1280, 1280, False, True),
+                                 (8192, 1280, 1280, True, False), (8192, 1280, 5120, False, True)):
         x = torch.randn(M, K, device="cuda").to(BF)
         w = ((torch.randn(K, N, device="cuda") if b_mn else torch.randn(N, K, device="cuda")) * 0.02).to(BF)
         bias = torch.zeros(N, device="cuda", dtype=BF)
@@ -55,6 +60,7 @@ def main():
         row["tflops_cold"] = [round(2.0 * M * N * K / row[f"wide{m}_cold_us"] * 1e-6, 1) for m in (0, 2)]
         rows.append(row)
         print(row, flush=True)
+    _lib.call("aoz_gemm_set_wide_max_rounds", 2)
     os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
     json.dump(rows, open(os.path.join(ROOT, "gpurun_out", "gemm_wide_bench.json"), "w"), indent=1)
 
