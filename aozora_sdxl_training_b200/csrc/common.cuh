@@ -85,6 +85,12 @@ __device__ __forceinline__ uint32_t pack_bf16(float lo, float hi) {
     return *reinterpret_cast<uint32_t*>(&v);
 }
 __device__ __forceinline__ float round_bf16(float x) { return __bfloat162float(__float2bfloat16_rn(x)); }
+// round_bf16 of two values with ONE packed conversion (F2FP.BF16.F32.PACK_AB) + two ALU unpacks instead of two F2F on the quarter-rate
+// conversion pipe: the epilogues / norm kernels that round eight values per 16-byte vector were issue-bound on it.  Same RN results.
+__device__ __forceinline__ void round2_bf16(float& a, float& b) {
+    const uint32_t pk = pack_bf16(a, b);
+    a = bf16lo(pk); b = bf16hi(pk);
+}
 
 // Standard normal CDF Phi(x) = 0.5 * erfc(-x / sqrt(2)) for the erf GELU (torch F.gelu default), and exp(-x^2 / 2).
 // Abramowitz-Stegun 7.1.26 evaluated in erfc form (no 1 - erf cancellation for x < 0): 1 rcp + 1 ex2 + 7 FMA-class ops

@@ -142,15 +142,23 @@ __global__ void geglu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __n
         unpack8e(ld_stream(dy + row * half + v * 8), d);
         unpack8e(ld_stream(aux + row * 2 * half + v * 8), h);
         unpack8e(ld_stream(aux + row * 2 * half + half + v * 8), g);
+        float slope[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
             float ex;                                           // exp(-g^2 / 2), shared by the CDF and the density
             const float cdf = gelu_cdf(g[e], ex);
             const float pdf = 0.39894228040143267794f * ex;
-            const float gelu = round_bf16(g[e] * cdf);          // forward rounded gelu(g) to bf16
-            dh[e] = d[e] * gelu;
-            dg[e] = round_bf16(d[e] * h[e]) * (cdf + g[e] * pdf);
+            dh[e] = g[e] * cdf;                                 // gelu(g), rounded to bf16 below as the forward did
+            dg[e] = d[e] * h[e];
+            slope[e] = cdf + g[e] * pdf;
         }
+#pragma unroll
+        for (int e = 0; e < 8; e += 2) {                        // the two bf16 rounding points, two values per packed conversion
+            round2_bf16(dh[e], dh[e + 1]);
+            round2_bf16(dg[e], dg[e + 1]);
+        }
+#pragma unroll
+        for (int e = 0; e < 8; ++e) { dh[e] *= d[e]; dg[e] *= slope[e]; }
         st_stream(daux + row * 2 * half + v * 8, pack8e(dh));
         st_stream(daux + row * 2 * half + half + v * 8, pack8e(dg));
     }

@@ -338,15 +338,6 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
         fence_mbar_init();
     }
     if (warp == 1) { if (CTA2) tmem_alloc2(tmem_slot, 512); else tmem_alloc(tmem_slot, 512); }
-    if (warp >= 2 && lane == 0) {
-        // Touch the kernel parameters' constant-bank lines (64 B apart) while warps 0 / 1 set up barriers and TMEM: the roles' first
-        // reads of P otherwise miss one after another (tools/gemm_timeline.py: ~2300 cycles from the prologue to the first TMA issue).
-        constexpr int kWords = (int)(offsetof(GemmParams, grp) / 4);
-        const int* pw = reinterpret_cast<const int*>(&P);
-        int v = 0;
-        for (int i = (warp - 2) * 16; i < kWords; i += 8 * 16) v ^= pw[i];
-        if (v == 0x5bd1e995 && P.dbg == -1) tmem_slot[1] = (uint32_t)v;          // never true: keeps the loads
-    }
     tc_fence_before();
     if (CTA2) cluster_sync_all(); else __syncthreads();
     tc_fence_after();

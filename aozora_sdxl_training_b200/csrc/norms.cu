@@ -26,6 +26,12 @@ __device__ __forceinline__ uint4 pack8(const float* f) {
     return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
 }
 __device__ __forceinline__ float sigmoidf_(float x) { return 1.0f / (1.0f + __expf(-x)); }
+// eight bf16 -> four float2 (elements 2e, 2e+1) for the packed fp32x2 instructions of sm_100 (FADD2 / FMUL2 / FFMA2: two IEEE
+// operations per issue slot)
+__device__ __forceinline__ void unpack8v(const uint4& a, float2* f) {
+    f[0] = make_float2(bf16lo(a.x), bf16hi(a.x)); f[1] = make_float2(bf16lo(a.y), bf16hi(a.y));
+    f[2] = make_float2(bf16lo(a.z), bf16hi(a.z)); f[3] = make_float2(bf16lo(a.w), bf16hi(a.w));
+}
 
 // ---------------------------------------------------------------------------------------------
 // GroupNorm statistics: x [NB, HW, C] -> partial [NB][chunks][GROUPS][2] (sum, sumsq) -> mean / rstd [NB][GROUPS]
@@ -378,7 +384,7 @@ gn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* _
                 float fr[8];
                 unpack8(pr, fr);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) fx[e] = round_bf16(fx[e]) + fr[e];
+                for (int e = 0; e < 8; e += 2) { round2_bf16(fx[e], fx[e + 1]); fx[e] += fr[e]; fx[e + 1] += fr[e + 1]; }
             }
             st_stream(dx + base + (size_t)r * C + v * 8, pack8(fx));
         };
@@ -564,7 +570,7 @@ gn_slab_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __
             float fr[8];
             unpack8(pr, fr);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) fx[e] = round_bf16(fx[e]) + fr[e];
+            for (int e = 0; e < 8; e += 2) { round2_bf16(fx[e], fx[e + 1]); fx[e] += fr[e]; fx[e + 1] += fr[e + 1]; }
         }
         st_stream(dx + goff + (size_t)r * C, pack8(fx));
     }
@@ -693,12 +699,14 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     uint8_t* ring = lnb_smem;                                                  // [2 slots][x | dy | dres][tensor_bytes]
     float* red = reinterpret_cast<float*>(lnb_smem + 6 * (size_t)tensor_bytes);   // [tile_rows][W][2]
     uint64_t* bars = reinterpret_cast<uint64_t*>(red + (size_t)tile_rows * W * 2);
-    float gm[8], ag[8], ab[8], ac[8];
+    // The kernel is issue-bound, not HBM-bound (15 warps, ~1000 issued instructions per thread and 12-row tile before this form):
+    // all per-element arithmetic runs as packed fp32x2 instructions on element pairs (2e, 2e+1).
+    float2 gm[4], ag[4], ab[4], ac[4];
     {
         const uint4 g4 = active ? *reinterpret_cast<const uint4*>(gamma + tc * 8) : make_uint4(0, 0, 0, 0);
-        unpack8(g4, gm);
+        unpack8v(g4, gm);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) { ag[e] = 0.f; ab[e] = 0.f; ac[e] = 0.f; }
+        for (int e = 0; e < 4; ++e) { ag[e] = make_float2(0.f, 0.f); ab[e] = ag[e]; ac[e] = ag[e]; }
     }
     const long long rb0 = (long long)blockIdx.x * rows_per_block;
     const long long rb1 = rb0 + rows_per_block < rows ? rb0 + rows_per_block : rows;
@@ -737,23 +745,24 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
         mbar_wait(&bars[i & 1], (uint32_t)((i >> 1) & 1));
 #pragma unroll
         for (int t = 0; t < LNB_T; ++t) {
-            float a = 0.f, b = 0.f;
+            float2 a = make_float2(0.f, 0.f), b = a;
             if (ok[t]) {
                 const size_t off = ((size_t)(t * RL + rl) * C + (size_t)tc * 8) * 2;
-                float fx[8], fd[8];
-                unpack8(*reinterpret_cast<const uint4*>(slot + off), fx);
-                unpack8(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
+                float2 fx[4], fd[4];
+                unpack8v(*reinterpret_cast<const uint4*>(slot + off), fx);
+                unpack8v(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
+                const float2 nmu = make_float2(-mu[t], -mu[t]), rs2 = make_float2(rs[t], rs[t]);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const float xh = (fx[e] - mu[t]) * rs[t];
-                    const float dg = fd[e] * gm[e];
-                    a += dg;
-                    b = fmaf(dg, xh, b);
-                    ag[e] = fmaf(fd[e], xh, ag[e]);
-                    ab[e] += fd[e];
+                for (int e = 0; e < 4; ++e) {
+                    const float2 xh = __fmul2_rn(__fadd2_rn(fx[e], nmu), rs2);
+                    const float2 dg = __fmul2_rn(fd[e], gm[e]);
+                    a = __fadd2_rn(a, dg);
+                    b = __ffma2_rn(dg, xh, b);
+                    ag[e] = __ffma2_rn(fd[e], xh, ag[e]);
+                    ab[e] = __fadd2_rn(ab[e], fd[e]);
                 }
             }
-            p1[t] = a; p2[t] = b;
+            p1[t] = a.x + a.y; p2[t] = b.x + b.y;
         }
         // eight warp sums as a reduce-scatter (9 shuffles instead of 8 x 5): after the xor-16 / 8 / 4 steps every lane owns ONE
         // of the eight values, two plain butterfly steps finish it.  Value v = which * 4 + t ends up in the lanes whose bits
@@ -785,23 +794,33 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
             for (int w = 0; w < W; ++w) { const float2 v = srow[w]; s1 += v.x; s2 += v.y; }
             s1 *= inv_c; s2 *= inv_c;
             const size_t off = ((size_t)(t * RL + rl) * C + (size_t)tc * 8) * 2;
-            float fx[8], fd[8], o[8];
-            unpack8(*reinterpret_cast<const uint4*>(slot + off), fx);
-            unpack8(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
+            float2 fx[4], fd[4], o[4];
+            unpack8v(*reinterpret_cast<const uint4*>(slot + off), fx);
+            unpack8v(*reinterpret_cast<const uint4*>(slot + tensor_bytes + off), fd);
+            const float2 nmu = make_float2(-mu[t], -mu[t]), rs2 = make_float2(rs[t], rs[t]);
+            const float2 ns1 = make_float2(-s1, -s1), ns2 = make_float2(-s2, -s2);
 #pragma unroll
-            for (int e = 0; e < 8; ++e) o[e] = rs[t] * (fd[e] * gm[e] - s1 - (fx[e] - mu[t]) * rs[t] * s2);
-            if (dres) {
-                float fr[8];
-                unpack8(*reinterpret_cast<const uint4*>(slot + 2 * (size_t)tensor_bytes + off), fr);
-#pragma unroll
-                for (int e = 0; e < 8; ++e) o[e] = round_bf16(o[e]) + fr[e];
+            for (int e = 0; e < 4; ++e) {
+                const float2 xh = __fmul2_rn(__fadd2_rn(fx[e], nmu), rs2);
+                // rstd * (dy*gamma - s1 - xhat*s2)
+                o[e] = __fmul2_rn(rs2, __ffma2_rn(xh, ns2, __fadd2_rn(__fmul2_rn(fd[e], gm[e]), ns1)));
             }
-            if (want_col) {
+            if (dres) {
+                float2 fr[4];
+                unpack8v(*reinterpret_cast<const uint4*>(slot + 2 * (size_t)tensor_bytes + off), fr);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) { o[e] = round_bf16(o[e]); ac[e] += o[e]; }
+                for (int e = 0; e < 4; ++e) { round2_bf16(o[e].x, o[e].y); o[e] = __fadd2_rn(o[e], fr[e]); }
+            }
+            // the stored (bf16-rounded) dx: one packed conversion serves the store and the column sums
+            const uint4 o4 = make_uint4(pack_bf16(o[0].x, o[0].y), pack_bf16(o[1].x, o[1].y), pack_bf16(o[2].x, o[2].y), pack_bf16(o[3].x, o[3].y));
+            if (want_col) {
+                float2 orr[4];
+                unpack8v(o4, orr);
+#pragma unroll
+                for (int e = 0; e < 4; ++e) ac[e] = __fadd2_rn(ac[e], orr[e]);
             }
             const long long row = base + (long long)t * RL + rl;
-            st_stream(dx + row * C + tc * 8, pack8(o));
+            st_stream(dx + row * C + tc * 8, o4);
         }
         __syncthreads();               // slot and table are free: refill the slot with the tile after next
         if (threadIdx.x == 0 && i + 2 < ntiles) issue(i + 2);
@@ -810,10 +829,10 @@ ln_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restr
     float* fin = reinterpret_cast<float*>(lnb_smem);
     if (active) {
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            fin[(size_t)(rl * ncomp + 0) * C + tc * 8 + e] = ag[e];
-            fin[(size_t)(rl * ncomp + 1) * C + tc * 8 + e] = ab[e];
-            if (want_col) fin[(size_t)(rl * ncomp + 2) * C + tc * 8 + e] = ac[e];
+        for (int e = 0; e < 4; ++e) {
+            *reinterpret_cast<float2*>(&fin[(size_t)(rl * ncomp + 0) * C + tc * 8 + 2 * e]) = ag[e];
+            *reinterpret_cast<float2*>(&fin[(size_t)(rl * ncomp + 1) * C + tc * 8 + 2 * e]) = ab[e];
+            if (want_col) *reinterpret_cast<float2*>(&fin[(size_t)(rl * ncomp + 2) * C + tc * 8 + 2 * e]) = ac[e];
         }
     }
     __syncthreads();

@@ -88,6 +88,12 @@ def norms():
         y, mean, rstd = ops.layernorm_fwd(x, g, bb)
         prof(f"ln_fwd_{C}", lambda: ops.layernorm_fwd(x, g, bb))
         prof(f"ln_bwd_{C}", lambda: ops.layernorm_bwd(x, x, g, mean, rstd, dres=x))
+        dy, dres, col = torch.randn_like(x), torch.randn_like(x), torch.empty(C, device="cuda", dtype=BF)
+        prof(f"ln_bwd_colsum_{C}", lambda: ops.layernorm_bwd(dy, x, g, mean, rstd, dres=dres, dx_colsum=col))
+    for M, half in [(4096, 5120), (16384, 2560)]:
+        dyy = torch.randn(M, half, device="cuda").to(BF)
+        aux = torch.randn(M, 2 * half, device="cuda").to(BF)
+        prof(f"geglu_bwd_{M}x{half}", lambda: ops.geglu_bwd(dyy, aux))
     for NB, HW, C in [(4, 1024, 1280), (4, 4096, 640), (4, 16384, 320), (4, 16384, 960), (4, 1024, 2560)]:
         x = torch.randn(NB, HW, C, device="cuda").to(BF)
         g, bb = torch.ones(C, device="cuda", dtype=BF), torch.zeros(C, device="cuda", dtype=BF)
