@@ -142,8 +142,8 @@ def gemm_roofline(torch, peaks, iters=20):
                 peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
                 flops_per_launch=flops,
                 # the whole GEMM / conv family inside the step (1211 launches, FLOP-weighted): tools/gemm_in_step.py, recorded once per round
-                family_in_step=dict(tflops=878.3, frac_of_burst=round(878.3 / peaks["tf_burst"], 4), ms=81.64, launches=1211,
-                                    source="profiles/r02_gemm_in_step_v1.txt (71.70 TFLOP of GEMM / conv work per step in 81.64 ms)"))
+                family_in_step=dict(tflops=946.8, frac_of_burst=round(946.8 / peaks["tf_burst"], 4), ms=75.73, launches=1211,
+                                    source="profiles/r02_gemm_in_step_v3.txt (71.70 TFLOP of GEMM / conv work per step in 75.73 ms)"))
 
 
 def kernel_table(torch, peaks, param_numels=None):
