@@ -1018,8 +1018,8 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     if (g_dbg & (32 | 64)) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
     const int stage_bytes = BM * BK * 2 + (P.b_mn ? ((b_rows + 63) / 64) * 8192 : b_rows * BK * 2);
-    if (P.bn == 320 && (!CTA2 || P.mode != GM_LINEAR || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
-        set_error("gemm: the 320-wide plan needs CTA pairs, GM_LINEAR, EPI_STORE and no tail split");
+    if (P.bn == 320 && (!CTA2 || P.mode == GM_CONV_WGRAD || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
+        set_error("gemm: the 320-wide plan needs CTA pairs, a Linear or conv-forward problem, EPI_STORE and no tail split");
         return AOZ_ERR_ARG;
     }
     P.stages = SMEM_TILE_BYTES / stage_bytes;
@@ -1495,6 +1495,7 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
         const int bn = tp.bn;
         const bool pair = tp.pair;
         Q.bn = bn;
+        Q.wide_n2 = 64;
         Q.n_tiles = tp.n_tiles;
         Q.splits = 1;
         Q.tail_tiles = tp.tail_tiles; Q.tail_splits = tp.tail_splits;
@@ -1525,6 +1526,10 @@ int aoz_conv_fwd_bf16(const void* x, int NB, int Hin, int Win, int Cin, const vo
         return (long long)(pair ? ceil_div(m_tiles128, 2) : m_tiles128) * (*n_tiles);
     };
     TilePlan tp = plan_tiles(m_tiles128, Cout, P.k_iters, 1, false, false, 1, /*allow_tail=*/true);
+    {   // the 320-wide plan (one or two rounds of 256 x 320 tiles): 1280- and 640-channel convolutions at 32 x 32 / 64 x 64
+        const double cyc = wide_plan_cycles(m_tiles128, Cout, P.k_iters);
+        if (cyc < 1e299 && (g_wide_mode == 2 || cyc < tp.cycles)) tp = TilePlan{320, true, Cout / 320, cyc, 0, 1};
+    }
     if (!accumulate && g_autotune && g_force_bn == 0 && g_pair_mode == 1 && g_tail_mode == 1) {
         char key[160];
         snprintf(key, sizeof(key), "C %d %d %d %d %d k%d s%d p%d f%d%d%d%d", NB, Hin, Win, Cin, Cout, ks, stride, pad, flip, bias != nullptr,

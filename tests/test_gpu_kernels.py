@@ -158,6 +158,42 @@ def test_conv_tail_split_with_time_embedding_and_residual():
         _lib.call("aoz_gemm_set_tail_mode", 1)
 
 
+def test_conv_wide_plan_equals_ordinary_tiles():
+    """The 320-wide plan on the implicit-GEMM convolution (forward with bias + time embedding = general epilogue, bias + residual =
+    fast epilogue, and the flipped dgrad pack): same K order per output element, so the bits equal the ordinary tiles', and both
+    match the fp32 convolution."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(60)
+    for NB, H, W, Cin, Cout in ((4, 32, 32, 256, 320), (2, 32, 32, 128, 640), (1, 18, 14, 320, 192), (4, 32, 32, 128, 1280)):
+        x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).to(BF16)
+        w = (torch.randn(Cout, Cin, 3, 3, device="cuda", generator=g) * 0.05).to(BF16)
+        b = torch.randn(Cout, device="cuda", generator=g).to(BF16)
+        temb = torch.randn(NB, Cout, device="cuda", generator=g).to(BF16)
+        res = torch.randn(NB, H, W, Cout, device="cuda", generator=g).to(BF16)
+        dy = torch.randn(NB, H, W, Cout, device="cuda", generator=g).to(BF16)
+        wf, wd = ops.pack_conv_weight(w)
+        runs = {}
+        for mode in (0, 2):
+            try:
+                _lib.call("aoz_gemm_set_wide_mode", mode, 0)
+                _lib.call("aoz_gemm_set_wide_max_rounds", 3)
+                _lib.call("aoz_gemm_set_tail_mode", 0)
+                runs[mode] = (ops.conv_fwd(x, wf, Cout, 3, bias=b, rowgroup_bias=temb), ops.conv_fwd(x, wf, Cout, 3, bias=b, residual=res),
+                              ops.conv_fwd(dy, wd, Cin, 3, stride=1, pad=1, flip=True))
+            finally:
+                _lib.call("aoz_gemm_set_wide_mode", 1, 0)
+                _lib.call("aoz_gemm_set_wide_max_rounds", 2)
+                _lib.call("aoz_gemm_set_tail_mode", 1)
+        conv = torch.nn.functional.conv2d(x.float().permute(0, 3, 1, 2), w.float(), b.float(), padding=1).permute(0, 2, 3, 1)
+        check(runs[2][0], conv.to(BF16).float() + temb.float()[:, None, None, :])
+        check(runs[2][1], conv.to(BF16).float() + res.float())
+        dx = torch.nn.functional.conv_transpose2d(dy.float().permute(0, 3, 1, 2), w.float(), padding=1).permute(0, 2, 3, 1)
+        check(runs[2][2], dx)
+        for got, ref in zip(runs[2], runs[0]):
+            assert torch.equal(got, ref), (NB, H, W, Cin, Cout)
+
+
 @pytest.mark.parametrize("M,C", [(512, 128), (4096, 640), (300, 64)])
 def test_geglu_fused_epilogue_and_backward(M, C):
     ops = _ops()
