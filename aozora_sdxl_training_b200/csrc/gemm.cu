@@ -705,17 +705,17 @@ gemm_bf16_kernel(const __grid_constant__ GemmParams P) {
             } else if (P.epi == EPI_PARTIAL) {
 #pragma unroll 1
                 for (int c = half * 32; c < OUT_COLS; c += 64) {
-                    if (col0 + c >= col_limit) break;          // warp-uniform
+                    const int cbase = col0 + out_c(c);
+                    if (cbase >= col_limit) { if (WIDE) continue; break; }          // warp-uniform
                     uint32_t r[32];
                     if (!empty_split) {
-                        tmem_ld32(taddr + c, r);
+                        tmem_ld32(taddr + tmem_c(c), r);
                         tc_wait_ld();
                     } else {
 #pragma unroll
                         for (int j = 0; j < 32; ++j) r[j] = 0u;
                     }
                     if (!row_ok) continue;
-                    const int cbase = col0 + c;
                     float* dst = P.partial + ((long long)split * P.M + row) * P.N + col_shift + cbase;
 #pragma unroll
                     for (int j = 0; j < 32; j += 4) {
@@ -1018,9 +1018,12 @@ static int launch_gemm_t(GemmParams& P, cudaStream_t stream) {
     if (g_dbg & (32 | 64)) P.tail_ws = g_tail_ws;            // epilogue clock log goes to the scratch buffer
     const int b_rows = CTA2 ? P.bn / 2 : P.bn;
     const int stage_bytes = BM * BK * 2 + (P.b_mn ? ((b_rows + 63) / 64) * 8192 : b_rows * BK * 2);
-    if (P.bn == 320 && (!CTA2 || P.mode == GM_CONV_WGRAD || P.epi != EPI_STORE || P.n_groups || P.tail_tiles)) {
-        set_error("gemm: the 320-wide plan needs CTA pairs, a Linear or conv-forward problem, EPI_STORE and no tail split");
-        return AOZ_ERR_ARG;
+    if (P.bn == 320) {
+        const bool epi_ok = P.mode == GM_CONV_WGRAD ? P.epi == EPI_PARTIAL : P.epi == EPI_STORE;
+        if (!CTA2 || !epi_ok || P.n_groups || P.tail_tiles) {
+            set_error("gemm: the 320-wide plan needs CTA pairs, a store epilogue (fp32 partials for conv weight gradients) and no tail split");
+            return AOZ_ERR_ARG;
+        }
     }
     P.stages = SMEM_TILE_BYTES / stage_bytes;
     if (P.stages > MAX_STAGES) P.stages = MAX_STAGES;
@@ -1564,9 +1567,17 @@ int aoz_conv_wgrad_bf16(const void* dy, const void* x, int NB, int H, int W, int
     P.m_tiles = ceil_div(Cout, BM);
     if (splits <= 0) splits = plan_splits(P.m_tiles, Cin, P.k_iters, (long long)Cout * taps * Cin, true, taps, false);
     if (splits > P.k_iters) splits = P.k_iters;
-    const TilePlan tp = plan_tiles(P.m_tiles, Cin, ceil_div(P.k_iters, splits), splits, true, false, taps);
+    TilePlan tp = plan_tiles(P.m_tiles, Cin, ceil_div(P.k_iters, splits), splits, true, false, taps);
+    if (g_wide_mode > 0 && g_pair_mode != 0 && g_force_bn == 0 && (Cin % 320) == 0 && P.m_tiles >= 2 && !(g_tail_mode == 2 && g_wide_mode != 2)) {
+        // 320-wide tiles: any number of rounds (a K iteration is 64 pixels, the single accumulator's exposed epilogue is small against it)
+        const long long units = (long long)ceil_div(P.m_tiles, 2) * taps * (Cin / 320) * splits;
+        const int slots = gemm_sms() / 2;
+        const double cyc = (double)((units + slots - 1) / slots) * ((double)ceil_div(P.k_iters, splits) * 775.0 + 2.0 * (6.0 * 320 + 400.0)) + 3000.0;
+        if (g_wide_mode == 2 || cyc < tp.cycles) tp = TilePlan{320, true, taps * (Cin / 320), cyc, 0, 1};
+    }
     const int bn = tp.bn;
     P.bn = bn;
+    P.wide_n2 = g_wide_mn_n2;
     P.n_tiles_per_tap = ceil_div(Cin, bn);
     P.n_tiles = taps * P.n_tiles_per_tap;
     P.splits = splits;

@@ -194,6 +194,32 @@ def test_conv_wide_plan_equals_ordinary_tiles():
             assert torch.equal(got, ref), (NB, H, W, Cin, Cout)
 
 
+def test_conv_wgrad_wide_plan_equals_ordinary_tiles():
+    """Weight gradients (both operands MN-major through 4-D TMA pixel tiles, fp32 partials + permuting reduce) on 320-wide tiles:
+    the third 64-channel chunk of a CTA's x tile is half used and the second MMA reads half a swizzle atom; with and without split-K,
+    stride 2, and an output-channel count that leaves the second CTA of the last pair partly empty."""
+    from aozora_sdxl_training_b200 import _lib
+    ops = _ops()
+    g = gen(61)
+    for NB, H, W, Cin, Cout, stride in ((1, 32, 32, 640, 320, 1), (2, 16, 16, 320, 256, 1), (1, 16, 16, 960, 640, 1), (2, 16, 16, 320, 640, 2)):
+        x = torch.randn(NB, H, W, Cin, device="cuda", generator=g).to(BF16)
+        Ho, Wo = H // stride, W // stride
+        dy = torch.randn(NB, Ho, Wo, Cout, device="cuda", generator=g).to(BF16)
+        runs = {}
+        for mode in (0, 2):
+            try:
+                _lib.call("aoz_gemm_set_wide_mode", mode, 0)
+                runs[mode] = [ops.conv_wgrad(dy, x, 3, stride=stride, pad=1, splits=sp) for sp in (1, 2, None)]
+            finally:
+                _lib.call("aoz_gemm_set_wide_mode", 1, 0)
+        xr = x.float().permute(0, 3, 1, 2)
+        wr = torch.zeros(Cout, Cin, 3, 3, device="cuda", requires_grad=True)
+        torch.nn.functional.conv2d(xr, wr, None, stride=stride, padding=1).backward(dy.float().permute(0, 3, 1, 2))
+        for got, ref in zip(runs[2], runs[0]):
+            check(got, wr.grad)
+            assert torch.equal(got, ref), (NB, H, W, Cin, Cout, stride)
+
+
 @pytest.mark.parametrize("M,C", [(512, 128), (4096, 640), (300, 64)])
 def test_geglu_fused_epilogue_and_backward(M, C):
     ops = _ops()
