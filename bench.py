@@ -138,7 +138,7 @@ def gemm_roofline(torch, peaks, iters=20):
                 peak=peaks["tf_burst"], unit="TFLOP/s", frac=round(ach / peaks["tf_burst"], 4),
                 # dram__bytes_read.sum + dram__bytes_write.sum of this exact launch from the committed `ncu --set full` capture
                 # (algorithmic bytes: 36.7 MB operands + 125.8 MB outputs, part of the output still in L2 when the kernel ends)
-                traffic=113007616, traffic_source="profiles/r02_gemm_geglu_ncu_v1.txt (dram__bytes_read 36.91 MB + dram__bytes_write 76.10 MB)",
+                traffic=113185536, traffic_source="profiles/r02_gemm_geglu_ncu_v2.txt (dram__bytes_read 36.92 MB + dram__bytes_write 76.26 MB)",
                 peak_source=f"{peaks['src']} bf16_tflops (burst: kernel timed alone)", ms_per_launch=round(ms, 4),
                 flops_per_launch=flops,
                 # the whole GEMM / conv family inside the step (1211 launches, FLOP-weighted): tools/gemm_in_step.py, recorded once per round

@@ -11,3 +11,6 @@ echo "launch list rc=$?"
 python tools/ncu_gemm.py 1 > gpurun_out/ncu_plain.log 2>&1 && \
 ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o gpurun_out/gemm_top python tools/ncu_gemm.py 1 > gpurun_out/ncu_full.log 2>&1
 echo "full capture rc=$?"
+python tools/ncu_gemm.py 1 proj > gpurun_out/ncu_plain_proj.log 2>&1 && \
+ncu --set full --clock-control none --import-source on -k regex:gemm_bf16 -s 2 -c 1 -o gpurun_out/gemm_proj python tools/ncu_gemm.py 1 proj > gpurun_out/ncu_full_proj.log 2>&1
+echo "projection capture rc=$?"
