@@ -25,7 +25,8 @@ def _line(name):
 @pytest.mark.parametrize("name,n", [("r01_bench_v7.json", 1), ("r01_bench_dp2_v2.json", 2), ("r01_bench_dp4_v1.json", 4),
                                     ("r01_bench_dp8_v2.json", 8), ("r02_bench_v3.json", 1), ("r02_bench_dp2_final.json", 2),
                                     ("r02_bench_dp8_mb512.json", 8), ("r02_bench_w3.json", 1), ("r02_bench_w4.json", 1),
-                                    ("r02_bench_dp8_w3.json", 8), ("r02_bench_dp8_w4.json", 8), ("r02_bench_dp1_v4.json", 1)])
+                                    ("r02_bench_dp8_w3.json", 8), ("r02_bench_dp8_w4.json", 8), ("r02_bench_dp1_v4.json", 1), ("r02_bench_dp1_v5.json", 1), ("r02_bench_dp2_v2.json", 2),
+                                    ("r02_bench_dp8_v2.json", 8)])
 def test_recorded_bench_lines_follow_the_contract(name, n):
     d = _line(name)
     assert BASE_KEYS <= set(d), BASE_KEYS - set(d)
