@@ -65,7 +65,8 @@ int aoz_gemm_set_tail_inkernel(int on);
 /* wide one-wave plan: outputs that are slightly more than one wave of 256 x 256 pair tiles (4096 x 1280 = 80 tiles on 74 SM pairs)
  * run as ONE round of 256 x 320 tiles (a single 320-column accumulator, two MMAs per K step).  mode 0 = off, 1 = cost model
  * decides (default), 2 = whenever the shape allows it (N % 320 == 0, tiles <= SM pairs, store epilogue, no split-K);
- * mn_n2 = 64 | 128 selects the second MMA's N for MN-major B (<= 0: keep). */
+ * mn_n2 = 64 | 128 selects the second MMA's N for MN-major B (<= 0: keep): 64 (default, the tested path) reads half a 64-wide
+ * swizzle atom per CTA, 128 reads the whole third chunk into 64 spare accumulator columns (fallback, not exercised by the tests). */
 int aoz_gemm_set_wide_mode(int mode, int mn_n2);
 /* rounds of 320-wide tiles per SM pair the planner may consider (default 2; the single accumulator serialises a pair's tiles) */
 int aoz_gemm_set_wide_max_rounds(int rounds);
